@@ -1,0 +1,171 @@
+/* ctr_b200.h - C ABI of libctr_b200.so: the B200 (sm_100a) CTR embedding +
+ * feature-interaction hot path.
+ *
+ * The reference (wangruichens/recsys) has no FFI: its hot path is the TensorFlow
+ * graph each model_fn builds.  Every entry point below replaces the TF ops of one
+ * reference call site (cited per function, paths relative to the reference root);
+ * INTEGRATION.md shows the ctypes / tf.load_op_library stubs that bind them.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, sizes, a cudaStream_t passed as void*.
+ *  - returns 0 (CTR_OK) or a negative code; ctr_last_error() has the text
+ *    (thread-local).  Never throws, never allocates device memory, never
+ *    synchronises: work is enqueued on `stream`; the caller owns every buffer.
+ *  - no CPU fallback: on a device that is not compute capability 10.x every
+ *    compute entry point returns CTR_ERR_ARCH.
+ *  - all float tensors fp32, row-major, 16-byte aligned; row ids int32 (global
+ *    row of the concatenated table [R, D]); "F axis" = the reference's
+ *    input_layer order (columns sorted by name).
+ */
+#ifndef CTR_B200_H_
+#define CTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_OK 0
+#define CTR_ERR_ARG (-1)   /* bad argument (null, misaligned, unsupported size) */
+#define CTR_ERR_CUDA (-2)  /* CUDA runtime error, text in ctr_last_error()      */
+#define CTR_ERR_ARCH (-3)  /* current device is not sm_100                      */
+
+#define CTR_MAX_FIELDS 64
+
+typedef void* ctr_stream_t; /* cudaStream_t */
+
+int ctr_version(void);
+const char* ctr_last_error(void);
+/* 0 when the current CUDA device can run this library (cc 10.x). */
+int ctr_device_check(void);
+
+/* ---------------------------------------------------------------- id pipeline
+ * Replaces the id-producing half of tf.feature_column.input_layer:
+ *   numeric_column(normalizer_fn=log(x+off)) -> bucketized_column(boundaries)
+ *   (fm/fm.py:76-80) and categorical_column_with_hash_bucket (fm/fm.py:89) for
+ *   already-hashed local ids.
+ * One descriptor per field, in F-axis order. */
+typedef struct {
+  int32_t kind;       /* 0 = log-bucketised numeric, 1 = pre-hashed categorical */
+  int32_t src;        /* column of xcont (kind 0) / xcat (kind 1)               */
+  int32_t n_rows;     /* rows of this field's table                             */
+  int32_t row_offset; /* first row of the field in the concatenated table       */
+  int32_t bnd_begin;  /* kind 0: first boundary in `boundaries`                 */
+  int32_t bnd_count;  /* kind 0: number of boundaries (n_rows - 1)              */
+  float log_offset;   /* kind 0: 1.0 (4.0 for _c2, fm/fm.py:77-78)              */
+  int32_t pad_;
+} ctr_field_desc;
+
+/* rows[b,f] = row_offset_f + (kind0: upper_bound(boundaries_f, logf(x+off)) | kind1: xcat id).
+ * logx (nullable): [B, n_cont] the log-normalised numerics (xdeepfm linear part,
+ * xdeepfm/xdeepfm.py:82).  status (nullable, device int): bit0 set if any
+ * categorical id was outside [0, n_rows) (it is wrapped by modulo). */
+int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_cat,
+                    const ctr_field_desc* fields_dev, const float* boundaries_dev, int B, int F,
+                    int32_t* rows, float* logx, int32_t* status, ctr_stream_t stream);
+
+/* FarmHash Fingerprint64(bytes) mod n_buckets for N strings (TF StringToHashBucketFast,
+ * fm/fm.py:89).  bytes: concatenated strings; offsets[N+1]; field_of[N] (nullable) selects
+ * n_buckets[field] and row_offset[field]; out[i] = row_offset + hash % n_buckets. */
+int ctr_hash_strings(const uint8_t* bytes, const int32_t* offsets, int64_t N,
+                     const int32_t* field_of, const int32_t* n_buckets_dev,
+                     const int32_t* row_offset_dev, int32_t* out, ctr_stream_t stream);
+
+/* --------------------------------------------------- fused multi-field lookup
+ * Forward.  Replaces input_layer(embedding columns) + input_layer(indicator
+ * columns) + the FM second-order block + (optionally) the DCN cross stack:
+ *   fm/fm.py:117-129, deepfm/deepfm.py:84-98, xdeepfm/xdeepfm.py:127-128,185,
+ *   dcn/dcn.py:122-142.
+ *   E[b, f*D:(f+1)*D] = table[rows[b,f]]                                 (nullable)
+ *   S[b, :]  = sum_f table[rows[b,f]]                                    (nullable)
+ *   y1[b]    = sum_{f in w1_fields} w1[rows[b,f]]   (pre-bias, pre-ReLU) (nullable)
+ *   y2[b]    = 0.5 * sum_d[(sum_f E)^2 - sum_f E^2]                      (nullable)
+ *   xl[b,:]  = cross stack on x0 = E[b,:]: xl <- (xl.w_l) x0 + xl + b_l  (nullable)
+ * D in {8,16,32}; F <= 64 and F*D <= 1280; w1_fields bit f = field f has a first-order weight. */
+int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
+                  uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
+                  const float* cross_w, const float* cross_b, int cross_layers, float* xl,
+                  ctr_stream_t stream);
+
+/* Backward: scatter-add of the row gradients into dtable / dw1 (the IndexedSlices
+ * gradient of the gathers, fm/fm.py:162-163), field-major, contention-free for
+ * fields with <= 32 rows.
+ *   g[b,f,:] = dE[b,f,:] (if given) + dy2[b] * (S[b,:] - E[b,f,:]) (if dy2 given)
+ *   dtable[rows[b,f], :] += g[b,f,:]  ;  dw1[rows[b,f]] += dy1[b] for f in w1_fields
+ * E nullable (rows are re-gathered from `table`).  row_offsets: HOST int64[F+1]. */
+int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const float* table,
+                  const float* S, const float* dy2, const float* dy1, uint64_t w1_fields,
+                  const int64_t* row_offsets_host, int B, int F, int D, float* dtable, float* dw1,
+                  ctr_stream_t stream);
+
+/* DCN cross stack, stand-alone (dcn/dcn.py:132-142) on x0[B,W] (W = F*D, W%4==0, W<=1280). */
+int ctr_dcn_cross_fwd(const float* x0, const float* w, const float* b, int L, int B, int W,
+                      float* xl, ctr_stream_t stream);
+/* dx0 = d(loss)/d(x0) through the cross stack (written, not accumulated);
+ * dw[L,W], db[L,W] accumulated (+=). */
+int ctr_dcn_cross_bwd(const float* x0, const float* w, const float* b, int L, int B, int W,
+                      const float* dxl, float* dx0, float* dw, float* db, ctr_stream_t stream);
+
+/* ------------------------------------------------------------------ optimiser
+ * tf.train.AdamOptimizer semantics (fm/fm.py:162): eps outside the sqrt, lr_t
+ * computed by the caller.  ctr_adam_dense: every element (TF's sparse apply decays
+ * m, v of every row).  g is zeroed afterwards when zero_g != 0. */
+int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, int zero_g, ctr_stream_t stream);
+/* Lazy variant: exactly one update per distinct row in rows[n] (claim[R] int32
+ * scratch, tag must differ from the previous call's), then zeroes the row of g. */
+int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
+                  float* g, int32_t* claim, int32_t tag, float lr_t, float beta1, float beta2,
+                  float eps, ctr_stream_t stream);
+
+/* -------------------------------------------------------- DIN activation unit
+ * din/din.py:103-125 `_attention`: for each sample b and position p with hist[b,p] > 0
+ *   h = table[hist[b,p]]; a = [h, q_b, h*q_b, h-q_b]; w = W3.relu(W2.relu(W1.a+b1)+b2)+b3
+ *   out[b,:] = sum_p w * h        (no softmax; padding id 0 is masked out)
+ * W1 [4E,H1], W2 [H1,H2], W3 [H2] row-major as tf.layers.dense kernels.  E in {8,16,32};
+ * H1 <= 128, H2 <= 64.  att_w (nullable) [B,P] receives the raw position weights. */
+int ctr_din_att_fwd(const float* table, const int32_t* hist, const float* query, int B, int P,
+                    int E, const float* W1, const float* b1, int H1, const float* W2,
+                    const float* b2, int H2, const float* W3, const float* b3, float* out,
+                    float* att_w, ctr_stream_t stream);
+/* Backward of the above: dtable rows += (RED scatter), dquery[B,E] written, weight and bias
+ * gradients (dW1..dW3, db1..db3) accumulated (+=).  workspace: ctr_din_workspace_bytes(B,P,E)
+ * bytes of scratch (per-position h1/dh1/dh2/h rows feeding the tall-skinny dW reductions). */
+int64_t ctr_din_workspace_bytes(int B, int P, int E);
+int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query, int B, int P,
+                    int E, const float* W1, const float* b1, int H1, const float* W2,
+                    const float* b2, int H2, const float* W3, const float* b3, const float* dout,
+                    float* dtable, float* dquery, float* dW1, float* db1, float* dW2, float* db2,
+                    float* dW3, float* db3, void* workspace, int64_t workspace_bytes,
+                    ctr_stream_t stream);
+
+/* --------------------------------------------------------------- xDeepFM CIN
+ * One CIN layer (xdeepfm/xdeepfm.py:145-169):
+ *   out[b,d,h] = relu( sum_{i<m, j<Hp} X0[b,d,i] * Xp[b,d,j] * W[i*Hp+j, h] + bias[h] )
+ * Internal layouts are "d-major rows": X0t [B*D, m_pad], Xp [B*D, Hp_pad], out [B*D, H]
+ * (row = b*D+d, feature contiguous; *_pad = leading dimension).
+ * prec: 0 = fp32 CUDA cores (exact-parity mode), 1 = TF32 tcgen05 tensor cores,
+ *       2 = 3xTF32 split on tcgen05 (fp32-grade accuracy). */
+#define CTR_CIN_FP32 0
+#define CTR_CIN_TF32 1
+#define CTR_CIN_TF32X3 2
+int64_t ctr_cin_workspace_bytes(int B, int D, int m, int Hp, int H, int prec);
+int ctr_cin_layer_fwd(const float* X0t, int ld0, const float* Xp, int ldp, const float* W,
+                      const float* bias, int B, int D, int m, int Hp, int H, float* out, int prec,
+                      void* workspace, int64_t workspace_bytes, ctr_stream_t stream);
+/* dpre[B*D,H] = d(loss)/d(pre-activation) (ReLU mask already applied by the caller).
+ * dX0t, dXp accumulated (+=) - X0 feeds every layer; dW [m*Hp,H], dbias [H] accumulated. */
+int ctr_cin_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp, const float* W,
+                      const float* dpre, int B, int D, int m, int Hp, int H, float* dX0t,
+                      float* dXp, float* dW, float* dbias, int prec, void* workspace,
+                      int64_t workspace_bytes, ctr_stream_t stream);
+/* [B, F, D] (E layout) <-> [B*D, ld] d-major rows (zero padded to ld). */
+int ctr_transpose_fd(const float* E, int B, int F, int D, float* Xt, int ld, ctr_stream_t stream);
+int ctr_transpose_df_add(const float* dXt, int ld, int B, int F, int D, float* dE,
+                         ctr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTR_B200_H_ */

@@ -1,0 +1,441 @@
+"""Model objects behind the five reference ``model_fn`` entry points.
+
+Each class holds the variables the reference's graph would create, runs the
+forward through the fused sm_100a kernels (ops.py) and the small dense towers
+through torch (cuBLAS; SURVEY 2.3 K7: "stays torch"), and exposes
+``spec(features, labels, mode)`` returning the EstimatorSpec the reference's
+model_fn returns.  Parameter names follow DESIGN.md "parameter names" (shared by
+convention with the oracle so tests can load identical weights).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as Fn
+
+from . import feature_column as fc
+from . import ops
+from .estimator import (DEFAULT_SERVING_SIGNATURE_DEF_KEY, EstimatorSpec, ModeKeys, PredictOutput,
+                        StreamingAccuracy, StreamingAUC, VariableStore)
+
+BN_EPS = 1e-3   # tf.layers.batch_normalization default (deepfm/deepfm.py:106)
+
+
+def _glorot_uniform(shape, gen):
+    if len(shape) == 1:
+        fi = fo = shape[0]
+    else:
+        fi, fo = shape[0], shape[1]
+    lim = math.sqrt(6.0 / (fi + fo))
+    return (torch.rand(shape, generator=gen) * 2 - 1) * lim
+
+
+def _glorot_normal(shape, gen):
+    if len(shape) == 1:
+        fi = fo = shape[0]
+    else:
+        fi, fo = shape[0], shape[1]
+    std = math.sqrt(2.0 / (fi + fo)) / 0.87962566103423978
+    t = torch.empty(shape)
+    torch.nn.init.trunc_normal_(t, std=std, a=-2 * std, b=2 * std, generator=gen)
+    return t
+
+
+def _device(params):
+    dev = params.get("device")
+    if dev is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("recsys_b200 needs a CUDA device (B200, sm_100); there is no CPU "
+                               "path - the oracle under oracle/ is test infrastructure only")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(dev)
+
+
+def bce_with_logits_mean(logits, labels):
+    """tf.reduce_mean(tf.nn.sigmoid_cross_entropy_with_logits) (fm/fm.py:146-149)."""
+    z = labels.to(logits.device, torch.float32).reshape(logits.shape)
+    return Fn.binary_cross_entropy_with_logits(logits, z)
+
+
+class _ModelBase:
+    name = "base"
+
+    def __init__(self, params: dict):
+        self.params = params
+        self.device = _device(params)
+        self.dropout = float(params.get("dropout", 0.0))
+        self.adam = ops.TFAdamState(lr=float(params.get("learning_rate", 1e-3)))
+        self.store: Optional[VariableStore] = None
+        self.last = {}
+
+    # towers ---------------------------------------------------------------------
+    def _tower_shapes(self, shapes, prefix, sizes, bn):
+        for l, (i, o) in enumerate(zip(sizes[:-1], sizes[1:])):
+            shapes[f"{prefix}.{l}.w"] = (i, o)
+            shapes[f"{prefix}.{l}.b"] = (o,)
+            if bn:
+                for s in ("gamma", "beta", "mean", "var"):
+                    shapes[f"{prefix}.{l}.bn.{s}"] = (o,)
+
+    def _init_dense(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        P = self.dense
+        with torch.no_grad():
+            for n in P.names:
+                v = P[n]
+                if n.endswith(".w"):
+                    v.copy_(self._init_weight(n, tuple(v.shape), g))
+                elif n.endswith((".bn.gamma", ".bn.var")):
+                    v.fill_(1.0)
+                else:
+                    v.zero_()
+
+    def _init_weight(self, name, shape, g):
+        return _glorot_uniform(shape, g)
+
+    def _tower(self, x, prefix, n_layers, training, bn=True):
+        P = self.dense
+        for l in range(n_layers):
+            x = torch.relu(torch.addmm(P[f"{prefix}.{l}.b"], x, P[f"{prefix}.{l}.w"]))
+            if bn:
+                if training:   # batch mean / biased variance; moving stats untouched
+                    x = Fn.batch_norm(x, None, None, P[f"{prefix}.{l}.bn.gamma"],
+                                      P[f"{prefix}.{l}.bn.beta"], True, 0.0, BN_EPS)
+                else:
+                    x = Fn.batch_norm(x, P[f"{prefix}.{l}.bn.mean"], P[f"{prefix}.{l}.bn.var"],
+                                      P[f"{prefix}.{l}.bn.gamma"], P[f"{prefix}.{l}.bn.beta"],
+                                      False, 0.0, BN_EPS)
+            if training and self.dropout > 0.0:
+                x = Fn.dropout(x, self.dropout, True)
+        return x
+
+    # state ----------------------------------------------------------------------
+    def load_state(self, state: Dict[str, torch.Tensor]):
+        """Load oracle-named parameters (tests, checkpoints)."""
+        self.dense.load(state)
+
+    def dense_grads(self):
+        return self.dense.grads()
+
+    # EstimatorSpec --------------------------------------------------------------
+    def logits(self, features, mode):
+        raise NotImplementedError
+
+    def _apply_gradients(self):
+        raise NotImplementedError
+
+    def spec(self, features, labels, mode) -> EstimatorSpec:
+        training = mode == ModeKeys.TRAIN
+        with torch.set_grad_enabled(training):
+            logits = self.logits(features, training)
+            pred = torch.sigmoid(logits)
+        predictions = {"prob": pred}
+        export_outputs = {DEFAULT_SERVING_SIGNATURE_DEF_KEY: PredictOutput(predictions)}
+        if mode == ModeKeys.PREDICT:
+            return EstimatorSpec(mode=mode, predictions=predictions, export_outputs=export_outputs)
+        with torch.set_grad_enabled(training):
+            loss = bce_with_logits_mean(logits, labels)
+        if mode == ModeKeys.EVAL:
+            ops_ = {"AUC": StreamingAUC().update(labels, pred),
+                    "Accuracy": StreamingAccuracy().update(labels, pred)}
+            return EstimatorSpec(mode=mode, predictions=predictions, loss=loss.detach(),
+                                 eval_metric_ops=ops_)
+
+        def train_op():
+            self.backward(loss)
+            self.apply_gradients()
+
+        self.last = {"loss": loss, "logits": logits}
+        return EstimatorSpec(mode=mode, predictions=predictions, loss=loss.detach(),
+                             train_op=train_op)
+
+    def backward(self, loss):
+        loss.backward()
+
+    def apply_gradients(self):
+        lr_t = self.adam.next_lr_t()
+        self._apply_gradients(lr_t)
+        if self.store is not None:
+            self.store.global_step += 1
+
+
+class _CriteoBase(_ModelBase):
+    """Shared by fm / deepfm / xdeepfm / dcn: one FieldEmbedding over the
+    embedding columns + the id pipeline."""
+
+    want_w1 = True
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.lay = fc.layout(params["embedding_feature_columns"])
+        if int(params.get("embedding_size", self.lay.dimension)) != self.lay.dimension:
+            raise ValueError("params['embedding_size'] disagrees with the embedding columns")
+        self.F, self.D = self.lay.F, self.lay.dimension
+        mask, self.numeric_linear = fc.first_order_fields(params.get("linear_feature_columns", []),
+                                                          self.lay) if self.want_w1 else (0, [])
+        seed = int(params.get("seed", 0))
+        self.emb = ops.FieldEmbedding(self.lay, self.device, with_w1=self.want_w1, w1_fields=mask,
+                                      adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
+        self.ids = ops.IdPipeline(self.lay, self.device)
+        self.rows = None
+
+    def load_state(self, state):
+        super().load_state(state)
+        self.emb.load(state.get("emb"), state.get("w1"))
+
+    def _apply_gradients(self, lr_t):
+        self.emb.adam_step(self.rows, lr_t, self.adam)
+        self.dense.adam_step(lr_t, self.adam)
+
+
+# ============================================================================ FM
+class FMModel(_CriteoBase):
+    """fm/fm.py:115-170."""
+    name = "fm"
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.dense = ops.DenseParams({"b1": (1,), "head.w": (2, 1), "head.b": (1,)}, self.device)
+        self._init_dense(int(params.get("seed", 0)) + 1)
+
+    def logits(self, features, training):
+        P = self.dense
+        self.rows = self.ids(features)
+        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
+        y1 = torch.relu(y1s + P["b1"])                                   # fm/fm.py:121
+        z = torch.stack([y1, y2], 1)                                      # :131
+        return torch.addmm(P["head.b"], z, P["head.w"])                   # :132  [B,1]
+
+
+# ======================================================================== DeepFM
+class DeepFMModel(_CriteoBase):
+    """deepfm/deepfm.py:73-150 (field-count agnostic; fed the Criteo columns)."""
+    name = "deepfm"
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.layers = list(map(int, str(params["deep_layers"]).split(",")))
+        shapes = {"b1": (1,)}
+        self._tower_shapes(shapes, "dnn", [self.F * self.D] + self.layers, bn=True)
+        shapes.update({"dnn.out.w": (self.layers[-1], 1), "dnn.out.b": (1,), "head.w": (3, 1),
+                       "head.b": (1,)})
+        frozen = [n for n in shapes if n.endswith((".bn.mean", ".bn.var"))]
+        self.dense = ops.DenseParams(shapes, self.device, frozen=frozen)
+        self._init_dense(int(params.get("seed", 0)) + 1)
+
+    def logits(self, features, training):
+        P = self.dense
+        self.rows = self.ids(features)
+        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
+        y1 = torch.relu(y1s + P["b1"])                                    # deepfm.py:91
+        h = self._tower(E, "dnn", len(self.layers), training)             # :100-107
+        y3 = torch.relu(torch.addmm(P["dnn.out.b"], h, P["dnn.out.w"]))   # :108
+        z = torch.cat([y1[:, None], y2[:, None], y3], 1)                  # :110
+        return torch.addmm(P["head.b"], z, P["head.w"]).reshape(-1)       # :111-112  [B]
+
+
+# =========================================================================== DCN
+class DCNModel(_CriteoBase):
+    """dcn/dcn.py:117-190.  linear_feature_columns are built but unused (:122,129-130)."""
+    name = "dcn"
+    want_w1 = False
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.layers = list(map(int, str(params["deep_layers"]).split(",")))
+        self.L = int(params.get("cross_layers", 4))       # FLAGS.cross_layers, dcn/dcn.py:24,134
+        W = self.F * self.D
+        shapes = {"cross.w": (self.L, W), "cross.b": (self.L, W)}
+        self._tower_shapes(shapes, "dnn", [W] + self.layers, bn=True)
+        shapes.update({"head.w": (self.layers[-1] + W, 1), "head.b": (1,)})
+        frozen = [n for n in shapes if n.endswith((".bn.mean", ".bn.var"))]
+        self.dense = ops.DenseParams(shapes, self.device, frozen=frozen)
+        self._init_dense(int(params.get("seed", 0)) + 1)
+
+    def _init_weight(self, name, shape, g):
+        if name == "cross.w":
+            return torch.stack([_glorot_normal((shape[1],), g) for _ in range(shape[0])])
+        return _glorot_uniform(shape, g)
+
+    def _init_dense(self, seed):
+        super()._init_dense(seed)
+        g = torch.Generator().manual_seed(seed + 7)
+        with torch.no_grad():   # cross bias is glorot-normal too (dcn/dcn.py:140)
+            self.dense["cross.b"].copy_(torch.stack(
+                [_glorot_normal((self.F * self.D,), g) for _ in range(self.L)]))
+
+    def load_state(self, state):
+        st = dict(state)
+        if "cross.0.w" in st:
+            st["cross.w"] = torch.stack([st[f"cross.{l}.w"] for l in range(self.L)])
+            st["cross.b"] = torch.stack([st[f"cross.{l}.b"] for l in range(self.L)])
+        super().load_state(st)
+
+    def logits(self, features, training):
+        P = self.dense
+        self.rows = self.ids(features)
+        E, _, _, xl = self.emb.lookup(self.rows, want_fm=False, want_y1=False,
+                                      cross_w=P["cross.w"], cross_b=P["cross.b"])
+        h = self._tower(E, "dnn", len(self.layers), training)             # dcn.py:144-149
+        z = torch.cat([h, xl], 1)                                         # :151
+        return torch.addmm(P["head.b"], z, P["head.w"])                   # :152  [B,1]
+
+
+# ======================================================================= xDeepFM
+class XDeepFMModel(_CriteoBase):
+    """xdeepfm/xdeepfm.py:123-233: linear (13 log-numerics + 26 one-hots, :82,91,131)
+    + CIN (:135-182) + DNN (:184-192).  The DNN branch has its own embedding tables
+    because the reference calls input_layer a second time (:185) [TF-sem]; pass
+    params['share_embeddings']=True to use one set."""
+    name = "xdeepfm"
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.layers = list(map(int, str(params["deep_layers"]).split(",")))
+        self.cin_layers = list(map(int, str(params["cross_layers"]).split(",")))
+        self.cin_precision = params.get("cin_precision", "tf32x3")
+        self.share = bool(params.get("share_embeddings", False))
+        seed = int(params.get("seed", 0))
+        self.emb_dnn = None if self.share else ops.FieldEmbedding(
+            self.lay, self.device, with_w1=False, adam_mode=params.get("embedding_adam", "lazy"),
+            seed=seed + 100)
+        shapes = {"b1": (1,), "wnum": (len(self.ids.cont_keys),)}
+        hp = self.F
+        for k, h in enumerate(self.cin_layers):
+            shapes[f"cin.{k}.w"] = (self.F * hp, h)
+            shapes[f"cin.{k}.b"] = (h,)
+            hp = h
+        shapes.update({"cin.out.w": (sum(self.cin_layers), 1), "cin.out.b": (1,)})
+        self._tower_shapes(shapes, "dnn", [self.F * self.D] + self.layers, bn=True)
+        shapes.update({"dnn.out.w": (self.layers[-1], 1), "dnn.out.b": (1,), "head.w": (3, 1),
+                       "head.b": (1,)})
+        frozen = [n for n in shapes if n.endswith((".bn.mean", ".bn.var"))]
+        self.dense = ops.DenseParams(shapes, self.device, frozen=frozen)
+        self._init_dense(seed + 1)
+        with torch.no_grad():
+            g = torch.Generator().manual_seed(seed + 2)
+            self.dense["wnum"].copy_(_glorot_uniform((len(self.ids.cont_keys), 1), g).reshape(-1))
+
+    def load_state(self, state):
+        super().load_state(state)
+        if self.emb_dnn is not None and "emb_dnn" in state:
+            self.emb_dnn.load(state["emb_dnn"])
+
+    def logits(self, features, training):
+        P = self.dense
+        want_num = len(self.numeric_linear) > 0
+        if want_num:
+            self.rows, logx = self.ids(features, want_logx=True)
+        else:
+            self.rows, logx = self.ids(features), None
+        E, y1s, _, _ = self.emb.lookup(self.rows, want_fm=False, want_y1=True)
+        lin = y1s + P["b1"]
+        if want_num:
+            lin = lin + logx @ P["wnum"]                                        # :82
+        linear_y = torch.relu(lin)                                              # :131
+        Ws = [P[f"cin.{k}.w"] for k in range(len(self.cin_layers))]
+        bs = [P[f"cin.{k}.b"] for k in range(len(self.cin_layers))]
+        pooled = ops.cin(E, self.F, self.D, Ws, bs, self.cin_precision)         # :135-181
+        cin_y = torch.relu(torch.addmm(P["cin.out.b"], pooled, P["cin.out.w"]))  # :182
+        if self.emb_dnn is not None:
+            Ed = self.emb_dnn.lookup(self.rows, want_fm=False, want_y1=False)[0]  # :185
+        else:
+            Ed = E
+        h = self._tower(Ed, "dnn", len(self.layers), training)                  # :188-191
+        dnn_y = torch.relu(torch.addmm(P["dnn.out.b"], h, P["dnn.out.w"]))      # :192
+        z = torch.cat([linear_y[:, None], cin_y, dnn_y], 1)                     # :194
+        return torch.addmm(P["head.b"], z, P["head.w"])                         # :195  [B,1]
+
+    def _apply_gradients(self, lr_t):
+        self.emb.adam_step(self.rows, lr_t, self.adam)
+        if self.emb_dnn is not None:
+            self.emb_dnn.adam_step(self.rows, lr_t, self.adam)
+        self.dense.adam_step(lr_t, self.adam)
+
+
+# =========================================================================== DIN
+DIN_ITEMS, DIN_CATES = 63002, 802          # din/din.py:88-90 (hard-coded there)
+DIN_ATT_LAYERS = [80, 40]                  # din/din.py:85
+DIN_MLP_LAYERS = [100, 50, 20]             # din/din.py:86
+
+
+class DINModel(_ModelBase):
+    """din/din.py:83-180.  The two tables (i_id, i_cate) live in one FieldEmbedding
+    (sub-table 0 and 1, same width); i_item is its first-order vector."""
+    name = "din"
+
+    def __init__(self, params):
+        super().__init__(params)
+        E = int(params["embedding_size"])
+        self.E = E
+        n_items = int(params.get("din_items", DIN_ITEMS))
+        n_cates = int(params.get("din_cates", DIN_CATES))
+        cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("i_id", n_items), E),
+                fc.embedding_column(fc.categorical_column_with_hash_bucket("i_cate", n_cates), E)]
+        self.lay = fc.Layout(cols, ["i_id", "i_cate"], [n_items, n_cates],
+                             [0, n_items, n_items + n_cates], E)
+        seed = int(params.get("seed", 0))
+        self.emb = ops.FieldEmbedding(self.lay, self.device, with_w1=True, w1_fields=0b01,
+                                      adam_mode=params.get("embedding_adam", "exact_tf"), seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():   # glorot_normal tables, zero item bias (din/din.py:88-90)
+            self.emb.table[:n_items].copy_(_glorot_normal((n_items, E), g))
+            self.emb.table[n_items:].copy_(_glorot_normal((n_cates, E), g))
+            self.emb.w1.zero_()
+        shapes = {}
+        for name in ("att_iid", "att_cat"):
+            self._tower_shapes(shapes, name, [4 * E] + DIN_ATT_LAYERS + [1], bn=False)
+        self._tower_shapes(shapes, "mlp", [3 * E] + DIN_MLP_LAYERS, bn=False)
+        shapes.update({"mlp.out.w": (DIN_MLP_LAYERS[-1], 1), "mlp.out.b": (1,)})
+        self.dense = ops.DenseParams(shapes, self.device)
+        self._init_dense(seed + 1)
+        self.n_items = n_items
+        self.rows = None
+
+    def load_state(self, state):
+        super().load_state(state)
+        if "i_id" in state:
+            tab = torch.cat([state["i_id"], state["i_cate"]], 0)
+            w1 = torch.cat([state["i_item"].reshape(-1),
+                            torch.zeros(self.lay.rows[1], dtype=state["i_item"].dtype)])
+            self.emb.load(tab, w1)
+
+    def _att(self, prefix, field, hist, query):
+        P = self.dense
+        return ops.din_attention(self.emb, field, hist, query, P[f"{prefix}.0.w"], P[f"{prefix}.0.b"],
+                                 P[f"{prefix}.1.w"], P[f"{prefix}.1.b"], P[f"{prefix}.2.w"],
+                                 P[f"{prefix}.2.b"])
+
+    def logits(self, features, training):
+        if training and self.dropout > 0.0:
+            raise NotImplementedError(
+                "dropout inside the fused DIN activation unit is not implemented; use dropout=0")
+        P = self.dense
+        dev = self.device
+        i_id = torch.as_tensor(features["i_id"]).to(dev, non_blocking=True).reshape(-1)
+        i_cate = torch.as_tensor(features["i_cate"]).to(dev, non_blocking=True).reshape(-1)
+        h_iid = torch.as_tensor(features["u_iid_seq"]).to(dev, non_blocking=True).to(torch.int32)
+        h_cat = torch.as_tensor(features["u_icat_seq"]).to(dev, non_blocking=True).to(torch.int32)
+        self.rows = torch.stack([i_id, i_cate + self.n_items], 1).to(torch.int32)
+        self.hist = (h_iid, h_cat)
+        Ecat, i_b, _, _ = self.emb.lookup(self.rows, want_fm=False, want_y1=True)   # :91-99
+        E = self.E
+        pkg_emb, pkgc_emb = Ecat[:, :E], Ecat[:, E:]
+        pkg_h = self._att("att_iid", 0, h_iid, pkg_emb)                             # :127
+        pkgc_h = self._att("att_cat", 1, h_cat, pkgc_emb)                           # :128
+        net = torch.cat([pkg_emb, pkg_h, pkgc_h], 1)                                # :131
+        net = self._tower(net, "mlp", len(DIN_MLP_LAYERS), training, bn=False)      # :133-137
+        out = torch.addmm(P["mlp.out.b"], net, P["mlp.out.w"])                      # :139
+        return out.reshape(-1) + i_b                                                # :140
+
+    def _apply_gradients(self, lr_t):
+        if self.emb.adam_mode == "exact_tf":
+            self.emb.adam_step(self.rows, lr_t, self.adam)
+        else:
+            h_iid, h_cat = self.hist
+            touched = torch.cat([self.rows.reshape(-1), h_iid.reshape(-1),
+                                 (h_cat + self.n_items).reshape(-1)])
+            self.emb.adam_step(touched, lr_t, self.adam)
+        self.dense.adam_step(lr_t, self.adam)

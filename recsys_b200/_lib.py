@@ -1,0 +1,97 @@
+"""ctypes binding of libctr_b200.so (include/ctr_b200.h).
+
+The shared library is the product: there is no Python or CPU fallback.  If it is
+missing (not built) the import of any compute symbol raises; if the current CUDA
+device is not sm_100 every compute call returns CTR_ERR_ARCH and ``check``
+raises ``RuntimeError`` with ``ctr_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctr_b200.so")
+
+_lib = None
+
+c_f = C.c_void_p      # device pointers are passed as integers (tensor.data_ptr())
+c_i = C.c_int
+c_i64 = C.c_int64
+c_u64 = C.c_uint64
+c_fl = C.c_float
+
+
+class FieldDesc(C.Structure):
+    """ctr_field_desc (include/ctr_b200.h)."""
+    _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("n_rows", C.c_int32),
+                ("row_offset", C.c_int32), ("bnd_begin", C.c_int32), ("bnd_count", C.c_int32),
+                ("log_offset", C.c_float), ("pad_", C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/ctr_b200.h declares.
+SIGNATURES = {
+    "ctr_version": (c_i, []),
+    "ctr_last_error": (C.c_char_p, []),
+    "ctr_device_check": (c_i, []),
+    "ctr_criteo_rows": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f]),
+    "ctr_hash_strings": (c_i, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "ctr_embed_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i,
+                            c_f, c_f]),
+    "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
+                            c_i, c_i, c_f, c_f, c_f]),
+    "ctr_dcn_cross_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f]),
+    "ctr_dcn_cross_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
+    "ctr_adam_dense": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_i, c_f]),
+    "ctr_adam_rows": (c_i, [c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_f, C.c_int32, c_fl, c_fl, c_fl,
+                            c_fl, c_f]),
+    "ctr_din_att_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,
+                              c_f, c_f, c_f]),
+    "ctr_din_workspace_bytes": (c_i64, [c_i, c_i, c_i]),
+    "ctr_din_att_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,
+                              c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_f]),
+    "ctr_cin_workspace_bytes": (c_i64, [c_i, c_i, c_i, c_i, c_i, c_i]),
+    "ctr_cin_layer_fwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_i,
+                                c_f, c_i64, c_f]),
+    "ctr_cin_layer_bwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f,
+                                c_f, c_f, c_i, c_f, c_i64, c_f]),
+    "ctr_transpose_fd": (c_i, [c_f, c_i, c_i, c_i, c_f, c_i, c_f]),
+    "ctr_transpose_df_add": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
+}
+
+
+def load():
+    """Load libctr_b200.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "recsys_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  There is no fallback path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().ctr_last_error().decode()
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("libctr_b200 error %d: %s" % (rc, last_error()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,78 @@
+// libctr_b200: version, error plumbing, device gate (no CPU fallback, sm_100 only).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ctr {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int fail_arg(const char* fn, const char* what) {
+  set_error(std::string(fn) + ": " + what);
+  return CTR_ERR_ARG;
+}
+
+int check_cuda(cudaError_t e, const char* fn) {
+  if (e == cudaSuccess) return CTR_OK;
+  set_error(std::string(fn) + ": CUDA error: " + cudaGetErrorString(e));
+  return CTR_ERR_CUDA;
+}
+
+static std::mutex g_mu;
+static int g_major[64];
+static int g_sms[64];
+static bool g_seen[64];
+
+static int query_device(int* major, int* sms) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return CTR_ERR_ARCH;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_seen[dev]) {
+    int mj = 0, sm = 0;
+    cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    g_major[dev] = mj;
+    g_sms[dev] = sm;
+    g_seen[dev] = true;
+  }
+  *major = g_major[dev];
+  *sms = g_sms[dev];
+  return CTR_OK;
+}
+
+int ensure_arch() {
+  int mj = 0, sm = 0;
+  int r = query_device(&mj, &sm);
+  if (r != CTR_OK) return r;
+  if (mj != 10) {
+    set_error("libctr_b200 is built for sm_100a only; current device has compute capability " +
+              std::to_string(mj) + ".x (no fallback path exists)");
+    return CTR_ERR_ARCH;
+  }
+  return CTR_OK;
+}
+
+int sm_count() {
+  int mj = 0, sm = 0;
+  if (query_device(&mj, &sm) != CTR_OK) return 148;
+  return sm > 0 ? sm : 148;
+}
+
+}  // namespace ctr
+
+extern "C" {
+
+int ctr_version(void) { return 100; }
+
+const char* ctr_last_error(void) { return ctr::g_last_error.c_str(); }
+
+int ctr_device_check(void) { return ctr::ensure_arch(); }
+
+}  // extern "C"

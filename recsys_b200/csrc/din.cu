@@ -1,0 +1,515 @@
+// DIN activation unit (din/din.py:103-125 `_attention`), fused: gather the history
+// rows, run the 4E->80->40->1 attention MLP per position in registers, masked
+// weighted sum - one warp per sample, one lane per history position.
+//
+// Algebra used to shrink layer 1 (a = [h, q, h*q, h-q], W1 = [W1a; W1b; W1c; W1d]):
+//   a.W1 = h.(W1a + W1d) + q.(W1b - W1d) + (h*q).W1c = cq + h.Weff,
+//   cq = b1 + q.Wq,  Weff[e][k] = Wh[e][k] + q[e] * Wp[e][k]   (per sample, in shared memory)
+// which takes the per-position cost from 5120+3200 to 1280+3200 MACs.
+//
+// Backward = kernel 1 (same structure): recompute, d(out) -> dw, dh2, dh1, dh (RED into the
+// table gradient), dq; it also leaves h1/dh1/dh2/h/h*q rows in scratch so that kernel 2
+// (`xtx`: C += A^T B over the valid rows) forms dW1/dW2 as tall-skinny reductions.
+// FP32 CUDA-core work, compute-bound: padding positions are skipped.
+#include "common.cuh"
+
+namespace ctr {
+
+constexpr int kH1 = 80, kH2 = 40;   // attention_layers = [80, 40] is hard-coded in din/din.py:85
+
+struct DinParams {
+  const float* table;
+  const int* hist;
+  const float* query;
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  const float* b2;
+  const float* W3;
+  const float* b3;
+  int B, P;
+  // forward
+  float* out;
+  float* att_w;
+  // backward
+  const float* dout;
+  float* dtable;
+  float* dquery;
+  float* sH1;    // [B*P, 80] relu(h1)
+  float* sdH1;   // [B*P, 80]
+  float* sdH2;   // [B*P, 40]
+  float* sHh;    // [B*P, E]
+  float* sHQ;    // [B*P, E]
+  float* sSd;    // [B, 80]  sum_p dh1
+  float* dW3;
+  float* db3;
+};
+
+template <int E>
+struct DinSmem {
+  float W2[kH1 * kH2];
+  float Wh[kH1 * E];     // [k][e] = W1a + W1d
+  float Wp[kH1 * E];     // [k][e] = W1c
+  float Wq[kH1 * E];     // [k][e] = W1b - W1d
+  float b1[kH1];
+  float b2[kH2];
+  float W3[kH2];
+  float Weff[8][kH1 * E];   // per warp
+  float cq[8][kH1];
+  float sd[8][kH1];         // per warp: sum_p dh1 (backward)
+};
+
+template <int E>
+__device__ __forceinline__ void din_load_weights(DinSmem<E>& s, const DinParams& p) {
+  for (int i = threadIdx.x; i < kH1 * kH2; i += blockDim.x) s.W2[i] = p.W2[i];
+  for (int i = threadIdx.x; i < kH1 * E; i += blockDim.x) {
+    const int k = i / E, e = i % E;
+    const float a = p.W1[(0 * E + e) * kH1 + k], b = p.W1[(1 * E + e) * kH1 + k];
+    const float c = p.W1[(2 * E + e) * kH1 + k], d = p.W1[(3 * E + e) * kH1 + k];
+    s.Wh[i] = a + d;
+    s.Wp[i] = c;
+    s.Wq[i] = b - d;
+  }
+  for (int i = threadIdx.x; i < kH1; i += blockDim.x) s.b1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < kH2; i += blockDim.x) {
+    s.b2[i] = p.b2[i];
+    s.W3[i] = p.W3[i];
+  }
+}
+
+// per-sample layer-1 folding, by the whole warp
+template <int E>
+__device__ __forceinline__ void din_fold_sample(DinSmem<E>& s, int warp, int lane, const float* q) {
+  for (int i = lane; i < kH1 * E; i += 32) s.Weff[warp][i] = fmaf(q[i % E], s.Wp[i], s.Wh[i]);
+  for (int k = lane; k < kH1; k += 32) {
+    float a = s.b1[k];
+#pragma unroll
+    for (int e = 0; e < E; ++e) a = fmaf(q[e], s.Wq[k * E + e], a);
+    s.cq[warp][k] = a;
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
+  extern __shared__ __align__(16) uint8_t din_smem_raw[];
+  DinSmem<E>& s = *reinterpret_cast<DinSmem<E>*>(din_smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  din_load_weights<E>(s, p);
+  __syncthreads();
+  const float b3 = p.b3[0];
+
+  for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
+    float q[E];
+#pragma unroll
+    for (int e = 0; e < E; e += 4) {
+      const float4 t = ldg4(p.query + static_cast<size_t>(b) * E + e);
+      q[e] = t.x; q[e + 1] = t.y; q[e + 2] = t.z; q[e + 3] = t.w;
+    }
+    __syncwarp();
+    din_fold_sample<E>(s, warp, lane, q);
+    __syncwarp();
+    float o[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) o[e] = 0.f;
+
+    for (int p0 = 0; p0 < p.P; p0 += 32) {
+      const int pos = p0 + lane;
+      const int id = pos < p.P ? __ldg(p.hist + static_cast<size_t>(b) * p.P + pos) : 0;
+      const bool valid = id > 0;                       // din/din.py:107 mask
+      if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
+      float w = 0.f;
+      if (valid) {
+        float h[E];
+#pragma unroll
+        for (int e = 0; e < E; e += 4) {
+          const float4 t = ldg4(p.table + static_cast<size_t>(id) * E + e);
+          h[e] = t.x; h[e + 1] = t.y; h[e + 2] = t.z; h[e + 3] = t.w;
+        }
+        float h2[kH2];
+#pragma unroll
+        for (int j = 0; j < kH2; ++j) h2[j] = s.b2[j];
+#pragma unroll 2
+        for (int k = 0; k < kH1; ++k) {
+          float a = s.cq[warp][k];
+          const float* we = &s.Weff[warp][k * E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
+          a = fmaxf(a, 0.f);
+          const float* w2 = &s.W2[k * kH2];
+#pragma unroll
+          for (int j = 0; j < kH2; ++j) h2[j] = fmaf(a, w2[j], h2[j]);
+        }
+        w = b3;
+#pragma unroll
+        for (int j = 0; j < kH2; ++j) w = fmaf(fmaxf(h2[j], 0.f), s.W3[j], w);
+#pragma unroll
+        for (int e = 0; e < E; ++e) o[e] = fmaf(w, h[e], o[e]);
+      }
+      if (p.att_w != nullptr && pos < p.P) p.att_w[static_cast<size_t>(b) * p.P + pos] = w;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) o[e] = warp_sum(o[e]);
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < E; e += 4)
+        *reinterpret_cast<float4*>(p.out + static_cast<size_t>(b) * E + e) =
+            make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
+  extern __shared__ __align__(16) uint8_t din_smem_raw[];
+  DinSmem<E>& s = *reinterpret_cast<DinSmem<E>*>(din_smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  din_load_weights<E>(s, p);
+  __syncthreads();
+  const float b3 = p.b3[0];
+  float dW3acc[kH2];
+#pragma unroll
+  for (int j = 0; j < kH2; ++j) dW3acc[j] = 0.f;
+  float db3acc = 0.f;
+
+  for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
+    float q[E], g[E], dq[E];
+#pragma unroll
+    for (int e = 0; e < E; e += 4) {
+      const float4 t = ldg4(p.query + static_cast<size_t>(b) * E + e);
+      q[e] = t.x; q[e + 1] = t.y; q[e + 2] = t.z; q[e + 3] = t.w;
+      const float4 u = ldg4(p.dout + static_cast<size_t>(b) * E + e);
+      g[e] = u.x; g[e + 1] = u.y; g[e + 2] = u.z; g[e + 3] = u.w;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) dq[e] = 0.f;
+    __syncwarp();
+    din_fold_sample<E>(s, warp, lane, q);
+    for (int k = lane; k < kH1; k += 32) s.sd[warp][k] = 0.f;
+    __syncwarp();
+
+    for (int p0 = 0; p0 < p.P; p0 += 32) {
+      const int pos = p0 + lane;
+      const int id = pos < p.P ? __ldg(p.hist + static_cast<size_t>(b) * p.P + pos) : 0;
+      const bool valid = id > 0;
+      if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
+      const size_t n = static_cast<size_t>(b) * p.P + pos;
+      float h[E], dh[E];
+      float h2[kH2];
+      unsigned m1[3] = {0u, 0u, 0u};   // relu mask of h1
+      float w = 0.f, dw = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < E; e += 4) {
+          const float4 t = ldg4(p.table + static_cast<size_t>(id) * E + e);
+          h[e] = t.x; h[e + 1] = t.y; h[e + 2] = t.z; h[e + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < kH2; ++j) h2[j] = s.b2[j];
+        float* oh1 = p.sH1 + n * kH1;
+#pragma unroll 2
+        for (int k = 0; k < kH1; ++k) {
+          float a = s.cq[warp][k];
+          const float* we = &s.Weff[warp][k * E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
+          if (a > 0.f) m1[k >> 5] |= 1u << (k & 31);
+          a = fmaxf(a, 0.f);
+          oh1[k] = a;
+          const float* w2 = &s.W2[k * kH2];
+#pragma unroll
+          for (int j = 0; j < kH2; ++j) h2[j] = fmaf(a, w2[j], h2[j]);
+        }
+        w = b3;
+#pragma unroll
+        for (int j = 0; j < kH2; ++j) w = fmaf(fmaxf(h2[j], 0.f), s.W3[j], w);
+        // out = sum_p w h  ->  dw = g . h
+#pragma unroll
+        for (int e = 0; e < E; ++e) dw = fmaf(g[e], h[e], dw);
+        db3acc += dw;
+        float* odh2 = p.sdH2 + n * kH2;
+#pragma unroll
+        for (int j = 0; j < kH2; ++j) {
+          const float r = fmaxf(h2[j], 0.f);
+          dW3acc[j] = fmaf(dw, r, dW3acc[j]);
+          h2[j] = h2[j] > 0.f ? dw * s.W3[j] : 0.f;    // h2 now holds dh2
+          odh2[j] = h2[j];
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) dh[e] = w * g[e];
+      }
+      // second sweep over k: dh1, dh, dq (Wp part) and the warp-wide sum of dh1
+      float* odh1 = p.sdH1 + n * kH1;
+      for (int k = 0; k < kH1; ++k) {
+        float d1 = 0.f;
+        if (valid && ((m1[k >> 5] >> (k & 31)) & 1u)) {
+          const float* w2 = &s.W2[k * kH2];
+#pragma unroll
+          for (int j = 0; j < kH2; ++j) d1 = fmaf(h2[j], w2[j], d1);
+        }
+        if (valid) {
+          odh1[k] = d1;
+          const float* we = &s.Weff[warp][k * E];
+          const float* wp = &s.Wp[k * E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            dh[e] = fmaf(d1, we[e], dh[e]);
+            dq[e] = fmaf(d1 * h[e], wp[e], dq[e]);
+          }
+        }
+        const float tot = warp_sum(d1);
+        if (lane == 0) s.sd[warp][k] += tot;
+      }
+      if (valid) {
+        float* oh = p.sHh + n * E;
+        float* ohq = p.sHQ + n * E;
+#pragma unroll
+        for (int e = 0; e < E; e += 4) {
+          *reinterpret_cast<float4*>(oh + e) = make_float4(h[e], h[e + 1], h[e + 2], h[e + 3]);
+          *reinterpret_cast<float4*>(ohq + e) =
+              make_float4(h[e] * q[e], h[e + 1] * q[e + 1], h[e + 2] * q[e + 2], h[e + 3] * q[e + 3]);
+          red_add_v4(p.dtable + static_cast<size_t>(id) * E + e,
+                     make_float4(dh[e], dh[e + 1], dh[e + 2], dh[e + 3]));
+        }
+      }
+    }
+    __syncwarp();
+    // dq += sum_k sd[k] * Wq[k][:]; write per-sample sums
+#pragma unroll
+    for (int e = 0; e < E; ++e) dq[e] = warp_sum(dq[e]);
+    for (int k = lane; k < kH1; k += 32) p.sSd[static_cast<size_t>(b) * kH1 + k] = s.sd[warp][k];
+    if (lane < E) {
+      float a = 0.f;
+      for (int k = 0; k < kH1; ++k) a = fmaf(s.sd[warp][k], s.Wq[k * E + lane], a);
+      float mine = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (e == lane) mine = dq[e];
+      p.dquery[static_cast<size_t>(b) * E + lane] = a + mine;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < kH2; ++j) {
+    const float t = warp_sum(dW3acc[j]);
+    if (lane == 0 && t != 0.f) red_add_f32(p.dW3 + j, t);
+  }
+  const float t3 = warp_sum(db3acc);
+  if (lane == 0 && t3 != 0.f) red_add_f32(p.db3, t3);
+}
+
+// C[a, c] += sum over valid rows n of A[n, a] * Bm[n, c]; rowmask (nullable): row n valid iff > 0.
+__global__ void __launch_bounds__(256)
+xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict__ Bm, int ldb,
+           int Kb, const int* __restrict__ rowmask, long long N, float* __restrict__ C, int ldc,
+           long long rows_per_split) {
+  __shared__ __align__(16) float As[16][64];
+  __shared__ __align__(16) float Bs[16][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int a0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const long long rbeg = blockIdx.z * rows_per_split;
+  const long long rend = min(N, rbeg + rows_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long rc = rbeg; rc < rend; rc += 16) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + 256 * t;
+      const int rr = e >> 6, cc = e & 63;
+      const long long r = rc + rr;
+      float va = 0.f, vb = 0.f;
+      if (r < rend && (rowmask == nullptr || __ldg(rowmask + r) > 0)) {
+        if (a0 + cc < Ka) va = A[r * lda + a0 + cc];
+        if (c0 + cc < Kb) vb = Bm[r * ldb + c0 + cc];
+      }
+      As[rr][cc] = va;
+      Bs[rr][cc] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float4 za = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+      const float4 zb = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+      const float z[4] = {za.x, za.y, za.z, za.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(z[i], zb.x, acc[i][0]);
+        acc[i][1] = fmaf(z[i], zb.y, acc[i][1]);
+        acc[i][2] = fmaf(z[i], zb.z, acc[i][2]);
+        acc[i][3] = fmaf(z[i], zb.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = a0 + ty * 4 + i;
+    if (a >= Ka) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + tx * 4 + j;
+      if (c < Kb && acc[i][j] != 0.f) red_add_f32(C + static_cast<size_t>(a) * ldc + c, acc[i][j]);
+    }
+  }
+}
+
+// out[c] += sum over valid rows of X[n, c]
+__global__ void __launch_bounds__(256)
+masked_colsum_kernel(const float* __restrict__ X, int ld, int K, const int* __restrict__ rowmask,
+                     long long N, float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float sacc = 0.f;
+  if (c < K)
+    for (long long r = blockIdx.y * 8LL + ry; r < N; r += gridDim.y * 8LL)
+      if (rowmask == nullptr || __ldg(rowmask + r) > 0) sacc += X[r * ld + c];
+  __shared__ float red[8][33];
+  red[ry][threadIdx.x & 31] = sacc;
+  __syncthreads();
+  if (ry == 0 && c < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+    red_add_f32(out + c, t);
+  }
+}
+
+// dW1[4E, 80] += [dWh; dWq; dWp; dWh - dWq] from the three [E, 80] partials in tmp.
+__global__ void din_assemble_dw1_kernel(const float* __restrict__ tmp, int E, float* __restrict__ dW1) {
+  const int n = E * kH1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float wh = tmp[i], wp = tmp[n + i], wq = tmp[2 * n + i];
+    dW1[0 * n + i] += wh;
+    dW1[1 * n + i] += wq;
+    dW1[2 * n + i] += wp;
+    dW1[3 * n + i] += wh - wq;
+  }
+}
+
+static void xtx_launch(const float* A, int lda, int Ka, const float* Bm, int ldb, int Kb,
+                       const int* mask, long long N, float* C, int ldc, cudaStream_t st) {
+  const int tiles = ((Ka + 63) / 64) * ((Kb + 63) / 64);
+  long long splits = std::max<long long>(1, std::min<long long>((sm_count() * 4) / tiles, (N + 255) / 256));
+  long long rps = (N + splits - 1) / splits;
+  rps = (rps + 15) / 16 * 16;
+  splits = (N + rps - 1) / rps;
+  dim3 grid((Ka + 63) / 64, (Kb + 63) / 64, static_cast<unsigned>(splits));
+  xtx_kernel<<<grid, 256, 0, st>>>(A, lda, Ka, Bm, ldb, Kb, mask, N, C, ldc, rps);
+}
+
+template <int E>
+static int din_fwd_launch(const DinParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(DinSmem<E>);
+  cudaFuncSetAttribute(din_att_fwd_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(smem));
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, din_att_fwd_kernel<E>, 256, smem);
+  const int grid = std::min((p.B + 7) / 8, sm_count() * std::max(1, occ));
+  din_att_fwd_kernel<E><<<grid, 256, smem, st>>>(p);
+  return CTR_OK;
+}
+
+template <int E>
+static int din_bwd_launch(const DinParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(DinSmem<E>);
+  cudaFuncSetAttribute(din_att_bwd_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(smem));
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, din_att_bwd_kernel<E>, 256, smem);
+  const int grid = std::min((p.B + 7) / 8, sm_count() * std::max(1, occ));
+  din_att_bwd_kernel<E><<<grid, 256, smem, st>>>(p);
+  return CTR_OK;
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" {
+
+int64_t ctr_din_workspace_bytes(int B, int P, int E) {
+  const int64_t n = static_cast<int64_t>(B) * P;
+  return (n * (kH1 + kH1 + kH2 + E + E) + static_cast<int64_t>(B) * kH1 + 3LL * E * kH1) * 4 + 1024;
+}
+
+int ctr_din_att_fwd(const float* table, const int32_t* hist, const float* query, int B, int P,
+                    int E, const float* W1, const float* b1, int H1, const float* W2,
+                    const float* b2, int H2, const float* W3, const float* b3, float* out,
+                    float* att_w, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(table && hist && query && W1 && b1 && W2 && b2 && W3 && b3 && out, "ctr_din_att_fwd",
+              "null pointer");
+  CTR_REQUIRE(H1 == kH1 && H2 == kH2, "ctr_din_att_fwd",
+              "attention layers must be [80, 40] (din/din.py:85 hard-codes them)");
+  CTR_REQUIRE(B >= 0 && P > 0, "ctr_din_att_fwd", "bad B/P");
+  CTR_REQUIRE(aligned16(table) && aligned16(query) && aligned16(out), "ctr_din_att_fwd",
+              "pointers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  DinParams p{};
+  p.table = table; p.hist = hist; p.query = query; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+  p.W3 = W3; p.b3 = b3; p.B = B; p.P = P; p.out = out; p.att_w = att_w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (E) {
+    case 8: din_fwd_launch<8>(p, st); break;
+    case 16: din_fwd_launch<16>(p, st); break;
+    case 32: din_fwd_launch<32>(p, st); break;
+    default: return fail_arg("ctr_din_att_fwd", "E must be 8, 16 or 32");
+  }
+  CTR_LAUNCH_CHECK("ctr_din_att_fwd");
+}
+
+int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query, int B, int P,
+                    int E, const float* W1, const float* b1, int H1, const float* W2,
+                    const float* b2, int H2, const float* W3, const float* b3, const float* dout,
+                    float* dtable, float* dquery, float* dW1, float* db1, float* dW2, float* db2,
+                    float* dW3, float* db3, void* workspace, int64_t workspace_bytes,
+                    ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(table && hist && query && W1 && b1 && W2 && b2 && W3 && b3 && dout && dtable &&
+                  dquery && dW1 && db1 && dW2 && db2 && dW3 && db3,
+              "ctr_din_att_bwd", "null pointer");
+  CTR_REQUIRE(H1 == kH1 && H2 == kH2, "ctr_din_att_bwd", "attention layers must be [80, 40]");
+  CTR_REQUIRE(B >= 0 && P > 0 && (E == 8 || E == 16 || E == 32), "ctr_din_att_bwd", "bad B/P/E");
+  CTR_REQUIRE(workspace && workspace_bytes >= ctr_din_workspace_bytes(B, P, E), "ctr_din_att_bwd",
+              "workspace too small (ctr_din_workspace_bytes)");
+  CTR_REQUIRE(aligned16(table) && aligned16(query) && aligned16(dout) && aligned16(dtable),
+              "ctr_din_att_bwd", "pointers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long N = static_cast<long long>(B) * P;
+  float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  DinParams p{};
+  p.table = table; p.hist = hist; p.query = query; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+  p.W3 = W3; p.b3 = b3; p.B = B; p.P = P; p.dout = dout; p.dtable = dtable; p.dquery = dquery;
+  p.sH1 = ws;
+  p.sdH1 = p.sH1 + N * kH1;
+  p.sdH2 = p.sdH1 + N * kH1;
+  p.sHh = p.sdH2 + N * kH2;
+  p.sHQ = p.sHh + N * E;
+  p.sSd = p.sHQ + N * E;
+  float* tmp = p.sSd + static_cast<long long>(B) * kH1;   // [3][E][80]
+  p.dW3 = dW3; p.db3 = db3;
+  cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(float) * 3 * E * kH1, st);
+  if (e != cudaSuccess) return check_cuda(e, "ctr_din_att_bwd");
+  switch (E) {
+    case 8: din_bwd_launch<8>(p, st); break;
+    case 16: din_bwd_launch<16>(p, st); break;
+    default: din_bwd_launch<32>(p, st); break;
+  }
+  // weight gradients: tall-skinny reductions over the valid positions
+  xtx_launch(p.sH1, kH1, kH1, p.sdH2, kH2, kH2, hist, N, dW2, kH2, st);            // dW2 = H1^T dH2
+  xtx_launch(p.sHh, E, E, p.sdH1, kH1, kH1, hist, N, tmp, kH1, st);                // dWh = H^T dH1
+  xtx_launch(p.sHQ, E, E, p.sdH1, kH1, kH1, hist, N, tmp + E * kH1, kH1, st);      // dWp = (H*q)^T dH1
+  xtx_launch(query, E, E, p.sSd, kH1, kH1, nullptr, B, tmp + 2 * E * kH1, kH1, st);  // dWq = Q^T sum dH1
+  din_assemble_dw1_kernel<<<(E * kH1 + 255) / 256, 256, 0, st>>>(tmp, E, dW1);
+  {
+    dim3 g1((kH1 + 31) / 32, 32), g2((kH2 + 31) / 32, 64);
+    masked_colsum_kernel<<<g1, 256, 0, st>>>(p.sSd, kH1, kH1, nullptr, B, db1);
+    masked_colsum_kernel<<<g2, 256, 0, st>>>(p.sdH2, kH2, kH2, hist, N, db2);
+  }
+  CTR_LAUNCH_CHECK("ctr_din_att_bwd");
+}
+
+}  // extern "C"

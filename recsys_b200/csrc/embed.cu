@@ -1,0 +1,797 @@
+// Fused multi-field embedding lookup + in-register interaction (FM second order,
+// first-order sum, DCN cross stack) and its field-major scatter-add backward.
+//
+// Forward (sample-major): a warp owns one sample at a time.  With D floats per
+// row a row is LPR = D/4 lanes x float4; one warp-wide load instruction
+// fetches RPW = 32/LPR rows (512 contiguous bytes of E[b,:]), so lane `l` of
+// iteration `it` holds float4 number it*32+l of the sample's concatenated
+// embedding - the same layout the coalesced E store and the cross stack want.
+// The tile's row ids ([TB, F] int32, contiguous) are staged into shared memory
+// by a 1-D TMA bulk copy (cp.async.bulk + mbarrier), double buffered across the
+// persistent CTA's tiles.
+//
+// Backward (field-major): a warp owns (field f, chunk of samples).  Fields with
+// <= 32 rows (13 bucketised numerics + the tiny hashed ones; H3 in SURVEY.md:
+// one of them puts every sample in one row) are accumulated one-hot in
+// registers and flushed with a handful of vector REDs; all other fields go
+// straight to red.global.add.v4.f32.
+#include "common.cuh"
+
+namespace ctr {
+
+// ------------------------------------------------------------------ forward
+struct EmbedFwdParams {
+  const float* table;
+  const float* w1;
+  const int* rows;
+  float* E;
+  float* S;
+  float* y1;
+  float* y2;
+  const float* cross_w;
+  const float* cross_b;
+  float* xl;
+  unsigned long long w1_fields;
+  int cross_layers;
+  int B;
+  int F;
+};
+
+constexpr int kFwdWarps = 8;
+constexpr int kFwdSPW = 2;                      // samples per warp per tile
+constexpr int kFwdTB = kFwdWarps * kFwdSPW;     // samples per tile (multiple of 4)
+
+template <int D, int NIT, bool CROSS>
+__global__ void __launch_bounds__(kFwdWarps * 32)
+embed_fwd_kernel(const EmbedFwdParams p) {
+  constexpr int LPR = D / 4;
+  constexpr int RPW = 32 / LPR;
+  constexpr int SPW = kFwdSPW;
+  constexpr int TB = kFwdTB;
+  __shared__ __align__(128) int s_rows[2][TB * CTR_MAX_FIELDS];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int r = lane / LPR;
+  const int q = lane % LPR;
+  const int F = p.F;
+  const int B = p.B;
+  const int ntiles = (B + TB - 1) / TB;
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // A tile can be bulk-copied when its byte count is a multiple of 16 (always
+  // true except possibly for the ragged last tile).
+  auto tile_bulk = [&](int tile) -> bool {
+    const int nb = min(TB, B - tile * TB);
+    return ((nb * F) & 3) == 0;
+  };
+  auto prefetch = [&](int tile, int buf) {
+    if (tid == 0 && tile_bulk(tile)) {
+      const int nb = min(TB, B - tile * TB);
+      const uint32_t bytes = static_cast<uint32_t>(nb * F) * 4u;
+      mbar_expect_tx(&s_bar[buf], bytes);
+      tma_load_1d(&s_rows[buf][0], p.rows + static_cast<size_t>(tile) * TB * F, bytes, &s_bar[buf]);
+    }
+  };
+
+  uint32_t phase0 = 0, phase1 = 0;
+  int buf = 0;
+  int tile = blockIdx.x;
+  if (tile < ntiles) prefetch(tile, 0);
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < ntiles) prefetch(nxt, buf ^ 1);
+    const int b0 = tile * TB;
+    if (tile_bulk(tile)) {
+      if (buf == 0) {
+        mbar_wait(&s_bar[0], phase0);
+        phase0 ^= 1;
+      } else {
+        mbar_wait(&s_bar[1], phase1);
+        phase1 ^= 1;
+      }
+    } else {
+      const int n = min(TB, B - b0) * F;
+      for (int i = tid; i < n; i += blockDim.x)
+        s_rows[buf][i] = p.rows[static_cast<size_t>(b0) * F + i];
+      __syncthreads();
+    }
+    const int* srow = &s_rows[buf][0];
+
+    float4 v[SPW][NIT];
+    int rid[SPW][NIT];
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) {
+      const int sidx = warp * SPW + s;
+      const bool sv = (b0 + sidx) < B;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int f = it * RPW + r;
+        const bool ok = sv && f < F;
+        rid[s][it] = ok ? srow[sidx * F + f] : -1;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        v[s][it] = rid[s][it] >= 0
+                       ? ldg4(p.table + static_cast<size_t>(rid[s][it]) * D + q * 4)
+                       : f4_zero();
+      }
+    }
+    float y1p[SPW];
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) {
+      y1p[s] = 0.f;
+      if (p.y1 != nullptr && q == 0) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int f = it * RPW + r;
+          if (rid[s][it] >= 0 && ((p.w1_fields >> f) & 1ull)) y1p[s] += __ldg(p.w1 + rid[s][it]);
+        }
+      }
+    }
+
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) {
+      const int b = b0 + warp * SPW + s;
+      if (b >= B) continue;  // warp-uniform
+      if (p.E != nullptr) {
+        float* e = p.E + static_cast<size_t>(b) * F * D;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+          if (rid[s][it] >= 0)
+            *reinterpret_cast<float4*>(e + (it * 32 + lane) * 4) = v[s][it];
+      }
+      if (p.y1 != nullptr) {
+        const float t = warp_sum(y1p[s]);
+        if (lane == 0) p.y1[b] = t;
+      }
+      if (p.S != nullptr || p.y2 != nullptr) {
+        float4 sm = f4_zero(), sq = f4_zero();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const float4 x = v[s][it];
+          sm = f4_add(sm, x);
+          sq = make_float4(fmaf(x.x, x.x, sq.x), fmaf(x.y, x.y, sq.y), fmaf(x.z, x.z, sq.z),
+                           fmaf(x.w, x.w, sq.w));
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o);
+          sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
+          sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o);
+          sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
+          sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o);
+          sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+          sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o);
+          sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+        }
+        if (p.S != nullptr && r == 0)
+          *reinterpret_cast<float4*>(p.S + static_cast<size_t>(b) * D + q * 4) = sm;
+        if (p.y2 != nullptr) {
+          float t = (sm.x * sm.x - sq.x) + (sm.y * sm.y - sq.y) + (sm.z * sm.z - sq.z) +
+                    (sm.w * sm.w - sq.w);
+#pragma unroll
+          for (int o = 1; o < LPR; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) p.y2[b] = 0.5f * t;
+        }
+      }
+      if (CROSS) {
+        // dcn/dcn.py:138-142: xl <- (xl . w_l) * x0 + xl + b_l, row in registers.
+        const int W = F * D;
+        float4 xl[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) xl[it] = v[s][it];
+        for (int l = 0; l < p.cross_layers; ++l) {
+          float4 bb[NIT];
+          float dot = 0.f;
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int c = (it * 32 + lane) * 4;
+            if (c < W) {
+              dot += f4_dot(xl[it], ldg4(p.cross_w + static_cast<size_t>(l) * W + c));
+              bb[it] = ldg4(p.cross_b + static_cast<size_t>(l) * W + c);
+            } else {
+              bb[it] = f4_zero();
+            }
+          }
+          dot = warp_sum(dot);
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) xl[it] = f4_add(f4_fma(dot, v[s][it], xl[it]), bb[it]);
+        }
+        float* o = p.xl + static_cast<size_t>(b) * W;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+          if ((it * 32 + lane) * 4 < W) *reinterpret_cast<float4*>(o + (it * 32 + lane) * 4) = xl[it];
+      }
+    }
+    __syncthreads();  // everyone is done with s_rows[buf] before it is refilled
+    buf ^= 1;
+  }
+}
+
+template <int D, int NIT, bool CROSS>
+static int launch_fwd(const EmbedFwdParams& p, cudaStream_t st) {
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, embed_fwd_kernel<D, NIT, CROSS>,
+                                                  kFwdWarps * 32, 0);
+    occ = o > 0 ? o : 1;
+  }
+  const int ntiles = (p.B + kFwdTB - 1) / kFwdTB;
+  const int grid = min(ntiles, sm_count() * occ);
+  embed_fwd_kernel<D, NIT, CROSS><<<grid, kFwdWarps * 32, 0, st>>>(p);
+  return CTR_OK;
+}
+
+template <int D, bool CROSS>
+static int dispatch_fwd_nit(const EmbedFwdParams& p, cudaStream_t st) {
+  constexpr int RPW = 32 / (D / 4);
+  const int need = (p.F + RPW - 1) / RPW;
+  if (need <= 1) return launch_fwd<D, 1, CROSS>(p, st);
+  if (need <= 2) return launch_fwd<D, 2, CROSS>(p, st);
+  if (need <= 3) return launch_fwd<D, 3, CROSS>(p, st);
+  if (need <= 4) return launch_fwd<D, 4, CROSS>(p, st);
+  if (need <= 5) return launch_fwd<D, 5, CROSS>(p, st);
+  if (need <= 6) return launch_fwd<D, 6, CROSS>(p, st);
+  if (need <= 8) return launch_fwd<D, 8, CROSS>(p, st);
+  if (need <= 10) return launch_fwd<D, 10, CROSS>(p, st);
+  return fail_arg("ctr_embed_fwd", "F*D too large (max 1280 floats per sample)");
+}
+
+template <bool CROSS>
+static int dispatch_fwd(const EmbedFwdParams& p, int D, cudaStream_t st) {
+  switch (D) {
+    case 8: return dispatch_fwd_nit<8, CROSS>(p, st);
+    case 16: return dispatch_fwd_nit<16, CROSS>(p, st);
+    case 32: return dispatch_fwd_nit<32, CROSS>(p, st);
+    default: return fail_arg("ctr_embed_fwd", "D must be 8, 16 or 32");
+  }
+}
+
+// ----------------------------------------------------------------- backward
+struct EmbedBwdParams {
+  const int* rows;
+  const float* dE;
+  const float* E;
+  const float* table;
+  const float* S;
+  const float* dy2;
+  const float* dy1;
+  float* dtable;
+  float* dw1;
+  unsigned long long w1_fields;
+  int B;
+  int F;
+  int chunk;
+  int nchunks;
+  int off[CTR_MAX_FIELDS + 1];
+};
+
+constexpr int kTinyRows = 32;
+
+template <int D>
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) {
+  constexpr int LPR = D / 4;
+  constexpr int RPW = 32 / LPR;
+  constexpr int J = kTinyRows / RPW;  // one-hot accumulators per lane
+  const int lane = threadIdx.x & 31;
+  const int r = lane / LPR;
+  const int q = lane % LPR;
+  const int F = p.F;
+  const int wpb = blockDim.x >> 5;
+  const int ntask = F * p.nchunks;
+
+  for (int task = blockIdx.x * wpb + (threadIdx.x >> 5); task < ntask; task += gridDim.x * wpb) {
+    const int f = task % F;
+    const int c = task / F;
+    const int b_begin = c * p.chunk;
+    const int b_end = min(p.B, b_begin + p.chunk);
+    const int off = p.off[f];
+    const int nrow = p.off[f + 1] - off;
+    const bool tiny = nrow <= kTinyRows;
+    const bool has_w1 = p.dw1 != nullptr && p.dy1 != nullptr && ((p.w1_fields >> f) & 1ull);
+
+    float4 acc[J];
+    float accw[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      acc[j] = f4_zero();
+      accw[j] = 0.f;
+    }
+
+    for (int bb = b_begin; bb < b_end; bb += RPW) {
+      const int b = bb + r;
+      const bool ok = b < b_end;
+      int rid = -1;
+      float4 g = f4_zero();
+      float gw = 0.f;
+      if (ok) {
+        rid = __ldg(p.rows + static_cast<size_t>(b) * F + f);
+        const size_t eo = (static_cast<size_t>(b) * F + f) * D + q * 4;
+        if (p.dE != nullptr) g = ld4_stream(p.dE + eo);
+        if (p.dy2 != nullptr) {
+          const float4 e = p.E != nullptr ? ldg4(p.E + eo)
+                                          : ldg4(p.table + static_cast<size_t>(rid) * D + q * 4);
+          const float4 s = ldg4(p.S + static_cast<size_t>(b) * D + q * 4);
+          const float cdy = __ldg(p.dy2 + b);
+          g.x = fmaf(cdy, s.x - e.x, g.x);
+          g.y = fmaf(cdy, s.y - e.y, g.y);
+          g.z = fmaf(cdy, s.z - e.z, g.z);
+          g.w = fmaf(cdy, s.w - e.w, g.w);
+        }
+        if (has_w1) gw = __ldg(p.dy1 + b);
+      }
+      if (!tiny) {
+        if (ok) {
+          red_add_v4(p.dtable + static_cast<size_t>(rid) * D + q * 4, g);
+          if (has_w1 && q == 0) red_add_f32(p.dw1 + rid, gw);
+        }
+      } else {
+        const int lid = rid - off;  // negative for inactive lanes: never matches
+#pragma unroll
+        for (int t = 0; t < RPW; ++t) {
+          const float4 gt = f4_shfl(g, t * LPR + q);
+          const int idt = __shfl_sync(0xffffffffu, lid, t * LPR);
+          const float gwt = __shfl_sync(0xffffffffu, gw, t * LPR);
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            if (idt == r + RPW * j) {
+              acc[j] = f4_add(acc[j], gt);
+              accw[j] += gwt;
+            }
+          }
+        }
+      }
+    }
+    if (tiny) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int lr = r + RPW * j;
+        if (lr < nrow) {
+          red_add_v4(p.dtable + static_cast<size_t>(off + lr) * D + q * 4, acc[j]);
+          if (has_w1 && q == 0) red_add_f32(p.dw1 + off + lr, accw[j]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ stand-alone cross
+// xl forward on an existing x0[B,W] (used when E comes from somewhere else, and
+// as the recompute inside the backward).  One warp per sample, NIT float4/lane.
+template <int NIT, int LMAX>
+__global__ void __launch_bounds__(256)
+cross_bwd_kernel(const float* __restrict__ x0g, const float* __restrict__ w,
+                 const float* __restrict__ bvec, int L, int B, int W,
+                 const float* __restrict__ dxl, float* __restrict__ dx0, float* __restrict__ dw,
+                 float* __restrict__ db) {
+  extern __shared__ float s_acc[];  // [2][L][W]: dw then db, CTA-private accumulation
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * L * W; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float* s_dw = s_acc;
+  float* s_db = s_acc + L * W;
+
+  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
+    float4 x0[NIT], xs[LMAX][NIT], d[NIT];
+    float sdot[LMAX];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      x0[it] = c < W ? ldg4(x0g + static_cast<size_t>(b) * W + c) : f4_zero();
+      d[it] = c < W ? ldg4(dxl + static_cast<size_t>(b) * W + c) : f4_zero();
+      xs[0][it] = x0[it];
+    }
+    // recompute forward, keeping every layer input xs[l] and its dot s_l
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < L) {
+        float dot = 0.f;
+        float4 bb[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = (it * 32 + lane) * 4;
+          if (c < W) {
+            dot += f4_dot(xs[l][it], ldg4(w + static_cast<size_t>(l) * W + c));
+            bb[it] = ldg4(bvec + static_cast<size_t>(l) * W + c);
+          } else {
+            bb[it] = f4_zero();
+          }
+        }
+        dot = warp_sum(dot);
+        sdot[l] = dot;
+        if (l + 1 < LMAX) {
+#pragma unroll
+          for (int it = 0; it < NIT; ++it)
+            xs[l + 1][it] = f4_add(f4_fma(dot, x0[it], xs[l][it]), bb[it]);
+        }
+      }
+    }
+    // backward: d = dL/dx_{l+1}
+    float4 dx0acc[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) dx0acc[it] = f4_zero();
+#pragma unroll
+    for (int l = LMAX - 1; l >= 0; --l) {
+      if (l < L) {
+        float ds = 0.f;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) ds += f4_dot(d[it], x0[it]);
+        ds = warp_sum(ds);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = (it * 32 + lane) * 4;
+          if (c < W) {
+            // db_l += d ; dw_l += ds * x_l ; dx0 += s_l * d ; d <- d + ds * w_l
+            float* pdb = s_db + l * W + c;
+            float* pdw = s_dw + l * W + c;
+            atomicAdd(pdb + 0, d[it].x);
+            atomicAdd(pdb + 1, d[it].y);
+            atomicAdd(pdb + 2, d[it].z);
+            atomicAdd(pdb + 3, d[it].w);
+            atomicAdd(pdw + 0, ds * xs[l][it].x);
+            atomicAdd(pdw + 1, ds * xs[l][it].y);
+            atomicAdd(pdw + 2, ds * xs[l][it].z);
+            atomicAdd(pdw + 3, ds * xs[l][it].w);
+            dx0acc[it] = f4_fma(sdot[l], d[it], dx0acc[it]);
+            d[it] = f4_fma(ds, ldg4(w + static_cast<size_t>(l) * W + c), d[it]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      if (c < W)
+        *reinterpret_cast<float4*>(dx0 + static_cast<size_t>(b) * W + c) = f4_add(dx0acc[it], d[it]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * W; i += blockDim.x) {
+    red_add_f32(dw + i, s_dw[i]);
+    red_add_f32(db + i, s_db[i]);
+  }
+}
+
+template <int NIT>
+__global__ void __launch_bounds__(256)
+cross_fwd_kernel(const float* __restrict__ x0g, const float* __restrict__ w,
+                 const float* __restrict__ bvec, int L, int B, int W, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
+    float4 x0[NIT], xl[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      x0[it] = c < W ? ldg4(x0g + static_cast<size_t>(b) * W + c) : f4_zero();
+      xl[it] = x0[it];
+    }
+    for (int l = 0; l < L; ++l) {
+      float dot = 0.f;
+      float4 bb[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int c = (it * 32 + lane) * 4;
+        if (c < W) {
+          dot += f4_dot(xl[it], ldg4(w + static_cast<size_t>(l) * W + c));
+          bb[it] = ldg4(bvec + static_cast<size_t>(l) * W + c);
+        } else {
+          bb[it] = f4_zero();
+        }
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) xl[it] = f4_add(f4_fma(dot, x0[it], xl[it]), bb[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      if (c < W) *reinterpret_cast<float4*>(out + static_cast<size_t>(b) * W + c) = xl[it];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ id pipeline
+__global__ void criteo_rows_kernel(const float* __restrict__ xcont, int n_cont,
+                                   const long long* __restrict__ xcat, int n_cat,
+                                   const ctr_field_desc* __restrict__ fields,
+                                   const float* __restrict__ bnd, int B, int F,
+                                   int* __restrict__ rows, float* __restrict__ logx,
+                                   int* __restrict__ status) {
+  const long long n = static_cast<long long>(B) * F;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / F);
+    const int f = static_cast<int>(i % F);
+    const ctr_field_desc fd = fields[f];
+    int id;
+    if (fd.kind == 0) {
+      // fm/fm.py:76-79: tf.log(x + off) in fp32, then Bucketize == upper_bound.
+      const float v = logf(xcont[static_cast<size_t>(b) * n_cont + fd.src] + fd.log_offset);
+      if (logx != nullptr) logx[static_cast<size_t>(b) * n_cont + fd.src] = v;
+      id = 0;
+      for (int k = 0; k < fd.bnd_count; ++k) id += (bnd[fd.bnd_begin + k] <= v) ? 1 : 0;
+      if (v != v) id = fd.bnd_count;
+    } else {
+      long long raw = xcat[static_cast<size_t>(b) * n_cat + fd.src];
+      if (raw < 0 || raw >= fd.n_rows) {
+        if (status != nullptr) atomicOr(status, 1);
+        raw %= fd.n_rows;
+        if (raw < 0) raw += fd.n_rows;
+      }
+      id = static_cast<int>(raw);
+    }
+    rows[i] = fd.row_offset + id;
+  }
+}
+
+// ----------------------------------------------------------------------- Adam
+__global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
+                                  float* __restrict__ v, float* __restrict__ g, long long n,
+                                  float lr_t, float b1, float b2, float eps, int zero_g) {
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += stride) {
+    float4 G = reinterpret_cast<float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    float4 T = reinterpret_cast<float4*>(th)[i];
+#define CTR_ADAM1(c)                               \
+  M.c = b1 * M.c + (1.f - b1) * G.c;               \
+  V.c = b2 * V.c + (1.f - b2) * G.c * G.c;         \
+  T.c -= lr_t * M.c / (sqrtf(V.c) + eps);
+    CTR_ADAM1(x) CTR_ADAM1(y) CTR_ADAM1(z) CTR_ADAM1(w)
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+    reinterpret_cast<float4*>(th)[i] = T;
+    if (zero_g) reinterpret_cast<float4*>(g)[i] = f4_zero();
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+       i < n; i += stride) {
+    const float G = g[i];
+    const float M = b1 * m[i] + (1.f - b1) * G;
+    const float V = b2 * v[i] + (1.f - b2) * G * G;
+    m[i] = M;
+    v[i] = V;
+    th[i] -= lr_t * M / (sqrtf(V) + eps);
+    if (zero_g) g[i] = 0.f;
+  }
+}
+
+// One group of LPR lanes per lookup; the first group to tag claim[row] this step
+// owns the row's update (exactly once per distinct row).
+template <int D>
+__global__ void __launch_bounds__(256)
+adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ th,
+                 float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
+                 int* __restrict__ claim, int tag, float lr_t, float b1, float b2, float eps) {
+  constexpr int LPR = D >= 4 ? D / 4 : 1;
+  const int lane = threadIdx.x & 31;
+  const int q = lane % LPR;
+  const long long groups_per_block = blockDim.x / LPR;
+  const long long stride = static_cast<long long>(gridDim.x) * groups_per_block;
+  const long long nr = (n + stride - 1) / stride;
+  long long i = blockIdx.x * groups_per_block + threadIdx.x / LPR;
+  for (long long k = 0; k < nr; ++k, i += stride) {
+    int rid = -1;
+    int won = 0;
+    if (i < n) {
+      rid = __ldg(rows + i);
+      if (q == 0) won = atomicExch(claim + rid, tag) != tag ? 1 : 0;
+    }
+    won = __shfl_sync(0xffffffffu, won, (lane / LPR) * LPR);
+    if (!won) continue;
+    if (D >= 4) {
+      const size_t o = static_cast<size_t>(rid) * D + q * 4;
+      float4 G = *reinterpret_cast<float4*>(g + o);
+      float4 M = *reinterpret_cast<float4*>(m + o);
+      float4 V = *reinterpret_cast<float4*>(v + o);
+      float4 T = *reinterpret_cast<float4*>(th + o);
+      CTR_ADAM1(x) CTR_ADAM1(y) CTR_ADAM1(z) CTR_ADAM1(w)
+      *reinterpret_cast<float4*>(m + o) = M;
+      *reinterpret_cast<float4*>(v + o) = V;
+      *reinterpret_cast<float4*>(th + o) = T;
+      *reinterpret_cast<float4*>(g + o) = f4_zero();
+    } else {
+      const float G = g[rid];
+      const float M = b1 * m[rid] + (1.f - b1) * G;
+      const float V = b2 * v[rid] + (1.f - b2) * G * G;
+      m[rid] = M;
+      v[rid] = V;
+      th[rid] -= lr_t * M / (sqrtf(V) + eps);
+      g[rid] = 0.f;
+    }
+  }
+}
+#undef CTR_ADAM1
+
+}  // namespace ctr
+
+// =========================================================================== C ABI
+using namespace ctr;
+
+template <int NIT>
+static int launch_cross_bwd(const float* x0, const float* w, const float* b, int L, int B, int W,
+                            const float* dxl, float* dx0, float* dw, float* db, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(2) * L * W * sizeof(float);
+  const int grid = std::min((B + 7) / 8, sm_count());
+#define CTR_XB(LM)                                                                            \
+  {                                                                                           \
+    cudaFuncSetAttribute(cross_bwd_kernel<NIT, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         static_cast<int>(smem));                                             \
+    cross_bwd_kernel<NIT, LM><<<grid, 256, smem, st>>>(x0, w, b, L, B, W, dxl, dx0, dw, db);  \
+  }
+  if (L <= 2) CTR_XB(2) else if (L <= 4) CTR_XB(4) else CTR_XB(6)
+#undef CTR_XB
+  return CTR_OK;
+}
+
+extern "C" {
+
+int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_cat,
+                    const ctr_field_desc* fields_dev, const float* boundaries_dev, int B, int F,
+                    int32_t* rows, float* logx, int32_t* status, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(rows && fields_dev, "ctr_criteo_rows", "null rows/fields");
+  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_criteo_rows", "bad B/F");
+  CTR_REQUIRE(n_cont == 0 || (xcont && boundaries_dev), "ctr_criteo_rows", "null xcont/boundaries");
+  CTR_REQUIRE(n_cat == 0 || xcat, "ctr_criteo_rows", "null xcat");
+  if (B == 0) return CTR_OK;
+  const long long n = static_cast<long long>(B) * F;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 8LL));
+  criteo_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      xcont, n_cont, reinterpret_cast<const long long*>(xcat), n_cat, fields_dev, boundaries_dev, B,
+      F, rows, logx, status);
+  CTR_LAUNCH_CHECK("ctr_criteo_rows");
+}
+
+int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
+                  uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
+                  const float* cross_w, const float* cross_b, int cross_layers, float* xl,
+                  ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(table && rows, "ctr_embed_fwd", "null table/rows");
+  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_embed_fwd", "need 0 < F <= 64");
+  CTR_REQUIRE(aligned16(table) && aligned16(rows) && aligned16(E) && aligned16(S) && aligned16(xl) &&
+                  aligned16(cross_w) && aligned16(cross_b),
+              "ctr_embed_fwd", "pointers must be 16-byte aligned");
+  CTR_REQUIRE(y1 == nullptr || w1 != nullptr, "ctr_embed_fwd", "y1 requested without w1");
+  const bool cross = xl != nullptr;
+  CTR_REQUIRE(!cross || (cross_w && cross_b && cross_layers >= 0), "ctr_embed_fwd",
+              "xl requested without cross_w/cross_b");
+  if (B == 0) return CTR_OK;
+  EmbedFwdParams p;
+  p.table = table; p.w1 = w1; p.rows = rows; p.E = E; p.S = S; p.y1 = y1; p.y2 = y2;
+  p.cross_w = cross_w; p.cross_b = cross_b; p.xl = xl; p.w1_fields = w1_fields;
+  p.cross_layers = cross_layers; p.B = B; p.F = F;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int r = cross ? dispatch_fwd<true>(p, D, st) : dispatch_fwd<false>(p, D, st);
+  if (r != CTR_OK) return r;
+  CTR_LAUNCH_CHECK("ctr_embed_fwd");
+}
+
+int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const float* table,
+                  const float* S, const float* dy2, const float* dy1, uint64_t w1_fields,
+                  const int64_t* row_offsets_host, int B, int F, int D, float* dtable, float* dw1,
+                  ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(rows && dtable && row_offsets_host, "ctr_embed_bwd", "null rows/dtable/row_offsets");
+  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_embed_bwd", "need 0 < F <= 64");
+  CTR_REQUIRE(dE || dy2, "ctr_embed_bwd", "nothing to scatter: dE and dy2 both null");
+  CTR_REQUIRE(!dy2 || (S && (E || table)), "ctr_embed_bwd", "dy2 needs S and E (or table)");
+  CTR_REQUIRE(aligned16(dE) && aligned16(E) && aligned16(table) && aligned16(S) && aligned16(dtable),
+              "ctr_embed_bwd", "pointers must be 16-byte aligned");
+  CTR_REQUIRE(row_offsets_host[F] < (1LL << 31), "ctr_embed_bwd", "table too large for int32 rows");
+  if (B == 0) return CTR_OK;
+  EmbedBwdParams p;
+  p.rows = rows; p.dE = dE; p.E = E; p.table = table; p.S = S; p.dy2 = dy2; p.dy1 = dy1;
+  p.dtable = dtable; p.dw1 = dw1; p.w1_fields = w1_fields; p.B = B; p.F = F;
+  for (int f = 0; f <= F; ++f) p.off[f] = static_cast<int>(row_offsets_host[f]);
+  // chunk: enough warp-tasks to fill the machine, few enough tiny-field flushes.
+  int chunk = 64;
+  while (chunk < 1024 && static_cast<long long>(F) * ((B + chunk - 1) / chunk) > sm_count() * 64LL)
+    chunk <<= 1;
+  p.chunk = chunk;
+  p.nchunks = (B + chunk - 1) / chunk;
+  const long long ntask = static_cast<long long>(F) * p.nchunks;
+  const int grid = static_cast<int>(std::min<long long>((ntask + 7) / 8, sm_count() * 8LL));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (D) {
+    case 8: embed_bwd_kernel<8><<<grid, 256, 0, st>>>(p); break;
+    case 16: embed_bwd_kernel<16><<<grid, 256, 0, st>>>(p); break;
+    case 32: embed_bwd_kernel<32><<<grid, 256, 0, st>>>(p); break;
+    default: return fail_arg("ctr_embed_bwd", "D must be 8, 16 or 32");
+  }
+  CTR_LAUNCH_CHECK("ctr_embed_bwd");
+}
+
+int ctr_dcn_cross_fwd(const float* x0, const float* w, const float* b, int L, int B, int W,
+                      float* xl, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(x0 && w && b && xl, "ctr_dcn_cross_fwd", "null pointer");
+  CTR_REQUIRE(L >= 0 && B >= 0 && W > 0 && (W & 3) == 0 && W <= 1280, "ctr_dcn_cross_fwd",
+              "need W%4==0, W<=1280");
+  CTR_REQUIRE(aligned16(x0) && aligned16(w) && aligned16(b) && aligned16(xl), "ctr_dcn_cross_fwd",
+              "pointers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  const int need = (W / 4 + 31) / 32;
+  const int grid = std::min((B + 7) / 8, sm_count() * 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (need <= 2) cross_fwd_kernel<2><<<grid, 256, 0, st>>>(x0, w, b, L, B, W, xl);
+  else if (need <= 5) cross_fwd_kernel<5><<<grid, 256, 0, st>>>(x0, w, b, L, B, W, xl);
+  else cross_fwd_kernel<10><<<grid, 256, 0, st>>>(x0, w, b, L, B, W, xl);
+  CTR_LAUNCH_CHECK("ctr_dcn_cross_fwd");
+}
+
+int ctr_dcn_cross_bwd(const float* x0, const float* w, const float* b, int L, int B, int W,
+                      const float* dxl, float* dx0, float* dw, float* db, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(x0 && w && b && dxl && dx0 && dw && db, "ctr_dcn_cross_bwd", "null pointer");
+  CTR_REQUIRE(L >= 1 && L <= 6, "ctr_dcn_cross_bwd", "need 1 <= L <= 6");
+  CTR_REQUIRE(B >= 0 && W > 0 && (W & 3) == 0 && W <= 1280, "ctr_dcn_cross_bwd",
+              "need W%4==0, W<=1280");
+  CTR_REQUIRE(static_cast<size_t>(2) * L * W * 4 <= 200 * 1024, "ctr_dcn_cross_bwd",
+              "L*W too large for the shared-memory accumulators");
+  CTR_REQUIRE(aligned16(x0) && aligned16(w) && aligned16(b) && aligned16(dxl) && aligned16(dx0),
+              "ctr_dcn_cross_bwd", "pointers must be 16-byte aligned");
+  if (B == 0) return CTR_OK;
+  const int need = (W / 4 + 31) / 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (need <= 2) launch_cross_bwd<2>(x0, w, b, L, B, W, dxl, dx0, dw, db, st);
+  else if (need <= 5) launch_cross_bwd<5>(x0, w, b, L, B, W, dxl, dx0, dw, db, st);
+  else launch_cross_bwd<10>(x0, w, b, L, B, W, dxl, dx0, dw, db, st);
+  CTR_LAUNCH_CHECK("ctr_dcn_cross_bwd");
+}
+
+int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, int zero_g, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(theta && m && v && g && n >= 0, "ctr_adam_dense", "null pointer / negative n");
+  CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_dense",
+              "pointers must be 16-byte aligned");
+  if (n == 0) return CTR_OK;
+  const int grid = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, sm_count() * 8LL));
+  adam_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g);
+  CTR_LAUNCH_CHECK("ctr_adam_dense");
+}
+
+int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
+                  float* g, int32_t* claim, int32_t tag, float lr_t, float beta1, float beta2,
+                  float eps, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(rows && theta && m && v && g && claim && n >= 0, "ctr_adam_rows", "null pointer");
+  CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_rows",
+              "pointers must be 16-byte aligned");
+  if (n == 0) return CTR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int lpr = D >= 4 ? D / 4 : 1;
+  const long long gpb = 256 / lpr;
+  const int grid = static_cast<int>(std::min<long long>((n + gpb - 1) / gpb, sm_count() * 8LL));
+  switch (D) {
+    case 1: adam_rows_kernel<1><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
+    case 8: adam_rows_kernel<8><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
+    case 16: adam_rows_kernel<16><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
+    case 32: adam_rows_kernel<32><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
+    default: return fail_arg("ctr_adam_rows", "D must be 1, 8, 16 or 32");
+  }
+  CTR_LAUNCH_CHECK("ctr_adam_rows");
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""The Estimator callback contract of the reference, mirrored for eager PyTorch.
+
+The only stable interface of the reference's hot path is
+``model_fn(features, labels, mode, params) -> EstimatorSpec`` (fm/fm.py:115,135-170
+and the same block in deepfm/xdeepfm/dcn/din).  This module keeps those names:
+``ModeKeys``, ``EstimatorSpec``, ``export.PredictOutput``, the two streaming
+metrics, and a variable store that plays the role of the TF graph's variable
+collection (variables are created by the first ``model_fn`` call and reused by
+later ones).  ``Estimator`` is a thin eager train/evaluate/predict loop - the
+reference's checkpointing / summaries / distribution strategy are out of scope.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Optional
+
+import torch
+
+
+class ModeKeys:
+    TRAIN = "train"
+    EVAL = "eval"
+    PREDICT = "infer"
+
+
+@dataclass
+class PredictOutput:
+    outputs: dict
+
+
+class export:  # namespace mirror of estimator.export
+    PredictOutput = PredictOutput
+
+
+DEFAULT_SERVING_SIGNATURE_DEF_KEY = "serving_default"
+
+
+@dataclass
+class EstimatorSpec:
+    mode: str
+    predictions: Optional[dict] = None
+    loss: Optional[torch.Tensor] = None
+    train_op: Optional[Callable[[], None]] = None
+    eval_metric_ops: Optional[dict] = None
+    export_outputs: Optional[dict] = None
+
+
+# ----------------------------------------------------------------------- metrics
+class StreamingAUC:
+    """tf.metrics.auc(labels, pred) (fm/fm.py:151): 200 thresholds
+    [-1e-7, 1/199..198/199, 1+1e-7], positive iff pred > thr, trapezoid over
+    (fpr, tpr) with tpr=(tp+1e-6)/(tp+fn+1e-6), fpr=fp/(fp+tn+1e-6); fp32 counters.
+    State lives on the device of the first update."""
+
+    def __init__(self, num_thresholds: int = 200):
+        n = num_thresholds
+        thr = [(i + 1) * 1.0 / (n - 1) for i in range(n - 2)]
+        self._thr_host = torch.tensor([0.0 - 1e-7] + thr + [1.0 + 1e-7], dtype=torch.float32)
+        self.thr = None
+        self.tp = self.fp = self.tn = self.fn = None
+
+    def update(self, labels, pred):
+        pred = pred.detach().reshape(-1).float()
+        y = labels.detach().reshape(-1).to(pred.device) > 0.5
+        if self.thr is None:
+            self.thr = self._thr_host.to(pred.device)
+            z = torch.zeros_like(self.thr)
+            self.tp, self.fp, self.tn, self.fn = z.clone(), z.clone(), z.clone(), z.clone()
+        pos = pred[None, :] > self.thr[:, None]
+        yy = y[None, :]
+        self.tp += (pos & yy).sum(1).float()
+        self.fp += (pos & ~yy).sum(1).float()
+        self.fn += (~pos & yy).sum(1).float()
+        self.tn += (~pos & ~yy).sum(1).float()
+        return self
+
+    def result(self) -> float:
+        eps = 1e-6
+        rec = (self.tp + eps) / (self.tp + self.fn + eps)
+        fpr = self.fp / (self.fp + self.tn + eps)
+        return float(((fpr[:-1] - fpr[1:]) * (rec[:-1] + rec[1:]) / 2.0).sum())
+
+
+class StreamingAccuracy:
+    """tf.metrics.accuracy(labels, tf.round(pred)) (fm/fm.py:152)."""
+
+    def __init__(self):
+        self.total = 0.0
+        self.count = 0.0
+
+    def update(self, labels, pred):
+        p = torch.round(pred.detach().reshape(-1).float())
+        y = labels.detach().reshape(-1).to(p.device).float()
+        self.total += float((p == y).sum())
+        self.count += float(y.numel())
+        return self
+
+    def result(self) -> float:
+        return self.total / max(self.count, 1.0)
+
+
+# ---------------------------------------------------------------- variable store
+class VariableStore:
+    """Stands in for the TF graph's variable collection: ``model_fn`` asks for its
+    model object by scope name; the first call builds it, later calls reuse it."""
+
+    def __init__(self):
+        self._objs: Dict[str, object] = {}
+        self.global_step = 0
+
+    def get(self, scope: str, factory: Callable[[], object]):
+        if scope not in self._objs:
+            self._objs[scope] = factory()
+        return self._objs[scope]
+
+    def reset(self):
+        self._objs.clear()
+        self.global_step = 0
+
+
+_DEFAULT_STORE = VariableStore()
+
+
+def default_store() -> VariableStore:
+    return _DEFAULT_STORE
+
+
+def store_of(params: dict) -> VariableStore:
+    """``params['variable_store']`` when the caller wants isolation, else the
+    process-wide default (the reference has one graph per Estimator)."""
+    return params.get("variable_store") or _DEFAULT_STORE
+
+
+# --------------------------------------------------------------------- Estimator
+class Estimator:
+    """Eager stand-in for ``tf.estimator.Estimator(model_fn, model_dir, params, config)``
+    limited to the calls the reference drivers make (fm/fm.py:204-224)."""
+
+    def __init__(self, model_fn, model_dir=None, params=None, config=None):
+        self.model_fn = model_fn
+        self.params = dict(params or {})
+        self.params.setdefault("variable_store", VariableStore())
+        self.model_dir = model_dir
+        self.config = config
+
+    def train(self, input_fn, steps=None, max_steps=None):
+        n = 0
+        last = None
+        for features, labels in input_fn():
+            spec = self.model_fn(features, labels, ModeKeys.TRAIN, self.params)
+            spec.train_op()
+            last = spec.loss
+            n += 1
+            if steps is not None and n >= steps:
+                break
+        return None if last is None else float(last)
+
+    def evaluate(self, input_fn, steps=None):
+        auc, acc = StreamingAUC(), StreamingAccuracy()
+        tot, n = 0.0, 0
+        for features, labels in input_fn():
+            spec = self.model_fn(features, labels, ModeKeys.EVAL, self.params)
+            auc.update(labels, spec.predictions["prob"])
+            acc.update(labels, spec.predictions["prob"])
+            tot += float(spec.loss)
+            n += 1
+            if steps is not None and n >= steps:
+                break
+        return {"AUC": auc.result(), "Accuracy": acc.result(), "loss": tot / max(n, 1),
+                "global_step": self.params["variable_store"].global_step}
+
+    def predict(self, input_fn):
+        for features, labels in input_fn():
+            spec = self.model_fn(features, None, ModeKeys.PREDICT, self.params)
+            yield from ({"prob": p} for p in spec.predictions["prob"].detach().cpu())

@@ -1,0 +1,525 @@
+"""Host-side operators over libctr_b200: id pipeline, fused multi-field lookup
+(+FM / +DCN cross) with its scatter-add backward, TF-Adam, and the flat
+dense-parameter store.  PyTorch supplies device memory, streams and autograd
+glue only; every op here launches hand-written sm_100a kernels through the C
+ABI and raises if the library is missing or the device is not a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from . import feature_column as fc
+
+LAUNCHES = {"n": 0}   # kernels launched through the C ABI (bench.py reports it)
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    LAUNCHES["n"] += 1
+    _lib.check(getattr(lib, name)(*args))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: recsys_b200 has no CPU path" % what)
+
+
+# ------------------------------------------------------------------ id pipeline
+class PackedFeatures(dict):
+    """A features dict whose per-key tensors are column views of two packed
+    buffers - ``cont`` f32 [B, n_cont] and ``cat`` i64 [B, n_cat] - so that the
+    model_fn can move a batch with two copies instead of 39."""
+
+    def __init__(self, cont: torch.Tensor, cat: torch.Tensor, cont_keys: Sequence[str],
+                 cat_keys: Sequence[str]):
+        super().__init__()
+        self.cont, self.cat = cont, cat
+        self.cont_keys, self.cat_keys = list(cont_keys), list(cat_keys)
+        for j, k in enumerate(self.cont_keys):
+            self[k] = cont[:, j:j + 1]
+        for j, k in enumerate(self.cat_keys):
+            self[k] = cat[:, j:j + 1]
+
+
+class IdPipeline:
+    """features -> rows[B,F] int32 on the device (ctr_criteo_rows).  Replaces the
+    id half of ``input_layer`` (fm/fm.py:76-80,89) for log-bucketised numerics and
+    pre-hashed categoricals; raw byte strings are hashed by ``hash_strings``."""
+
+    def __init__(self, lay: fc.Layout, device):
+        self.lay = lay
+        self.device = device
+        self.cont_keys: List[str] = []
+        self.cat_keys: List[str] = []
+        descs = (_lib.FieldDesc * lay.F)()
+        bnd: List[float] = []
+        for f, col in enumerate(lay.columns):
+            cc = col.categorical_column
+            d = descs[f]
+            d.n_rows, d.row_offset = lay.rows[f], lay.offsets[f]
+            if isinstance(cc, fc.BucketizedColumn):
+                d.kind, d.src = 0, len(self.cont_keys)
+                d.bnd_begin, d.bnd_count = len(bnd), len(cc.boundaries)
+                off = cc.source_column.log_offset
+                if off is None:
+                    raise ValueError("numeric column %s needs a log(x+c) normalizer" % cc.key)
+                d.log_offset = off
+                bnd.extend(cc.boundaries)
+                self.cont_keys.append(cc.key)
+            else:
+                d.kind, d.src = 1, len(self.cat_keys)
+                self.cat_keys.append(cc.key)
+        raw = bytes(descs)
+        self.fields_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.bnd_dev = torch.tensor(bnd if bnd else [0.0], dtype=torch.float32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.n_buckets_dev = torch.tensor(lay.rows, dtype=torch.int32, device=device)
+        self.row_offset_dev = torch.tensor(lay.offsets[:-1], dtype=torch.int32, device=device)
+
+    def pack(self, features) -> tuple:
+        """-> (cont f32 [B,n_cont], cat i64 [B,n_cat]) on the device."""
+        if isinstance(features, PackedFeatures) and features.cont_keys == self.cont_keys \
+                and features.cat_keys == self.cat_keys:
+            cont, cat = features.cont, features.cat
+        else:
+            cont = torch.cat([torch.as_tensor(features[k]).reshape(-1, 1).float()
+                              for k in self.cont_keys], 1) if self.cont_keys else None
+            cats = []
+            for k in self.cat_keys:
+                v = features[k]
+                if not torch.is_tensor(v):
+                    v = self.hash_strings_host(k, v)
+                cats.append(v.reshape(-1, 1).long())
+            cat = torch.cat(cats, 1) if cats else None
+        if cont is not None:
+            cont = cont.to(self.device, non_blocking=True).contiguous()
+        if cat is not None:
+            cat = cat.to(self.device, non_blocking=True).contiguous()
+        return cont, cat
+
+    def hash_strings_host(self, key, values) -> torch.Tensor:
+        """Raw byte strings of one categorical column -> local ids (device hash)."""
+        f = self.lay.field_of(key)
+        flat = [bytes(v) for v in _flatten(values)]
+        return hash_strings(flat, self.lay.rows[f], self.device)
+
+    def __call__(self, features, want_logx: bool = False):
+        cont, cat = self.pack(features)
+        B = (cont if cont is not None else cat).shape[0]
+        rows = torch.empty((B, self.lay.F), dtype=torch.int32, device=self.device)
+        logx = torch.empty((B, len(self.cont_keys)), dtype=torch.float32, device=self.device) \
+            if want_logx else None
+        _call("ctr_criteo_rows", _p(cont), len(self.cont_keys), _p(cat), len(self.cat_keys),
+              _p(self.fields_dev), _p(self.bnd_dev), B, self.lay.F, _p(rows), _p(logx),
+              _p(self.status), _stream())
+        return (rows, logx) if want_logx else rows
+
+
+def _flatten(values):
+    for v in values:
+        if isinstance(v, (bytes, bytearray)):
+            yield v
+        else:
+            yield from _flatten(v)
+
+
+def hash_strings(strings: Sequence[bytes], n_buckets: int, device) -> torch.Tensor:
+    """FarmHash Fingerprint64(s) mod n_buckets on the device (ctr_hash_strings);
+    TF StringToHashBucketFast as used by fm/fm.py:89."""
+    n = len(strings)
+    offs = [0]
+    for s in strings:
+        offs.append(offs[-1] + len(s))
+    blob = torch.frombuffer(bytearray(b"".join(strings) + b"\0" * 16), dtype=torch.uint8).to(device)
+    offsets = torch.tensor(offs, dtype=torch.int32, device=device)
+    nb = torch.tensor([n_buckets], dtype=torch.int32, device=device)
+    ro = torch.zeros(1, dtype=torch.int32, device=device)
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    _call("ctr_hash_strings", _p(blob), _p(offsets), n, None, _p(nb), _p(ro), _p(out), _stream())
+    return out.long()
+
+
+# ---------------------------------------------------------------- Adam (TF rule)
+class TFAdamState:
+    """Step counter + lr_t of tf.train.AdamOptimizer (fm/fm.py:162):
+    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), eps outside the sqrt."""
+
+    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.t = 0
+
+    def next_lr_t(self) -> float:
+        self.t += 1
+        return self.lr * math.sqrt(1 - self.beta2 ** self.t) / (1 - self.beta1 ** self.t)
+
+
+class DenseParams:
+    """All dense (non-table) parameters of a model in ONE flat fp32 buffer, their
+    gradients in another, so the optimiser is a single ctr_adam_dense launch.
+    ``self[name]`` is a view with ``requires_grad`` whose ``.grad`` is a view of
+    the flat gradient buffer."""
+
+    def __init__(self, shapes: Dict[str, tuple], device, frozen: Sequence[str] = ()):
+        self.names = list(shapes)
+        self.shapes = dict(shapes)
+        sizes = [int(torch.Size(s).numel()) for s in shapes.values()]
+        # 4-float aligned slots so every view is 16-byte aligned
+        self.slots, off = {}, 0
+        for n, sz in zip(self.names, sizes):
+            self.slots[n] = (off, sz)
+            off += (sz + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.frozen = set(frozen)
+        self.views: Dict[str, torch.Tensor] = {}
+        for n in self.names:
+            o, sz = self.slots[n]
+            v = self.flat[o:o + sz].view(self.shapes[n])
+            if n not in self.frozen:
+                v.requires_grad_(True)
+                v.grad = self.grad[o:o + sz].view(self.shapes[n])
+            self.views[n] = v
+
+    def __getitem__(self, n):
+        return self.views[n]
+
+    def __contains__(self, n):
+        return n in self.views
+
+    def load(self, state: Dict[str, torch.Tensor]):
+        with torch.no_grad():
+            for n in self.names:
+                if n in state:
+                    self.views[n].copy_(state[n].to(self.flat.device, torch.float32)
+                                        .reshape(self.shapes[n]))
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        return {n: self.views[n].grad for n in self.names if n not in self.frozen}
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def adam_step(self, lr_t, st: TFAdamState):
+        """One launch over the flat buffer; frozen slots have zero gradient and
+        zero moments, so the rule leaves them untouched."""
+        _call("ctr_adam_dense", _p(self.flat), _p(self.m), _p(self.v), _p(self.grad), self.numel,
+              lr_t, st.beta1, st.beta2, st.eps, 1, _stream())
+
+
+# ------------------------------------------------------- fused multi-field lookup
+class FieldEmbedding:
+    """The concatenated embedding table [R, D] (+ first-order weights w1 [R]) of a
+    list of embedding columns, with its gradient accumulators and Adam moments.
+
+    Gradients are not autograd tensors: the backward kernel scatter-adds into the
+    persistent ``dtable`` / ``dw1`` accumulators (dense, kept all-zero between steps
+    by the optimiser kernels), which is what the reference's IndexedSlices
+    gradient + AdamOptimizer amount to (fm/fm.py:162-163).
+    """
+
+    def __init__(self, lay: fc.Layout, device, with_w1: bool = True, w1_fields: int = 0,
+                 adam_mode: str = "lazy", seed: int = 0):
+        self.lay, self.device = lay, device
+        self.D, self.F, self.R = lay.dimension, lay.F, lay.total_rows
+        if self.D not in (8, 16, 32):
+            raise ValueError("embedding_size must be 8, 16 or 32 (got %d)" % self.D)
+        if self.F > 64:
+            raise ValueError("at most 64 fields")
+        g = torch.Generator(device=device).manual_seed(seed)
+        # embedding_column default initialiser: truncated normal, stddev 1/sqrt(D) [TF-sem];
+        # drawn on the device (the R-full table is 2 GB)
+        self.table = torch.empty(self.R, self.D, dtype=torch.float32, device=device)
+        torch.nn.init.trunc_normal_(self.table, std=self.D ** -0.5, a=-2 * self.D ** -0.5,
+                                    b=2 * self.D ** -0.5, generator=g)
+        self.dtable = torch.zeros_like(self.table)
+        self.with_w1 = with_w1
+        self.w1_fields = w1_fields
+        if with_w1:
+            lim = math.sqrt(6.0 / (self.R + 1))        # dense(onehot,1) glorot-uniform kernel
+            self.w1 = (torch.rand(self.R, generator=g, device=device) * 2 - 1) * lim
+            self.dw1 = torch.zeros_like(self.w1)
+        else:
+            self.w1 = self.dw1 = None
+        self.adam_mode = adam_mode
+        self._m = self._v = self._m1 = self._v1 = None
+        self._claim = self._claim1 = None
+        self._tag = 0
+        self._offsets_host = (C.c_int64 * (self.F + 1))(*lay.offsets)
+        self._anchor = torch.zeros((), device=device, requires_grad=True)
+
+    # -- state ------------------------------------------------------------------
+    def load(self, table=None, w1=None):
+        with torch.no_grad():
+            if table is not None:
+                self.table.copy_(table.to(self.device, torch.float32))
+            if w1 is not None and self.with_w1:
+                self.w1.copy_(w1.to(self.device, torch.float32).reshape(-1))
+
+    def _ensure_adam(self):
+        if self._m is None:
+            self._m = torch.zeros_like(self.table)
+            self._v = torch.zeros_like(self.table)
+            self._claim = torch.zeros(self.R, dtype=torch.int32, device=self.device)
+            if self.with_w1:
+                self._m1 = torch.zeros_like(self.w1)
+                self._v1 = torch.zeros_like(self.w1)
+                self._claim1 = torch.zeros(self.R, dtype=torch.int32, device=self.device)
+
+    # -- forward / backward -----------------------------------------------------
+    def lookup(self, rows: torch.Tensor, want_fm: bool = True, want_y1: bool = True,
+               cross_w: Optional[torch.Tensor] = None, cross_b: Optional[torch.Tensor] = None):
+        """-> dict(E [B,F*D], y1 [B] (pre-bias), y2 [B], xl [B,F*D]) with autograd."""
+        require_cuda(rows, "rows")
+        return _EmbedFn.apply(self._anchor, self, rows, want_fm, want_y1 and self.with_w1,
+                              cross_w, cross_b)
+
+    def zero_grad(self):
+        self.dtable.zero_()
+        if self.with_w1:
+            self.dw1.zero_()
+
+    def adam_step(self, rows: torch.Tensor, lr_t: float, st: TFAdamState):
+        """Consume (and re-zero) the accumulated gradients.  ``lazy``: one update per
+        touched row (LazyAdam); ``exact_tf``: every row, as TF's sparse apply does."""
+        self._ensure_adam()
+        if self.adam_mode == "exact_tf":
+            _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
+                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, _stream())
+            if self.with_w1:
+                _call("ctr_adam_dense", _p(self.w1), _p(self._m1), _p(self._v1), _p(self.dw1),
+                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, _stream())
+            return
+        self._tag += 1
+        n = rows.numel()
+        _call("ctr_adam_rows", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
+              _p(self.dtable), _p(self._claim), self._tag, lr_t, st.beta1, st.beta2, st.eps,
+              _stream())
+        if self.with_w1:
+            _call("ctr_adam_rows", _p(rows), n, 1, _p(self.w1), _p(self._m1), _p(self._v1),
+                  _p(self.dw1), _p(self._claim1), self._tag, lr_t, st.beta1, st.beta2, st.eps,
+                  _stream())
+
+
+class _EmbedFn(torch.autograd.Function):
+    """ctr_embed_fwd / ctr_embed_bwd (+ ctr_dcn_cross_bwd when the cross stack is fused)."""
+
+    @staticmethod
+    def forward(ctx, anchor, emb: FieldEmbedding, rows, want_fm, want_y1, cross_w, cross_b):
+        ctx.set_materialize_grads(False)
+        B, F, D = rows.shape[0], emb.F, emb.D
+        dev = rows.device
+        rows = rows.contiguous()
+        E = torch.empty((B, F * D), dtype=torch.float32, device=dev)
+        S = torch.empty((B, D), dtype=torch.float32, device=dev) if want_fm else None
+        y2 = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
+        y1 = torch.empty((B,), dtype=torch.float32, device=dev) if want_y1 else None
+        cross = cross_w is not None
+        xl = torch.empty((B, F * D), dtype=torch.float32, device=dev) if cross else None
+        L = cross_w.shape[0] if cross else 0
+        _call("ctr_embed_fwd", _p(emb.table), _p(emb.w1), _p(rows), B, F, D, emb.w1_fields, _p(E),
+              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _stream())
+        ctx.emb, ctx.rows, ctx.E, ctx.S = emb, rows, E, S
+        ctx.cross_w, ctx.cross_b = cross_w, cross_b
+        ctx.flags = (want_fm, want_y1, cross)
+        outs = [E, y1 if want_y1 else E.new_zeros(()), y2 if want_fm else E.new_zeros(()),
+                xl if cross else E.new_zeros(())]
+        non_diff = [o for o, f in zip(outs[1:], (want_y1, want_fm, cross)) if not f]
+        if non_diff:
+            ctx.mark_non_differentiable(*non_diff)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dE, dy1, dy2, dxl):
+        emb = ctx.emb
+        want_fm, want_y1, cross = ctx.flags
+        rows, E, S = ctx.rows, ctx.E, ctx.S
+        B, F, D = rows.shape[0], emb.F, emb.D
+        dcw = dcb = None
+        if cross and dxl is not None:
+            L, W = ctx.cross_w.shape
+            dx0 = torch.empty_like(E)
+            dcw = torch.zeros_like(ctx.cross_w)
+            dcb = torch.zeros_like(ctx.cross_b)
+            _call("ctr_dcn_cross_bwd", _p(E), _p(ctx.cross_w), _p(ctx.cross_b), L, B, W,
+                  _p(dxl.contiguous()), _p(dx0), _p(dcw), _p(dcb), _stream())
+            dE = dx0 if dE is None else dE + dx0
+        dE = None if dE is None else dE.contiguous()
+        dy2 = dy2.contiguous() if (want_fm and dy2 is not None) else None
+        dy1 = dy1.contiguous() if (want_y1 and dy1 is not None) else None
+        if dE is not None or dy2 is not None:
+            _call("ctr_embed_bwd", _p(rows), _p(dE), _p(E), _p(emb.table), _p(S), _p(dy2), _p(dy1),
+                  emb.w1_fields, emb._offsets_host, B, F, D, _p(emb.dtable), _p(emb.dw1), _stream())
+        return None, None, None, None, None, dcw, dcb
+
+
+# ------------------------------------------------------------------- DCN cross
+class _CrossFn(torch.autograd.Function):
+    """Stand-alone cross stack on a dense x0 (ctr_dcn_cross_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x0, w, b):
+        x0, w, b = x0.contiguous(), w.contiguous(), b.contiguous()
+        L, W = w.shape
+        xl = torch.empty_like(x0)
+        _call("ctr_dcn_cross_fwd", _p(x0), _p(w), _p(b), L, x0.shape[0], W, _p(xl), _stream())
+        ctx.save_for_backward(x0, w, b)
+        return xl
+
+    @staticmethod
+    def backward(ctx, dxl):
+        x0, w, b = ctx.saved_tensors
+        L, W = w.shape
+        dx0 = torch.empty_like(x0)
+        dw, db = torch.zeros_like(w), torch.zeros_like(b)
+        _call("ctr_dcn_cross_bwd", _p(x0), _p(w), _p(b), L, x0.shape[0], W, _p(dxl.contiguous()),
+              _p(dx0), _p(dw), _p(db), _stream())
+        return dx0, dw, db
+
+
+def dcn_cross(x0, w, b):
+    require_cuda(x0, "x0")
+    return _CrossFn.apply(x0, w, b)
+
+
+# ------------------------------------------------------------------ xDeepFM CIN
+CIN_PREC = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+_WS_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
+    key = (tag, str(device))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+class _CINFn(torch.autograd.Function):
+    """The whole CIN stack (xdeepfm/xdeepfm.py:135-181): E [B, m*D] -> pooled [B, sum H].
+    Layers run through ctr_cin_layer_fwd/_bwd on d-major rows; the [B,D,m*Hp] outer
+    product the reference materialises never exists."""
+
+    @staticmethod
+    def forward(ctx, E, m, D, prec, *wb):
+        n = len(wb) // 2
+        Ws, bs = wb[:n], wb[n:]
+        B = E.shape[0]
+        dev = E.device
+        ld0 = (m + 3) // 4 * 4
+        X0t = torch.empty((B * D, ld0), dtype=torch.float32, device=dev)
+        _call("ctr_transpose_fd", _p(E.contiguous()), B, m, D, _p(X0t), ld0, _stream())
+        lib = _lib.load()
+        hp_list = [m] + [int(W.shape[1]) for W in Ws[:-1]]
+        nbytes = max(int(lib.ctr_cin_workspace_bytes(B, D, m, hp, int(W.shape[1]), prec))
+                     for hp, W in zip(hp_list, Ws))
+        ws = _workspace(nbytes, dev, "cin")
+        outs = []
+        Xp, ldp, Hp = X0t, ld0, m
+        for W, b in zip(Ws, bs):
+            H = int(W.shape[1])
+            out = torch.empty((B * D, H), dtype=torch.float32, device=dev)
+            _call("ctr_cin_layer_fwd", _p(X0t), ld0, _p(Xp), ldp, _p(W.contiguous()), _p(b), B, D,
+                  m, Hp, H, _p(out), prec, _p(ws), ws.numel(), _stream())
+            outs.append(out)
+            Xp, ldp, Hp = out, H, H
+        pooled = torch.cat([o.view(B, D, -1).sum(1) for o in outs], 1)      # :180-181
+        ctx.meta = (m, D, prec, ld0, B)
+        ctx.saved = (X0t, outs, Ws, ws)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dp):
+        m, D, prec, ld0, B = ctx.meta
+        X0t, outs, Ws, ws = ctx.saved
+        dev = dp.device
+        n = len(Ws)
+        Hs = [int(W.shape[1]) for W in Ws]
+        offs = [0]
+        for h in Hs:
+            offs.append(offs[-1] + h)
+        dX0t = torch.zeros_like(X0t)
+        dWs = [torch.zeros_like(W) for W in Ws]
+        dbs = [torch.zeros(h, dtype=torch.float32, device=dev) for h in Hs]
+        # gradient arriving at each layer output from the sum-pool (broadcast over d)
+        douts = [dp[:, offs[k]:offs[k + 1]].unsqueeze(1).expand(B, D, Hs[k]).reshape(B * D, Hs[k])
+                 .contiguous() for k in range(n)]
+        for k in range(n - 1, -1, -1):
+            dpre = (douts[k] * (outs[k] > 0)).contiguous()
+            if k > 0:
+                Xp, ldp, Hp, dXp = outs[k - 1], Hs[k - 1], Hs[k - 1], douts[k - 1]
+            else:
+                Xp, ldp, Hp, dXp = X0t, ld0, m, dX0t
+            _call("ctr_cin_layer_bwd", _p(X0t), ld0, _p(Xp), ldp, _p(Ws[k].contiguous()), _p(dpre),
+                  B, D, m, Hp, Hs[k], _p(dX0t), _p(dXp), _p(dWs[k]), _p(dbs[k]), prec, _p(ws),
+                  ws.numel(), _stream())
+        dE = torch.zeros((B, m * D), dtype=torch.float32, device=dev)
+        _call("ctr_transpose_df_add", _p(dX0t), ld0, B, m, D, _p(dE), _stream())
+        return (dE, None, None, None) + tuple(dWs) + tuple(dbs)
+
+
+def cin(E, m, D, Ws, bs, precision="tf32x3"):
+    require_cuda(E, "E")
+    return _CINFn.apply(E, m, D, CIN_PREC[precision], *Ws, *bs)
+
+
+# ------------------------------------------------------------ DIN activation unit
+class _DinAttFn(torch.autograd.Function):
+    """din/din.py:103-125 through ctr_din_att_fwd / ctr_din_att_bwd.  ``table`` /
+    ``dtable`` are views of a FieldEmbedding's buffers starting at the sub-table's
+    first row; the table gradient is RED-accumulated there, not returned."""
+
+    @staticmethod
+    def forward(ctx, anchor, table, dtable, hist, query, W1, b1, W2, b2, W3, b3):
+        B, P = hist.shape
+        E = query.shape[1]
+        hist = hist.contiguous()
+        query = query.contiguous()
+        out = torch.empty((B, E), dtype=torch.float32, device=query.device)
+        _call("ctr_din_att_fwd", _p(table), _p(hist), _p(query), B, P, E, _p(W1), _p(b1),
+              W1.shape[1], _p(W2), _p(b2), W2.shape[1], _p(W3), _p(b3), _p(out), None, _stream())
+        ctx.save_for_backward(hist, query, W1, b1, W2, b2, W3, b3)
+        ctx.tabs = (table, dtable)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        hist, query, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
+        table, dtable = ctx.tabs
+        B, P = hist.shape
+        E = query.shape[1]
+        lib = _lib.load()
+        nbytes = int(lib.ctr_din_workspace_bytes(B, P, E))
+        ws = _workspace(nbytes, query.device, "din")
+        dq = torch.empty_like(query)
+        g = [torch.zeros_like(t) for t in (W1, b1, W2, b2, W3, b3)]
+        _call("ctr_din_att_bwd", _p(table), _p(hist), _p(query), B, P, E, _p(W1), _p(b1),
+              W1.shape[1], _p(W2), _p(b2), W2.shape[1], _p(W3), _p(b3), _p(dout.contiguous()),
+              _p(dtable), _p(dq), _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(g[5]),
+              _p(ws), ws.numel(), _stream())
+        return (None, None, None, None, dq) + tuple(g)
+
+
+def din_attention(emb: "FieldEmbedding", field: int, hist, query, W1, b1, W2, b2, W3, b3):
+    """Attention of ``query`` over the history ids ``hist`` (local ids of sub-table
+    ``field`` of ``emb``; 0 = padding)."""
+    require_cuda(hist, "hist")
+    lo, hi = emb.lay.offsets[field], emb.lay.offsets[field + 1]
+    return _DinAttFn.apply(emb._anchor, emb.table[lo:hi], emb.dtable[lo:hi], hist, query,
+                           W1.contiguous(), b1, W2.contiguous(), b2, W3.reshape(-1), b3)
