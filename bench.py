@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py - the hot path's headline benchmark (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--model deepfm|fm|dcn|xdeepfm|din] [--batch B] [--table full|ref] [--dist uniform|zipf]
+
+A "step" = one pass of the hot path over one synthetic batch: ids -> fused multi-field
+lookup + interaction forward -> dense tower (torch) -> loss -> backward scatter-add ->
+Adam on the touched rows and the dense weights.  N=1 workload = BASELINE configs[1]:
+DeepFM, Criteo 39 fields, emb 16, batch 4096, fwd+bwd.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver's contract; see DESIGN.md
+"measurement" for how each number is taken.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_FWD = 2816          # ids 156 + rows 2496 + w1 156 + label 4 + logit 4
+ALG_BYTES_BWD = 5460          # ids 156 + table-grad RMW 2*2496 + w1-grad RMW 2*156
+ALG_BYTES = ALG_BYTES_FWD + ALG_BYTES_BWD   # 8276 B / sample, F=39, D=16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="deepfm")
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--table", default="full", choices=["full", "ref"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--n-batches", type=int, default=32)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph (debug)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------- CPU reference arm
+def oracle_setup(model, batch, table, dist, n_batches, seed=0):
+    import numpy as np
+    import torch
+    from oracle import criteo, models as om
+    spec = criteo.CriteoSpec(full_cardinality=(table == "full"))
+    p = om.init_params_fast(model, spec.total_rows) if hasattr(om, "init_params_fast") else None
+    if p is None:
+        g = torch.Generator().manual_seed(seed)
+        p = {"emb": torch.randn(spec.total_rows, 16, generator=g) * 0.25,
+             "w1": torch.randn(spec.total_rows, generator=g) * 0.01}
+        small = om.init_params(model, 1, seed=seed, dtype=torch.float32)
+        p.update({k: v for k, v in small.items() if k not in ("emb", "w1", "emb_dnn")})
+        if model == "xdeepfm":
+            p["emb_dnn"] = torch.randn(spec.total_rows, 16, generator=g) * 0.25
+    rng = np.random.default_rng(seed)
+    batches = []
+    for _ in range(n_batches):
+        cols = []
+        for f in range(spec.F):
+            n = spec.rows[f]
+            ids = np.minimum(rng.zipf(1.05, size=batch) - 1, n - 1) if dist == "zipf" \
+                else rng.integers(0, n, size=batch)
+            cols.append(ids + spec.offsets[f])
+        b = {"rows": torch.from_numpy(np.stack(cols, 1)),
+             "labels": torch.from_numpy((rng.random(batch) < 0.22).astype(np.float32))}
+        if model == "xdeepfm":
+            b["logx"] = torch.from_numpy(rng.normal(size=(batch, 13)).astype(np.float32))
+            b["cat_mask"] = torch.tensor([0.0 if c else 1.0 for c in spec.is_cont])
+        batches.append(b)
+    return p, batches
+
+
+def oracle_step(model, p, b):
+    """fwd + bwd of the restated reference graph on torch-CPU fp32 (sparse table grads,
+    as TF's IndexedSlices)."""
+    from oracle import models as om
+    leaves = {}
+    for k, v in p.items():
+        leaves[k] = v.detach().requires_grad_(not k.endswith((".bn.mean", ".bn.var")))
+    out = om.MODELS[model](leaves, **b, training=True, sparse_grad=True)
+    out["loss"].backward()
+    return float(out["loss"])
+
+
+def time_oracle(model, batch, table, dist, max_seconds, steps=None, warmup=2):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    p, batches = oracle_setup(model, batch, table, dist, n_batches=4)
+    for i in range(warmup):
+        oracle_step(model, p, batches[i % len(batches)])
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        oracle_step(model, p, batches[n % len(batches)])
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or el > max_seconds:
+            break
+    return n, el, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = args.model if args.model != "din" else "deepfm"
+    steps = max(1, min(args.steps, 50))
+    n, el, cores = time_oracle(model, args.batch, args.table, args.dist, max_seconds=90.0,
+                               steps=steps, warmup=min(args.warmup, 3))
+    v = n * args.batch / el
+    line = {
+        "impl": "reference", "metric": "CTR samples/sec (Criteo 39-field emb16)", "value": v,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 3),
+        "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d fwd+bwd steps of batch %d, oracle torch-CPU fp32 restatement "
+                                   "of deepfm.model_fn (TF is not installable here)" % (n, args.batch)},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    rows = 33762673 if args.table == "full" else 840646
+    return {"workload": "%s Criteo 39-field emb16 batch=%d fwd+bwd+Adam(lazy rows)" % (args.model, args.batch),
+            "fields": 39, "embedding_size": 16, "batch": args.batch, "deep_layers": "100,100",
+            "table_rows": rows, "table": args.table, "id_dist": args.dist,
+            "l2": "table %.2f GB > 126 MB L2; a distinct id batch every step (no flush needed)"
+                  % (rows * 64 / 1e9) if args.table == "full" else
+                  "reference-capped table 53.8 MB is L2-resident; distinct id batch every step",
+            "parallelism": "1 GPU" if args.gpus == 1 else "row-sharded table, %d GPUs" % args.gpus}
+
+
+# ------------------------------------------------------------------------ our arm
+def build_model(args, dev):
+    import importlib
+    from recsys_b200.estimator import VariableStore
+    mod = importlib.import_module("recsys_b200.%s.%s" % (args.model, args.model))
+    lin, emb = mod.build_feature_columns(16, full_cardinality=(args.table == "full"))
+    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
+              "learning_rate": 1e-3, "dropout": 0.5, "deep_layers": "100,100",
+              "cross_layers": "128,128" if args.model == "xdeepfm" else 4,
+              "cin_precision": "tf32", "variable_store": VariableStore(), "device": dev,
+              "embedding_adam": "lazy"}
+    return mod, params
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from recsys_b200 import sharded
+        return sharded.bench_main(args, rank, local, world)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from recsys_b200 import _lib, ops
+    from recsys_b200 import feature_column as fc
+    from recsys_b200.data import SyntheticCriteo
+    from recsys_b200.estimator import GraphedTrainStep
+    _lib.load()
+    mod, params = build_model(args, dev)
+    lay = fc.layout(params["embedding_feature_columns"])
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    host = SyntheticCriteo(lay, B, args.n_batches, dist=args.dist, seed=0, device=None)
+    devb = [(ops.PackedFeatures(f.cont.to(dev), f.cat.to(dev), f.cont_keys, f.cat_keys), l.to(dev))
+            for f, l in host.batches]
+
+    # one eager step: creates the variables and counts our kernels per step
+    n0 = ops.LAUNCHES["n"]
+    sp = mod.model_fn(devb[0][0], devb[0][1], "train", params)
+    sp.train_op()
+    per_step_launches = ops.LAUNCHES["n"] - n0
+    model = params["variable_store"]._objs[args.model]
+    torch.cuda.synchronize()
+    # ---- graph-captured whole step
+    f0, l0 = host.batches[0]
+    step = None if args.eager else GraphedTrainStep(mod.model_fn, params, f0, l0, warmup=3)
+    torch.cuda.synchronize()
+
+    def resident_step(i):
+        f, l = devb[i % len(devb)]
+        if step is None:
+            sp = mod.model_fn(f, l, "train", params)
+            sp.train_op()
+            return sp.loss
+        return step(f, l)     # device->device copy of the batch into the static buffers + replay
+
+    def e2e_step(i, slot):
+        f, l = host.batches[i % len(host.batches)]
+        if step is None:
+            sp = mod.model_fn(f, l, "train", params)
+            sp.train_op()
+            slot.copy_(sp.loss, non_blocking=True)
+        else:
+            step(f, l)
+            step.loss_to_host(slot)
+
+    stream = step.stream if step is not None else torch.cuda.current_stream()
+    # ---- (1) value: inputs resident in HBM
+    for i in range(W):
+        resident_step(i)
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+        for i in range(K):
+            resident_step(W + i)
+        with torch.cuda.stream(stream):
+            e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        # ---- (2) e2e: pinned host batches in, loss out, every step
+        losses = torch.zeros(K, dtype=torch.float32).pin_memory()
+        for i in range(W):
+            e2e_step(i, losses[0:1].view(()))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record()
+        for i in range(K):
+            e2e_step(W + i, losses[i:i + 1].view(()))
+        with torch.cuda.stream(stream):
+            e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms_e2e = max(e0.elapsed_time(e1), wall * 1e3)
+        # ---- (3) the two hot kernels alone, back to back on distinct id batches
+        kern = time_hot_kernels(model, devb, K, W, stream) if model is not None else None
+    clocks = clk.summary()
+    value = K * B / (ms / 1e3)
+    e2e = K * B / (ms_e2e / 1e3)
+    f, l = host.batches[0]
+    h2d = f.cont.numel() * 4 + f.cat.numel() * 8 + l.numel() * 4
+    peak, peak_src = measured_peak()
+    line = {
+        "metric": "CTR samples/sec (Criteo 39-field emb16)", "value": value, "unit": "samples/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                "api": "estimator.GraphedTrainStep(model_fn, params)(pinned PackedFeatures, labels)"
+                       if step is not None else "model_fn(features, labels, 'train', params).train_op()"},
+        "gpu_launches": per_step_launches * K,
+        "gpu_launches_per_step": per_step_launches,
+        "final_loss": float(losses[K - 1]),
+    }
+    if kern is not None:
+        t_pair = kern["fwd_us"] + kern["bwd_us"]
+        ach = ALG_BYTES * B / (t_pair * 1e-6) / 1e9
+        line["roofline"] = {
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "peak_source": peak_src,
+            "kernel": "embed_fwd_kernel<16,5,false> + embed_bwd_kernel<16> (one pair per step)",
+            "algorithmic_bytes_per_launch_pair": ALG_BYTES * B,
+            "fwd": {"us": kern["fwd_us"], "GBps": ALG_BYTES_FWD * B / kern["fwd_us"] / 1e3,
+                    "moved_GBps": kern["fwd_moved"] * B / kern["fwd_us"] / 1e3},
+            "bwd": {"us": kern["bwd_us"], "GBps": ALG_BYTES_BWD * B / kern["bwd_us"] / 1e3,
+                    "moved_GBps": kern["bwd_moved"] * B / kern["bwd_us"] / 1e3},
+            "adam_rows_us": kern["adam_us"],
+            "large_batch": kern.get("large"),
+        }
+    if not args.no_cpu_baseline:
+        om = args.model if args.model != "din" else "deepfm"
+        n, el, cores = time_oracle(om, B, args.table, args.dist, max_seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {
+            "value": n * B / el, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d fwd+bwd steps of batch %d (%.1f s) of the oracle's torch-CPU fp32 "
+                      "restatement of %s.model_fn; gather-based first order (flatters TF's one-hot "
+                      "matmul); no optimizer step" % (n, B, el, om)}
+    print(json.dumps(line), flush=True)
+
+
+def time_hot_kernels(model, devb, K, W, stream):
+    """Average device time of the fused lookup forward and the scatter-add backward,
+    each launched alone K times on distinct id batches (CUDA events on the launch stream)."""
+    import torch
+    from recsys_b200 import ops
+    emb = model.emb
+    B = devb[0][1].shape[0]
+    F, D = emb.F, emb.D
+    with torch.no_grad(), torch.cuda.stream(stream):
+        rows = [model.ids(f) for f, _ in devb]
+        dE = torch.randn(B, F * D, device=emb.device)
+        dy = torch.randn(B, device=emb.device)
+        outs = emb.lookup(rows[0])
+        E = outs[0]
+        S = E.view(B, F, D).sum(1).contiguous()
+        p = ops._p
+        st = stream.cuda_stream
+        from recsys_b200 import _lib
+        lib = _lib.load()
+        Eb = torch.empty_like(E)
+        Sb = torch.empty_like(S)
+        y1 = torch.empty(B, device=emb.device)
+        y2 = torch.empty(B, device=emb.device)
+
+        def fwd(i):
+            lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rows[i % len(rows)]), B, F, D,
+                              emb.w1_fields, p(Eb), p(Sb), p(y1), p(y2), None, None, 0, None, st)
+
+        def bwd(i):
+            lib.ctr_embed_bwd(p(rows[i % len(rows)]), p(dE), p(Eb), p(emb.table), p(Sb), p(dy),
+                              p(dy), emb.w1_fields, emb._offsets_host, B, F, D, p(emb.dtable),
+                              p(emb.dw1), st)
+
+        emb._ensure_adam()
+
+        def adam(i):
+            emb._tag += 1
+            lib.ctr_adam_rows(p(rows[i % len(rows)]), B * F, D, p(emb.table), p(emb._m), p(emb._v),
+                              p(emb.dtable), p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, st)
+
+        def timeit(fn):
+            for i in range(W):
+                fn(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K):
+                fn(W + i)
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / K
+
+        res = {"fwd_us": timeit(fwd), "bwd_us": timeit(bwd), "adam_us": timeit(adam)}
+        ops.LAUNCHES["n"] += 3 * (K + W)
+        # bytes the implementation actually moves per sample (DESIGN.md "data layout")
+        res["fwd_moved"] = 156 + 2496 + 156 + 2496 + 64 + 8          # ids, rows, w1, E, S, y1/y2
+        res["bwd_moved"] = 156 + 2496 + 2496 + 64 + 8 + 2 * 2496 + 2 * 156
+        emb.dtable.zero_()
+        emb.dw1.zero_()
+        # the same two kernels at a batch that fills the machine (asymptotic bandwidth)
+        try:
+            BL = 65536
+            g = torch.Generator(device=emb.device).manual_seed(1)
+            offs = torch.tensor(emb.lay.offsets, device=emb.device)
+            nr = (offs[1:] - offs[:-1]).float()
+            rl = [torch.minimum((torch.rand(BL, F, device=emb.device, generator=g) * nr).long(),
+                                (offs[1:] - offs[:-1]) - 1).add_(offs[:-1]).to(torch.int32)
+                  for _ in range(4)]
+            EL = torch.empty(BL, F * D, device=emb.device)
+            SL = torch.empty(BL, D, device=emb.device)
+            yl = torch.empty(BL, device=emb.device)
+            dEL = torch.randn(BL, F * D, device=emb.device)
+
+            def fwdL(i):
+                lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rl[i % 4]), BL, F, D, emb.w1_fields,
+                                  p(EL), p(SL), p(yl), p(yl), None, None, 0, None, st)
+
+            def bwdL(i):
+                lib.ctr_embed_bwd(p(rl[i % 4]), p(dEL), p(EL), p(emb.table), p(SL), p(yl), p(yl),
+                                  emb.w1_fields, emb._offsets_host, BL, F, D, p(emb.dtable),
+                                  p(emb.dw1), st)
+            tf_, tb_ = timeit(fwdL), timeit(bwdL)
+            res["large"] = {"batch": BL, "fwd_us": tf_, "bwd_us": tb_,
+                            "alg_GBps": ALG_BYTES * BL / (tf_ + tb_) / 1e3,
+                            "moved_GBps": (res["fwd_moved"] + res["bwd_moved"]) * BL / (tf_ + tb_) / 1e3}
+            emb.dtable.zero_()
+            emb.dw1.zero_()
+        except Exception as e:  # pragma: no cover
+            res["large"] = {"error": str(e)[:200]}
+    return res
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,16 +108,23 @@ int ctr_dcn_cross_bwd(const float* x0, const float* w, const float* b, int L, in
                       const float* dxl, float* dx0, float* dw, float* db, ctr_stream_t stream);
 
 /* ------------------------------------------------------------------ optimiser
- * tf.train.AdamOptimizer semantics (fm/fm.py:162): eps outside the sqrt, lr_t
- * computed by the caller.  ctr_adam_dense: every element (TF's sparse apply decays
- * m, v of every row).  g is zeroed afterwards when zero_g != 0. */
+ * tf.train.AdamOptimizer semantics (fm/fm.py:162): eps outside the sqrt,
+ *   lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t).
+ * The schedule can live on the device so that a captured CUDA graph advances it on
+ * replay: state_dev = float[2] {t, lr_t}; ctr_adam_tick does t += 1 and recomputes lr_t.
+ * When state_dev is non-null the kernels read lr_t (and the claim tag = t) from it and
+ * ignore the by-value arguments.
+ * ctr_adam_dense: every element (TF's sparse apply decays m, v of every row [TF-sem]).
+ * g is zeroed afterwards when zero_g != 0. */
+int ctr_adam_tick(float* state_dev, float lr, float beta1, float beta2, ctr_stream_t stream);
 int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
-                   float beta2, float eps, int zero_g, ctr_stream_t stream);
+                   float beta2, float eps, int zero_g, const float* state_dev,
+                   ctr_stream_t stream);
 /* Lazy variant: exactly one update per distinct row in rows[n] (claim[R] int32
  * scratch, tag must differ from the previous call's), then zeroes the row of g. */
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
                   float* g, int32_t* claim, int32_t tag, float lr_t, float beta1, float beta2,
-                  float eps, ctr_stream_t stream);
+                  float eps, const float* state_dev, ctr_stream_t stream);
 
 /* -------------------------------------------------------- DIN activation unit
  * din/din.py:103-125 `_attention`: for each sample b and position p with hist[b,p] > 0

@@ -66,7 +66,7 @@ class _ModelBase:
         self.params = params
         self.device = _device(params)
         self.dropout = float(params.get("dropout", 0.0))
-        self.adam = ops.TFAdamState(lr=float(params.get("learning_rate", 1e-3)))
+        self.adam = ops.TFAdamState(lr=float(params.get("learning_rate", 1e-3)), device=self.device)
         self.store: Optional[VariableStore] = None
         self.last = {}
 

@@ -541,9 +541,21 @@ __global__ void criteo_rows_kernel(const float* __restrict__ xcont, int n_cont,
 }
 
 // ----------------------------------------------------------------------- Adam
+// state (nullable, device): [0] = step count t (as float), [1] = lr_t; written by
+// adam_tick_kernel so that a captured CUDA graph advances the schedule on replay.
+__global__ void adam_tick_kernel(float* __restrict__ state, float lr, float b1, float b2) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float t = state[0] + 1.f;
+    state[0] = t;
+    state[1] = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+  }
+}
+
 __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
                                   float* __restrict__ v, float* __restrict__ g, long long n,
-                                  float lr_t, float b1, float b2, float eps, int zero_g) {
+                                  float lr_t, float b1, float b2, float eps, int zero_g,
+                                  const float* __restrict__ state) {
+  if (state != nullptr) lr_t = state[1];
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
@@ -580,7 +592,12 @@ template <int D>
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ th,
                  float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
-                 int* __restrict__ claim, int tag, float lr_t, float b1, float b2, float eps) {
+                 int* __restrict__ claim, int tag, float lr_t, float b1, float b2, float eps,
+                 const float* __restrict__ state) {
+  if (state != nullptr) {
+    tag = static_cast<int>(state[0]);
+    lr_t = state[1];
+  }
   constexpr int LPR = D >= 4 ? D / 4 : 1;
   const int lane = threadIdx.x & 31;
   const int q = lane % LPR;
@@ -759,8 +776,16 @@ int ctr_dcn_cross_bwd(const float* x0, const float* w, const float* b, int L, in
   CTR_LAUNCH_CHECK("ctr_dcn_cross_bwd");
 }
 
+int ctr_adam_tick(float* state_dev, float lr, float beta1, float beta2, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(state_dev, "ctr_adam_tick", "null state");
+  adam_tick_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(state_dev, lr, beta1, beta2);
+  CTR_LAUNCH_CHECK("ctr_adam_tick");
+}
+
 int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
-                   float beta2, float eps, int zero_g, ctr_stream_t stream) {
+                   float beta2, float eps, int zero_g, const float* state_dev,
+                   ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(theta && m && v && g && n >= 0, "ctr_adam_dense", "null pointer / negative n");
   CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_dense",
@@ -768,13 +793,13 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
   if (n == 0) return CTR_OK;
   const int grid = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, sm_count() * 8LL));
   adam_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g);
+      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g, state_dev);
   CTR_LAUNCH_CHECK("ctr_adam_dense");
 }
 
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
                   float* g, int32_t* claim, int32_t tag, float lr_t, float beta1, float beta2,
-                  float eps, ctr_stream_t stream) {
+                  float eps, const float* state_dev, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(rows && theta && m && v && g && claim && n >= 0, "ctr_adam_rows", "null pointer");
   CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_rows",
@@ -785,10 +810,10 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
   const long long gpb = 256 / lpr;
   const int grid = static_cast<int>(std::min<long long>((n + gpb - 1) / gpb, sm_count() * 8LL));
   switch (D) {
-    case 1: adam_rows_kernel<1><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
-    case 8: adam_rows_kernel<8><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
-    case 16: adam_rows_kernel<16><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
-    case 32: adam_rows_kernel<32><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps); break;
+    case 1: adam_rows_kernel<1><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 8: adam_rows_kernel<8><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 16: adam_rows_kernel<16><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 32: adam_rows_kernel<32><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
     default: return fail_arg("ctr_adam_rows", "D must be 1, 8, 16 or 32");
   }
   CTR_LAUNCH_CHECK("ctr_adam_rows");

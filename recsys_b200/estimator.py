@@ -173,3 +173,64 @@ class Estimator:
         for features, labels in input_fn():
             spec = self.model_fn(features, None, ModeKeys.PREDICT, self.params)
             yield from ({"prob": p} for p in spec.predictions["prob"].detach().cpu())
+
+
+# ------------------------------------------------------------------ graphed step
+class GraphedTrainStep:
+    """One whole train step - ``spec = model_fn(features, labels, TRAIN, params);
+    spec.train_op()`` - captured once into a CUDA graph over static device input
+    buffers and replayed per batch.  ``__call__(features, labels)`` copies the
+    batch (pinned host or device ``PackedFeatures``) into the static buffers on the
+    step stream, replays the graph and returns the device loss tensor without
+    synchronising; ``losses_to_host`` streams losses into a pinned ring so that
+    reading them does not stall the pipeline."""
+
+    def __init__(self, model_fn, params, example_features, example_labels, warmup: int = 3):
+        from .ops import PackedFeatures
+        if not isinstance(example_features, PackedFeatures):
+            raise TypeError("GraphedTrainStep needs PackedFeatures batches (see data.SyntheticCriteo)")
+        dev = params.get("device") or torch.device("cuda", torch.cuda.current_device())
+        self.model_fn, self.params = model_fn, params
+        self.stream = torch.cuda.Stream(device=dev)
+        f = example_features
+        self.cont = torch.empty_like(f.cont, device=dev)
+        self.cat = torch.empty_like(f.cat, device=dev)
+        self.labels = torch.empty_like(example_labels, device=dev)
+        self.features = PackedFeatures(self.cont, self.cat, f.cont_keys, f.cat_keys)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self._load(example_features, example_labels)
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):                 # allocator + lazy-init warm-up, eager
+                self._eager()
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._eager()
+        self.stream.synchronize()
+
+    def _eager(self):
+        spec = self.model_fn(self.features, self.labels, ModeKeys.TRAIN, self.params)
+        spec.train_op()
+        self.loss.copy_(spec.loss)
+
+    def _load(self, features, labels):
+        with torch.cuda.stream(self.stream):
+            self.cont.copy_(features.cont, non_blocking=True)
+            self.cat.copy_(features.cat, non_blocking=True)
+            self.labels.copy_(labels, non_blocking=True)
+
+    def __call__(self, features, labels):
+        self._load(features, labels)
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        return self.loss
+
+    def replay_resident(self):
+        """Replay on whatever is in the static buffers (inputs already in HBM)."""
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        return self.loss
+
+    def loss_to_host(self, pinned_slot: torch.Tensor):
+        with torch.cuda.stream(self.stream):
+            pinned_slot.copy_(self.loss, non_blocking=True)

@@ -155,15 +155,25 @@ def hash_strings(strings: Sequence[bytes], n_buckets: int, device) -> torch.Tens
 # ---------------------------------------------------------------- Adam (TF rule)
 class TFAdamState:
     """Step counter + lr_t of tf.train.AdamOptimizer (fm/fm.py:162):
-    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), eps outside the sqrt."""
+    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), eps outside the sqrt.  The schedule
+    lives on the device ({t, lr_t}, advanced by ctr_adam_tick) so a captured CUDA
+    graph of the train step stays correct on replay."""
 
-    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, device=None):
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.t = 0
+        self.state = torch.zeros(2, dtype=torch.float32, device=device) if device is not None \
+            else None
 
     def next_lr_t(self) -> float:
         self.t += 1
+        if self.state is not None:
+            _call("ctr_adam_tick", _p(self.state), self.lr, self.beta1, self.beta2, _stream())
         return self.lr * math.sqrt(1 - self.beta2 ** self.t) / (1 - self.beta1 ** self.t)
+
+    @property
+    def state_ptr(self):
+        return None if self.state is None else self.state.data_ptr()
 
 
 class DenseParams:
@@ -219,7 +229,7 @@ class DenseParams:
         """One launch over the flat buffer; frozen slots have zero gradient and
         zero moments, so the rule leaves them untouched."""
         _call("ctr_adam_dense", _p(self.flat), _p(self.m), _p(self.v), _p(self.grad), self.numel,
-              lr_t, st.beta1, st.beta2, st.eps, 1, _stream())
+              lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
 
 
 # ------------------------------------------------------- fused multi-field lookup
@@ -300,20 +310,21 @@ class FieldEmbedding:
         self._ensure_adam()
         if self.adam_mode == "exact_tf":
             _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
-                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, _stream())
+                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
             if self.with_w1:
                 _call("ctr_adam_dense", _p(self.w1), _p(self._m1), _p(self._v1), _p(self.dw1),
-                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, _stream())
+                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr,
+                      _stream())
             return
         self._tag += 1
         n = rows.numel()
         _call("ctr_adam_rows", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
               _p(self.dtable), _p(self._claim), self._tag, lr_t, st.beta1, st.beta2, st.eps,
-              _stream())
+              st.state_ptr, _stream())
         if self.with_w1:
             _call("ctr_adam_rows", _p(rows), n, 1, _p(self.w1), _p(self._m1), _p(self._v1),
                   _p(self.dw1), _p(self._claim1), self._tag, lr_t, st.beta1, st.beta2, st.eps,
-                  _stream())
+                  st.state_ptr, _stream())
 
 
 class _EmbedFn(torch.autograd.Function):

@@ -1,0 +1,389 @@
+"""GPU parity, kernel level: every C-ABI entry point against the oracle on the same
+seeded inputs (bit-exact for ids / hashes, fp32 tolerance stated per test)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import criteo, farmhash, models as om, synth, tfsem
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _ops():
+    from recsys_b200 import ops
+    return ops
+
+
+def _criteo_layout(D=16, full=False):
+    from recsys_b200 import feature_column as fc
+    from recsys_b200.fm import fm
+    lin, emb = fm.build_feature_columns(D, full_cardinality=full)
+    return fc.layout(emb), lin
+
+
+def _to_torch_features(feats):
+    out = {}
+    for k, v in feats.items():
+        out[k] = torch.from_numpy(np.asarray(v)) if np.asarray(v).dtype.kind in "fiu" else v
+    return out
+
+
+# ------------------------------------------------------------------ id pipeline
+@pytest.mark.parametrize("B", [1, 7, 256, 4099])
+def test_criteo_rows_bit_exact(cuda, B):
+    ops = _ops()
+    lay, _ = _criteo_layout()
+    spec = criteo.CriteoSpec()
+    feats, _ = criteo.synthetic_features(B, seed=B, spec=spec, dist="zipf")
+    want = criteo.criteo_rows(feats, spec)
+    pipe = ops.IdPipeline(lay, cuda)
+    rows, logx = pipe(_to_torch_features(feats), want_logx=True)
+    assert rows.dtype == torch.int32 and tuple(rows.shape) == (B, 39)
+    got = rows.cpu().numpy().astype(np.int64)
+    # logf on the device vs numpy may differ by 1 ulp: a mismatch is only legal when the
+    # log value sits within 1 ulp of a boundary.
+    bad = np.argwhere(got != want)
+    lx = criteo.criteo_logx(feats, spec)
+    for b, f in bad:
+        key = spec.fields[f]
+        assert key in criteo.CONT
+        v = lx[b, spec.cont_fields.index(key)]
+        bnd = np.asarray(spec.boundaries(key), np.float32)
+        assert np.min(np.abs(bnd - v)) <= 2 * np.spacing(np.float32(abs(v) + 1e-30))
+    assert len(bad) <= max(1, B // 1000)
+    assert np.allclose(logx.cpu().numpy(), lx, rtol=3e-7, atol=1e-7, equal_nan=True)
+    assert int(pipe.status.item()) == 0
+
+
+def test_criteo_rows_real_shard_strings(cuda):
+    """Raw byte strings (b'NULL' default included) hashed on the device == oracle == fixture."""
+    ops = _ops()
+    lay, _ = _criteo_layout()
+    z = np.load(os.path.join(GOLD, "criteo_shard256.npz"))
+    feats = {k: torch.from_numpy(z[k]) for k in criteo.CONT}
+    feats.update({k: np.array([bytes(v) for v in z[k]], dtype=object).reshape(-1, 1)
+                  for k in criteo.CAT})
+    rows = ops.IdPipeline(lay, cuda)(feats)
+    assert np.array_equal(rows.cpu().numpy().astype(np.int64), z["rows"])
+
+
+def test_hash_strings_all_length_branches(cuda):
+    ops = _ops()
+    rng = np.random.default_rng(0)
+    strs = [b"Hello", b"TensorFlow", b"2.x", b"", b"NULL"]
+    for n in list(range(1, 70)) + [100, 127, 128, 129, 200, 333]:
+        strs.append(bytes(rng.integers(0, 256, size=n, dtype=np.uint8)))
+    for nb in (3, 100000, 2 ** 31 - 1):
+        got = ops.hash_strings(strs, nb, cuda).cpu().numpy()
+        want = np.array([farmhash.hash_bucket_fast(s, nb) for s in strs])
+        assert np.array_equal(got, want)
+    assert ops.hash_strings(strs[:3], 3, cuda).cpu().tolist() == [0, 2, 2]   # TF doc example
+
+
+def test_out_of_range_categorical_sets_status(cuda):
+    ops = _ops()
+    lay, _ = _criteo_layout()
+    spec = criteo.CriteoSpec()
+    feats, _ = criteo.synthetic_features(8, seed=1, spec=spec)
+    feats["_c14"] = feats["_c14"] + 10 ** 7
+    pipe = ops.IdPipeline(lay, cuda)
+    rows = pipe(_to_torch_features(feats))
+    f = spec.fields.index("_c14")
+    r = rows.cpu().numpy()[:, f]
+    assert ((r >= spec.offsets[f]) & (r < spec.offsets[f + 1])).all()
+    assert int(pipe.status.item()) == 1
+
+
+# ------------------------------------------------------------------ embed fwd/bwd
+def _rand_rows(B, offsets, seed, hot=False):
+    rng = np.random.default_rng(seed)
+    cols = []
+    for f in range(len(offsets) - 1):
+        n = offsets[f + 1] - offsets[f]
+        ids = np.zeros(B, np.int64) if (hot and f % 3 == 0) else rng.integers(0, n, size=B)
+        cols.append(ids + offsets[f])
+    return np.stack(cols, 1)
+
+
+@pytest.mark.parametrize("B,F,D", [(1, 39, 16), (5, 39, 16), (16, 39, 16), (4096, 39, 16),
+                                   (333, 2, 32), (130, 39, 32), (257, 64, 8), (64, 7, 16)])
+def test_embed_fwd_matches_oracle(cuda, B, F, D):
+    ops = _ops()
+    from recsys_b200 import feature_column as fc
+    rng = np.random.default_rng(B + F + D)
+    nrows = [int(n) for n in rng.integers(3, 400, size=F)]
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("k%02d" % i, n), D)
+            for i, n in enumerate(nrows)]
+    lay = fc.layout(cols)
+    mask = (int.from_bytes(rng.bytes(8), "little") & ((1 << F) - 1)) | 1
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask)
+    rows_np = _rand_rows(B, lay.offsets, seed=B, hot=True)
+    rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
+    with torch.no_grad():
+        E, y1, y2, _ = emb.lookup(rows)
+    t64 = emb.table.double().cpu()
+    Eo = t64[torch.from_numpy(rows_np)]                               # [B,F,D]
+    assert torch.equal(E.cpu(), Eo.float().reshape(B, F * D))        # gather is a copy: bit exact
+    fm_mask = torch.tensor([(mask >> f) & 1 for f in range(F)], dtype=torch.float64)
+    y1o = (emb.w1.double().cpu()[torch.from_numpy(rows_np)] * fm_mask).sum(1)
+    y2o = om.fm_second_order(Eo).reshape(-1)
+    assert torch.allclose(y1.cpu().double(), y1o, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(y2.cpu().double(), y2o, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,D,use_dE,use_fm,regather", [
+    (1, 16, True, True, False), (77, 16, True, True, False), (4096, 16, True, True, False),
+    (300, 16, False, True, True), (300, 16, True, False, False), (515, 32, True, True, False),
+    (129, 8, True, True, True)])
+def test_embed_bwd_matches_oracle(cuda, B, D, use_dE, use_fm, regather):
+    """dtable / dw1 against the dense autograd gradient of the oracle; includes fields with
+    3..32 rows (register one-hot path), a field where every sample hits one row, and big fields."""
+    ops = _ops()
+    from recsys_b200 import _lib
+    from recsys_b200 import feature_column as fc
+    nrows = [3, 10, 32, 33, 7, 1000, 50000, 4, 64, 31, 200]
+    F = len(nrows)
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("k%02d" % i, n), D)
+            for i, n in enumerate(nrows)]
+    lay = fc.layout(cols)
+    mask = 0b10110101101
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask)
+    rows_np = _rand_rows(B, lay.offsets, seed=B + D, hot=True)
+    rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
+    g = torch.Generator().manual_seed(B)
+    dE = torch.randn(B, F * D, generator=g)
+    dy1 = torch.randn(B, generator=g)
+    dy2 = torch.randn(B, generator=g)
+    with torch.no_grad():
+        E, y1, y2, _ = emb.lookup(rows)
+    S = E.view(B, F, D).sum(1).contiguous()
+    lib = _lib.load()
+    offs = (C.c_int64 * (F + 1))(*lay.offsets)
+    p = ops._p
+    dEc, dy2c, dy1c = dE.to(cuda), dy2.to(cuda), dy1.to(cuda)
+    rc = lib.ctr_embed_bwd(p(rows), p(dEc) if use_dE else None, None if regather else p(E),
+                           p(emb.table), p(S) if use_fm else None, p(dy2c) if use_fm else None,
+                           p(dy1c), mask, offs, B, F, D, p(emb.dtable), p(emb.dw1),
+                           torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    # oracle: autograd through gather + FM second order
+    t = emb.table.double().cpu().requires_grad_(True)
+    w = emb.w1.double().cpu().requires_grad_(True)
+    r = torch.from_numpy(rows_np)
+    Eo = t[r]
+    loss = torch.zeros((), dtype=torch.float64)
+    if use_dE:
+        loss = loss + (Eo.reshape(B, -1) * dE.double()).sum()
+    if use_fm:
+        loss = loss + (om.fm_second_order(Eo).reshape(-1) * dy2.double()).sum()
+    fm_mask = torch.tensor([(mask >> f) & 1 for f in range(F)], dtype=torch.float64)
+    loss = loss + ((w[r] * fm_mask).sum(1) * dy1.double()).sum()
+    loss.backward()
+    scale = float(t.grad.abs().max()) + 1e-12
+    assert float((emb.dtable.cpu().double() - t.grad).abs().max()) <= 2e-5 * scale + 1e-5
+    assert float((emb.dw1.cpu().double() - w.grad).abs().max()) <= 1e-5 * float(w.grad.abs().max()) + 1e-5
+
+
+def test_embed_rejects_bad_arguments(cuda):
+    from recsys_b200 import _lib
+    lib = _lib.load()
+    t = torch.zeros(10, 16, device=cuda)
+    rows = torch.zeros(4, 3, dtype=torch.int32, device=cuda)
+    rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 4, 3, 12, 0, None, None, None, None,
+                           None, None, 0, None, None)
+    assert rc == -1 and "D must be" in _lib.last_error()
+    rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 4, 65, 16, 0, None, None, None, None,
+                           None, None, 0, None, None)
+    assert rc == -1
+    rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 0, 3, 16, 0, None, None, None, None,
+                           None, None, 0, None, None)
+    assert rc == 0                                                 # empty batch is a no-op
+
+
+# ------------------------------------------------------------------- DCN cross
+@pytest.mark.parametrize("B,W,L", [(1, 624, 4), (100, 624, 4), (4096, 624, 4), (33, 64, 1),
+                                   (257, 1248, 3), (65, 128, 6)])
+def test_dcn_cross_fwd_bwd(cuda, B, W, L):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + W)
+    x0 = torch.randn(B, W, generator=g) * 0.5
+    w = torch.randn(L, W, generator=g) * 0.05
+    b = torch.randn(L, W, generator=g) * 0.05
+    dxl = torch.randn(B, W, generator=g)
+    x0c = x0.to(cuda).requires_grad_(True)
+    wc = w.to(cuda).requires_grad_(True)
+    bc = b.to(cuda).requires_grad_(True)
+    xl = ops.dcn_cross(x0c, wc, bc)
+    xl.backward(dxl.to(cuda))
+    p = {}
+    x0o = x0.double().requires_grad_(True)
+    for l in range(L):
+        p[f"cross.{l}.w"] = w[l].double().requires_grad_(True)
+        p[f"cross.{l}.b"] = b[l].double().requires_grad_(True)
+    xlo = om.dcn_cross(p, x0o)
+    xlo.backward(dxl.double())
+    assert torch.allclose(xl.detach().cpu().double(), xlo.detach(), rtol=1e-4, atol=1e-5)
+    s = float(x0o.grad.abs().max())
+    assert float((x0c.grad.cpu().double() - x0o.grad).abs().max()) <= 1e-4 * s + 1e-6
+    for l in range(L):
+        gw, gb = p[f"cross.{l}.w"].grad, p[f"cross.{l}.b"].grad
+        assert float((wc.grad[l].cpu().double() - gw).abs().max()) <= 1e-4 * float(gw.abs().max()) + 1e-5
+        assert float((bc.grad[l].cpu().double() - gb).abs().max()) <= 1e-4 * float(gb.abs().max()) + 1e-5
+
+
+# ------------------------------------------------------------------------- Adam
+def test_adam_rows_and_dense_match_tf_rule(cuda):
+    ops = _ops()
+    from recsys_b200 import feature_column as fc
+    D = 16
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("a", 50), D),
+            fc.embedding_column(fc.categorical_column_with_hash_bucket("b", 5000), D)]
+    lay = fc.layout(cols)
+    for mode in ("lazy", "exact_tf"):
+        emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=0b11, adam_mode=mode, seed=1)
+        p = {"emb": emb.table.double().cpu().clone(), "w1": emb.w1.double().cpu().clone()}
+        opt = tfsem.TFAdam(p, lr=1e-2)
+        st = ops.TFAdamState(lr=1e-2, device=cuda if mode == "lazy" else None)
+        rng = np.random.default_rng(0)
+        for step in range(3):
+            rows_np = _rand_rows(300, lay.offsets, seed=step)
+            rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
+            g = torch.from_numpy(rng.normal(size=(lay.total_rows, D))).float()
+            g1 = torch.from_numpy(rng.normal(size=lay.total_rows)).float()
+            touched = torch.zeros(lay.total_rows, dtype=torch.bool)
+            touched[torch.from_numpy(rows_np).reshape(-1)] = True
+            g[~touched] = 0
+            g1[~touched] = 0
+            emb.dtable.copy_(g)
+            emb.dw1.copy_(g1)
+            emb.adam_step(rows, st.next_lr_t(), st)
+            lazy = {"emb": torch.from_numpy(rows_np).reshape(-1),
+                    "w1": torch.from_numpy(rows_np).reshape(-1)} if mode == "lazy" else None
+            opt.step(p, {"emb": g.double(), "w1": g1.double()}, lazy_rows=lazy)
+            assert float(emb.dtable.abs().max()) == 0.0 and float(emb.dw1.abs().max()) == 0.0
+        assert torch.allclose(emb.table.cpu().double(), p["emb"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(emb.w1.cpu().double(), p["w1"], rtol=1e-5, atol=1e-6)
+
+
+# -------------------------------------------------------------------------- CIN
+def _cin_oracle(E, Ws, bs, m, D):
+    p = {}
+    for k, (W, b) in enumerate(zip(Ws, bs)):
+        p[f"cin.{k}.w"], p[f"cin.{k}.b"] = W, b
+    B = E.shape[0]
+    X0 = E.view(B, m, D)
+    hidden, finals = X0, []
+    for k in range(len(Ws)):
+        Hp = hidden.shape[1]
+        z = torch.einsum("bid,bjd->bdij", X0, hidden).reshape(B, D, m * Hp)
+        out = torch.relu(z @ Ws[k] + bs[k]).permute(0, 2, 1)
+        finals.append(out)
+        hidden = out
+    return torch.cat(finals, 1).sum(-1)
+
+
+CIN_TOL = {"fp32": 2e-5, "tf32x3": 5e-5, "tf32": 5e-3}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("B,m,D,layers", [(9, 39, 16, (128, 128)), (64, 39, 16, (20, 10, 10)),
+                                          (300, 39, 16, (128, 128)), (17, 5, 8, (16,))])
+def test_cin_fwd_bwd(cuda, prec, B, m, D, layers):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + m)
+    E = torch.randn(B, m * D, generator=g) * 0.25
+    Ws, bs = [], []
+    hp = m
+    for h in layers:
+        Ws.append(torch.randn(m * hp, h, generator=g) * (2.0 / (m * hp + h)) ** 0.5)
+        bs.append(torch.randn(h, generator=g) * 0.01)
+        hp = h
+    dp = torch.randn(B, sum(layers), generator=g)
+    Ec = E.to(cuda).requires_grad_(True)
+    Wc = [w.to(cuda).requires_grad_(True) for w in Ws]
+    bc = [b.to(cuda).requires_grad_(True) for b in bs]
+    out = ops.cin(Ec, m, D, Wc, bc, prec)
+    out.backward(dp.to(cuda))
+    Eo = E.double().requires_grad_(True)
+    Wo = [w.double().requires_grad_(True) for w in Ws]
+    bo = [b.double().requires_grad_(True) for b in bs]
+    ref = _cin_oracle(Eo, Wo, bo, m, D)
+    ref.backward(dp.double())
+    tol = CIN_TOL[prec]
+
+    def close(a, b, what):
+        err = float((a.detach().cpu().double() - b.detach()).abs().max())
+        s = float(b.detach().abs().max()) + 1e-9
+        assert err <= tol * s, "%s: max err %.3e vs scale %.3e (%s)" % (what, err, s, prec)
+
+    close(out, ref, "pooled")
+    close(Ec.grad, Eo.grad, "dE")
+    for k in range(len(layers)):
+        close(Wc[k].grad, Wo[k].grad, "dW%d" % k)
+        close(bc[k].grad, bo[k].grad, "db%d" % k)
+
+
+def test_transpose_roundtrip(cuda):
+    from recsys_b200 import _lib
+    lib = _lib.load()
+    B, F, D, ld = 37, 39, 16, 40
+    E = torch.randn(B, F * D, device=cuda)
+    Xt = torch.full((B * D, ld), 7.0, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.ctr_transpose_fd(E.data_ptr(), B, F, D, Xt.data_ptr(), ld, st) == 0
+    want = E.view(B, F, D).permute(0, 2, 1).reshape(B * D, F)
+    assert torch.equal(Xt[:, :F], want) and float(Xt[:, F:].abs().max()) == 0.0
+    dE = torch.ones(B, F * D, device=cuda)
+    assert lib.ctr_transpose_df_add(Xt.data_ptr(), ld, B, F, D, dE.data_ptr(), st) == 0
+    assert torch.allclose(dE, E + 1.0)
+
+
+# -------------------------------------------------------------------------- DIN
+@pytest.mark.parametrize("B,P,E", [(1, 100, 16), (33, 100, 16), (257, 37, 16), (40, 100, 32),
+                                   (40, 64, 8)])
+def test_din_attention_fwd_bwd(cuda, B, P, E):
+    ops = _ops()
+    from recsys_b200 import feature_column as fc
+    n_items = 500
+    feats, _ = synth.synthetic_din(B, P=P, seed=B, n_items=n_items, n_cates=50)
+    if B > 1:
+        feats["u_iid_seq"][1] = 0                       # a sample whose whole history is padding
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("i_id", n_items), E)]
+    lay = fc.Layout(cols, ["i_id"], [n_items], [0, n_items], E)
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=False, seed=2)
+    g = torch.Generator().manual_seed(B)
+    p64 = {}
+    sizes = [4 * E, 80, 40, 1]
+    for l in range(3):
+        p64[f"att.{l}.w"] = (torch.randn(sizes[l], sizes[l + 1], generator=g) *
+                             (2.0 / (sizes[l] + sizes[l + 1])) ** 0.5).double()
+        p64[f"att.{l}.b"] = (torch.randn(sizes[l + 1], generator=g) * 0.1).double()
+    query = torch.randn(B, E, generator=g) * 0.5
+    dout = torch.randn(B, E, generator=g)
+    hist = torch.from_numpy(feats["u_iid_seq"])
+    pc = {k: v.float().to(cuda).requires_grad_(True) for k, v in p64.items()}
+    qc = query.to(cuda).requires_grad_(True)
+    out = ops.din_attention(emb, 0, hist.to(cuda, torch.int32), qc, pc["att.0.w"], pc["att.0.b"],
+                            pc["att.1.w"], pc["att.1.b"], pc["att.2.w"], pc["att.2.b"])
+    out.backward(dout.to(cuda))
+    po = {k: v.clone().requires_grad_(True) for k, v in p64.items()}
+    tab = emb.table.double().cpu().requires_grad_(True)
+    qo = query.double().requires_grad_(True)
+    ref = om.din_attention(po, "att", tab, hist, qo, False, 0.0, None)
+    ref.backward(dout.double())
+
+    def close(a, b, what, tol=2e-4):
+        err = float((a.detach().cpu().double() - b.detach()).abs().max())
+        s = float(b.detach().abs().max()) + 1e-9
+        assert err <= tol * s + 1e-6, "%s: max err %.3e vs scale %.3e" % (what, err, s)
+
+    close(out, ref, "out")
+    close(qc.grad, qo.grad, "dquery")
+    close(emb.dtable, tab.grad, "dtable")
+    for k in p64:
+        close(pc[k].grad, po[k].grad.reshape(pc[k].grad.shape), "d" + k)

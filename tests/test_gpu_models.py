@@ -1,0 +1,208 @@
+"""GPU parity, model_fn level: the five reference entry points against the fp64 oracle on
+the same seeded Criteo-/DIN-shaped inputs.  Tolerance from BASELINE north_star: logits
+<= 1e-4 relative (plus 1e-5 absolute for values near zero); loss to 1e-5; gradients to
+1e-3 of their max-norm; AUC / logloss equal to 4 decimals."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import make_golden as mg
+from oracle import criteo, models as om, synth, tfsem
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _features_to_torch(feats):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in feats.items()}
+
+
+def _build(model, spec, cuda, deep_layers="32,16", cin_layers="16,8", **extra):
+    from recsys_b200 import _core
+    from recsys_b200 import criteo_schema as cs
+    from recsys_b200.estimator import VariableStore
+    hb = [spec.rows[spec.fields.index(k)] for k in criteo.CAT]
+    linear = {"fm": "indicator_all", "deepfm": "indicator_all", "xdeepfm": "numeric+indicator",
+              "dcn": "numeric"}[model]
+    lin, emb = cs.build_columns(16, linear=linear, hash_buckets=hb)
+    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb,
+              "embedding_size": 16, "learning_rate": 1e-3, "dropout": 0.0,
+              "deep_layers": deep_layers, "cross_layers": cin_layers if model == "xdeepfm" else 4,
+              "variable_store": VariableStore(), "device": cuda}
+    params.update(extra)
+    cls = {"fm": _core.FMModel, "deepfm": _core.DeepFMModel, "xdeepfm": _core.XDeepFMModel,
+           "dcn": _core.DCNModel}[model]
+    m = params["variable_store"].get(model, lambda: cls(params))
+    return m, params
+
+
+def _model_fn(model):
+    import importlib
+    return importlib.import_module("recsys_b200.%s.%s" % (model, model)).model_fn
+
+
+def _check_grads(m, grads64, rows_key="emb", tol=1e-3):
+    def close(a, b, what):
+        err = float((a.detach().cpu().double() - b).abs().max())
+        s = float(b.abs().max()) + 1e-12
+        assert err <= tol * s + 1e-7, "%s: err %.3e scale %.3e" % (what, err, s)
+    close(m.emb.dtable, grads64["emb"], "d emb")
+    if m.emb.with_w1 and "w1" in grads64:
+        close(m.emb.dw1, grads64["w1"], "d w1")
+    dg = m.dense_grads()
+    for k, g in grads64.items():
+        if k in ("emb", "w1", "emb_dnn"):
+            continue
+        if k.startswith("cross."):
+            l, wb = k.split(".")[1:]
+            close(dg["cross." + wb][int(l)], g, k)
+        else:
+            close(dg[k], g.reshape(dg[k].shape), k)
+
+
+@pytest.mark.parametrize("model", ["fm", "deepfm", "dcn", "xdeepfm"])
+@pytest.mark.parametrize("B", [64, 1000])
+def test_criteo_models_match_oracle(cuda, model, B):
+    spec = mg.small_spec()
+    kw = dict(cin_layers=(16, 8)) if model == "xdeepfm" else {}
+    p64 = om.init_params(model, spec.total_rows, deep_layers=(32, 16), seed=3, **kw)
+    feats, batch = mg.model_batch(model, B, 7, spec)
+    out64, g64 = om.loss_and_grads(model, p64, batch)
+    m, params = _build(model, spec, cuda, cin_precision="tf32x3")
+    m.load_state(p64)
+    spec_ = _model_fn(model)(_features_to_torch(feats), batch["labels"], "train", params)
+    logits = m.last["logits"].detach().cpu().double().reshape(-1)
+    ref = out64["logits"].reshape(-1)
+    assert float(((logits - ref).abs() / (ref.abs() + 0.1)).max()) <= 1e-4
+    assert abs(float(spec_.loss) - float(out64["loss"])) <= 1e-5
+    assert spec_.predictions["prob"].shape == out64["prob"].shape        # [B,1] or [B] as the reference
+    m.backward(m.last["loss"])
+    _check_grads(m, g64)
+    if model == "xdeepfm":
+        def close(a, b):
+            return float((a.cpu().double() - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-7
+        assert close(m.emb_dnn.dtable, g64["emb_dnn"])
+
+
+def test_modes_and_estimator_spec_contract(cuda):
+    """fm/fm.py:135-170: PREDICT -> predictions+export_outputs, EVAL -> +loss+metrics,
+    TRAIN -> +train_op; eval-mode BN uses the (never updated) moving stats."""
+    from recsys_b200.deepfm import deepfm
+    from recsys_b200.estimator import ModeKeys
+    spec = mg.small_spec()
+    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
+    feats, batch = mg.model_batch("deepfm", 200, 11, spec)
+    m, params = _build("deepfm", spec, cuda)
+    m.load_state(p64)
+    tf = _features_to_torch(feats)
+    sp = deepfm.model_fn(tf, None, ModeKeys.PREDICT, params)
+    assert sp.loss is None and sp.train_op is None and "serving_default" in sp.export_outputs
+    se = deepfm.model_fn(tf, batch["labels"], ModeKeys.EVAL, params)
+    o = om.deepfm(p64, **batch, training=False)
+    assert torch.allclose(se.predictions["prob"].cpu().double(), o["prob"], rtol=1e-4, atol=1e-6)
+    assert abs(float(se.loss) - float(o["loss"])) <= 1e-5
+    auc, acc = tfsem.StreamingAUC(), tfsem.StreamingAccuracy()
+    auc.update(batch["labels"].numpy(), o["prob"].numpy())
+    acc.update(batch["labels"].numpy(), o["prob"].numpy())
+    assert round(se.eval_metric_ops["AUC"].result(), 4) == round(auc.result(), 4)
+    assert round(se.eval_metric_ops["Accuracy"].result(), 4) == round(acc.result(), 4)
+    st = deepfm.model_fn(tf, batch["labels"], ModeKeys.TRAIN, params)
+    assert callable(st.train_op) and params["variable_store"].global_step == 0
+    st.train_op()
+    assert params["variable_store"].global_step == 1
+
+
+@pytest.mark.parametrize("mode", ["exact_tf", "lazy"])
+def test_training_steps_follow_tf_adam(cuda, mode):
+    """Three optimiser steps of DeepFM == oracle forward/backward + tfsem.TFAdam
+    (dense-decay semantics for exact_tf; touched rows only for lazy)."""
+    from recsys_b200.deepfm import deepfm
+    spec = mg.small_spec()
+    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
+    m, params = _build("deepfm", spec, cuda, embedding_adam=mode, learning_rate=1e-2)
+    m.load_state(p64)
+    train = {k: v for k, v in p64.items() if not k.endswith((".bn.mean", ".bn.var"))}
+    opt = tfsem.TFAdam(train, lr=1e-2)
+    for step in range(3):
+        feats, batch = mg.model_batch("deepfm", 128, 20 + step, spec)
+        out, g = om.loss_and_grads("deepfm", p64, batch)
+        lazy = {"emb": batch["rows"].reshape(-1), "w1": batch["rows"].reshape(-1)} \
+            if mode == "lazy" else None
+        opt.step(train, g, lazy_rows=lazy)
+        p64.update(train)
+        sp = deepfm.model_fn(_features_to_torch(feats), batch["labels"], "train", params)
+        assert abs(float(sp.loss) - float(out["loss"])) <= 2e-4 * (1 + step)
+        sp.train_op()
+    assert torch.allclose(m.emb.table.cpu().double(), p64["emb"], rtol=1e-3, atol=2e-4)
+    assert torch.allclose(m.dense["dnn.0.w"].detach().cpu().double(), p64["dnn.0.w"], rtol=1e-3,
+                          atol=2e-4)
+
+
+def test_real_shard_fm_logloss_and_auc(cuda):
+    """BASELINE config 1 on the reference's own records (raw strings hashed on the device):
+    logloss and AUC equal to 4 decimals between the CUDA path and the oracle."""
+    from recsys_b200 import _core
+    from recsys_b200.estimator import VariableStore
+    from recsys_b200.fm import fm
+    z = np.load(os.path.join(GOLD, "criteo_shard256.npz"))
+    spec = criteo.CriteoSpec()
+    p64 = om.init_params("fm", spec.total_rows, seed=1)
+    rows = torch.from_numpy(z["rows"])
+    labels = torch.from_numpy(z["labels"])
+    o = om.fm(p64, rows, labels)
+    lin, emb = fm.build_feature_columns(16)
+    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
+              "learning_rate": 1e-3, "dropout": 0.5, "variable_store": VariableStore(), "device": cuda}
+    m = params["variable_store"].get("fm", lambda: _core.FMModel(params))
+    m.load_state(p64)
+    feats = {k: torch.from_numpy(z[k]) for k in criteo.CONT}
+    feats.update({k: np.array([bytes(v) for v in z[k]], dtype=object).reshape(-1, 1)
+                  for k in criteo.CAT})
+    se = fm.model_fn(feats, labels, "eval", params)
+    assert round(float(se.loss), 4) == round(float(o["loss"]), 4)
+    auc = tfsem.StreamingAUC()
+    auc.update(labels.numpy(), o["prob"].numpy())
+    assert round(se.eval_metric_ops["AUC"].result(), 4) == round(auc.result(), 4)
+    assert se.predictions["prob"].shape == (256, 1)
+
+
+@pytest.mark.parametrize("B,P", [(32, 20), (300, 100)])
+def test_din_matches_oracle(cuda, B, P):
+    from recsys_b200 import _core
+    from recsys_b200.din import din
+    from recsys_b200.estimator import VariableStore
+    feats, labels = synth.synthetic_din(B, P=P, seed=5, n_items=500, n_cates=50)
+    p64 = om.init_params("din", D=16, seed=3, din_items=500, din_cates=50)
+    g = torch.Generator().manual_seed(1)
+    p64["i_item"] = torch.randn(500, generator=g, dtype=torch.float64) * 0.1
+    for k in list(p64):
+        if k.endswith(".b"):
+            p64[k] = torch.randn(p64[k].shape, generator=g, dtype=torch.float64) * 0.05
+    batch = {k: torch.from_numpy(v) for k, v in feats.items()}
+    batch["labels"] = torch.from_numpy(labels)
+    out64, g64 = om.loss_and_grads("din", p64, batch)
+    params = {"embedding_size": 16, "learning_rate": 1e-3, "dropout": 0.0, "din_items": 500,
+              "din_cates": 50, "variable_store": VariableStore(), "device": cuda}
+    m = params["variable_store"].get("din", lambda: _core.DINModel(params))
+    m.load_state(p64)
+    tfeat = {k: torch.from_numpy(v) for k, v in feats.items()}
+    sp = din.model_fn(tfeat, torch.from_numpy(labels), "train", params)
+    logits = m.last["logits"].detach().cpu().double()
+    ref = out64["logits"]
+    assert float(((logits - ref).abs() / (ref.abs() + 0.1)).max()) <= 1e-4
+    assert abs(float(sp.loss) - float(out64["loss"])) <= 1e-5
+    m.backward(m.last["loss"])
+
+    def close(a, b, what, tol=1e-3):
+        err = float((a.detach().cpu().double() - b).abs().max())
+        s = float(b.abs().max()) + 1e-12
+        assert err <= tol * s + 1e-7, "%s: err %.3e scale %.3e" % (what, err, s)
+    close(m.emb.dtable[:500], g64["i_id"], "d i_id")
+    close(m.emb.dtable[500:], g64["i_cate"], "d i_cate")
+    close(m.emb.dw1[:500], g64["i_item"], "d i_item")
+    dg = m.dense_grads()
+    for k, gg in g64.items():
+        if k in dg:
+            close(dg[k], gg.reshape(dg[k].shape), k)
