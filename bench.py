@@ -218,6 +218,8 @@ def run_ours(args):
         return sharded.bench_main(args, rank, local, world)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # everything (variables, autograd nodes, capture) lives on one side stream
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     from recsys_b200 import _lib, ops
     from recsys_b200 import feature_column as fc
     from recsys_b200.data import SyntheticCriteo
@@ -235,11 +237,21 @@ def run_ours(args):
     sp = mod.model_fn(devb[0][0], devb[0][1], "train", params)
     sp.train_op()
     per_step_launches = ops.LAUNCHES["n"] - n0
+    del sp
     model = params["variable_store"]._objs[args.model]
     torch.cuda.synchronize()
     # ---- graph-captured whole step
     f0, l0 = host.batches[0]
-    step = None if args.eager else GraphedTrainStep(mod.model_fn, params, f0, l0, warmup=3)
+    step = None
+    graph_note = "eager (--eager)"
+    if not args.eager:
+        try:
+            step = GraphedTrainStep(mod.model_fn, params, f0, l0, warmup=3)
+            graph_note = "whole step captured in one CUDA graph"
+        except Exception as e:   # keep the bench alive: an eager number is still a valid number
+            sys.stderr.write("CUDA-graph capture failed, running eagerly: %r\n" % (e,))
+            graph_note = "eager (graph capture failed: %s)" % str(e)[:120]
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
 
     def resident_step(i):
@@ -309,7 +321,7 @@ def run_ours(args):
                        if step is not None else "model_fn(features, labels, 'train', params).train_op()"},
         "gpu_launches": per_step_launches * K,
         "gpu_launches_per_step": per_step_launches,
-        "final_loss": float(losses[K - 1]),
+        "final_loss": float(losses[K - 1]), "launch_mode": graph_note,
     }
     if kern is not None:
         t_pair = kern["fwd_us"] + kern["bwd_us"]

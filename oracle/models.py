@@ -73,7 +73,9 @@ def init_params(model: str, total_rows: int = 0, F: int = 39, D: int = 16,
             p[f"cin.{k}.w"] = T.glorot_uniform((1, F * hp, h), g, dtype).reshape(F * hp, h)
             p[f"cin.{k}.b"] = torch.zeros(h, dtype=dtype)
             hp = h
-        p["cin.out.w"] = T.glorot_uniform((sum(cin_layers), 1), g, dtype)
+        # |.|: the pooled CIN maps are >= 0, a negative kernel would leave the ReLU of
+        # xdeepfm.py:182 dead for every sample and the parity tests would not exercise CIN
+        p["cin.out.w"] = T.glorot_uniform((sum(cin_layers), 1), g, dtype).abs()
         p["cin.out.b"] = torch.full((1,), 0.1, dtype=dtype)
     if model == "dcn":
         for l in range(cross_layers):

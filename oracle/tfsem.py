@@ -84,9 +84,16 @@ def dropout(x, rate, training, mask=None):
 
 
 def sigmoid_cross_entropy_with_logits(logits, labels):
-    """tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log1p(exp(-|x|))
-    (fm/fm.py:146-149)."""
-    return torch.clamp(logits, min=0) - logits * labels + torch.log1p(torch.exp(-logits.abs()))
+    """tf.nn.sigmoid_cross_entropy_with_logits (fm/fm.py:146-149), written as TF writes it
+    so that autodiff agrees at logits == 0 exactly (all three ReLU branches dead happens):
+        cond = x >= 0; relu = where(cond, x, 0); neg_abs = where(cond, -x, x)
+        loss = relu - x*z + log1p(exp(neg_abs))            -> d/dx = sigmoid(x) - z everywhere
+    (clamp/abs would give 1 - z at x == 0)."""
+    cond = logits >= 0
+    zeros = torch.zeros_like(logits)
+    relu_logits = torch.where(cond, logits, zeros)
+    neg_abs = torch.where(cond, -logits, logits)
+    return relu_logits - logits * labels + torch.log1p(torch.exp(neg_abs))
 
 
 # ----------------------------------------------------------------------- metrics

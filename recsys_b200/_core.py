@@ -153,6 +153,9 @@ class _ModelBase:
 
     def backward(self, loss):
         loss.backward()
+        # drop the autograd graph: a live graph keeps the leaves' AccumulateGrad nodes (and the
+        # stream they were created on) alive, which breaks a later CUDA-graph capture
+        self.last = {k: v.detach() for k, v in self.last.items()}
 
     def apply_gradients(self):
         lr_t = self.adam.next_lr_t()

@@ -294,6 +294,14 @@ cin_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ prep kernels
+// The tensor core reads fp32 operands as tf32 by dropping the low 13 mantissa bits
+// (truncation, biased).  Operands are therefore pre-rounded to nearest tf32 (cvt.rna) so
+// that what the MMA truncates is already zero; the 3xTF32 split keeps the remainder.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 // Bp[(i*Gp + g)*Kp + k] = (g < G && k < K) ? W[i*slab + g*sg + k*sk] : 0, for i < m_pad fields.
 __global__ void cin_prep_b_kernel(const float* __restrict__ W, float* __restrict__ Bp,
                                   float* __restrict__ Bp_lo, int m, int m_pad, int G, int Gp, int K,
@@ -307,24 +315,23 @@ __global__ void cin_prep_b_kernel(const float* __restrict__ W, float* __restrict
     const int i = static_cast<int>(ig / Gp);
     float w = 0.f;
     if (i < m && g < G && k < K) w = __ldg(W + i * slab + g * sg + k * sk);
-    if (Bp_lo != nullptr) {
-      const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
-      Bp[e] = hi;
-      Bp_lo[e] = w - hi;
-    } else {
-      Bp[e] = w;
-    }
+    const float hi = round_tf32(w);
+    Bp[e] = hi;
+    if (Bp_lo != nullptr) Bp_lo[e] = round_tf32(w - hi);
   }
 }
-// hi = x truncated to tf32 (what the tensor core reads), lo = x - hi (exact).
-__global__ void cin_split_kernel(const float* __restrict__ x, float* __restrict__ hi,
-                                 float* __restrict__ lo, long long n) {
+// A [M, K] pitch lda -> hi (and lo) [M, Kp] pitch Kp, zero padded: 16-byte aligned rows for TMA.
+__global__ void cin_prep_a_kernel(const float* __restrict__ A, int lda, int K, float* __restrict__ hi,
+                                  float* __restrict__ lo, int Kp, long long M) {
+  const long long n = M * Kp;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float v = x[e];
-    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const long long r = e / Kp;
+    const int k = static_cast<int>(e - r * Kp);
+    const float v = k < K ? A[r * lda + k] : 0.f;
+    const float h = round_tf32(v);
     hi[e] = h;
-    lo[e] = v - h;
+    if (lo != nullptr) lo[e] = round_tf32(v - h);
   }
 }
 
@@ -433,37 +440,30 @@ static int cin_tc_pass(int mode, const float* A, int lda, int K, const float* W,
                        int prec, void* ws, int64_t ws_bytes, cudaStream_t st, const char* fn) {
   const CinTcPlan pl = cin_tc_plan(m, G, K, mode == MODE_SCALE, prec);
   if (!pl.ok) return fail_arg(fn, "shape not supported by the tensor-core path (need G<=128, K<=256)");
-  CTR_REQUIRE((lda & 3) == 0 && aligned16(A), fn, "A must be 16-byte aligned with a pitch multiple of 4");
   const size_t bp_elems = static_cast<size_t>(pl.m_pad) * pl.Gp * pl.Kp;
+  const size_t a_elems = static_cast<size_t>(M) * pl.Kp;
   const bool split = prec == CTR_CIN_TF32X3;
-  size_t need = bp_elems * 4 * (split ? 2 : 1) + 256;
-  if (split) need += static_cast<size_t>(M) * lda * 4 * 2 + 256;
+  const size_t need = (bp_elems + a_elems) * 4 * (split ? 2 : 1) + 1024;
   CTR_REQUIRE(ws != nullptr && static_cast<size_t>(ws_bytes) >= need, fn, "workspace too small");
-  uint8_t* w8 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
-  float* Bp = reinterpret_cast<float*>(w8);
-  float* Bp_lo = split ? Bp + bp_elems : nullptr;
-  float* A_hi = nullptr;
-  float* A_lo = nullptr;
-  if (split) {
-    uint8_t* a8 = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(Bp_lo + bp_elems) + 255) & ~uintptr_t(255));
-    A_hi = reinterpret_cast<float*>(a8);
-    A_lo = A_hi + static_cast<size_t>(M) * lda;
-  }
+  auto align256 = [](void* q) {
+    return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q) + 255) & ~uintptr_t(255));
+  };
+  float* Bp = align256(ws);
+  float* Bp_lo = split ? align256(Bp + bp_elems) : nullptr;
+  float* A_hi = align256((split ? Bp_lo : Bp) + bp_elems);
+  float* A_lo = split ? align256(A_hi + a_elems) : nullptr;
   {
     const long long n = static_cast<long long>(bp_elems);
     const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 8LL));
     cin_prep_b_kernel<<<grid, 256, 0, st>>>(W, Bp, Bp_lo, m, pl.m_pad, G, pl.Gp, K, pl.Kp, slab, sg, sk);
-    if (split) {
-      const long long na = static_cast<long long>(M) * lda;
-      const int g2 = static_cast<int>(std::min<long long>((na + 255) / 256, sm_count() * 8LL));
-      cin_split_kernel<<<g2, 256, 0, st>>>(A, A_hi, A_lo, na);
-    }
+    const long long na = static_cast<long long>(a_elems);
+    const int g2 = static_cast<int>(std::min<long long>((na + 255) / 256, sm_count() * 8LL));
+    cin_prep_a_kernel<<<g2, 256, 0, st>>>(A, lda, K, A_hi, A_lo, pl.Kp, M);
   }
   CUtensorMap tA0, tA1, tB0, tB1;
-  int r = make_map(&tA0, split ? A_hi : A, M, K, lda, kTcBM);
+  int r = make_map(&tA0, A_hi, M, K, pl.Kp, kTcBM);
   if (r != CTR_OK) return r;
-  r = make_map(&tA1, split ? A_lo : A, M, K, lda, kTcBM);
+  r = make_map(&tA1, split ? A_lo : A_hi, M, K, pl.Kp, kTcBM);
   if (r != CTR_OK) return r;
   r = make_map(&tB0, Bp, static_cast<long long>(pl.m_pad) * pl.Gp, K, pl.Kp, pl.NT);
   if (r != CTR_OK) return r;
@@ -493,20 +493,18 @@ static int cin_tc_pass(int mode, const float* A, int lda, int K, const float* W,
   return check_cuda(cudaGetLastError(), fn);
 }
 
-static int64_t cin_tc_pass_ws(int M, int lda, int m, int G, int K, bool scale, int prec) {
+static int64_t cin_tc_pass_ws(int M, int m, int G, int K, bool scale, int prec) {
   const CinTcPlan pl = cin_tc_plan(m, G, K, scale, prec);
   if (!pl.ok) return 0;
-  const size_t bp = static_cast<size_t>(pl.m_pad) * pl.Gp * pl.Kp * 4;
-  size_t need = bp * (prec == CTR_CIN_TF32X3 ? 2 : 1) + 512;
-  if (prec == CTR_CIN_TF32X3) need += static_cast<size_t>(M) * lda * 4 * 2 + 512;
-  return static_cast<int64_t>(need);
+  const size_t bp = static_cast<size_t>(pl.m_pad) * pl.Gp * pl.Kp;
+  const size_t a = static_cast<size_t>(M) * pl.Kp;
+  return static_cast<int64_t>((bp + a) * 4 * (prec == CTR_CIN_TF32X3 ? 2 : 1) + 1024);
 }
 
 static int64_t cin_tc_workspace_bytes(int B, int D, int m, int Hp, int H, int prec) {
   const int M = B * D;
-  const int ldp = (Hp + 3) / 4 * 4 + 4;
-  int64_t a = cin_tc_pass_ws(M, ldp, m, H, Hp, true, prec);   // fwd / dX0t: A = Xp, K = Hp, G = H
-  int64_t b = cin_tc_pass_ws(M, H, m, Hp, H, true, prec);     // dXp: A = dpre, K = H, G = Hp
+  int64_t a = cin_tc_pass_ws(M, m, H, Hp, true, prec);   // fwd / dX0t: A = Xp, K = Hp, G = H
+  int64_t b = cin_tc_pass_ws(M, m, Hp, H, true, prec);   // dXp: A = dpre, K = H, G = Hp
   return std::max(a, b) + 1024;
 }
 

@@ -191,7 +191,10 @@ class GraphedTrainStep:
             raise TypeError("GraphedTrainStep needs PackedFeatures batches (see data.SyntheticCriteo)")
         dev = params.get("device") or torch.device("cuda", torch.cuda.current_device())
         self.model_fn, self.params = model_fn, params
-        self.stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        # capture on the caller's stream when it is already a side stream (keeps every autograd
+        # node on one stream); the legacy default stream cannot be captured
+        self.stream = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(device=dev)
         f = example_features
         self.cont = torch.empty_like(f.cont, device=dev)
         self.cat = torch.empty_like(f.cat, device=dev)
@@ -203,6 +206,8 @@ class GraphedTrainStep:
             for _ in range(warmup):                 # allocator + lazy-init warm-up, eager
                 self._eager()
         self.stream.synchronize()
+        import gc
+        gc.collect()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             self._eager()
