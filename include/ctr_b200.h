@@ -172,6 +172,24 @@ int ctr_transpose_fd(const float* E, int B, int F, int D, float* Xt, int ld, ctr
 int ctr_transpose_df_add(const float* dXt, int ld, int B, int F, int D, float* dE,
                          ctr_stream_t stream);
 
+/* ------------------------------------------------------- row-sharded table (multi-GPU)
+ * The reference only replicates (tf.distribute.MirroredStrategy, fm/fm.py:184-194); row
+ * sharding is the north-star extension for tables larger than one GPU's HBM.  owner(row) =
+ * row % G, local index = row / G.  These are the device halves of the exchange; the
+ * all-to-all itself is NCCL (torch.distributed) in recsys_b200/sharded.py.
+ *
+ * ctr_shard_bucket: requester side.  For lookup i: slot[i] = owner*capacity + pos and
+ *   send_local[slot[i]] = rows[i] / G; unused slab entries are -1; counts[owner] = number of
+ *   lookups for that owner (> capacity means overflow: those lookups got slot -1). */
+int ctr_shard_bucket(const int32_t* rows, int64_t n, int G, int capacity, int32_t* send_local,
+                     int32_t* slot, int32_t* counts, ctr_stream_t stream);
+/* Owner side: out[i,:] = table[ids[i],:] (zeros for ids[i] < 0); out_w1[i] = w1[ids[i]]. */
+int ctr_gather_rows(const float* table, const float* w1, const int32_t* ids, int64_t n, int D,
+                    float* out, float* out_w1, ctr_stream_t stream);
+/* Owner side: dtable[ids[i],:] += g[i,:]; dw1[ids[i]] += gw1[i]; ids < 0 skipped. */
+int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, int64_t n, int D,
+                         float* dtable, float* dw1, ctr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,8 +179,20 @@ class _CriteoBase(_ModelBase):
         mask, self.numeric_linear = fc.first_order_fields(params.get("linear_feature_columns", []),
                                                           self.lay) if self.want_w1 else (0, [])
         seed = int(params.get("seed", 0))
-        self.emb = ops.FieldEmbedding(self.lay, self.device, with_w1=self.want_w1, w1_fields=mask,
-                                      adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
+        self.world = 1
+        if params.get("shard_embedding"):
+            # row-sharded table over the ranks of the default process group (sharded.py)
+            import torch.distributed as dist
+            from . import sharded
+            self.world = dist.get_world_size()
+            self.emb = sharded.ShardedFieldEmbedding(
+                self.lay, self.device, with_w1=self.want_w1, w1_fields=mask,
+                adam_mode=params.get("embedding_adam", "lazy"), seed=seed,
+                slack=float(params.get("shard_slack", 1.5)), shard_ops=params.get("shard_ops"))
+        else:
+            self.emb = ops.FieldEmbedding(self.lay, self.device, with_w1=self.want_w1,
+                                          w1_fields=mask,
+                                          adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
         self.ids = ops.IdPipeline(self.lay, self.device)
         self.rows = None
 
@@ -188,7 +200,17 @@ class _CriteoBase(_ModelBase):
         super().load_state(state)
         self.emb.load(state.get("emb"), state.get("w1"))
 
+    def backward(self, loss):
+        # data parallel: the global loss is the mean over all replicas' batches
+        super().backward(loss / self.world if self.world > 1 else loss)
+
+    def _sync_dense_grads(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.dense.grad)      # replicated dense weights: sum of per-rank grads
+
     def _apply_gradients(self, lr_t):
+        self._sync_dense_grads()
         self.emb.adam_step(self.rows, lr_t, self.adam)
         self.dense.adam_step(lr_t, self.adam)
 
@@ -352,6 +374,7 @@ class XDeepFMModel(_CriteoBase):
         return torch.addmm(P["head.b"], z, P["head.w"])                         # :195  [B,1]
 
     def _apply_gradients(self, lr_t):
+        self._sync_dense_grads()
         self.emb.adam_step(self.rows, lr_t, self.adam)
         if self.emb_dnn is not None:
             self.emb_dnn.adam_step(self.rows, lr_t, self.adam)

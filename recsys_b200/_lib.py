@@ -56,6 +56,9 @@ SIGNATURES = {
                                 c_f, c_i64, c_f]),
     "ctr_cin_layer_bwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f,
                                 c_f, c_f, c_i, c_f, c_i64, c_f]),
+    "ctr_shard_bucket": (c_i, [c_f, c_i64, c_i, c_i, c_f, c_f, c_f, c_f]),
+    "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),
+    "ctr_scatter_add_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),
     "ctr_transpose_fd": (c_i, [c_f, c_i, c_i, c_i, c_f, c_i, c_f]),
     "ctr_transpose_df_add": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
 }

@@ -150,7 +150,7 @@ embed_fwd_kernel(const EmbedFwdParams p) {
         float* e = p.E + static_cast<size_t>(b) * F * D;
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
-          if (rid[s][it] >= 0)
+          if (it * RPW + r < F)     // a negative row id (sharded overflow slot) reads as zeros
             *reinterpret_cast<float4*>(e + (it * 32 + lane) * 4) = v[s][it];
       }
       if (p.y1 != nullptr) {
@@ -318,8 +318,9 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
       int rid = -1;
       float4 g = f4_zero();
       float gw = 0.f;
-      if (ok) {
-        rid = __ldg(p.rows + static_cast<size_t>(b) * F + f);
+      if (ok) rid = __ldg(p.rows + static_cast<size_t>(b) * F + f);
+      const bool live = ok && rid >= 0;   // negative ids (sharded overflow slots) are skipped
+      if (live) {
         const size_t eo = (static_cast<size_t>(b) * F + f) * D + q * 4;
         if (p.dE != nullptr) g = ld4_stream(p.dE + eo);
         if (p.dy2 != nullptr) {
@@ -335,12 +336,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
         if (has_w1) gw = __ldg(p.dy1 + b);
       }
       if (!tiny) {
-        if (ok) {
+        if (live) {
           red_add_v4(p.dtable + static_cast<size_t>(rid) * D + q * 4, g);
           if (has_w1 && q == 0) red_add_f32(p.dw1 + rid, gw);
         }
       } else {
-        const int lid = rid - off;  // negative for inactive lanes: never matches
+        const int lid = live ? rid - off : -1;  // negative for inactive lanes: never matches
 #pragma unroll
         for (int t = 0; t < RPW; ++t) {
           const float4 gt = f4_shfl(g, t * LPR + q);
@@ -609,8 +610,8 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
     int rid = -1;
     int won = 0;
     if (i < n) {
-      rid = __ldg(rows + i);
-      if (q == 0) won = atomicExch(claim + rid, tag) != tag ? 1 : 0;
+      rid = __ldg(rows + i);    // negative ids are padding (sharded exchange slabs)
+      if (rid >= 0 && q == 0) won = atomicExch(claim + rid, tag) != tag ? 1 : 0;
     }
     won = __shfl_sync(0xffffffffu, won, (lane / LPR) * LPR);
     if (!won) continue;

@@ -1,6 +1,350 @@
-"""Row-sharded embedding table over the GPUs of one box (placeholder until the
-all-to-all path lands; see DESIGN.md "multi-GPU")."""
+"""Row-sharded embedding table over the GPUs of one box (BASELINE config 5).
+
+The reference only replicates its tables (tf.distribute.MirroredStrategy, fm/fm.py:184-194);
+sharding is the north-star extension for a table that exceeds one GPU's HBM.  One process per
+GPU; rows are owned round-robin (owner = row % G, local index = row // G); dense weights are
+replicated and their gradients all-reduced (NCCL).  Per step and rank:
+
+  forward   bucket lookups by owner (ctr_shard_bucket, fixed-capacity slabs, no host sync)
+            -> all-to-all ids -> owner gather (ctr_gather_rows) -> all-to-all vectors back
+            -> ctr_embed_fwd over the received slab (slots play the role of row ids)
+  backward  ctr_embed_bwd into a per-slot gradient slab -> all-to-all back to the owners
+            -> ctr_scatter_add_rows into the local gradient accumulator -> Adam on touched rows
+
+The exchange moves (G-1)/G * (4 + 64 + 64) B per lookup over NVLink; nothing else crosses.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import feature_column as fc
+from . import ops
+from .ops import _call, _p, _stream
+
+
+class CudaShardOps:
+    """The device halves of the exchange (libctr_b200)."""
+
+    def bucket(self, rows_flat, G, capacity):
+        n = rows_flat.numel()
+        dev = rows_flat.device
+        send = torch.empty(G * capacity, dtype=torch.int32, device=dev)
+        slot = torch.empty(n, dtype=torch.int32, device=dev)
+        counts = torch.empty(G, dtype=torch.int32, device=dev)
+        _call("ctr_shard_bucket", _p(rows_flat), n, G, capacity, _p(send), _p(slot), _p(counts),
+              _stream())
+        return send, slot, counts
+
+    def gather(self, table, w1, ids):
+        n, D = ids.numel(), table.shape[1]
+        vec = torch.empty((n, D), dtype=torch.float32, device=ids.device)
+        w1v = torch.empty(n, dtype=torch.float32, device=ids.device) if w1 is not None else None
+        _call("ctr_gather_rows", _p(table), _p(w1), _p(ids), n, D, _p(vec), _p(w1v), _stream())
+        return vec, w1v
+
+    def scatter_add(self, ids, g, gw1, dtable, dw1):
+        _call("ctr_scatter_add_rows", _p(ids), _p(g), _p(gw1) if dw1 is not None else None,
+              ids.numel(), dtable.shape[1], _p(dtable), _p(dw1), _stream())
+
+    def interact_fwd(self, vec, w1v, slot2d, D, w1_fields, want_fm, want_y1, cross_w, cross_b):
+        B, F = slot2d.shape
+        dev = slot2d.device
+        E = torch.empty((B, F * D), dtype=torch.float32, device=dev)
+        S = torch.empty((B, D), dtype=torch.float32, device=dev) if want_fm else None
+        y2 = torch.empty(B, dtype=torch.float32, device=dev) if want_fm else None
+        y1 = torch.empty(B, dtype=torch.float32, device=dev) if want_y1 else None
+        cross = cross_w is not None
+        xl = torch.empty((B, F * D), dtype=torch.float32, device=dev) if cross else None
+        _call("ctr_embed_fwd", _p(vec), _p(w1v), _p(slot2d), B, F, D, w1_fields, _p(E), _p(S), _p(y1),
+              _p(y2), _p(cross_w), _p(cross_b), cross_w.shape[0] if cross else 0, _p(xl), _stream())
+        return E, S, y1, y2, xl
+
+    def interact_bwd(self, slot2d, dE, E, vec, S, dy2, dy1, w1_fields, D, n_slots):
+        B, F = slot2d.shape
+        dev = slot2d.device
+        gsend = torch.zeros((n_slots, D), dtype=torch.float32, device=dev)
+        gw1 = torch.zeros(n_slots, dtype=torch.float32, device=dev) if dy1 is not None else None
+        # slots are unique per lookup: no field is "tiny" (fake offsets 1000 apart)
+        offs = (C.c_int64 * (F + 1))(*[1000 * f for f in range(F + 1)])
+        _call("ctr_embed_bwd", _p(slot2d), _p(dE), _p(E), _p(vec), _p(S), _p(dy2), _p(dy1),
+              w1_fields, offs, B, F, D, _p(gsend), _p(gw1), _stream())
+        return gsend, gw1
+
+
+def _a2a(x: torch.Tensor, group) -> torch.Tensor:
+    out = torch.empty_like(x)
+    dist.all_to_all_single(out, x, group=group)
+    return out
+
+
+def slab_capacity(n_lookups: int, G: int, slack: float) -> int:
+    return int(math.ceil(n_lookups / G * slack / 4.0)) * 4
+
+
+class ShardedFieldEmbedding:
+    """Same surface as ops.FieldEmbedding (lookup / adam_step / dtable), rows split over the
+    ranks of ``group``.  ``table`` holds this rank's rows only."""
+
+    def __init__(self, lay: fc.Layout, device, group=None, with_w1=True, w1_fields=0,
+                 adam_mode="lazy", seed=0, slack=1.5, shard_ops=None, capacity=None):
+        self.lay, self.device, self.group = lay, device, group
+        self.G = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.D, self.F, self.R = lay.dimension, lay.F, lay.total_rows
+        self.R_local = (self.R - self.rank + self.G - 1) // self.G
+        self.slack = slack
+        self.fixed_capacity = capacity      # per-(src,dst) slab size; must agree on all ranks
+        self.ops = shard_ops or CudaShardOps()
+        g = torch.Generator(device=device).manual_seed(seed * 1000 + self.rank)
+        self.table = torch.empty(self.R_local, self.D, dtype=torch.float32, device=device)
+        torch.nn.init.trunc_normal_(self.table, std=self.D ** -0.5, a=-2 * self.D ** -0.5,
+                                    b=2 * self.D ** -0.5, generator=g)
+        self.dtable = torch.zeros_like(self.table)
+        self.with_w1, self.w1_fields = with_w1, w1_fields
+        if with_w1:
+            lim = math.sqrt(6.0 / (self.R + 1))
+            self.w1 = (torch.rand(self.R_local, generator=g, device=device) * 2 - 1) * lim
+            self.dw1 = torch.zeros_like(self.w1)
+        else:
+            self.w1 = self.dw1 = None
+        self.adam_mode = adam_mode
+        self._m = self._v = self._m1 = self._v1 = self._claim = self._claim1 = None
+        self._tag = 0
+        self._anchor = torch.zeros((), device=device, requires_grad=True)
+        self.recv_ids = None
+        self.counts = None
+        self.capacity = 0
+
+    # state -----------------------------------------------------------------------
+    def load(self, table=None, w1=None):
+        """Load a FULL [R, D] table (tests): each rank keeps rows rank, rank+G, ..."""
+        with torch.no_grad():
+            if table is not None:
+                self.table.copy_(table[self.rank::self.G].to(self.device, torch.float32))
+            if w1 is not None and self.with_w1:
+                self.w1.copy_(w1.reshape(-1)[self.rank::self.G].to(self.device, torch.float32))
+
+    def full_grad(self):
+        """All-gather the sharded gradient accumulator into [R, D] (tests)."""
+        rl = (self.R + self.G - 1) // self.G
+        mine = torch.zeros(rl, self.D, dtype=torch.float32, device=self.device)
+        mine[:self.R_local] = self.dtable
+        parts = [torch.empty_like(mine) for _ in range(self.G)]
+        dist.all_gather(parts, mine, group=self.group)
+        full = torch.zeros(self.R, self.D, dtype=torch.float32, device=self.device)
+        for r in range(self.G):
+            n = (self.R - r + self.G - 1) // self.G
+            full[r::self.G] = parts[r][:n]
+        return full
+
+    def check_overflow(self):
+        """Raises if a slab overflowed in the last lookup (synchronises)."""
+        if self.counts is not None and int(self.counts.max()) > self.capacity:
+            raise RuntimeError("sharded exchange slab overflow: %d lookups for one owner, capacity "
+                               "%d; raise slack" % (int(self.counts.max()), self.capacity))
+
+    # forward / backward -----------------------------------------------------------
+    def lookup(self, rows, want_fm=True, want_y1=True, cross_w=None, cross_b=None):
+        return _ShardedEmbedFn.apply(self._anchor, self, rows, want_fm, want_y1 and self.with_w1,
+                                     cross_w, cross_b)
+
+    def zero_grad(self):
+        self.dtable.zero_()
+        if self.with_w1:
+            self.dw1.zero_()
+
+    def adam_step(self, rows_unused, lr_t, st):
+        if self._m is None:
+            self._m, self._v = torch.zeros_like(self.table), torch.zeros_like(self.table)
+            self._claim = torch.zeros(self.R_local, dtype=torch.int32, device=self.device)
+            if self.with_w1:
+                self._m1, self._v1 = torch.zeros_like(self.w1), torch.zeros_like(self.w1)
+                self._claim1 = torch.zeros(self.R_local, dtype=torch.int32, device=self.device)
+        if self.adam_mode == "exact_tf":
+            _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
+                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
+            if self.with_w1:
+                _call("ctr_adam_dense", _p(self.w1), _p(self._m1), _p(self._v1), _p(self.dw1),
+                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
+            return
+        self._tag += 1
+        ids = self.recv_ids
+        _call("ctr_adam_rows", _p(ids), ids.numel(), self.D, _p(self.table), _p(self._m),
+              _p(self._v), _p(self.dtable), _p(self._claim), self._tag, lr_t, st.beta1, st.beta2,
+              st.eps, st.state_ptr, _stream())
+        if self.with_w1:
+            _call("ctr_adam_rows", _p(ids), ids.numel(), 1, _p(self.w1), _p(self._m1), _p(self._v1),
+                  _p(self.dw1), _p(self._claim1), self._tag, lr_t, st.beta1, st.beta2, st.eps,
+                  st.state_ptr, _stream())
+
+
+class _ShardedEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, emb: ShardedFieldEmbedding, rows, want_fm, want_y1, cross_w, cross_b):
+        ctx.set_materialize_grads(False)
+        B, F, D, G = rows.shape[0], emb.F, emb.D, emb.G
+        rows = rows.contiguous()
+        cap = emb.fixed_capacity or slab_capacity(B * F, G, emb.slack)
+        send_ids, slot, counts = emb.ops.bucket(rows.view(-1), G, cap)
+        recv_ids = _a2a(send_ids, emb.group)                       # ids this rank owns
+        vec, w1v = emb.ops.gather(emb.table, emb.w1 if want_y1 else None, recv_ids)
+        vec_back = _a2a(vec, emb.group)                            # [G*cap, D]
+        w1_back = _a2a(w1v, emb.group) if want_y1 else None
+        slot2d = slot.view(B, F)
+        E, S, y1, y2, xl = emb.ops.interact_fwd(vec_back, w1_back, slot2d, D, emb.w1_fields, want_fm,
+                                                want_y1, cross_w, cross_b)
+        emb.recv_ids, emb.counts, emb.capacity = recv_ids, counts, cap
+        ctx.emb, ctx.slot2d, ctx.recv_ids, ctx.E, ctx.S, ctx.vec = emb, slot2d, recv_ids, E, S, vec_back
+        ctx.cross_w, ctx.cross_b = cross_w, cross_b
+        cross = cross_w is not None
+        ctx.flags = (want_fm, want_y1, cross, G * cap)
+        z = E.new_zeros(())
+        outs = [E, y1 if want_y1 else z, y2 if want_fm else z, xl if cross else z]
+        nd = [o for o, f in zip(outs[1:], (want_y1, want_fm, cross)) if not f]
+        if nd:
+            ctx.mark_non_differentiable(*nd)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dE, dy1, dy2, dxl):
+        emb = ctx.emb
+        want_fm, want_y1, cross, n_slots = ctx.flags
+        D = emb.D
+        dcw = dcb = None
+        if cross and dxl is not None:
+            L, W = ctx.cross_w.shape
+            dx0 = torch.empty_like(ctx.E)
+            dcw, dcb = torch.zeros_like(ctx.cross_w), torch.zeros_like(ctx.cross_b)
+            _call("ctr_dcn_cross_bwd", _p(ctx.E), _p(ctx.cross_w), _p(ctx.cross_b), L, ctx.E.shape[0],
+                  W, _p(dxl.contiguous()), _p(dx0), _p(dcw), _p(dcb), _stream())
+            dE = dx0 if dE is None else dE + dx0
+        dE = None if dE is None else dE.contiguous()
+        dy2 = dy2.contiguous() if (want_fm and dy2 is not None) else None
+        dy1 = dy1.contiguous() if (want_y1 and dy1 is not None) else None
+        if dE is None and dy2 is None and dy1 is None:
+            return None, None, None, None, None, dcw, dcb
+        if dE is None and dy2 is None:
+            dE = torch.zeros_like(ctx.E)
+        gsend, gw1 = emb.ops.interact_bwd(ctx.slot2d, dE, ctx.E, ctx.vec, ctx.S, dy2, dy1,
+                                          emb.w1_fields, D, n_slots)
+        grecv = _a2a(gsend, emb.group)
+        gw1recv = _a2a(gw1, emb.group) if gw1 is not None else None
+        emb.ops.scatter_add(ctx.recv_ids, grecv, gw1recv, emb.dtable,
+                            emb.dw1 if gw1 is not None else None)
+        return None, None, None, None, None, dcw, dcb
+
+
+# ------------------------------------------------------------------- bench (N > 1)
+def sharded_columns(total_rows: int, embedding_size: int, n_fields: int = 39):
+    """Synthetic config 5: ``n_fields`` hashed fields sharing ``total_rows`` rows."""
+    per = total_rows // n_fields
+    lin, emb = [], []
+    for i in range(n_fields):
+        c = fc.categorical_column_with_hash_bucket("_c%d" % (i + 1), per)
+        lin.append(fc.indicator_column(c))
+        emb.append(fc.embedding_column(c, embedding_size))
+    return lin, emb
 
 
 def bench_main(args, rank, local, world):
-    raise NotImplementedError("sharded bench path not implemented yet")
+    """DeepFM, 39 fields, emb 16, 1e9-row table row-sharded over ``world`` GPUs, local batch
+    ``args.batch`` per GPU (weak scaling).  Rank 0 prints the JSON line."""
+    import json
+    import time
+
+    import numpy as np
+
+    from .deepfm import deepfm
+    from .estimator import VariableStore
+    from .ops import PackedFeatures
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    total_rows = int(os.environ.get("CTR_SHARDED_ROWS", "1000000000"))
+    lin, emb = sharded_columns(total_rows, 16)
+    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
+              "learning_rate": 1e-3, "dropout": 0.5, "deep_layers": "100,100", "device": dev,
+              "variable_store": VariableStore(), "embedding_adam": "lazy", "shard_embedding": True,
+              "seed": 0}
+    lay = fc.layout(emb)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    rng = np.random.default_rng(1234 + rank)
+    host, devb = [], []
+    keys = [c.key for c in lay.columns]
+    for _ in range(min(args.n_batches, 16)):
+        cat = torch.from_numpy(np.stack([rng.integers(0, n, size=B) for n in lay.rows], 1)).pin_memory()
+        cont = torch.zeros((B, 0), dtype=torch.float32).pin_memory()
+        lab = torch.from_numpy((rng.random((B, 1)) < 0.22).astype(np.float32)).pin_memory()
+        host.append((PackedFeatures(cont, cat, [], keys), lab))
+        devb.append((PackedFeatures(cont.to(dev), cat.to(dev), [], keys), lab.to(dev)))
+    n0 = ops.LAUNCHES["n"]
+    sp = deepfm.model_fn(devb[0][0], devb[0][1], "train", params)
+    sp.train_op()
+    per_step_launches = ops.LAUNCHES["n"] - n0
+    del sp
+    model = params["variable_store"]._objs["deepfm"]
+
+    def step(batch):
+        f, l = batch
+        s = deepfm.model_fn(f, l, "train", params)
+        s.train_op()
+        return s.loss
+
+    def timed(batches, read_loss):
+        for i in range(W):
+            step(batches[i % len(batches)])
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        slot = torch.zeros(1, dtype=torch.float32).pin_memory()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            loss = step(batches[(W + i) % len(batches)])
+            if read_loss:
+                slot.copy_(loss.reshape(1), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1), wall], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    ms, _ = timed(devb, False)
+    ms_e2e, wall_e2e = timed(host, True)
+    model.emb.check_overflow()
+    if rank == 0:
+        f, l = host[0]
+        G = world
+        line = {
+            "metric": "CTR samples/sec (Criteo 39-field emb16)", "value": K * B * world / (ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "deepfm 39-field emb16, %d-row table row-sharded (row %% G) over %d "
+                                   "GPUs, NCCL all-to-all of ids/vectors/grads, local batch %d, "
+                                   "fwd+bwd+Adam(lazy rows)" % (total_rows, world, B),
+                       "fields": 39, "embedding_size": 16, "batch_per_gpu": B, "global_batch": B * world,
+                       "table_rows": total_rows, "id_dist": "uniform",
+                       "l2": "%.1f GB table shard per GPU > L2; distinct id batch every step"
+                             % (total_rows / world * 64 / 1e9),
+                       "parallelism": "row-sharded table x%d + replicated dense weights (all-reduce)" % world},
+            "e2e": {"value": K * B * world / (max(ms_e2e, wall_e2e) / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": (f.cat.numel() * 8 + l.numel() * 4) * world,
+                    "d2h_bytes_per_step": 4 * world,
+                    "api": "deepfm.model_fn(pinned PackedFeatures, labels, 'train', params).train_op()"},
+            "gpu_launches": per_step_launches * K * world, "gpu_launches_per_step": per_step_launches,
+            "nvlink_bytes_per_gpu_per_step": int((G - 1) / G * B * 39 * (4 + 64 + 64 + 8)),
+            "launch_mode": "eager (NCCL collectives between kernels)",
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
