@@ -37,13 +37,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="deepfm")
-    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=None,
+                    help="default 4096 (8192 for xdeepfm, BASELINE config 3)")
     ap.add_argument("--table", default="full", choices=["full", "ref"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--n-batches", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (debug)")
+    ap.add_argument("--cin-precision", default="tf32", choices=["fp32", "tf32", "tf32x3"])
     return ap.parse_args()
 
 
@@ -182,8 +184,16 @@ def run_reference(args):
 
 
 def workload_config(args):
+    if args.model == "din":
+        return {"workload": "din Amazon-Electro synth seq_len=100 emb16 batch=%d fwd+bwd+Adam" % args.batch,
+                "embedding_size": 16, "batch": args.batch, "seq_len": 100, "items": 63002, "cates": 802,
+                "l2": "tables 4 MB are L2-resident by nature (din/din.py:88-90); distinct batch every step",
+                "parallelism": "1 GPU"}
     rows = 33762673 if args.table == "full" else 840646
-    return {"workload": "%s Criteo 39-field emb16 batch=%d fwd+bwd+Adam(lazy rows)" % (args.model, args.batch),
+    extra = ""
+    if args.model == "xdeepfm":
+        extra = " CIN=[128,128] (%s tcgen05)" % args.cin_precision
+    return {"workload": "%s Criteo 39-field emb16 batch=%d%s fwd+bwd+Adam(lazy rows)" % (args.model, args.batch, extra),
             "fields": 39, "embedding_size": 16, "batch": args.batch, "deep_layers": "100,100",
             "table_rows": rows, "table": args.table, "id_dist": args.dist,
             "l2": "table %.2f GB > 126 MB L2; a distinct id batch every step (no flush needed)"
@@ -201,7 +211,7 @@ def build_model(args, dev):
     params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
               "learning_rate": 1e-3, "dropout": 0.5, "deep_layers": "100,100",
               "cross_layers": "128,128" if args.model == "xdeepfm" else 4,
-              "cin_precision": "tf32", "variable_store": VariableStore(), "device": dev,
+              "cin_precision": args.cin_precision, "variable_store": VariableStore(), "device": dev,
               "embedding_adam": "lazy"}
     return mod, params
 
@@ -225,12 +235,17 @@ def run_ours(args):
     from recsys_b200.data import SyntheticCriteo
     from recsys_b200.estimator import GraphedTrainStep
     _lib.load()
-    mod, params = build_model(args, dev)
-    lay = fc.layout(params["embedding_feature_columns"])
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    host = SyntheticCriteo(lay, B, args.n_batches, dist=args.dist, seed=0, device=None)
-    devb = [(ops.PackedFeatures(f.cont.to(dev), f.cat.to(dev), f.cont_keys, f.cat_keys), l.to(dev))
-            for f, l in host.batches]
+    if args.model == "din":
+        mod, params, host_batches = build_din(args, dev)
+        devb = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in host_batches]
+    else:
+        mod, params = build_model(args, dev)
+        lay = fc.layout(params["embedding_feature_columns"])
+        host = SyntheticCriteo(lay, B, args.n_batches, dist=args.dist, seed=0, device=None)
+        host_batches = host.batches
+        devb = [(ops.PackedFeatures(f.cont.to(dev), f.cat.to(dev), f.cont_keys, f.cat_keys), l.to(dev))
+                for f, l in host_batches]
 
     # one eager step: creates the variables and counts our kernels per step
     n0 = ops.LAUNCHES["n"]
@@ -241,7 +256,7 @@ def run_ours(args):
     model = params["variable_store"]._objs[args.model]
     torch.cuda.synchronize()
     # ---- graph-captured whole step
-    f0, l0 = host.batches[0]
+    f0, l0 = host_batches[0]
     step = None
     graph_note = "eager (--eager)"
     if not args.eager:
@@ -263,7 +278,7 @@ def run_ours(args):
         return step(f, l)     # device->device copy of the batch into the static buffers + replay
 
     def e2e_step(i, slot):
-        f, l = host.batches[i % len(host.batches)]
+        f, l = host_batches[i % len(host_batches)]
         if step is None:
             sp = mod.model_fn(f, l, "train", params)
             sp.train_op()
@@ -303,12 +318,19 @@ def run_ours(args):
         wall = time.perf_counter() - t0
         ms_e2e = max(e0.elapsed_time(e1), wall * 1e3)
         # ---- (3) the two hot kernels alone, back to back on distinct id batches
-        kern = time_hot_kernels(model, devb, K, W, stream) if model is not None else None
+        kern = cin = din = None
+        if args.model == "din":
+            din = time_din_kernels(model, devb, K, W, stream)
+        else:
+            kern = time_hot_kernels(model, devb, K, W, stream)
+            if args.model == "xdeepfm":
+                cin = time_cin_kernels(model, B, K, W, stream, args.cin_precision)
     clocks = clk.summary()
     value = K * B / (ms / 1e3)
     e2e = K * B / (ms_e2e / 1e3)
-    f, l = host.batches[0]
-    h2d = f.cont.numel() * 4 + f.cat.numel() * 8 + l.numel() * 4
+    f, l = host_batches[0]
+    tens = [f.cont, f.cat] if hasattr(f, "cont") else list(f.values())
+    h2d = sum(t.numel() * t.element_size() for t in tens) + l.numel() * l.element_size()
     peak, peak_src = measured_peak()
     line = {
         "metric": "CTR samples/sec (Criteo 39-field emb16)", "value": value, "unit": "samples/s",
@@ -338,8 +360,13 @@ def run_ours(args):
             "adam_rows_us": kern["adam_us"],
             "large_batch": kern.get("large"),
         }
-    if not args.no_cpu_baseline:
-        om = args.model if args.model != "din" else "deepfm"
+    if cin is not None:
+        line["roofline_embed"] = line.pop("roofline")
+        line["roofline"] = cin
+    if din is not None:
+        line["roofline"] = din
+    if not args.no_cpu_baseline and args.model != "din":
+        om = args.model
         n, el, cores = time_oracle(om, B, args.table, args.dist, max_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {
             "value": n * B / el, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -387,7 +414,8 @@ def time_hot_kernels(model, devb, K, W, stream):
         def adam(i):
             emb._tag += 1
             lib.ctr_adam_rows(p(rows[i % len(rows)]), B * F, D, p(emb.table), p(emb._m), p(emb._v),
-                              p(emb.dtable), p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, st)
+                              p(emb.dtable), p(emb.w1), p(emb._m1), p(emb._v1), p(emb.dw1),
+                              p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, st)
 
         def timeit(fn):
             for i in range(W):
@@ -440,8 +468,142 @@ def time_hot_kernels(model, devb, K, W, stream):
     return res
 
 
+def build_din(args, dev):
+    import numpy as np
+    import torch
+    from recsys_b200.din import din as mod
+    from recsys_b200.estimator import VariableStore
+    params = {"embedding_size": 16, "learning_rate": 1e-3, "dropout": 0.0,
+              "variable_store": VariableStore(), "device": dev}
+    rng = np.random.default_rng(0)
+    B, P = args.batch, 100
+    batches = []
+    for _ in range(args.n_batches):
+        lens = rng.integers(1, P + 1, size=B)
+        mask = np.arange(P)[None, :] < lens[:, None]
+        f = {"i_id": np.minimum(rng.zipf(1.2, size=B), 63001),
+             "i_cate": np.minimum(rng.zipf(1.2, size=B), 801),
+             "u_iid_seq": np.minimum(rng.zipf(1.2, size=(B, P)), 63001) * mask,
+             "u_icat_seq": np.minimum(rng.zipf(1.2, size=(B, P)), 801) * mask}
+        f = {k: torch.from_numpy(v.astype(np.int64)).pin_memory() for k, v in f.items()}
+        lab = torch.from_numpy((rng.random(B) < 0.3).astype(np.float32)).pin_memory()
+        batches.append((f, lab))
+    return mod, params, batches
+
+
+def time_cin_kernels(model, B, K, W, stream, prec):
+    """The CIN stack alone (ctr_cin_layer_fwd x2, then the backward), CUDA events."""
+    import torch
+    from recsys_b200 import ops
+    F, D = model.F, model.D
+    dev = model.device
+    P = model.dense
+    layers = model.cin_layers
+    with torch.cuda.stream(stream):
+        E = (torch.randn(B, F * D, device=dev) * 0.25).requires_grad_(True)
+        Ws = [P["cin.%d.w" % k] for k in range(len(layers))]
+        bs = [P["cin.%d.b" % k] for k in range(len(layers))]
+        dp = torch.randn(B, sum(layers), device=dev)
+
+        def fwd():
+            with torch.no_grad():
+                return ops.cin(E, F, D, Ws, bs, prec)
+
+        def fwdbwd():
+            out = ops.cin(E, F, D, Ws, bs, prec)
+            out.backward(dp)
+
+        def timeit(fn, n):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / n
+        n = max(5, min(K, 30))
+        t_f = timeit(fwd, n)
+        t_fb = timeit(fwdbwd, n)
+        P.grad.zero_()
+    hp, flops = F, 0
+    for h in layers:
+        flops += 2 * D * F * hp * h
+        hp = h
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    passes = 3 if prec == "tf32x3" else 1
+    ach = flops * B / (t_f * 1e-6) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": ach / (bf16 / 2),
+            "traffic": None,
+            "peak_source": "tf32 dense = half of the measured cuBLAS bf16 burst (%.0f TF/s, %s)"
+                           % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback"),
+            "kernel": "cin_tc_kernel<MODE_SCALE,32> x%d layers (forward, %s: %d MMA pass%s per k-block)"
+                      % (len(layers), prec, passes, "es" if passes > 1 else ""),
+            "algorithmic_flops_per_sample_fwd": flops, "fwd_us": t_f, "fwd_bwd_us": t_fb,
+            "fwd_bwd_TFLOPs_algorithmic": 3 * flops * B / (t_fb * 1e-6) / 1e12,
+            "note": "fwd includes the operand prep (tf32 rounding copies, W relayout) and the "
+                    "transpose of E; bwd runs dXp/dX0 on tcgen05 and dW on fp32 CUDA cores"}
+
+
+def time_din_kernels(model, devb, K, W, stream):
+    """ctr_din_att_fwd / _bwd alone on the first batch's item history (CUDA events)."""
+    import torch
+    from recsys_b200 import ops
+    dev = model.device
+    P = model.dense
+    f, _ = devb[0]
+    with torch.cuda.stream(stream):
+        hist = f["u_iid_seq"].to(torch.int32)
+        B, Pn = hist.shape
+        q = model.emb.table[f["i_id"].long()].clone().requires_grad_(True)
+        args_ = [P["att_iid.%d.%s" % (l, t)] for l in range(3) for t in ("w", "b")]
+        dout = torch.randn(B, model.E, device=dev)
+
+        def fwd():
+            with torch.no_grad():
+                return ops.din_attention(model.emb, 0, hist, q, *args_)
+
+        def fwdbwd():
+            ops.din_attention(model.emb, 0, hist, q, *args_).backward(dout)
+
+        def timeit(fn, n):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / n
+        n = max(5, min(K, 50))
+        t_f, t_fb = timeit(fwd, n), timeit(fwdbwd, n)
+        valid = int((hist > 0).sum())
+        model.emb.dtable.zero_()
+        P.grad.zero_()
+    E = model.E
+    ref_flops = 2 * (4 * E * 80 + 80 * 40 + 40)          # per position, as the reference computes it
+    our_flops = 2 * (E * 80 + 80 * 40 + 40)              # after folding layer 1 per sample
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    ach = our_flops * valid / (t_f * 1e-6) / 1e12
+    return {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": None, "peak_source": "computed: 148 SM x 128 lanes x 2 x 1.965 GHz",
+            "kernel": "din_att_fwd_kernel<16> (one history sequence)", "fwd_us": t_f,
+            "fwd_bwd_us": t_fb, "valid_positions": valid, "positions": B * Pn,
+            "flops_per_position_executed": our_flops, "flops_per_position_reference": ref_flops,
+            "reference_equivalent_TFLOPs": ref_flops * B * Pn / (t_f * 1e-6) / 1e12}
+
+
 def main():
     args = parse()
+    if args.batch is None:
+        args.batch = 8192 if args.model == "xdeepfm" else 4096
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -121,10 +121,13 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
                    float beta2, float eps, int zero_g, const float* state_dev,
                    ctr_stream_t stream);
 /* Lazy variant: exactly one update per distinct row in rows[n] (claim[R] int32
- * scratch, tag must differ from the previous call's), then zeroes the row of g. */
+ * scratch, tag must differ from the previous call's), then zeroes the row of g.  Negative
+ * row ids are skipped.  theta1/m1/v1/g1 (nullable): a per-row scalar parameter indexed by the
+ * same rows (the first-order weights w1) updated under the same claim. */
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
-                  float* g, int32_t* claim, int32_t tag, float lr_t, float beta1, float beta2,
-                  float eps, const float* state_dev, ctr_stream_t stream);
+                  float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
+                  int32_t tag, float lr_t, float beta1, float beta2, float eps,
+                  const float* state_dev, ctr_stream_t stream);
 
 /* -------------------------------------------------------- DIN activation unit
  * din/din.py:103-125 `_attention`: for each sample b and position p with hist[b,p] > 0

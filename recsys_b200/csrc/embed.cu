@@ -593,8 +593,9 @@ template <int D>
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ th,
                  float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
-                 int* __restrict__ claim, int tag, float lr_t, float b1, float b2, float eps,
-                 const float* __restrict__ state) {
+                 float* __restrict__ th1, float* __restrict__ m1, float* __restrict__ v1,
+                 float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
+                 float b2, float eps, const float* __restrict__ state) {
   if (state != nullptr) {
     tag = static_cast<int>(state[0]);
     lr_t = state[1];
@@ -626,6 +627,15 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
       *reinterpret_cast<float4*>(v + o) = V;
       *reinterpret_cast<float4*>(th + o) = T;
       *reinterpret_cast<float4*>(g + o) = f4_zero();
+      if (th1 != nullptr && q == 0) {   // the row's first-order weight rides on the same claim
+        const float G1 = g1[rid];
+        const float M1 = b1 * m1[rid] + (1.f - b1) * G1;
+        const float V1 = b2 * v1[rid] + (1.f - b2) * G1 * G1;
+        m1[rid] = M1;
+        v1[rid] = V1;
+        th1[rid] -= lr_t * M1 / (sqrtf(V1) + eps);
+        g1[rid] = 0.f;
+      }
     } else {
       const float G = g[rid];
       const float M = b1 * m[rid] + (1.f - b1) * G;
@@ -799,10 +809,13 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
 }
 
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
-                  float* g, int32_t* claim, int32_t tag, float lr_t, float beta1, float beta2,
-                  float eps, const float* state_dev, ctr_stream_t stream) {
+                  float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
+                  int32_t tag, float lr_t, float beta1, float beta2, float eps,
+                  const float* state_dev, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(rows && theta && m && v && g && claim && n >= 0, "ctr_adam_rows", "null pointer");
+  CTR_REQUIRE(theta1 == nullptr || (m1 && v1 && g1 && D >= 4), "ctr_adam_rows",
+              "first-order vector needs m1/v1/g1 and a D >= 4 table");
   CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_rows",
               "pointers must be 16-byte aligned");
   if (n == 0) return CTR_OK;
@@ -811,10 +824,10 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
   const long long gpb = 256 / lpr;
   const int grid = static_cast<int>(std::min<long long>((n + gpb - 1) / gpb, sm_count() * 8LL));
   switch (D) {
-    case 1: adam_rows_kernel<1><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
-    case 8: adam_rows_kernel<8><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
-    case 16: adam_rows_kernel<16><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
-    case 32: adam_rows_kernel<32><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 1: adam_rows_kernel<1><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 8: adam_rows_kernel<8><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 16: adam_rows_kernel<16><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 32: adam_rows_kernel<32><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
     default: return fail_arg("ctr_adam_rows", "D must be 1, 8, 16 or 32");
   }
   CTR_LAUNCH_CHECK("ctr_adam_rows");

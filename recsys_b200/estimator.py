@@ -187,8 +187,6 @@ class GraphedTrainStep:
 
     def __init__(self, model_fn, params, example_features, example_labels, warmup: int = 3):
         from .ops import PackedFeatures
-        if not isinstance(example_features, PackedFeatures):
-            raise TypeError("GraphedTrainStep needs PackedFeatures batches (see data.SyntheticCriteo)")
         dev = params.get("device") or torch.device("cuda", torch.cuda.current_device())
         self.model_fn, self.params = model_fn, params
         cur = torch.cuda.current_stream(dev)
@@ -196,10 +194,15 @@ class GraphedTrainStep:
         # node on one stream); the legacy default stream cannot be captured
         self.stream = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(device=dev)
         f = example_features
-        self.cont = torch.empty_like(f.cont, device=dev)
-        self.cat = torch.empty_like(f.cat, device=dev)
+        if isinstance(f, PackedFeatures):
+            self._static = {"cont": torch.empty_like(f.cont, device=dev),
+                            "cat": torch.empty_like(f.cat, device=dev)}
+            self.features = PackedFeatures(self._static["cont"], self._static["cat"], f.cont_keys,
+                                           f.cat_keys)
+        else:       # plain dict of tensors (e.g. the DIN features)
+            self._static = {k: torch.empty_like(torch.as_tensor(v), device=dev) for k, v in f.items()}
+            self.features = dict(self._static)
         self.labels = torch.empty_like(example_labels, device=dev)
-        self.features = PackedFeatures(self.cont, self.cat, f.cont_keys, f.cat_keys)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self._load(example_features, example_labels)
         with torch.cuda.stream(self.stream):
@@ -219,9 +222,14 @@ class GraphedTrainStep:
         self.loss.copy_(spec.loss)
 
     def _load(self, features, labels):
+        from .ops import PackedFeatures
         with torch.cuda.stream(self.stream):
-            self.cont.copy_(features.cont, non_blocking=True)
-            self.cat.copy_(features.cat, non_blocking=True)
+            if isinstance(features, PackedFeatures):
+                self._static["cont"].copy_(features.cont, non_blocking=True)
+                self._static["cat"].copy_(features.cat, non_blocking=True)
+            else:
+                for k, dst in self._static.items():
+                    dst.copy_(torch.as_tensor(features[k]), non_blocking=True)
             self.labels.copy_(labels, non_blocking=True)
 
     def __call__(self, features, labels):

@@ -289,7 +289,6 @@ class FieldEmbedding:
             if self.with_w1:
                 self._m1 = torch.zeros_like(self.w1)
                 self._v1 = torch.zeros_like(self.w1)
-                self._claim1 = torch.zeros(self.R, dtype=torch.int32, device=self.device)
 
     # -- forward / backward -----------------------------------------------------
     def lookup(self, rows: torch.Tensor, want_fm: bool = True, want_y1: bool = True,
@@ -318,13 +317,11 @@ class FieldEmbedding:
             return
         self._tag += 1
         n = rows.numel()
+        w = self.with_w1
         _call("ctr_adam_rows", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
-              _p(self.dtable), _p(self._claim), self._tag, lr_t, st.beta1, st.beta2, st.eps,
-              st.state_ptr, _stream())
-        if self.with_w1:
-            _call("ctr_adam_rows", _p(rows), n, 1, _p(self.w1), _p(self._m1), _p(self._v1),
-                  _p(self.dw1), _p(self._claim1), self._tag, lr_t, st.beta1, st.beta2, st.eps,
-                  st.state_ptr, _stream())
+              _p(self.dtable), _p(self.w1) if w else None, _p(self._m1) if w else None,
+              _p(self._v1) if w else None, _p(self.dw1) if w else None, _p(self._claim), self._tag,
+              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, _stream())
 
 
 class _EmbedFn(torch.autograd.Function):

@@ -165,7 +165,6 @@ class ShardedFieldEmbedding:
             self._claim = torch.zeros(self.R_local, dtype=torch.int32, device=self.device)
             if self.with_w1:
                 self._m1, self._v1 = torch.zeros_like(self.w1), torch.zeros_like(self.w1)
-                self._claim1 = torch.zeros(self.R_local, dtype=torch.int32, device=self.device)
         if self.adam_mode == "exact_tf":
             _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
                   self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
@@ -175,13 +174,11 @@ class ShardedFieldEmbedding:
             return
         self._tag += 1
         ids = self.recv_ids
+        w = self.with_w1
         _call("ctr_adam_rows", _p(ids), ids.numel(), self.D, _p(self.table), _p(self._m),
-              _p(self._v), _p(self.dtable), _p(self._claim), self._tag, lr_t, st.beta1, st.beta2,
-              st.eps, st.state_ptr, _stream())
-        if self.with_w1:
-            _call("ctr_adam_rows", _p(ids), ids.numel(), 1, _p(self.w1), _p(self._m1), _p(self._v1),
-                  _p(self.dw1), _p(self._claim1), self._tag, lr_t, st.beta1, st.beta2, st.eps,
-                  st.state_ptr, _stream())
+              _p(self._v), _p(self.dtable), _p(self.w1) if w else None, _p(self._m1) if w else None,
+              _p(self._v1) if w else None, _p(self.dw1) if w else None, _p(self._claim), self._tag,
+              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, _stream())
 
 
 class _ShardedEmbedFn(torch.autograd.Function):
@@ -256,6 +253,7 @@ def bench_main(args, rank, local, world):
     """DeepFM, 39 fields, emb 16, 1e9-row table row-sharded over ``world`` GPUs, local batch
     ``args.batch`` per GPU (weak scaling).  Rank 0 prints the JSON line."""
     import json
+    import sys
     import time
 
     import numpy as np
@@ -284,15 +282,33 @@ def bench_main(args, rank, local, world):
         lab = torch.from_numpy((rng.random((B, 1)) < 0.22).astype(np.float32)).pin_memory()
         host.append((PackedFeatures(cont, cat, [], keys), lab))
         devb.append((PackedFeatures(cont.to(dev), cat.to(dev), [], keys), lab.to(dev)))
+    from .estimator import GraphedTrainStep
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))     # one side stream for everything
     n0 = ops.LAUNCHES["n"]
     sp = deepfm.model_fn(devb[0][0], devb[0][1], "train", params)
     sp.train_op()
     per_step_launches = ops.LAUNCHES["n"] - n0
     del sp
     model = params["variable_store"]._objs["deepfm"]
+    torch.cuda.synchronize()
+    dist.barrier()
+    graphed, mode = None, "eager"
+    if not args.eager:
+        try:     # NCCL collectives are captured with the kernels; every rank captures the same graph
+            graphed = GraphedTrainStep(deepfm.model_fn, params, host[0][0], host[0][1], warmup=3)
+            mode = "whole step incl. NCCL all-to-all captured in one CUDA graph per rank"
+        except Exception as e:
+            sys.stderr.write("rank %d: graph capture failed, eager: %r\n" % (rank, e))
+            mode = "eager (graph capture failed: %s)" % str(e)[:100]
+    ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok) == 0:
+        graphed = None
 
     def step(batch):
         f, l = batch
+        if graphed is not None:
+            return graphed(f, l)
         s = deepfm.model_fn(f, l, "train", params)
         s.train_op()
         return s.loss
@@ -303,15 +319,16 @@ def bench_main(args, rank, local, world):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        stream = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        slot = torch.zeros(1, dtype=torch.float32).pin_memory()
+        slot = torch.zeros(K, dtype=torch.float32).pin_memory()
         t0 = time.perf_counter()
-        e0.record()
+        e0.record(stream)
         for i in range(K):
             loss = step(batches[(W + i) % len(batches)])
             if read_loss:
-                slot.copy_(loss.reshape(1), non_blocking=True)
-        e1.record()
+                slot[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        e1.record(stream)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         dist.barrier()
@@ -344,7 +361,7 @@ def bench_main(args, rank, local, world):
                     "api": "deepfm.model_fn(pinned PackedFeatures, labels, 'train', params).train_op()"},
             "gpu_launches": per_step_launches * K * world, "gpu_launches_per_step": per_step_launches,
             "nvlink_bytes_per_gpu_per_step": int((G - 1) / G * B * 39 * (4 + 64 + 64 + 8)),
-            "launch_mode": "eager (NCCL collectives between kernels)",
+            "launch_mode": mode,
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
