@@ -397,7 +397,7 @@ def time_hot_kernels(model, devb, K, W, stream):
         lib = _lib.load()
         Eb = torch.empty_like(E)
         Sb = torch.empty_like(S)
-        y1 = torch.empty(B, device=emb.device)
+        y1 = torch.empty(B, device=emb.device) if emb.w1 is not None else None
         y2 = torch.empty(B, device=emb.device)
 
         def fwd(i):
@@ -414,7 +414,8 @@ def time_hot_kernels(model, devb, K, W, stream):
         def adam(i):
             emb._tag += 1
             lib.ctr_adam_rows(p(rows[i % len(rows)]), B * F, D, p(emb.table), p(emb._m), p(emb._v),
-                              p(emb.dtable), p(emb.w1), p(emb._m1), p(emb._v1), p(emb.dw1),
+                              p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
+                              p(getattr(emb, "_v1", None)), p(emb.dw1),
                               p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, st)
 
         def timeit(fn):
@@ -434,7 +435,8 @@ def time_hot_kernels(model, devb, K, W, stream):
         res["fwd_moved"] = 156 + 2496 + 156 + 2496 + 64 + 8          # ids, rows, w1, E, S, y1/y2
         res["bwd_moved"] = 156 + 2496 + 2496 + 64 + 8 + 2 * 2496 + 2 * 156
         emb.dtable.zero_()
-        emb.dw1.zero_()
+        if emb.dw1 is not None:
+            emb.dw1.zero_()
         # the same two kernels at a batch that fills the machine (asymptotic bandwidth)
         try:
             BL = 65536
@@ -451,7 +453,8 @@ def time_hot_kernels(model, devb, K, W, stream):
 
             def fwdL(i):
                 lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rl[i % 4]), BL, F, D, emb.w1_fields,
-                                  p(EL), p(SL), p(yl), p(yl), None, None, 0, None, st)
+                                  p(EL), p(SL), p(yl) if emb.w1 is not None else None, p(yl), None,
+                                  None, 0, None, st)
 
             def bwdL(i):
                 lib.ctr_embed_bwd(p(rl[i % 4]), p(dEL), p(EL), p(emb.table), p(SL), p(yl), p(yl),
@@ -462,7 +465,8 @@ def time_hot_kernels(model, devb, K, W, stream):
                             "alg_GBps": ALG_BYTES * BL / (tf_ + tb_) / 1e3,
                             "moved_GBps": (res["fwd_moved"] + res["bwd_moved"]) * BL / (tf_ + tb_) / 1e3}
             emb.dtable.zero_()
-            emb.dw1.zero_()
+            if emb.dw1 is not None:
+                emb.dw1.zero_()
         except Exception as e:  # pragma: no cover
             res["large"] = {"error": str(e)[:200]}
     return res

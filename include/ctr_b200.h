@@ -175,6 +175,78 @@ int ctr_transpose_fd(const float* E, int B, int F, int D, float* Xt, int ld, ctr
 int ctr_transpose_df_add(const float* dXt, int ld, int B, int F, int D, float* dE,
                          ctr_stream_t stream);
 
+/* ------------------------------------------------------------- dense tower + loss head
+ * The reference's tower is `dense(relu) -> batch_normalization -> dropout` per layer plus a
+ * final dense(1, relu) (deepfm/deepfm.py:100-108, xdeepfm/xdeepfm.py:184-192,
+ * dcn/dcn.py:144-149), then dense(concat[...], 1), sigmoid and the mean
+ * sigmoid-cross-entropy (deepfm/deepfm.py:110-129).  fp32 CUDA-core kernels; BN and dropout are
+ * never materialised: they are a prologue of the consuming GEMM, recomputed in the backward
+ * (dropout masks are counter based: Philox4x32-10 over (seed, layer, step, row, col)).
+ *
+ * ctr_bn_drop: how to turn a stored post-ReLU activation A[r,k] into the next layer's input:
+ *   x' = ((A - mu) * rstd * gamma + beta) * keep/(1-p).  Train: mu / biased var from the column
+ *   sums `sums` = [2][K] (sum A, sum A^2) over the B rows; eval: moving `mean` / `var`. */
+typedef struct {
+  const float* sums;   /* train: device [2][K]; NULL in eval                         */
+  const float* mean;   /* eval: device [K] moving mean / variance (sums == NULL)     */
+  const float* var;
+  const float* gamma;  /* device [K]                                                 */
+  const float* beta;
+  const float* state;  /* device {t, lr_t} (ctr_adam_tick): t selects the dropout stream; NULL -> 0 */
+  float eps;           /* 1e-3 (tf.layers.batch_normalization default)               */
+  float p_drop;        /* dropout rate, 0 disables                                   */
+  uint32_t seed;
+  uint32_t layer;
+  int32_t enabled;     /* 0: identity prologue                                       */
+  int32_t pad_;
+} ctr_bn_drop;
+/* ctr_grad_src: gradient arriving at a layer's stored post-ReLU output a[r,n]:
+ *   kind 0: g = G[r*ldg+n];  kind 1: g = BN-backward of the stored dn = G through the BN that
+ *   follows a (needs the column sums dbeta = sum dn, dgamma = sum dn*xhat in train mode).
+ *   The kernels then use dpre = g * 1[a > 0]. */
+typedef struct {
+  const float* G;
+  const float* a;
+  const float* sums;
+  const float* mean;
+  const float* var;
+  const float* gamma;
+  const float* dbeta;
+  const float* dgamma;
+  int32_t ldg;
+  int32_t lda;
+  float eps;
+  int32_t kind;
+  int32_t train;
+  int32_t pad_;
+} ctr_grad_src;
+/* out[B,N] = act(P(X)[B,K] . W[K,N] + bias); stats (nullable) [2][N] += column sums of out, out^2. */
+int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, const float* W,
+                        const float* bias, int N, float* out, int ldo, float* stats, int relu,
+                        int B, ctr_stream_t stream);
+/* out[B,K] = P(A): the last BN+dropout of a tower that does not end in a dense layer (DCN). */
+int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out, int B,
+                      ctr_stream_t stream);
+/* dn_out[B,K] = (dpre[B,N] . W[K,N]^T) * keep  (keep from `pro`, the prologue that produced this
+ * layer's input from Aprev); dbeta_prev/dgamma_prev [K] += column sums of dn, dn*xhat(Aprev).
+ * pro disabled (first layer): dn_out = dpre . W^T, nothing else. */
+int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int K,
+                             const ctr_bn_drop* pro, const float* Aprev, float* dn_out, int ldn,
+                             float* dbeta_prev, float* dgamma_prev, int B, ctr_stream_t stream);
+/* dW[K,N] += P(X)^T . dpre;  db[N] (nullable) += column sums of dpre. */
+int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_drop* pro,
+                                const ctr_grad_src* gs, int N, float* dW, float* db, int B,
+                                ctr_stream_t stream);
+/* Loss head (deepfm/deepfm.py:110-129): logit = sum_{c<C} hw[c]*act_c(z_c) + hb with
+ * act_0 = relu(. + b1) when relu0 (the ReLU'd first-order term), identity otherwise; C <= 4.
+ * logits/prob (nullable) written; *loss += mean BCE.  With dz != NULL the gradients are produced in
+ * the same launch: dz[c][b] written, dhw[C], dhb, db1 accumulated, all times grad_scale*B
+ * (grad_scale = 1/(B*world)).  z / dz are HOST arrays of C device pointers. */
+int ctr_loss_head(const float* const* z, float* const* dz, int C, int relu0, const float* hw,
+                  const float* hb, const float* b1, const float* labels, int B, float* logits,
+                  float* prob, float* loss, float* dhw, float* dhb, float* db1, float grad_scale,
+                  ctr_stream_t stream);
+
 /* ------------------------------------------------------- row-sharded table (multi-GPU)
  * The reference only replicates (tf.distribute.MirroredStrategy, fm/fm.py:184-194); row
  * sharding is the north-star extension for tables larger than one GPU's HBM.  owner(row) =

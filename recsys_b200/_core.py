@@ -126,17 +126,23 @@ class _ModelBase:
     def _apply_gradients(self):
         raise NotImplementedError
 
+    def forward(self, features, labels, training):
+        """-> (logits, prob, loss or None).  Default: ``logits()`` + torch sigmoid / BCE; the
+        Criteo models with a fused loss head override it."""
+        logits = self.logits(features, training)
+        pred = torch.sigmoid(logits)
+        loss = bce_with_logits_mean(logits, labels) if labels is not None else None
+        return logits, pred, loss
+
     def spec(self, features, labels, mode) -> EstimatorSpec:
         training = mode == ModeKeys.TRAIN
         with torch.set_grad_enabled(training):
-            logits = self.logits(features, training)
-            pred = torch.sigmoid(logits)
+            logits, pred, loss = self.forward(features, None if mode == ModeKeys.PREDICT else labels,
+                                              training)
         predictions = {"prob": pred}
         export_outputs = {DEFAULT_SERVING_SIGNATURE_DEF_KEY: PredictOutput(predictions)}
         if mode == ModeKeys.PREDICT:
             return EstimatorSpec(mode=mode, predictions=predictions, export_outputs=export_outputs)
-        with torch.set_grad_enabled(training):
-            loss = bce_with_logits_mean(logits, labels)
         if mode == ModeKeys.EVAL:
             ops_ = {"AUC": StreamingAUC().update(labels, pred),
                     "Accuracy": StreamingAccuracy().update(labels, pred)}
@@ -195,14 +201,28 @@ class _CriteoBase(_ModelBase):
                                           adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
         self.ids = ops.IdPipeline(self.lay, self.device)
         self.rows = None
+        # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower
+        self.fused = bool(params.get("fused_tower", True))
+        self._head_anchor = torch.zeros((), device=self.device, requires_grad=True)
 
     def load_state(self, state):
         super().load_state(state)
         self.emb.load(state.get("emb"), state.get("w1"))
 
+    def _fused_head(self, zs, labels, training, shape):
+        """ctr_loss_head over the columns ``zs`` (column 0 = pre-bias first-order sum)."""
+        B = zs[0].shape[0]
+        if labels is None:
+            labels = torch.zeros(B, dtype=torch.float32, device=self.device)
+        loss, logits, prob = ops.loss_head(self._head_anchor, self.dense, zs, labels, relu0=True,
+                                           grad_scale=1.0 / (B * self.world), training=training)
+        return logits.view(shape), prob.view(shape), loss
+
     def backward(self, loss):
-        # data parallel: the global loss is the mean over all replicas' batches
-        super().backward(loss / self.world if self.world > 1 else loss)
+        # data parallel: the global loss is the mean over all replicas' batches (the fused loss
+        # head already folds 1/world into the gradients it emits)
+        fused_head = self.fused and hasattr(self, "_uses_fused_head")
+        super().backward(loss / self.world if (self.world > 1 and not fused_head) else loss)
 
     def _sync_dense_grads(self):
         if self.world > 1:
@@ -225,6 +245,8 @@ class FMModel(_CriteoBase):
         self.dense = ops.DenseParams({"b1": (1,), "head.w": (2, 1), "head.b": (1,)}, self.device)
         self._init_dense(int(params.get("seed", 0)) + 1)
 
+    _uses_fused_head = True
+
     def logits(self, features, training):
         P = self.dense
         self.rows = self.ids(features)
@@ -232,6 +254,13 @@ class FMModel(_CriteoBase):
         y1 = torch.relu(y1s + P["b1"])                                   # fm/fm.py:121
         z = torch.stack([y1, y2], 1)                                      # :131
         return torch.addmm(P["head.b"], z, P["head.w"])                   # :132  [B,1]
+
+    def forward(self, features, labels, training):
+        if not self.fused:
+            return super().forward(features, labels, training)
+        self.rows = self.ids(features)
+        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
+        return self._fused_head([y1s, y2], labels, training, (-1, 1))     # fm/fm.py:121-149
 
 
 # ======================================================================== DeepFM
@@ -249,6 +278,18 @@ class DeepFMModel(_CriteoBase):
         frozen = [n for n in shapes if n.endswith((".bn.mean", ".bn.var"))]
         self.dense = ops.DenseParams(shapes, self.device, frozen=frozen)
         self._init_dense(int(params.get("seed", 0)) + 1)
+        self.tower = ops.FusedTower(self.dense, "dnn", [self.F * self.D] + self.layers, True,
+                                    self.dropout, self.adam, seed=int(params.get("seed", 0)))
+
+    _uses_fused_head = True
+
+    def forward(self, features, labels, training):
+        if not self.fused:
+            return super().forward(features, labels, training)
+        self.rows = self.ids(features)
+        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
+        y3 = self.tower(E, training)                                      # deepfm.py:100-108
+        return self._fused_head([y1s, y2, y3], labels, training, (-1,))   # :91,110-129
 
     def logits(self, features, training):
         P = self.dense
@@ -342,6 +383,30 @@ class XDeepFMModel(_CriteoBase):
         with torch.no_grad():
             g = torch.Generator().manual_seed(seed + 2)
             self.dense["wnum"].copy_(_glorot_uniform((len(self.ids.cont_keys), 1), g).reshape(-1))
+        self.tower = ops.FusedTower(self.dense, "dnn", [self.F * self.D] + self.layers, True,
+                                    self.dropout, self.adam, seed=seed)
+
+    _uses_fused_head = True
+
+    def forward(self, features, labels, training):
+        if not self.fused:
+            return super().forward(features, labels, training)
+        P = self.dense
+        want_num = len(self.numeric_linear) > 0
+        if want_num:
+            self.rows, logx = self.ids(features, want_logx=True)
+        else:
+            self.rows, logx = self.ids(features), None
+        E, y1s, _, _ = self.emb.lookup(self.rows, want_fm=False, want_y1=True)
+        lin = y1s + logx @ P["wnum"] if want_num else y1s                        # :82
+        Ws = [P[f"cin.{k}.w"] for k in range(len(self.cin_layers))]
+        bs = [P[f"cin.{k}.b"] for k in range(len(self.cin_layers))]
+        pooled = ops.cin(E, self.F, self.D, Ws, bs, self.cin_precision)          # :135-181
+        cin_y = torch.relu(torch.addmm(P["cin.out.b"], pooled, P["cin.out.w"])).view(-1)  # :182
+        Ed = self.emb_dnn.lookup(self.rows, want_fm=False, want_y1=False)[0] \
+            if self.emb_dnn is not None else E                                    # :185
+        dnn_y = self.tower(Ed, training)                                          # :188-192
+        return self._fused_head([lin, cin_y, dnn_y], labels, training, (-1, 1))   # :131,194-212
 
     def load_state(self, state):
         super().load_state(state)

@@ -22,6 +22,22 @@ c_u64 = C.c_uint64
 c_fl = C.c_float
 
 
+class BnDrop(C.Structure):
+    """ctr_bn_drop (include/ctr_b200.h)."""
+    _fields_ = [("sums", C.c_void_p), ("mean", C.c_void_p), ("var", C.c_void_p),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("state", C.c_void_p),
+                ("eps", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint32),
+                ("layer", C.c_uint32), ("enabled", C.c_int32), ("pad_", C.c_int32)]
+
+
+class GradSrc(C.Structure):
+    """ctr_grad_src (include/ctr_b200.h)."""
+    _fields_ = [("G", C.c_void_p), ("a", C.c_void_p), ("sums", C.c_void_p), ("mean", C.c_void_p),
+                ("var", C.c_void_p), ("gamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("dgamma", C.c_void_p), ("ldg", C.c_int32), ("lda", C.c_int32), ("eps", C.c_float),
+                ("kind", C.c_int32), ("train", C.c_int32), ("pad_", C.c_int32)]
+
+
 class FieldDesc(C.Structure):
     """ctr_field_desc (include/ctr_b200.h)."""
     _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("n_rows", C.c_int32),
@@ -56,6 +72,15 @@ SIGNATURES = {
                                 c_f, c_i64, c_f]),
     "ctr_cin_layer_bwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f,
                                 c_f, c_f, c_i, c_f, c_i64, c_f]),
+    "ctr_tower_layer_fwd": (c_i, [c_f, c_i, c_i, C.POINTER(BnDrop), c_f, c_f, c_i, c_f, c_i, c_f, c_i,
+                                  c_i, c_f]),
+    "ctr_bn_drop_apply": (c_i, [c_f, c_i, C.POINTER(BnDrop), c_f, c_i, c_f]),
+    "ctr_tower_layer_bwd_data": (c_i, [C.POINTER(GradSrc), c_i, c_f, c_i, C.POINTER(BnDrop), c_f,
+                                       c_f, c_i, c_f, c_f, c_i, c_f]),
+    "ctr_tower_layer_bwd_weights": (c_i, [c_f, c_i, c_i, C.POINTER(BnDrop), C.POINTER(GradSrc), c_i,
+                                          c_f, c_f, c_i, c_f]),
+    "ctr_loss_head": (c_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i, c_i, c_f, c_f, c_f,
+                            c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_fl, c_f]),
     "ctr_shard_bucket": (c_i, [c_f, c_i64, c_i, c_i, c_f, c_f, c_f, c_f]),
     "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),
     "ctr_scatter_add_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),

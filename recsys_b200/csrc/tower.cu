@@ -1,0 +1,611 @@
+// Fused dense tower + loss head of the CTR models, fp32 CUDA cores.
+//
+// The reference's tower is `dense(relu) -> batch_normalization -> dropout` per layer and a
+// final `dense(1, relu)` (deepfm/deepfm.py:100-108, xdeepfm/xdeepfm.py:184-192,
+// dcn/dcn.py:144-149), followed by `dense(concat[...], 1)`, sigmoid and the mean
+// sigmoid-cross-entropy (deepfm/deepfm.py:110-129).  TF (and torch) run it as ~80 tiny
+// kernels per step at batch 4096; here it is 3 + 1 launches forward and 6 backward:
+//
+//   tower_layer_fwd   out = relu( P(X) . W + b ),  column sums of out / out^2 for the next BN,
+//                     P = identity | BN(batch stats or moving stats) + dropout of the previous
+//                     activation, recomputed on the fly (the normalised/dropped tensors are
+//                     never written)
+//   loss_head         logit = sum_c hw[c] * act_c(z_c) + hb, prob, mean BCE, and - because it is
+//                     the end of the graph - d(loss)/dz_c, d hw, d hb, d b1 in the same launch
+//   tower_layer_bwd_data     dX' = dpre . W^T -> dropout/BN bookkeeping for the layer below
+//   tower_layer_bwd_weights  dW += P(X)^T . dpre,  db += colsum(dpre)   (split over rows, RED)
+//
+// Dropout masks are counter based (Philox4x32-10 keyed by seed, layer and the device-side step
+// counter), regenerated in the backward instead of stored.
+#include "common.cuh"
+
+namespace ctr {
+
+// ------------------------------------------------------------------------ dropout RNG
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// keep-scale (0 or 1/(1-p)) of element (row, col): one Philox block covers 4 consecutive columns.
+__device__ __forceinline__ float drop_scale(unsigned seed, unsigned layer, unsigned step, int row,
+                                            int col, float p, float inv_keep) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<unsigned>(row), static_cast<unsigned>(col >> 2),
+                                           layer, step),
+                                make_uint2(seed, 0x5EEDu));
+  const unsigned w = (col & 3) == 0 ? r.x : (col & 3) == 1 ? r.y : (col & 3) == 2 ? r.z : r.w;
+  const float u = (w >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+
+// ------------------------------------------------------------------- prologue descriptors
+// Normalise + drop a stored post-ReLU activation A[r,k] (k < K <= kMaxBn):
+//   xhat = (A - mu) * rstd;  x' = (xhat * gamma + beta) * keep
+struct BnDrop {
+  const float* sums;    // train: [2][K] column sums of A and A^2 over the batch; else nullptr
+  const float* mean;    // eval: moving mean / variance (sums == nullptr)
+  const float* var;
+  const float* gamma;
+  const float* beta;
+  const float* state;   // device step counter {t, lr_t} (dropout stream), nullable
+  float inv_B, eps, p, inv_keep;
+  unsigned seed, layer;
+  int enabled;          // 0: identity
+};
+// Gradient source for a layer's post-ReLU output a[r,n]:
+//   kind 0: g = G[r*ldg + n]                                     (given directly)
+//   kind 1: g = BN-backward of the stored dn[r,n] through the BN that follows a:
+//           g = gamma*rstd * (dn - dbeta/B - xhat*dgamma/B)      (train)   or gamma*rstd*dn (eval)
+// then dpre = g * 1[a > 0].
+struct GradSrc {
+  const float* G;
+  int ldg;
+  const float* a;       // the layer's stored output (post-ReLU), [B, N]
+  int lda;
+  const float* sums;    // stats of a (train) / nullptr
+  const float* mean;
+  const float* var;
+  const float* gamma;
+  const float* dbeta;   // column sums of dn and dn*xhat (train)
+  const float* dgamma;
+  float inv_B, eps;
+  int kind, train;
+};
+
+constexpr int kMaxBn = 256;
+
+__device__ __forceinline__ void bn_consts(const float* sums, const float* mean, const float* var,
+                                          int k, int K, float inv_B, float eps, float* mu,
+                                          float* rstd) {
+  if (sums != nullptr) {
+    const float m = sums[k] * inv_B;
+    const float v = fmaxf(sums[K + k] * inv_B - m * m, 0.f);   // biased batch variance
+    *mu = m;
+    *rstd = rsqrtf(v + eps);
+  } else {
+    *mu = mean[k];
+    *rstd = rsqrtf(var[k] + eps);
+  }
+}
+
+// --------------------------------------------------------------------------- forward
+constexpr int kTwBM = 32, kTwBN = 128, kTwKC = 16;
+
+template <bool PRO>
+__global__ void __launch_bounds__(256)
+tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
+                       const float* __restrict__ W, const float* __restrict__ bias, int N,
+                       float* __restrict__ out, int ldo, float* __restrict__ stats, int relu, int B) {
+  __shared__ __align__(16) float Xs[kTwKC][kTwBM + 4];
+  __shared__ __align__(16) float Ws[kTwKC][kTwBN];
+  __shared__ float s_mu[PRO ? kMaxBn : 1], s_sc[PRO ? kMaxBn : 1], s_sh[PRO ? kMaxBn : 1];
+  __shared__ float s_red[2][8][kTwBN];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int r0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
+  unsigned step = 0;
+  if (PRO) {
+    for (int k = tid; k < K; k += 256) {
+      float mu, rstd;
+      bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+      s_mu[k] = mu;
+      s_sc[k] = rstd * pro.gamma[k];
+      s_sh[k] = pro.beta[k];
+    }
+    if (pro.state != nullptr) step = static_cast<unsigned>(pro.state[0]);
+    __syncthreads();
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += kTwKC) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int e = tid + 256 * t;
+      const int rr = e >> 4, kk = e & 15;
+      const int r = r0 + rr, k = k0 + kk;
+      float v = 0.f;
+      if (r < B && k < K) {
+        v = X[static_cast<size_t>(r) * ldx + k];
+        if (PRO) {
+          v = fmaf((v - s_mu[k]) , s_sc[k], s_sh[k]);
+          if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+        }
+      }
+      Xs[kk][rr] = v;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = tid + 256 * t;
+      const int kk = e >> 7, c = e & 127;
+      const int k = k0 + kk, n = n0 + c;
+      Ws[kk][c] = (k < K && n < N) ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTwKC; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (r < B && n < N) {
+        float v = acc[i][j] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        out[static_cast<size_t>(r) * ldo + n] = v;
+        cs[j] += v;
+        cq[j] = fmaf(v, v, cq[j]);
+      }
+    }
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_red[0][ty][tx * 4 + j] = cs[j];
+      s_red[1][ty][tx * 4 + j] = cq[j];
+    }
+    __syncthreads();
+    if (tid < kTwBN) {
+      const int n = n0 + tid;
+      if (n < N) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          a += s_red[0][y][tid];
+          q += s_red[1][y][tid];
+        }
+        red_add_f32(stats + n, a);
+        red_add_f32(stats + N + n, q);
+      }
+    }
+  }
+}
+
+// BN + dropout of a stored activation written out (towers without a final dense layer, DCN).
+__global__ void __launch_bounds__(256)
+bn_drop_apply_kernel(const float* __restrict__ A, int K, const BnDrop pro, float* __restrict__ out,
+                     int B) {
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const long long n = static_cast<long long>(B) * K;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += gridDim.x * 256LL) {
+    const int r = static_cast<int>(e / K), k = static_cast<int>(e % K);
+    float mu, rstd;
+    bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+    float v = fmaf((A[e] - mu) * rstd, pro.gamma[k], pro.beta[k]);
+    if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+    out[e] = v;
+  }
+}
+
+// -------------------------------------------------------------------------- backward
+__device__ __forceinline__ float load_dpre(const GradSrc& g, int r, int n, int N) {
+  const float a = g.a[static_cast<size_t>(r) * g.lda + n];
+  if (!(a > 0.f)) return 0.f;
+  float v = g.G[static_cast<size_t>(r) * g.ldg + n];
+  if (g.kind == 1) {
+    float mu, rstd;
+    bn_consts(g.sums, g.mean, g.var, n, N, g.inv_B, g.eps, &mu, &rstd);
+    if (g.train) {
+      const float xhat = (a - mu) * rstd;
+      v = v - g.dbeta[n] * g.inv_B - xhat * g.dgamma[n] * g.inv_B;
+    }
+    v *= rstd * g.gamma[n];
+  }
+  return v;
+}
+
+// dXin[r,k] = sum_n dpre[r,n] * W[k,n]; then through the dropout + BN that produced Xin from the
+// stored activation Aprev (pro): dn = dXin * keep is stored, and its column sums
+// dbeta_prev += sum_r dn, dgamma_prev += sum_r dn * xhat_prev are accumulated for the layer below.
+// With pro.enabled == 0 (first layer) dXin is stored as is.
+__global__ void __launch_bounds__(256)
+tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W, int K,
+                            const BnDrop pro, const float* __restrict__ Aprev,
+                            float* __restrict__ dn_out, int ldn, float* __restrict__ dbeta_prev,
+                            float* __restrict__ dgamma_prev, int B) {
+  __shared__ __align__(16) float Gs[kTwKC][kTwBM + 4];    // dpre chunk  [n][row]
+  __shared__ __align__(16) float Ws[kTwKC][kTwBN];        // W^T chunk   [n][k]
+  __shared__ float s_red[2][8][kTwBN];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int r0 = blockIdx.x * kTwBM, k0 = blockIdx.y * kTwBN;
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int nb = 0; nb < N; nb += kTwKC) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int e = tid + 256 * t;
+      const int rr = e >> 4, nn = e & 15;
+      const int r = r0 + rr, n = nb + nn;
+      Gs[nn][rr] = (r < B && n < N) ? load_dpre(gs, r, n, N) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = tid + 256 * t;
+      const int c = e >> 4, nn = e & 15;        // consecutive threads walk n (contiguous in W rows)
+      const int k = k0 + c, n = nb + nn;
+      Ws[nn][c] = (k < K && n < N) ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nn = 0; nn < kTwKC; ++nn) {
+      const float4 a = *reinterpret_cast<const float4*>(&Gs[nn][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[nn][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  float cb[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = k0 + tx * 4 + j;
+    if (k >= K) continue;
+    float mu = 0.f, rstd = 0.f;
+    if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty * 4 + i;
+      if (r >= B) continue;
+      float v = acc[i][j];
+      if (pro.enabled) {
+        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+        const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
+        cb[j] += v;
+        cg[j] = fmaf(v, xhat, cg[j]);
+      }
+      dn_out[static_cast<size_t>(r) * ldn + k] = v;
+    }
+  }
+  if (pro.enabled && dbeta_prev != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_red[0][ty][tx * 4 + j] = cb[j];
+      s_red[1][ty][tx * 4 + j] = cg[j];
+    }
+    __syncthreads();
+    if (tid < kTwBN) {
+      const int k = k0 + tid;
+      if (k < K) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          a += s_red[0][y][tid];
+          q += s_red[1][y][tid];
+        }
+        red_add_f32(dbeta_prev + k, a);
+        red_add_f32(dgamma_prev + k, q);
+      }
+    }
+  }
+}
+
+// dW[k,n] += sum_r P(X)[r,k] * dpre[r,n];  db[n] += sum_r dpre[r,n]  (rows split over gridDim.z)
+__global__ void __launch_bounds__(256)
+tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
+                               const GradSrc gs, int N, float* __restrict__ dW,
+                               float* __restrict__ db, int B, int rows_per_split) {
+  __shared__ __align__(16) float Xs[16][64];
+  __shared__ __align__(16) float Gs[16][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int rbeg = blockIdx.z * rows_per_split, rend = min(B, rbeg + rows_per_split);
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;   // threads 0..63 of CTAs with blockIdx.x == 0 own db[n0 + tid]
+  for (int rc = rbeg; rc < rend; rc += 16) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + 256 * t;
+      const int rr = e >> 6, c = e & 63;
+      const int r = rc + rr;
+      float xv = 0.f, gv = 0.f;
+      if (r < rend) {
+        const int k = k0 + c, n = n0 + c;
+        if (k < K) {
+          xv = X[static_cast<size_t>(r) * ldx + k];
+          if (pro.enabled) {
+            float mu, rstd;
+            bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+            xv = fmaf((xv - mu) * rstd, pro.gamma[k], pro.beta[k]);
+            if (pro.p > 0.f) xv *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+          }
+        }
+        if (n < N) gv = load_dpre(gs, r, n, N);
+      }
+      Xs[rr][c] = xv;
+      Gs[rr][c] = gv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float4 a = *reinterpret_cast<const float4*>(&Xs[rr][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Gs[rr][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+    if (blockIdx.x == 0 && tid < 64) {
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) bsum += Gs[rr][tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) red_add_f32(dW + static_cast<size_t>(k) * N + n, acc[i][j]);
+    }
+  }
+  if (db != nullptr && blockIdx.x == 0 && tid < 64 && n0 + tid < N) red_add_f32(db + n0 + tid, bsum);
+}
+
+// ------------------------------------------------------------------------- loss head
+// logit[b] = sum_{c<C} hw[c] * act_c(z_c[b]) + hb, act_0 = relu(. + b1) when relu0, identity else.
+// loss += mean BCE; grads: dz_c[b], dhw[c], dhb, db1 accumulated (RED).  scale = 1/(B*world).
+struct HeadParams {
+  const float* z[4];
+  float* dz[4];
+  const float* hw;
+  const float* hb;
+  const float* b1;
+  const float* labels;
+  float* logits;
+  float* prob;
+  float* loss;       // scalar, += sum_b bce_b * loss_scale
+  float* dhw;
+  float* dhb;
+  float* db1;
+  float loss_scale;  // 1/B
+  float grad_scale;  // 1/(B * world)
+  int C, relu0, B, want_grad;
+};
+
+__global__ void __launch_bounds__(256) loss_head_kernel(const HeadParams p) {
+  __shared__ float s_part[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float hw[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < p.C; ++c) hw[c] = p.hw[c];
+  const float hb = p.hb[0];
+  const float b1 = p.relu0 ? p.b1[0] : 0.f;
+  float a_loss = 0.f, a_hb = 0.f, a_b1 = 0.f, a_hw[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = blockIdx.x * 256 + threadIdx.x; b < p.B; b += gridDim.x * 256) {
+    float act[4];
+    float logit = hb;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      act[c] = 0.f;
+      if (c < p.C) {
+        float v = p.z[c][b];
+        if (c == 0 && p.relu0) v = fmaxf(v + b1, 0.f);
+        act[c] = v;
+        logit = fmaf(hw[c], v, logit);
+      }
+    }
+    const float z = p.labels[b];
+    const float pr = 1.f / (1.f + expf(-logit));
+    // tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x z + log1p(exp(-|x|))
+    const float bce = fmaxf(logit, 0.f) - logit * z + log1pf(expf(-fabsf(logit)));
+    if (p.logits != nullptr) p.logits[b] = logit;
+    if (p.prob != nullptr) p.prob[b] = pr;
+    a_loss += bce;
+    if (p.want_grad) {
+      const float dl = (pr - z) * p.grad_scale;
+      a_hb += dl;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < p.C) {
+          a_hw[c] = fmaf(dl, act[c], a_hw[c]);
+          float g = dl * hw[c];
+          if (c == 0 && p.relu0) {
+            g = act[0] > 0.f ? g : 0.f;
+            a_b1 += g;
+          }
+          p.dz[c][b] = g;
+        }
+      }
+    }
+  }
+  float vals[8] = {a_loss, a_hb, a_b1, a_hw[0], a_hw[1], a_hw[2], a_hw[3], 0.f};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float t = warp_sum(vals[i]);
+    if (lane == 0) s_part[warp][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+    const int i = threadIdx.x;
+    if (i == 0) red_add_f32(p.loss, t * p.loss_scale);
+    else if (p.want_grad) {
+      if (i == 1) red_add_f32(p.dhb, t);
+      else if (i == 2) { if (p.relu0) red_add_f32(p.db1, t); }
+      else if (i - 3 < p.C) red_add_f32(p.dhw + (i - 3), t);
+    }
+  }
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" {
+
+static BnDrop make_pro(const ctr_bn_drop* d, int B) {
+  BnDrop p{};
+  if (d == nullptr || !d->enabled) return p;
+  p.sums = d->sums; p.mean = d->mean; p.var = d->var; p.gamma = d->gamma; p.beta = d->beta;
+  p.state = d->state; p.inv_B = 1.f / static_cast<float>(B); p.eps = d->eps; p.p = d->p_drop;
+  p.inv_keep = d->p_drop > 0.f ? 1.f / (1.f - d->p_drop) : 1.f;
+  p.seed = d->seed; p.layer = d->layer; p.enabled = 1;
+  return p;
+}
+static GradSrc make_gs(const ctr_grad_src* s, int B) {
+  GradSrc g{};
+  g.G = s->G; g.ldg = s->ldg; g.a = s->a; g.lda = s->lda; g.sums = s->sums; g.mean = s->mean;
+  g.var = s->var; g.gamma = s->gamma; g.dbeta = s->dbeta; g.dgamma = s->dgamma;
+  g.inv_B = 1.f / static_cast<float>(B); g.eps = s->eps; g.kind = s->kind; g.train = s->train;
+  return g;
+}
+
+int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, const float* W,
+                        const float* bias, int N, float* out, int ldo, float* stats, int relu,
+                        int B, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(X && W && out && B >= 0 && K > 0 && N > 0 && ldx >= K && ldo >= N,
+              "ctr_tower_layer_fwd", "bad argument");
+  const bool has_pro = pro != nullptr && pro->enabled;
+  CTR_REQUIRE(!has_pro || K <= kMaxBn, "ctr_tower_layer_fwd", "BN prologue needs K <= 256");
+  CTR_REQUIRE(!has_pro || (pro->gamma && pro->beta && (pro->sums || (pro->mean && pro->var))),
+              "ctr_tower_layer_fwd", "BN prologue needs gamma/beta and stats");
+  if (B == 0) return CTR_OK;
+  dim3 grid((B + kTwBM - 1) / kTwBM, (N + kTwBN - 1) / kTwBN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BnDrop p = make_pro(pro, B);
+  if (has_pro)
+    tower_layer_fwd_kernel<true><<<grid, 256, 0, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+  else
+    tower_layer_fwd_kernel<false><<<grid, 256, 0, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+  CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
+}
+
+int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out, int B,
+                      ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(A && out && pro && pro->enabled && K > 0 && B >= 0, "ctr_bn_drop_apply", "bad argument");
+  if (B == 0) return CTR_OK;
+  const long long n = static_cast<long long>(B) * K;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 8LL));
+  bn_drop_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, K, make_pro(pro, B), out, B);
+  CTR_LAUNCH_CHECK("ctr_bn_drop_apply");
+}
+
+int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int K,
+                             const ctr_bn_drop* pro, const float* Aprev, float* dn_out, int ldn,
+                             float* dbeta_prev, float* dgamma_prev, int B, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(gs && gs->G && gs->a && W && dn_out && K > 0 && N > 0 && B >= 0 && ldn >= K,
+              "ctr_tower_layer_bwd_data", "bad argument");
+  const bool has_pro = pro != nullptr && pro->enabled;
+  CTR_REQUIRE(!has_pro || (Aprev && K <= kMaxBn), "ctr_tower_layer_bwd_data",
+              "BN bookkeeping needs Aprev and K <= 256");
+  if (B == 0) return CTR_OK;
+  dim3 grid((B + kTwBM - 1) / kTwBM, (K + kTwBN - 1) / kTwBN);
+  tower_layer_bwd_data_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      make_gs(gs, B), N, W, K, make_pro(pro, B), Aprev, dn_out, ldn, dbeta_prev, dgamma_prev, B);
+  CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
+}
+
+int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_drop* pro,
+                                const ctr_grad_src* gs, int N, float* dW, float* db, int B,
+                                ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(X && gs && gs->G && gs->a && dW && K > 0 && N > 0 && B >= 0 && ldx >= K,
+              "ctr_tower_layer_bwd_weights", "bad argument");
+  if (B == 0) return CTR_OK;
+  const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
+  int splits = std::max(1, std::min((sm_count() * 3) / tiles, (B + 127) / 128));
+  int rps = (B + splits - 1) / splits;
+  rps = (rps + 15) / 16 * 16;
+  splits = (B + rps - 1) / rps;
+  dim3 grid((K + 63) / 64, (N + 63) / 64, splits);
+  tower_layer_bwd_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X, ldx, K, make_pro(pro, B), make_gs(gs, B), N, dW, db, B, rps);
+  CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_weights");
+}
+
+int ctr_loss_head(const float* const* z, float* const* dz, int C, int relu0, const float* hw,
+                  const float* hb, const float* b1, const float* labels, int B, float* logits,
+                  float* prob, float* loss, float* dhw, float* dhb, float* db1, float grad_scale,
+                  ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(z && hw && hb && labels && loss && C >= 1 && C <= 4 && B >= 0, "ctr_loss_head",
+              "bad argument");
+  CTR_REQUIRE(!relu0 || b1, "ctr_loss_head", "relu0 needs b1");
+  const bool want_grad = dz != nullptr;
+  CTR_REQUIRE(!want_grad || (dhw && dhb && (!relu0 || db1)), "ctr_loss_head", "missing gradient outputs");
+  if (B == 0) return CTR_OK;
+  HeadParams p{};
+  for (int c = 0; c < C; ++c) {
+    p.z[c] = z[c];
+    p.dz[c] = want_grad ? dz[c] : nullptr;
+    CTR_REQUIRE(p.z[c] && (!want_grad || p.dz[c]), "ctr_loss_head", "null column");
+  }
+  p.hw = hw; p.hb = hb; p.b1 = b1; p.labels = labels; p.logits = logits; p.prob = prob; p.loss = loss;
+  p.dhw = dhw; p.dhb = dhb; p.db1 = db1; p.loss_scale = 1.f / static_cast<float>(B);
+  p.grad_scale = grad_scale; p.C = C; p.relu0 = relu0; p.B = B; p.want_grad = want_grad ? 1 : 0;
+  const int grid = std::min((B + 255) / 256, sm_count());
+  loss_head_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CTR_LAUNCH_CHECK("ctr_loss_head");
+}
+
+}  // extern "C"

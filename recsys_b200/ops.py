@@ -531,3 +531,160 @@ def din_attention(emb: "FieldEmbedding", field: int, hist, query, W1, b1, W2, b2
     lo, hi = emb.lay.offsets[field], emb.lay.offsets[field + 1]
     return _DinAttFn.apply(emb._anchor, emb.table[lo:hi], emb.dtable[lo:hi], hist, query,
                            W1.contiguous(), b1, W2.contiguous(), b2, W3.reshape(-1), b3)
+
+
+# ------------------------------------------------------- fused dense tower + loss head
+BN_EPS = 1e-3
+
+
+class FusedTower:
+    """dense(relu) -> BN -> dropout stack (+ optional final dense(1, relu)) through the
+    ctr_tower_* kernels (deepfm/deepfm.py:100-108).  Parameters live in ``dense``
+    (DenseParams) under ``prefix``; weight / BN gradients are accumulated straight into the
+    flat gradient buffer by the backward kernels (no per-parameter autograd adds)."""
+
+    def __init__(self, dense: "DenseParams", prefix: str, sizes, out_layer: bool, dropout: float,
+                 adam: "TFAdamState", seed: int = 0):
+        self.dense, self.prefix, self.sizes = dense, prefix, list(sizes)
+        self.out_layer, self.dropout, self.adam, self.seed = out_layer, float(dropout), adam, seed
+        self._anchor = torch.zeros((), device=dense.flat.device, requires_grad=True)
+
+    def P(self, name):
+        return self.dense[self.prefix + "." + name]
+
+    def G(self, name):
+        return self.dense[self.prefix + "." + name].grad
+
+    def __call__(self, X, training: bool):
+        require_cuda(X, "tower input")
+        return _TowerFn.apply(X, self._anchor, self, training)
+
+    def bn_drop(self, l, sums, training):
+        d = _lib.BnDrop()
+        d.sums = _p(sums) if training else None
+        d.mean, d.var = _p(self.P("%d.bn.mean" % l)), _p(self.P("%d.bn.var" % l))
+        d.gamma, d.beta = _p(self.P("%d.bn.gamma" % l)), _p(self.P("%d.bn.beta" % l))
+        d.state = self.adam.state_ptr
+        d.eps = BN_EPS
+        d.p_drop = self.dropout if training else 0.0
+        d.seed, d.layer, d.enabled = self.seed & 0xFFFFFFFF, l, 1
+        return d
+
+
+class _TowerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, anchor, tw: FusedTower, training):
+        X = X.contiguous()
+        B, dev = X.shape[0], X.device
+        L = len(tw.sizes) - 1
+        acts, stats, pros = [], [], []
+        x, K, pro = X, tw.sizes[0], None
+        for l in range(L):
+            H = tw.sizes[l + 1]
+            a = torch.empty((B, H), dtype=torch.float32, device=dev)
+            st = torch.zeros((2, H), dtype=torch.float32, device=dev) if training else None
+            _call("ctr_tower_layer_fwd", _p(x), K, K, C.byref(pro) if pro is not None else None,
+                  _p(tw.P("%d.w" % l)), _p(tw.P("%d.b" % l)), H, _p(a), H, _p(st), 1, B, _stream())
+            pro = tw.bn_drop(l, st, training)
+            acts.append(a)
+            stats.append(st)
+            pros.append(pro)
+            x, K = a, H
+        if tw.out_layer:
+            y = torch.empty((B, 1), dtype=torch.float32, device=dev)
+            _call("ctr_tower_layer_fwd", _p(x), K, K, C.byref(pro), _p(tw.P("out.w")),
+                  _p(tw.P("out.b")), 1, _p(y), 1, None, 1, B, _stream())
+            out = y.view(B)
+        else:
+            y = None
+            out = torch.empty((B, K), dtype=torch.float32, device=dev)
+            _call("ctr_bn_drop_apply", _p(x), K, C.byref(pro), _p(out), B, _stream())
+        ctx.tw, ctx.training = tw, training
+        ctx.saved = (X, acts, stats, pros, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tw = ctx.tw
+        X, acts, stats, pros, y = ctx.saved
+        if not ctx.training:
+            raise RuntimeError("FusedTower backward is only defined in training mode")
+        if not tw.out_layer:
+            raise NotImplementedError("backward of a tower without a final dense layer")
+        B, dev = X.shape[0], X.device
+        L = len(tw.sizes) - 1
+        dout = dout.contiguous().view(B, 1)
+
+        def grad_src(G, ldg, a, lda, kind, l=None):
+            g = _lib.GradSrc()
+            g.G, g.ldg, g.a, g.lda, g.kind, g.train, g.eps = _p(G), ldg, _p(a), lda, kind, 1, BN_EPS
+            if kind == 1:
+                g.sums = _p(stats[l])
+                g.gamma = _p(tw.P("%d.bn.gamma" % l))
+                g.dbeta, g.dgamma = _p(tw.G("%d.bn.beta" % l)), _p(tw.G("%d.bn.gamma" % l))
+            return g
+
+        # final dense(1, relu): dpre = dout * 1[y > 0]
+        gs = grad_src(dout, 1, y, 1, 0)
+        HL = tw.sizes[L]
+        _call("ctr_tower_layer_bwd_weights", _p(acts[L - 1]), HL, HL, C.byref(pros[L - 1]),
+              C.byref(gs), 1, _p(tw.G("out.w")), _p(tw.G("out.b")), B, _stream())
+        dn = torch.empty((B, HL), dtype=torch.float32, device=dev)
+        _call("ctr_tower_layer_bwd_data", C.byref(gs), 1, _p(tw.P("out.w")), HL,
+              C.byref(pros[L - 1]), _p(acts[L - 1]), _p(dn), HL, _p(tw.G("%d.bn.beta" % (L - 1))),
+              _p(tw.G("%d.bn.gamma" % (L - 1))), B, _stream())
+        for l in range(L - 1, -1, -1):
+            H, K = tw.sizes[l + 1], tw.sizes[l]
+            gs = grad_src(dn, H, acts[l], H, 1, l)
+            xin = acts[l - 1] if l > 0 else X
+            pro = C.byref(pros[l - 1]) if l > 0 else None
+            _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs), H,
+                  _p(tw.G("%d.w" % l)), _p(tw.G("%d.b" % l)), B, _stream())
+            dnext = torch.empty((B, K), dtype=torch.float32, device=dev)
+            _call("ctr_tower_layer_bwd_data", C.byref(gs), H, _p(tw.P("%d.w" % l)), K, pro,
+                  _p(xin) if l > 0 else None, _p(dnext), K,
+                  _p(tw.G("%d.bn.beta" % (l - 1))) if l > 0 else None,
+                  _p(tw.G("%d.bn.gamma" % (l - 1))) if l > 0 else None, B, _stream())
+            dn = dnext
+        return dn, None, None, None
+
+
+class _LossHeadFn(torch.autograd.Function):
+    """ctr_loss_head: logits, prob, mean BCE and (training) the input / head-parameter
+    gradients in one launch.  The head-parameter gradients are accumulated into the flat
+    gradient buffer during the forward; the input gradients are handed to autograd."""
+
+    @staticmethod
+    def forward(ctx, anchor, dense, names, relu0, grad_scale, labels, want_grad, *zs):
+        B, dev = zs[0].shape[0], zs[0].device
+        Cn = len(zs)
+        zs = [z.contiguous().view(B) for z in zs]
+        labels = labels.to(dev, torch.float32).contiguous().view(B)
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        prob = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        zp = (C.c_void_p * Cn)(*[z.data_ptr() for z in zs])
+        dzs = [torch.empty(B, dtype=torch.float32, device=dev) for _ in zs] if want_grad else None
+        dzp = (C.c_void_p * Cn)(*[d.data_ptr() for d in dzs]) if want_grad else None
+        hw, hb, b1 = names
+        _call("ctr_loss_head", zp, dzp, Cn, 1 if relu0 else 0, _p(dense[hw]), _p(dense[hb]),
+              _p(dense[b1]) if relu0 else None, _p(labels), B, _p(logits), _p(prob), _p(loss),
+              _p(dense[hw].grad) if want_grad else None, _p(dense[hb].grad) if want_grad else None,
+              _p(dense[b1].grad) if (want_grad and relu0) else None, float(grad_scale), _stream())
+        ctx.dzs = dzs
+        ctx.mark_non_differentiable(logits, prob)
+        return loss, logits, prob
+
+    @staticmethod
+    def backward(ctx, gl, _g1, _g2):
+        # d(loss)/dz was produced with the final scale (1/(B*world)); the caller backpropagates
+        # the loss itself (upstream gradient 1).
+        return (None, None, None, None, None, None, None) + tuple(ctx.dzs)
+
+
+def loss_head(anchor, dense, zs, labels, hw="head.w", hb="head.b", b1="b1", relu0=True,
+              grad_scale=None, training=True):
+    B = zs[0].shape[0]
+    if grad_scale is None:
+        grad_scale = 1.0 / B
+    return _LossHeadFn.apply(anchor, dense, (hw, hb, b1), relu0, grad_scale, labels, training, *zs)

@@ -66,17 +66,20 @@ def _check_grads(m, grads64, tol=1e-3):
     assert not bad, "; ".join(bad)
 
 
-@pytest.mark.parametrize("model", ["fm", "deepfm", "dcn", "xdeepfm", "xdeepfm-fp32"])
+@pytest.mark.parametrize("model", ["fm", "deepfm", "dcn", "xdeepfm", "xdeepfm-fp32", "fm-torch",
+                                   "deepfm-torch", "xdeepfm-torch"])
 @pytest.mark.parametrize("B", [64, 1000])
 def test_criteo_models_match_oracle(cuda, model, B):
+    """Default = fused tower / loss-head kernels; ``-torch`` = the torch (cuBLAS) tower."""
     prec = "fp32" if model.endswith("-fp32") else "tf32x3"
+    fused = not model.endswith("-torch")
     model = model.split("-")[0]
     spec = mg.small_spec()
     kw = dict(cin_layers=(16, 8)) if model == "xdeepfm" else {}
     p64 = om.init_params(model, spec.total_rows, deep_layers=(32, 16), seed=3, **kw)
     feats, batch = mg.model_batch(model, B, 7, spec)
     out64, g64 = om.loss_and_grads(model, p64, batch)
-    m, params = _build(model, spec, cuda, cin_precision=prec)
+    m, params = _build(model, spec, cuda, cin_precision=prec, fused_tower=fused)
     m.load_state(p64)
     spec_ = _model_fn(model)(_features_to_torch(feats), batch["labels"], "train", params)
     logits = m.last["logits"].detach().cpu().double().reshape(-1)
@@ -90,6 +93,60 @@ def test_criteo_models_match_oracle(cuda, model, B):
         def close(a, b):
             return float((a.cpu().double() - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-7
         assert close(m.emb_dnn.dtable, g64["emb_dnn"])
+
+
+def _dropout_masks(m, B):
+    """The keep masks the fused tower will use at the current step: run the BN+dropout prologue
+    on an all-ones activation with identity BN (mean 0, var 1-eps, gamma 1, beta 0)."""
+    import ctypes as C
+    from recsys_b200 import _lib
+    lib = _lib.load()
+    masks = []
+    tw = m.tower
+    for l, H in enumerate(tw.sizes[1:]):
+        ones = torch.ones(B, H, device=m.device)
+        out = torch.empty_like(ones)
+        zero, one = torch.zeros(H, device=m.device), torch.ones(H, device=m.device)
+        d = _lib.BnDrop()
+        d.sums, d.mean, d.var = None, zero.data_ptr(), (one - 1e-3).data_ptr()
+        d.gamma, d.beta, d.state = one.data_ptr(), zero.data_ptr(), tw.adam.state_ptr
+        d.eps, d.p_drop, d.seed, d.layer, d.enabled = 1e-3, tw.dropout, tw.seed, l, 1
+        var = one - 1e-3
+        d.var = var.data_ptr()
+        rc = lib.ctr_bn_drop_apply(ones.data_ptr(), H, C.byref(d), out.data_ptr(), B,
+                                   torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        keep = (out > 0).float().cpu()
+        assert torch.allclose(out.cpu(), keep / (1 - tw.dropout), atol=1e-5)
+        masks.append(keep)
+    return masks
+
+
+def test_fused_tower_dropout_matches_oracle_with_same_masks(cuda):
+    """dropout 0.5 (the reference's training default): the fused kernels regenerate the mask in
+    the backward from (seed, layer, step); with those masks injected into the oracle, logits,
+    loss and every gradient agree; the keep rate is ~0.5 and masks differ between layers/steps."""
+    from recsys_b200.deepfm import deepfm
+    spec = mg.small_spec()
+    B = 512
+    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
+    feats, batch = mg.model_batch("deepfm", B, 9, spec)
+    m, params = _build("deepfm", spec, cuda, dropout=0.5)
+    m.load_state(p64)
+    masks = _dropout_masks(m, B)
+    assert all(0.4 < float(k.mean()) < 0.6 for k in masks) and not torch.equal(masks[0][:, :16], masks[1])
+    out64, g64 = om.loss_and_grads("deepfm", p64, batch, dropout=0.5, masks=[k.double() for k in masks])
+    sp = deepfm.model_fn(_features_to_torch(feats), batch["labels"], "train", params)
+    logits = m.last["logits"].detach().cpu().double().reshape(-1)
+    ref = out64["logits"].reshape(-1)
+    assert float(((logits - ref).abs() / (ref.abs() + 0.1)).max()) <= 1e-4
+    assert abs(float(sp.loss) - float(out64["loss"])) <= 1e-5
+    m.backward(m.last["loss"])
+    _check_grads(m, g64)
+    m.apply_gradients()                               # advances the device step counter
+    masks2 = _dropout_masks(m, B)
+    assert not torch.equal(masks[0], masks2[0])
 
 
 def test_modes_and_estimator_spec_contract(cuda):
