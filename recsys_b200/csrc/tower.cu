@@ -95,66 +95,65 @@ __device__ __forceinline__ void bn_consts(const float* sums, const float* mean, 
   }
 }
 
-// --------------------------------------------------------------------------- forward
-constexpr int kTwBM = 32, kTwBN = 128, kTwKC = 16;
+// ----------------------------------------------------------------- tiled GEMM core
+// C[32 x 128] += A[32 x nk] . B[nk x 128], operands produced element-wise by functors (so the
+// BN/dropout prologue and the ReLU/BN-backward gradient source are applied on the way into
+// shared memory).  Register-prefetch double buffering: the global loads of chunk i+1 are in
+// flight while chunk i is multiplied; one __syncthreads per chunk.  256 threads, 4x4 micro-tile.
+constexpr int kTwBM = 32, kTwBN = 128, kTwKC = 32;
+constexpr int kTwAP = kTwBM + 4, kTwBP = kTwBN + 4;   // padded pitches (16-byte aligned rows)
 
-template <bool PRO>
-__global__ void __launch_bounds__(256)
-tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
-                       const float* __restrict__ W, const float* __restrict__ bias, int N,
-                       float* __restrict__ out, int ldo, float* __restrict__ stats, int relu, int B) {
-  __shared__ __align__(16) float Xs[kTwKC][kTwBM + 4];
-  __shared__ __align__(16) float Ws[kTwKC][kTwBN];
-  __shared__ float s_mu[PRO ? kMaxBn : 1], s_sc[PRO ? kMaxBn : 1], s_sh[PRO ? kMaxBn : 1];
-  __shared__ float s_red[2][8][kTwBN];
+struct TowerSmem {
+  float A[2][kTwKC][kTwAP];
+  float B[2][kTwKC][kTwBP];
+  float mu[kMaxBn], sc[kMaxBn], sh[kMaxBn];                              // prologue tables
+  float gmu[kMaxBn], grs[kMaxBn], gc1[kMaxBn], gc2[kMaxBn], gsc[kMaxBn];  // gradient-source tables
+  float red[2][8][kTwBN];
+};
+
+template <bool A_KFAST, bool B_KFAST, typename FA, typename FB>
+__device__ __forceinline__ void gemm_32x128(TowerSmem& sm, int nk, FA fa, FB fb, float (&acc)[4][4]) {
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int r0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
-  unsigned step = 0;
-  if (PRO) {
-    for (int k = tid; k < K; k += 256) {
-      float mu, rstd;
-      bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
-      s_mu[k] = mu;
-      s_sc[k] = rstd * pro.gamma[k];
-      s_sh[k] = pro.beta[k];
-    }
-    if (pro.state != nullptr) step = static_cast<unsigned>(pro.state[0]);
-    __syncthreads();
-  }
-  float acc[4][4];
+  float ra[4], rb[16];
+  auto load = [&](int k0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < K; k0 += kTwKC) {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 4; ++t) {
       const int e = tid + 256 * t;
-      const int rr = e >> 4, kk = e & 15;
-      const int r = r0 + rr, k = k0 + kk;
-      float v = 0.f;
-      if (r < B && k < K) {
-        v = X[static_cast<size_t>(r) * ldx + k];
-        if (PRO) {
-          v = fmaf((v - s_mu[k]) , s_sc[k], s_sh[k]);
-          if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
-        }
-      }
-      Xs[kk][rr] = v;
+      const int kk = A_KFAST ? (e & 31) : (e >> 5), rr = A_KFAST ? (e >> 5) : (e & 31);
+      ra[t] = (k0 + kk < nk) ? fa(rr, k0 + kk) : 0.f;
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < 16; ++t) {
       const int e = tid + 256 * t;
-      const int kk = e >> 7, c = e & 127;
-      const int k = k0 + kk, n = n0 + c;
-      Ws[kk][c] = (k < K && n < N) ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+      const int kk = B_KFAST ? (e & 31) : (e >> 7), c = B_KFAST ? (e >> 5) : (e & 127);
+      rb[t] = (k0 + kk < nk) ? fb(k0 + kk, c) : 0.f;
     }
-    __syncthreads();
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + 256 * t;
+      const int kk = A_KFAST ? (e & 31) : (e >> 5), rr = A_KFAST ? (e >> 5) : (e & 31);
+      sm.A[buf][kk][rr] = ra[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int e = tid + 256 * t;
+      const int kk = B_KFAST ? (e & 31) : (e >> 7), c = B_KFAST ? (e >> 5) : (e & 127);
+      sm.B[buf][kk][c] = rb[t];
+    }
+  };
+  load(0);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < nk; k0 += kTwKC) {
+    const bool more = k0 + kTwKC < nk;
+    if (more) load(k0 + kTwKC);
 #pragma unroll
     for (int kk = 0; kk < kTwKC; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&sm.A[buf][kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sm.B[buf][kk][tx * 4]);
       const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -164,8 +163,85 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
         acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
       }
     }
+    if (more) store(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+__device__ __forceinline__ void fill_pro_tables(TowerSmem& sm, const BnDrop& pro, int K) {
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float mu, rstd;
+    bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+    sm.mu[k] = mu;
+    sm.sc[k] = rstd * pro.gamma[k];
+    sm.sh[k] = pro.beta[k];
+  }
+}
+__device__ __forceinline__ void fill_gs_tables(TowerSmem& sm, const GradSrc& g, int N) {
+  if (g.kind != 1) return;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float mu, rstd;
+    bn_consts(g.sums, g.mean, g.var, n, N, g.inv_B, g.eps, &mu, &rstd);
+    sm.gmu[n] = mu;
+    sm.grs[n] = rstd;
+    sm.gc1[n] = g.train ? g.dbeta[n] * g.inv_B : 0.f;
+    sm.gc2[n] = g.train ? g.dgamma[n] * g.inv_B : 0.f;
+    sm.gsc[n] = rstd * g.gamma[n];
+  }
+}
+// x' = P(X)[r,k] with the tables in shared memory
+__device__ __forceinline__ float pro_value(const TowerSmem& sm, const BnDrop& pro, unsigned step,
+                                           float v, int r, int k) {
+  v = fmaf(v - sm.mu[k], sm.sc[k], sm.sh[k]);
+  if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+  return v;
+}
+// dpre[r,n] = g * 1[a > 0] with the tables in shared memory
+__device__ __forceinline__ float dpre_value(const TowerSmem& sm, const GradSrc& g, int r, int n) {
+  const float a = g.a[static_cast<size_t>(r) * g.lda + n];
+  if (!(a > 0.f)) return 0.f;
+  float v = g.G[static_cast<size_t>(r) * g.ldg + n];
+  if (g.kind == 1) {
+    const float xhat = (a - sm.gmu[n]) * sm.grs[n];
+    v = (v - sm.gc1[n] - xhat * sm.gc2[n]) * sm.gsc[n];
+  }
+  return v;
+}
+
+// --------------------------------------------------------------------------- forward
+template <bool PRO>
+__global__ void __launch_bounds__(256)
+tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
+                       const float* __restrict__ W, const float* __restrict__ bias, int N,
+                       float* __restrict__ out, int ldo, float* __restrict__ stats, int relu, int B) {
+  extern __shared__ __align__(16) uint8_t tw_smem[];
+  TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int r0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
+  unsigned step = 0;
+  if (PRO) {
+    fill_pro_tables(sm, pro, K);
+    if (pro.state != nullptr) step = static_cast<unsigned>(pro.state[0]);
     __syncthreads();
   }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  auto fa = [&](int rr, int k) -> float {
+    const int r = r0 + rr;
+    if (r >= B) return 0.f;
+    const float v = X[static_cast<size_t>(r) * ldx + k];
+    return PRO ? pro_value(sm, pro, step, v, r, k) : v;
+  };
+  auto fb = [&](int k, int c) -> float {
+    const int n = n0 + c;
+    return n < N ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+  };
+  gemm_32x128<true, false>(sm, K, fa, fb, acc);
+
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -185,8 +261,8 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
   if (stats != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      s_red[0][ty][tx * 4 + j] = cs[j];
-      s_red[1][ty][tx * 4 + j] = cq[j];
+      sm.red[0][ty][tx * 4 + j] = cs[j];
+      sm.red[1][ty][tx * 4 + j] = cq[j];
     }
     __syncthreads();
     if (tid < kTwBN) {
@@ -195,12 +271,53 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
         float a = 0.f, q = 0.f;
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
-          a += s_red[0][y][tid];
-          q += s_red[1][y][tid];
+          a += sm.red[0][y][tid];
+          q += sm.red[1][y][tid];
         }
         red_add_f32(stats + n, a);
         red_add_f32(stats + N + n, q);
       }
+    }
+  }
+}
+
+// N == 1 (the final dense(1, relu)): one warp per row.
+__global__ void __launch_bounds__(256)
+tower_out_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
+                     const float* __restrict__ W, const float* __restrict__ bias,
+                     float* __restrict__ out, int ldo, int relu, int B) {
+  __shared__ float s_mu[kMaxBn], s_sc[kMaxBn], s_sh[kMaxBn], s_w[kMaxBn];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool use_tab = K <= kMaxBn;
+  if (use_tab) {
+    for (int k = threadIdx.x; k < K; k += 256) {
+      s_w[k] = W[k];
+      if (pro.enabled) {
+        float mu, rstd;
+        bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+        s_mu[k] = mu;
+        s_sc[k] = rstd * pro.gamma[k];
+        s_sh[k] = pro.beta[k];
+      }
+    }
+    __syncthreads();
+  }
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  for (int r = blockIdx.x * 8 + warp; r < B; r += gridDim.x * 8) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float v = X[static_cast<size_t>(r) * ldx + k];
+      if (pro.enabled) {
+        v = fmaf(v - s_mu[k], s_sc[k], s_sh[k]);
+        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+      }
+      acc = fmaf(v, use_tab ? s_w[k] : W[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + (bias != nullptr ? bias[0] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      out[static_cast<size_t>(r) * ldo] = v;
     }
   }
 }
@@ -222,22 +339,6 @@ bn_drop_apply_kernel(const float* __restrict__ A, int K, const BnDrop pro, float
 }
 
 // -------------------------------------------------------------------------- backward
-__device__ __forceinline__ float load_dpre(const GradSrc& g, int r, int n, int N) {
-  const float a = g.a[static_cast<size_t>(r) * g.lda + n];
-  if (!(a > 0.f)) return 0.f;
-  float v = g.G[static_cast<size_t>(r) * g.ldg + n];
-  if (g.kind == 1) {
-    float mu, rstd;
-    bn_consts(g.sums, g.mean, g.var, n, N, g.inv_B, g.eps, &mu, &rstd);
-    if (g.train) {
-      const float xhat = (a - mu) * rstd;
-      v = v - g.dbeta[n] * g.inv_B - xhat * g.dgamma[n] * g.inv_B;
-    }
-    v *= rstd * g.gamma[n];
-  }
-  return v;
-}
-
 // dXin[r,k] = sum_n dpre[r,n] * W[k,n]; then through the dropout + BN that produced Xin from the
 // stored activation Aprev (pro): dn = dXin * keep is stored, and its column sums
 // dbeta_prev += sum_r dn, dgamma_prev += sum_r dn * xhat_prev are accumulated for the layer below.
@@ -247,56 +348,34 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
                             const BnDrop pro, const float* __restrict__ Aprev,
                             float* __restrict__ dn_out, int ldn, float* __restrict__ dbeta_prev,
                             float* __restrict__ dgamma_prev, int B) {
-  __shared__ __align__(16) float Gs[kTwKC][kTwBM + 4];    // dpre chunk  [n][row]
-  __shared__ __align__(16) float Ws[kTwKC][kTwBN];        // W^T chunk   [n][k]
-  __shared__ float s_red[2][8][kTwBN];
+  extern __shared__ __align__(16) uint8_t tw_smem[];
+  TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int r0 = blockIdx.x * kTwBM, k0 = blockIdx.y * kTwBN;
   const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  fill_gs_tables(sm, gs, N);
+  if (pro.enabled) fill_pro_tables(sm, pro, K);
+  __syncthreads();
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  auto fa = [&](int rr, int n) -> float {
+    const int r = r0 + rr;
+    return r < B ? dpre_value(sm, gs, r, n) : 0.f;
+  };
+  auto fb = [&](int n, int c) -> float {
+    const int k = k0 + c;
+    return k < K ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+  };
+  gemm_32x128<true, true>(sm, N, fa, fb, acc);
 
-  for (int nb = 0; nb < N; nb += kTwKC) {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int e = tid + 256 * t;
-      const int rr = e >> 4, nn = e & 15;
-      const int r = r0 + rr, n = nb + nn;
-      Gs[nn][rr] = (r < B && n < N) ? load_dpre(gs, r, n, N) : 0.f;
-    }
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int e = tid + 256 * t;
-      const int c = e >> 4, nn = e & 15;        // consecutive threads walk n (contiguous in W rows)
-      const int k = k0 + c, n = nb + nn;
-      Ws[nn][c] = (k < K && n < N) ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int nn = 0; nn < kTwKC; ++nn) {
-      const float4 a = *reinterpret_cast<const float4*>(&Gs[nn][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Ws[nn][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
-        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
-        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
-        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
-      }
-    }
-    __syncthreads();
-  }
   float cb[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int k = k0 + tx * 4 + j;
     if (k >= K) continue;
-    float mu = 0.f, rstd = 0.f;
-    if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = r0 + ty * 4 + i;
@@ -304,6 +383,9 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
       float v = acc[i][j];
       if (pro.enabled) {
         if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+        // xhat = (A - mu) * rstd; sm.sc = rstd * gamma, so keep rstd separately
+        float mu, rstd;
+        bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
         const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
         cb[j] += v;
         cg[j] = fmaf(v, xhat, cg[j]);
@@ -314,8 +396,8 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
   if (pro.enabled && dbeta_prev != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      s_red[0][ty][tx * 4 + j] = cb[j];
-      s_red[1][ty][tx * 4 + j] = cg[j];
+      sm.red[0][ty][tx * 4 + j] = cb[j];
+      sm.red[1][ty][tx * 4 + j] = cg[j];
     }
     __syncthreads();
     if (tid < kTwBN) {
@@ -324,8 +406,8 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
         float a = 0.f, q = 0.f;
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
-          a += s_red[0][y][tid];
-          q += s_red[1][y][tid];
+          a += sm.red[0][y][tid];
+          q += sm.red[1][y][tid];
         }
         red_add_f32(dbeta_prev + k, a);
         red_add_f32(dgamma_prev + k, q);
@@ -334,66 +416,79 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
   }
 }
 
+// N == 1: dn[r,k] = dpre[r] * W[k] * keep, column sums for the BN below.  CTA = 64 rows x K cols.
+__global__ void __launch_bounds__(256)
+tower_out_bwd_data_kernel(const GradSrc gs, const float* __restrict__ W, int K, const BnDrop pro,
+                          const float* __restrict__ Aprev, float* __restrict__ dn_out, int ldn,
+                          float* __restrict__ dbeta_prev, float* __restrict__ dgamma_prev, int B) {
+  __shared__ float s_dp[64];
+  const int r0 = blockIdx.x * 64;
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  if (threadIdx.x < 64) {
+    const int r = r0 + threadIdx.x;
+    float v = 0.f;
+    if (r < B) {
+      const float a = gs.a[static_cast<size_t>(r) * gs.lda];
+      v = a > 0.f ? gs.G[static_cast<size_t>(r) * gs.ldg] : 0.f;
+    }
+    s_dp[threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float w = W[k];
+    float mu = 0.f, rstd = 0.f;
+    if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+    float cb = 0.f, cg = 0.f;
+    for (int rr = 0; rr < 64; ++rr) {
+      const int r = r0 + rr;
+      if (r >= B) break;
+      float v = s_dp[rr] * w;
+      if (pro.enabled) {
+        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+        const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
+        cb += v;
+        cg = fmaf(v, xhat, cg);
+      }
+      dn_out[static_cast<size_t>(r) * ldn + k] = v;
+    }
+    if (pro.enabled && dbeta_prev != nullptr) {
+      red_add_f32(dbeta_prev + k, cb);
+      red_add_f32(dgamma_prev + k, cg);
+    }
+  }
+}
+
 // dW[k,n] += sum_r P(X)[r,k] * dpre[r,n];  db[n] += sum_r dpre[r,n]  (rows split over gridDim.z)
+// Output tile 32 (k) x 128 (n); the reduction runs over the CTA's row range.
 __global__ void __launch_bounds__(256)
 tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
                                const GradSrc gs, int N, float* __restrict__ dW,
                                float* __restrict__ db, int B, int rows_per_split) {
-  __shared__ __align__(16) float Xs[16][64];
-  __shared__ __align__(16) float Gs[16][64];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  extern __shared__ __align__(16) uint8_t tw_smem[];
+  TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int k0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
   const int rbeg = blockIdx.z * rows_per_split, rend = min(B, rbeg + rows_per_split);
   const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  fill_gs_tables(sm, gs, N);
+  if (pro.enabled) fill_pro_tables(sm, pro, K);
+  __syncthreads();
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bsum = 0.f;   // threads 0..63 of CTAs with blockIdx.x == 0 own db[n0 + tid]
-  for (int rc = rbeg; rc < rend; rc += 16) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int e = tid + 256 * t;
-      const int rr = e >> 6, c = e & 63;
-      const int r = rc + rr;
-      float xv = 0.f, gv = 0.f;
-      if (r < rend) {
-        const int k = k0 + c, n = n0 + c;
-        if (k < K) {
-          xv = X[static_cast<size_t>(r) * ldx + k];
-          if (pro.enabled) {
-            float mu, rstd;
-            bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
-            xv = fmaf((xv - mu) * rstd, pro.gamma[k], pro.beta[k]);
-            if (pro.p > 0.f) xv *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
-          }
-        }
-        if (n < N) gv = load_dpre(gs, r, n, N);
-      }
-      Xs[rr][c] = xv;
-      Gs[rr][c] = gv;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-      const float4 a = *reinterpret_cast<const float4*>(&Xs[rr][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Gs[rr][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
-        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
-        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
-        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
-      }
-    }
-    if (blockIdx.x == 0 && tid < 64) {
-#pragma unroll
-      for (int rr = 0; rr < 16; ++rr) bsum += Gs[rr][tid];
-    }
-    __syncthreads();
-  }
+  auto fa = [&](int m, int rr) -> float {      // A[m = k index][kk = row]
+    const int k = k0 + m, r = rbeg + rr;
+    if (k >= K) return 0.f;
+    const float v = X[static_cast<size_t>(r) * ldx + k];
+    return pro.enabled ? pro_value(sm, pro, step, v, r, k) : v;
+  };
+  auto fb = [&](int rr, int c) -> float {
+    const int n = n0 + c;
+    return n < N ? dpre_value(sm, gs, rbeg + rr, n) : 0.f;
+  };
+  gemm_32x128<false, false>(sm, rend - rbeg, fa, fb, acc);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = k0 + ty * 4 + i;
@@ -404,7 +499,68 @@ tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, cons
       if (n < N) red_add_f32(dW + static_cast<size_t>(k) * N + n, acc[i][j]);
     }
   }
-  if (db != nullptr && blockIdx.x == 0 && tid < 64 && n0 + tid < N) red_add_f32(db + n0 + tid, bsum);
+  if (db != nullptr) {   // column sums of dpre: this split's rows are shared out over blockIdx.x
+    const int len = rend - rbeg, gx = gridDim.x;
+    const int per = (len + gx - 1) / gx;
+    const int rb = rbeg + blockIdx.x * per, re = min(rend, rb + per);
+    const int c = tid & 127, half = tid >> 7;
+    const int n = n0 + c;
+    float sacc = 0.f;
+    if (n < N)
+      for (int r = rb + half; r < re; r += 2) sacc += dpre_value(sm, gs, r, n);
+    sm.red[0][half][c] = sacc;
+    __syncthreads();
+    if (half == 0 && n < N) {
+      const float t = sm.red[0][0][c] + sm.red[0][1][c];
+      if (t != 0.f) red_add_f32(db + n, t);
+    }
+  }
+}
+
+// N == 1: dW[k] += sum_r P(X)[r,k] * dpre[r]; db += sum_r dpre[r].  CTA = 128 rows x K cols.
+__global__ void __launch_bounds__(256)
+tower_out_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
+                             const GradSrc gs, float* __restrict__ dW, float* __restrict__ db, int B) {
+  __shared__ float s_dp[128];
+  const int r0 = blockIdx.x * 128;
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  if (threadIdx.x < 128) {
+    const int r = r0 + threadIdx.x;
+    float v = 0.f;
+    if (r < B) {
+      const float a = gs.a[static_cast<size_t>(r) * gs.lda];
+      v = a > 0.f ? gs.G[static_cast<size_t>(r) * gs.ldg] : 0.f;
+    }
+    s_dp[threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float mu = 0.f, rstd = 0.f, sc = 1.f, sh = 0.f;
+    if (pro.enabled) {
+      bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+      sc = rstd * pro.gamma[k];
+      sh = pro.beta[k];
+    }
+    float acc = 0.f;
+    for (int rr = 0; rr < 128; ++rr) {
+      const int r = r0 + rr;
+      if (r >= B) break;
+      const float d = s_dp[rr];
+      if (d == 0.f) continue;
+      float v = X[static_cast<size_t>(r) * ldx + k];
+      if (pro.enabled) {
+        v = fmaf(v - mu, sc, sh);
+        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+      }
+      acc = fmaf(v, d, acc);
+    }
+    red_add_f32(dW + k, acc);
+  }
+  if (db != nullptr && threadIdx.x < 32) {
+    float t = s_dp[threadIdx.x] + s_dp[threadIdx.x + 32] + s_dp[threadIdx.x + 64] + s_dp[threadIdx.x + 96];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red_add_f32(db, t);
+  }
 }
 
 // ------------------------------------------------------------------------- loss head
@@ -500,6 +656,17 @@ using namespace ctr;
 
 extern "C" {
 
+static void tower_smem_optin() {
+  static bool done = false;
+  if (done) return;
+  const int bytes = static_cast<int>(sizeof(TowerSmem));
+  cudaFuncSetAttribute(tower_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done = true;
+}
+
 static BnDrop make_pro(const ctr_bn_drop* d, int B) {
   BnDrop p{};
   if (d == nullptr || !d->enabled) return p;
@@ -528,13 +695,19 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
   CTR_REQUIRE(!has_pro || (pro->gamma && pro->beta && (pro->sums || (pro->mean && pro->var))),
               "ctr_tower_layer_fwd", "BN prologue needs gamma/beta and stats");
   if (B == 0) return CTR_OK;
-  dim3 grid((B + kTwBM - 1) / kTwBM, (N + kTwBN - 1) / kTwBN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const BnDrop p = make_pro(pro, B);
+  if (N == 1 && stats == nullptr && (!has_pro || K <= kMaxBn)) {
+    const int g1 = std::min((B + 7) / 8, sm_count() * 8);
+    tower_out_fwd_kernel<<<g1, 256, 0, st>>>(X, ldx, K, p, W, bias, out, ldo, relu, B);
+    CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
+  }
+  tower_smem_optin();
+  dim3 grid((B + kTwBM - 1) / kTwBM, (N + kTwBN - 1) / kTwBN);
   if (has_pro)
-    tower_layer_fwd_kernel<true><<<grid, 256, 0, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+    tower_layer_fwd_kernel<true><<<grid, 256, sizeof(TowerSmem), st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
   else
-    tower_layer_fwd_kernel<false><<<grid, 256, 0, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+    tower_layer_fwd_kernel<false><<<grid, 256, sizeof(TowerSmem), st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
   CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
 }
 
@@ -558,9 +731,17 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
   const bool has_pro = pro != nullptr && pro->enabled;
   CTR_REQUIRE(!has_pro || (Aprev && K <= kMaxBn), "ctr_tower_layer_bwd_data",
               "BN bookkeeping needs Aprev and K <= 256");
+  CTR_REQUIRE(gs->kind == 0 || N <= kMaxBn, "ctr_tower_layer_bwd_data", "BN gradient source needs N <= 256");
   if (B == 0) return CTR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 1 && gs->kind == 0) {
+    tower_out_bwd_data_kernel<<<(B + 63) / 64, 128, 0, st>>>(make_gs(gs, B), W, K, make_pro(pro, B), Aprev,
+                                                            dn_out, ldn, dbeta_prev, dgamma_prev, B);
+    CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
+  }
+  tower_smem_optin();
   dim3 grid((B + kTwBM - 1) / kTwBM, (K + kTwBN - 1) / kTwBN);
-  tower_layer_bwd_data_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  tower_layer_bwd_data_kernel<<<grid, 256, sizeof(TowerSmem), st>>>(
       make_gs(gs, B), N, W, K, make_pro(pro, B), Aprev, dn_out, ldn, dbeta_prev, dgamma_prev, B);
   CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
 }
@@ -571,14 +752,24 @@ int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_dro
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(X && gs && gs->G && gs->a && dW && K > 0 && N > 0 && B >= 0 && ldx >= K,
               "ctr_tower_layer_bwd_weights", "bad argument");
+  const bool has_pro = pro != nullptr && pro->enabled;
+  CTR_REQUIRE(!has_pro || K <= kMaxBn, "ctr_tower_layer_bwd_weights", "BN prologue needs K <= 256");
+  CTR_REQUIRE(gs->kind == 0 || N <= kMaxBn, "ctr_tower_layer_bwd_weights", "BN gradient source needs N <= 256");
   if (B == 0) return CTR_OK;
-  const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
-  int splits = std::max(1, std::min((sm_count() * 3) / tiles, (B + 127) / 128));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 1 && gs->kind == 0) {
+    tower_out_bwd_weights_kernel<<<(B + 127) / 128, 128, 0, st>>>(X, ldx, K, make_pro(pro, B),
+                                                                make_gs(gs, B), dW, db, B);
+    CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_weights");
+  }
+  tower_smem_optin();
+  const int tiles = ((K + kTwBM - 1) / kTwBM) * ((N + kTwBN - 1) / kTwBN);
+  int splits = std::max(1, std::min((sm_count() * 2) / tiles, (B + 127) / 128));
   int rps = (B + splits - 1) / splits;
-  rps = (rps + 15) / 16 * 16;
+  rps = (rps + kTwKC - 1) / kTwKC * kTwKC;
   splits = (B + rps - 1) / rps;
-  dim3 grid((K + 63) / 64, (N + 63) / 64, splits);
-  tower_layer_bwd_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  dim3 grid((K + kTwBM - 1) / kTwBM, (N + kTwBN - 1) / kTwBN, splits);
+  tower_layer_bwd_weights_kernel<<<grid, 256, sizeof(TowerSmem), st>>>(
       X, ldx, K, make_pro(pro, B), make_gs(gs, B), N, dW, db, B, rps);
   CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_weights");
 }
