@@ -201,8 +201,10 @@ class _CriteoBase(_ModelBase):
                                           adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
         self.ids = ops.IdPipeline(self.lay, self.device)
         self.rows = None
-        # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower
-        self.fused = bool(params.get("fused_tower", True))
+        # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower.
+        # Default off for the deep models until the fused GEMMs beat cuBLAS at batch 4096
+        # (profiles/r01_*tower*); FM (no tower, loss head only) always uses the fused head.
+        self.fused = bool(params.get("fused_tower", self.name == "fm"))
         self._head_anchor = torch.zeros((), device=self.device, requires_grad=True)
 
     def load_state(self, state):

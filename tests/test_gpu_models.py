@@ -132,7 +132,7 @@ def test_fused_tower_dropout_matches_oracle_with_same_masks(cuda):
     B = 512
     p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
     feats, batch = mg.model_batch("deepfm", B, 9, spec)
-    m, params = _build("deepfm", spec, cuda, dropout=0.5)
+    m, params = _build("deepfm", spec, cuda, dropout=0.5, fused_tower=True)
     m.load_state(p64)
     masks = _dropout_masks(m, B)
     assert all(0.4 < float(k.mean()) < 0.6 for k in masks) and not torch.equal(masks[0][:, :16], masks[1])
