@@ -358,10 +358,18 @@ def bench_main(args, rank, local, world):
             "e2e": {"value": K * B * world / (max(ms_e2e, wall_e2e) / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": (f.cat.numel() * 8 + l.numel() * 4) * world,
                     "d2h_bytes_per_step": 4 * world,
-                    "api": "deepfm.model_fn(pinned PackedFeatures, labels, 'train', params).train_op()"},
+                    "api": "estimator.GraphedTrainStep(deepfm.model_fn, params)(pinned PackedFeatures, "
+                           "labels)" if graphed is not None else
+                           "deepfm.model_fn(pinned PackedFeatures, labels, 'train', params).train_op()"},
             "gpu_launches": per_step_launches * K * world, "gpu_launches_per_step": per_step_launches,
             "nvlink_bytes_per_gpu_per_step": int((G - 1) / G * B * 39 * (4 + 64 + 64 + 8)),
             "launch_mode": mode,
         }
         print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
+    # Tearing NCCL down under live CUDA graphs that captured its collectives can hang at exit:
+    # agree that everyone is done, then leave without running the destructors.
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
