@@ -2,6 +2,7 @@
 // (cin_simt.cuh); prec 1/2 -> tcgen05 tensor cores (cin_tc.cuh).
 #include "cin_simt.cuh"
 #include "cin_tc.cuh"
+#include "cin_dw_tc.cuh"
 
 namespace ctr {
 
@@ -132,7 +133,7 @@ int ctr_cin_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp, const
     cin_dw_kernel<<<grid, 256, 0, st>>>(X0t, ld0, Xp, ldp, dpre, M, m, Hp, H, dW, rps);
   }
   if (dbias != nullptr) {
-    dim3 grid((H + 31) / 32, std::min(64, (M + 7) / 8));
+    dim3 grid((H + 31) / 32, std::max(1, std::min(1024, (M + 63) / 64)));
     cin_colsum_kernel<<<grid, 256, 0, st>>>(dpre, M, H, dbias);
   }
   CTR_LAUNCH_CHECK("ctr_cin_layer_bwd");

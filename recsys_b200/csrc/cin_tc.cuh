@@ -336,6 +336,8 @@ __global__ void cin_prep_a_kernel(const float* __restrict__ A, int lda, int K, f
 }
 
 // ------------------------------------------------------------------- host side
+static bool cin_dw_tc_supported(int H);
+static int64_t cin_dw_tc_ws(int M, int m, int Hp, int H, int prec);
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -505,7 +507,8 @@ static int64_t cin_tc_workspace_bytes(int B, int D, int m, int Hp, int H, int pr
   const int M = B * D;
   int64_t a = cin_tc_pass_ws(M, m, H, Hp, true, prec);   // fwd / dX0t: A = Xp, K = Hp, G = H
   int64_t b = cin_tc_pass_ws(M, m, Hp, H, true, prec);   // dXp: A = dpre, K = H, G = Hp
-  return std::max(a, b) + 1024;
+  int64_t c = cin_dw_tc_supported(H) ? cin_dw_tc_ws(M, m, Hp, H, prec) : 0;   // dW: ZT + dpreT
+  return std::max(std::max(a, b), c) + 1024;
 }
 
 static int cin_tc_layer_fwd(const float* X0t, int ld0, const float* Xp, int ldp, const float* W,
@@ -515,6 +518,12 @@ static int cin_tc_layer_fwd(const float* X0t, int ld0, const float* Xp, int ldp,
   return cin_tc_pass(MODE_SCALE, Xp, ldp, Hp, W, static_cast<long long>(Hp) * H, 1, H, m, H, X0t,
                      ld0, bias, 1, 0, out, H, B * D, prec, ws, ws_bytes, st, "ctr_cin_layer_fwd");
 }
+
+static bool cin_dw_tc_supported(int H);
+static int64_t cin_dw_tc_ws(int M, int m, int Hp, int H, int prec);
+static int cin_dw_tc(const float* X0t, int ld0, const float* Xp, int ldp, const float* dpre, int M,
+                     int m, int Hp, int H, float* dW, int prec, void* ws, int64_t ws_bytes,
+                     cudaStream_t st, const char* fn);
 
 static int cin_tc_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp, const float* W,
                             const float* dpre, int B, int D, int m, int Hp, int H, float* dX0t,
@@ -536,8 +545,11 @@ static int cin_tc_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp,
                     prec, ws, ws_bytes, st, "ctr_cin_layer_bwd");
     if (r != CTR_OK) return r;
   }
-  // dW / dbias: reduction over all B*D rows - fp32 CUDA-core kernels for now.
-  {
+  // dW: split-K tcgen05 GEMM over the rows (cin_dw_tc.cuh); fp32 CUDA cores when H > 128
+  if (cin_dw_tc_supported(H)) {
+    r = cin_dw_tc(X0t, ld0, Xp, ldp, dpre, M, m, Hp, H, dW, prec, ws, ws_bytes, st, "ctr_cin_layer_bwd");
+    if (r != CTR_OK) return r;
+  } else {
     const int Kq = m * Hp;
     int splits = std::max(1, std::min(64, (sm_count() * 4) / (((Kq + 63) / 64) * ((H + 63) / 64))));
     int rps = (M + splits - 1) / splits;
@@ -547,7 +559,7 @@ static int cin_tc_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp,
     cin_dw_kernel<<<grid, 256, 0, st>>>(X0t, ld0, Xp, ldp, dpre, M, m, Hp, H, dW, rps);
   }
   if (dbias != nullptr) {
-    dim3 grid((H + 31) / 32, std::min(64, (M + 7) / 8));
+    dim3 grid((H + 31) / 32, std::max(1, std::min(1024, (M + 63) / 64)));
     cin_colsum_kernel<<<grid, 256, 0, st>>>(dpre, M, H, dbias);
   }
   return check_cuda(cudaGetLastError(), "ctr_cin_layer_bwd");

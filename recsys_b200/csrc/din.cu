@@ -11,7 +11,7 @@
 // table gradient), dq; it also leaves h1/dh1/dh2/h/h*q rows in scratch so that kernel 2
 // (`xtx`: C += A^T B over the valid rows) forms dW1/dW2 as tall-skinny reductions.
 // FP32 CUDA-core work, compute-bound: padding positions are skipped.
-#include "common.cuh"
+#include "gemm_core.cuh"
 
 namespace ctr {
 
@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
       const bool valid = id > 0;
       if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
       const size_t n = static_cast<size_t>(b) * p.P + pos;
-      float h[E], dh[E];
+      float h[E], dh[E], tq[E];
       float h2[kH2];
-      unsigned m1[3] = {0u, 0u, 0u};   // relu mask of h1
+      unsigned m1a = 0u, m1b = 0u, m1c = 0u;   // relu mask of h1 (80 bits)
       float w = 0.f, dw = 0.f;
       if (valid) {
 #pragma unroll
@@ -206,18 +206,27 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 #pragma unroll
         for (int j = 0; j < kH2; ++j) h2[j] = s.b2[j];
         float* oh1 = p.sH1 + n * kH1;
-#pragma unroll 2
-        for (int k = 0; k < kH1; ++k) {
-          float a = s.cq[warp][k];
-          const float* we = &s.Weff[warp][k * E];
+        for (int k4 = 0; k4 < kH1; k4 += 4) {
+          float a4[4];
 #pragma unroll
-          for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
-          if (a > 0.f) m1[k >> 5] |= 1u << (k & 31);
-          a = fmaxf(a, 0.f);
-          oh1[k] = a;
-          const float* w2 = &s.W2[k * kH2];
+          for (int u = 0; u < 4; ++u) {
+            const int k = k4 + u;
+            float a = s.cq[warp][k];
+            const float* we = &s.Weff[warp][k * E];
 #pragma unroll
-          for (int j = 0; j < kH2; ++j) h2[j] = fmaf(a, w2[j], h2[j]);
+            for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
+            a = fmaxf(a, 0.f);
+            a4[u] = a;
+            const float* w2 = &s.W2[k * kH2];
+#pragma unroll
+            for (int j = 0; j < kH2; ++j) h2[j] = fmaf(a, w2[j], h2[j]);
+          }
+          const unsigned bits = (a4[0] > 0.f ? 1u : 0u) | (a4[1] > 0.f ? 2u : 0u) |
+                                (a4[2] > 0.f ? 4u : 0u) | (a4[3] > 0.f ? 8u : 0u);
+          if (k4 < 32) m1a |= bits << k4;
+          else if (k4 < 64) m1b |= bits << (k4 - 32);
+          else m1c |= bits << (k4 - 64);
+          *reinterpret_cast<float4*>(oh1 + k4) = make_float4(a4[0], a4[1], a4[2], a4[3]);
         }
         w = b3;
 #pragma unroll
@@ -232,32 +241,46 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
           const float r = fmaxf(h2[j], 0.f);
           dW3acc[j] = fmaf(dw, r, dW3acc[j]);
           h2[j] = h2[j] > 0.f ? dw * s.W3[j] : 0.f;    // h2 now holds dh2
-          odh2[j] = h2[j];
         }
 #pragma unroll
-        for (int e = 0; e < E; ++e) dh[e] = w * g[e];
+        for (int j = 0; j < kH2; j += 4)
+          *reinterpret_cast<float4*>(odh2 + j) = make_float4(h2[j], h2[j + 1], h2[j + 2], h2[j + 3]);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          dh[e] = w * g[e];
+          tq[e] = 0.f;
+        }
       }
       // second sweep over k: dh1, dh, dq (Wp part) and the warp-wide sum of dh1
       float* odh1 = p.sdH1 + n * kH1;
-      for (int k = 0; k < kH1; ++k) {
-        float d1 = 0.f;
-        if (valid && ((m1[k >> 5] >> (k & 31)) & 1u)) {
-          const float* w2 = &s.W2[k * kH2];
+      for (int k4 = 0; k4 < kH1; k4 += 4) {
+        const unsigned mw = k4 < 32 ? (m1a >> k4) : k4 < 64 ? (m1b >> (k4 - 32)) : (m1c >> (k4 - 64));
+        float d4[4];
 #pragma unroll
-          for (int j = 0; j < kH2; ++j) d1 = fmaf(h2[j], w2[j], d1);
-        }
-        if (valid) {
-          odh1[k] = d1;
-          const float* we = &s.Weff[warp][k * E];
-          const float* wp = &s.Wp[k * E];
+        for (int u = 0; u < 4; ++u) {
+          const int k = k4 + u;
+          float d1 = 0.f;
+          if (valid && ((mw >> u) & 1u)) {
+            const float* w2 = &s.W2[k * kH2];
 #pragma unroll
-          for (int e = 0; e < E; ++e) {
-            dh[e] = fmaf(d1, we[e], dh[e]);
-            dq[e] = fmaf(d1 * h[e], wp[e], dq[e]);
+            for (int j = 0; j < kH2; ++j) d1 = fmaf(h2[j], w2[j], d1);
+            const float* we = &s.Weff[warp][k * E];
+            const float* wp = &s.Wp[k * E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              dh[e] = fmaf(d1, we[e], dh[e]);
+              tq[e] = fmaf(d1, wp[e], tq[e]);
+            }
           }
+          d4[u] = d1;
+          const float tot = warp_sum(d1);
+          if (lane == 0) s.sd[warp][k] += tot;
         }
-        const float tot = warp_sum(d1);
-        if (lane == 0) s.sd[warp][k] += tot;
+        if (valid) *reinterpret_cast<float4*>(odh1 + k4) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+      }
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) dq[e] = fmaf(h[e], tq[e], dq[e]);
       }
       if (valid) {
         float* oh = p.sHh + n * E;
@@ -298,14 +321,17 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 }
 
 // C[a, c] += sum over valid rows n of A[n, a] * Bm[n, c]; rowmask (nullable): row n valid iff > 0.
+// colsum (nullable): colsum[c] += sum over valid rows of Bm[n, c].  Tile 32 (a) x 128 (c), rows
+// split over gridDim.z, register-prefetch double buffering (gemm_core.cuh).
 __global__ void __launch_bounds__(256)
 xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict__ Bm, int ldb,
            int Kb, const int* __restrict__ rowmask, long long N, float* __restrict__ C, int ldc,
-           long long rows_per_split) {
-  __shared__ __align__(16) float As[16][64];
-  __shared__ __align__(16) float Bs[16][64];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int a0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+           float* __restrict__ colsum, long long rows_per_split) {
+  extern __shared__ __align__(16) uint8_t xtx_smem[];
+  GemmSmem& sm = *reinterpret_cast<GemmSmem*>(xtx_smem);
+  __shared__ float s_red[2][kTwBN];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int a0 = blockIdx.x * kTwBM, c0 = blockIdx.y * kTwBN;
   const long long rbeg = blockIdx.z * rows_per_split;
   const long long rend = min(N, rbeg + rows_per_split);
   float acc[4][4];
@@ -313,36 +339,18 @@ xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long rc = rbeg; rc < rend; rc += 16) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int e = tid + 256 * t;
-      const int rr = e >> 6, cc = e & 63;
-      const long long r = rc + rr;
-      float va = 0.f, vb = 0.f;
-      if (r < rend && (rowmask == nullptr || __ldg(rowmask + r) > 0)) {
-        if (a0 + cc < Ka) va = A[r * lda + a0 + cc];
-        if (c0 + cc < Kb) vb = Bm[r * ldb + c0 + cc];
-      }
-      As[rr][cc] = va;
-      Bs[rr][cc] = vb;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-      const float4 za = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
-      const float4 zb = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
-      const float z[4] = {za.x, za.y, za.z, za.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] = fmaf(z[i], zb.x, acc[i][0]);
-        acc[i][1] = fmaf(z[i], zb.y, acc[i][1]);
-        acc[i][2] = fmaf(z[i], zb.z, acc[i][2]);
-        acc[i][3] = fmaf(z[i], zb.w, acc[i][3]);
-      }
-    }
-    __syncthreads();
-  }
+  auto ok = [&](long long r) -> bool { return rowmask == nullptr || __ldg(rowmask + r) > 0; };
+  auto fa = [&](int m, int rr) -> float {
+    const long long r = rbeg + rr;
+    const int a = a0 + m;
+    return (a < Ka && ok(r)) ? A[r * lda + a] : 0.f;
+  };
+  auto fb = [&](int rr, int c) -> float {
+    const long long r = rbeg + rr;
+    const int cc = c0 + c;
+    return (cc < Kb && ok(r)) ? Bm[r * ldb + cc] : 0.f;
+  };
+  gemm_32x128<false, false>(sm, static_cast<int>(rend - rbeg), fa, fb, acc);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int a = a0 + ty * 4 + i;
@@ -353,26 +361,22 @@ xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict
       if (c < Kb && acc[i][j] != 0.f) red_add_f32(C + static_cast<size_t>(a) * ldc + c, acc[i][j]);
     }
   }
-}
-
-// out[c] += sum over valid rows of X[n, c]
-__global__ void __launch_bounds__(256)
-masked_colsum_kernel(const float* __restrict__ X, int ld, int K, const int* __restrict__ rowmask,
-                     long long N, float* __restrict__ out) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ry = threadIdx.x >> 5;
-  float sacc = 0.f;
-  if (c < K)
-    for (long long r = blockIdx.y * 8LL + ry; r < N; r += gridDim.y * 8LL)
-      if (rowmask == nullptr || __ldg(rowmask + r) > 0) sacc += X[r * ld + c];
-  __shared__ float red[8][33];
-  red[ry][threadIdx.x & 31] = sacc;
-  __syncthreads();
-  if (ry == 0 && c < K) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-    red_add_f32(out + c, t);
+  if (colsum != nullptr) {   // this split's rows shared out over blockIdx.x
+    const long long len = rend - rbeg;
+    const long long per = (len + gridDim.x - 1) / gridDim.x;
+    const long long rb = rbeg + blockIdx.x * per, re = min(rend, rb + per);
+    const int c = tid & 127, half = tid >> 7;
+    const int cc = c0 + c;
+    float sacc = 0.f;
+    if (cc < Kb)
+      for (long long r = rb + half; r < re; r += 2)
+        if (ok(r)) sacc += Bm[r * ldb + cc];
+    s_red[half][c] = sacc;
+    __syncthreads();
+    if (half == 0 && cc < Kb) {
+      const float t = s_red[0][c] + s_red[1][c];
+      if (t != 0.f) red_add_f32(colsum + cc, t);
+    }
   }
 }
 
@@ -389,14 +393,21 @@ __global__ void din_assemble_dw1_kernel(const float* __restrict__ tmp, int E, fl
 }
 
 static void xtx_launch(const float* A, int lda, int Ka, const float* Bm, int ldb, int Kb,
-                       const int* mask, long long N, float* C, int ldc, cudaStream_t st) {
-  const int tiles = ((Ka + 63) / 64) * ((Kb + 63) / 64);
+                       const int* mask, long long N, float* C, int ldc, float* colsum,
+                       cudaStream_t st) {
+  static bool optin = false;
+  if (!optin) {
+    cudaFuncSetAttribute(xtx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(sizeof(GemmSmem)));
+    optin = true;
+  }
+  const int tiles = ((Ka + kTwBM - 1) / kTwBM) * ((Kb + kTwBN - 1) / kTwBN);
   long long splits = std::max<long long>(1, std::min<long long>((sm_count() * 4) / tiles, (N + 255) / 256));
   long long rps = (N + splits - 1) / splits;
-  rps = (rps + 15) / 16 * 16;
+  rps = (rps + kTwKC - 1) / kTwKC * kTwKC;
   splits = (N + rps - 1) / rps;
-  dim3 grid((Ka + 63) / 64, (Kb + 63) / 64, static_cast<unsigned>(splits));
-  xtx_kernel<<<grid, 256, 0, st>>>(A, lda, Ka, Bm, ldb, Kb, mask, N, C, ldc, rps);
+  dim3 grid((Ka + kTwBM - 1) / kTwBM, (Kb + kTwBN - 1) / kTwBN, static_cast<unsigned>(splits));
+  xtx_kernel<<<grid, 256, sizeof(GemmSmem), st>>>(A, lda, Ka, Bm, ldb, Kb, mask, N, C, ldc, colsum, rps);
 }
 
 template <int E>
@@ -498,17 +509,13 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
     case 16: din_bwd_launch<16>(p, st); break;
     default: din_bwd_launch<32>(p, st); break;
   }
-  // weight gradients: tall-skinny reductions over the valid positions
-  xtx_launch(p.sH1, kH1, kH1, p.sdH2, kH2, kH2, hist, N, dW2, kH2, st);            // dW2 = H1^T dH2
-  xtx_launch(p.sHh, E, E, p.sdH1, kH1, kH1, hist, N, tmp, kH1, st);                // dWh = H^T dH1
-  xtx_launch(p.sHQ, E, E, p.sdH1, kH1, kH1, hist, N, tmp + E * kH1, kH1, st);      // dWp = (H*q)^T dH1
-  xtx_launch(query, E, E, p.sSd, kH1, kH1, nullptr, B, tmp + 2 * E * kH1, kH1, st);  // dWq = Q^T sum dH1
+  // weight gradients: tall-skinny reductions over the valid positions; the bias gradients are
+  // the column sums of the same B operands
+  xtx_launch(p.sH1, kH1, kH1, p.sdH2, kH2, kH2, hist, N, dW2, kH2, db2, st);               // dW2 = H1^T dH2
+  xtx_launch(p.sHh, E, E, p.sdH1, kH1, kH1, hist, N, tmp, kH1, nullptr, st);               // dWh = H^T dH1
+  xtx_launch(p.sHQ, E, E, p.sdH1, kH1, kH1, hist, N, tmp + E * kH1, kH1, nullptr, st);     // dWp = (H*q)^T dH1
+  xtx_launch(query, E, E, p.sSd, kH1, kH1, nullptr, B, tmp + 2 * E * kH1, kH1, db1, st);   // dWq = Q^T sum dH1
   din_assemble_dw1_kernel<<<(E * kH1 + 255) / 256, 256, 0, st>>>(tmp, E, dW1);
-  {
-    dim3 g1((kH1 + 31) / 32, 32), g2((kH2 + 31) / 32, 64);
-    masked_colsum_kernel<<<g1, 256, 0, st>>>(p.sSd, kH1, kH1, nullptr, B, db1);
-    masked_colsum_kernel<<<g2, 256, 0, st>>>(p.sdH2, kH2, kH2, hist, N, db2);
-  }
   CTR_LAUNCH_CHECK("ctr_din_att_bwd");
 }
 
