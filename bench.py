@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (debug)")
     ap.add_argument("--cin-precision", default="tf32", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--fused-tower", type=int, default=None, help="1/0: force the fused tower kernels")
     return ap.parse_args()
 
 
@@ -213,6 +214,8 @@ def build_model(args, dev):
               "cross_layers": "128,128" if args.model == "xdeepfm" else 4,
               "cin_precision": args.cin_precision, "variable_store": VariableStore(), "device": dev,
               "embedding_adam": "lazy"}
+    if args.fused_tower is not None:
+        params["fused_tower"] = bool(args.fused_tower)
     return mod, params
 
 

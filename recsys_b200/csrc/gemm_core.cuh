@@ -75,5 +75,117 @@ __device__ __forceinline__ void gemm_32x128(GemmSmem& sm, int nk, FA fa, FB fb, 
   }
 }
 
+// ------------------------------------------------------------------ vectorised variant
+// Same pipeline, but the functors hand over 4 consecutive elements along the operand's
+// contiguous axis (one LDG.128 when aligned), and the row tile is RT*8 rows (RT = 2 -> 16-row
+// tiles: twice the CTAs when the batch alone cannot fill the machine).
+//   fa4(rr, k)  A_KFAST : elements (rr, k..k+3)          !A_KFAST : elements (rr..rr+3, k)
+//   fb4(k, c)   B_KFAST : elements (k..k+3, c)           !B_KFAST : elements (k, c..c+3)
+template <int RT, bool A_KFAST, bool B_KFAST, typename FA, typename FB>
+__device__ __forceinline__ void gemm_tile_v4(GemmSmem& sm, int nk, FA fa4, FB fb4,
+                                             float (&acc)[RT][4]) {
+  constexpr int BM = RT * 8;
+  constexpr int NA4 = BM * kTwKC / 4;              // float4 loads for the A chunk
+  constexpr int TA = (NA4 + 255) / 256;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  float4 ra[TA], rb[4];
+  auto a_pos = [&](int e, int& rr, int& kk) {
+    if (A_KFAST) { rr = e >> 3; kk = (e & 7) * 4; }
+    else { kk = e / (BM / 4); rr = (e % (BM / 4)) * 4; }
+  };
+  auto b_pos = [&](int e, int& kk, int& c) {
+    if (B_KFAST) { c = e >> 3; kk = (e & 7) * 4; }
+    else { kk = e >> 5; c = (e & 31) * 4; }
+  };
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+      const int e = tid + 256 * t;
+      if (e < NA4) {
+        int rr, kk;
+        a_pos(e, rr, kk);
+        ra[t] = fa4(rr, k0 + kk);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int kk, c;
+      b_pos(tid + 256 * t, kk, c);
+      rb[t] = fb4(k0 + kk, c);
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+      const int e = tid + 256 * t;
+      if (e < NA4) {
+        int rr, kk;
+        a_pos(e, rr, kk);
+        if (A_KFAST) {
+          sm.A[buf][kk][rr] = ra[t].x;
+          sm.A[buf][kk + 1][rr] = ra[t].y;
+          sm.A[buf][kk + 2][rr] = ra[t].z;
+          sm.A[buf][kk + 3][rr] = ra[t].w;
+        } else {
+          *reinterpret_cast<float4*>(&sm.A[buf][kk][rr]) = ra[t];
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int kk, c;
+      b_pos(tid + 256 * t, kk, c);
+      if (B_KFAST) {
+        sm.B[buf][kk][c] = rb[t].x;
+        sm.B[buf][kk + 1][c] = rb[t].y;
+        sm.B[buf][kk + 2][c] = rb[t].z;
+        sm.B[buf][kk + 3][c] = rb[t].w;
+      } else {
+        *reinterpret_cast<float4*>(&sm.B[buf][kk][c]) = rb[t];
+      }
+    }
+  };
+  load(0);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < nk; k0 += kTwKC) {
+    const bool more = k0 + kTwKC < nk;
+    if (more) load(k0 + kTwKC);
+#pragma unroll
+    for (int kk = 0; kk < kTwKC; ++kk) {
+      float av[RT];
+      if constexpr (RT == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&sm.A[buf][kk][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(&sm.A[buf][kk][ty * 2]);
+        av[0] = a.x; av[1] = a.y;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&sm.B[buf][kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+    if (more) store(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+// 4 consecutive floats at p (elements beyond `valid` read as 0); LDG.128 when possible.
+__device__ __forceinline__ float4 load4_guard(const float* p, int valid, bool aligned) {
+  if (valid >= 4 && aligned) return *reinterpret_cast<const float4*>(p);
+  float4 v = f4_zero();
+  if (valid > 0) v.x = p[0];
+  if (valid > 1) v.y = p[1];
+  if (valid > 2) v.z = p[2];
+  if (valid > 3) v.w = p[3];
+  return v;
+}
 
 }  // namespace ctr

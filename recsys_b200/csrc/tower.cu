@@ -141,43 +141,77 @@ __device__ __forceinline__ float dpre_value(const TowerSmem& sm, const GradSrc& 
   return v;
 }
 
+__device__ __forceinline__ bool aligned16_dev(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+// dpre for 4 consecutive columns n..n+3 of row r (columns >= N read as 0)
+__device__ __forceinline__ float4 dpre4(const TowerSmem& sm, const GradSrc& g, int r, int n, int N) {
+  const bool al = (g.lda & 3) == 0 && (g.ldg & 3) == 0 && aligned16_dev(g.a) && aligned16_dev(g.G);
+  const float4 a = load4_guard(g.a + static_cast<size_t>(r) * g.lda + n, N - n, al);
+  float4 v = load4_guard(g.G + static_cast<size_t>(r) * g.ldg + n, N - n, al);
+  if (g.kind == 1) {
+#define CTR_DP1(c, o)                                                          \
+    if (n + o < N) {                                                           \
+      const float xhat = (a.c - sm.gmu[n + o]) * sm.grs[n + o];                \
+      v.c = (v.c - sm.gc1[n + o] - xhat * sm.gc2[n + o]) * sm.gsc[n + o];      \
+    }
+    CTR_DP1(x, 0) CTR_DP1(y, 1) CTR_DP1(z, 2) CTR_DP1(w, 3)
+#undef CTR_DP1
+  }
+  v.x = a.x > 0.f ? v.x : 0.f;
+  v.y = a.y > 0.f ? v.y : 0.f;
+  v.z = a.z > 0.f ? v.z : 0.f;
+  v.w = a.w > 0.f ? v.w : 0.f;
+  return v;
+}
+
 // --------------------------------------------------------------------------- forward
-template <bool PRO>
+template <bool PRO, int RT>
 __global__ void __launch_bounds__(256)
 tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
                        const float* __restrict__ W, const float* __restrict__ bias, int N,
                        float* __restrict__ out, int ldo, float* __restrict__ stats, int relu, int B) {
   extern __shared__ __align__(16) uint8_t tw_smem[];
   TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
+  constexpr int BM = RT * 8;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int r0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
+  const int r0 = blockIdx.x * BM, n0 = blockIdx.y * kTwBN;
   unsigned step = 0;
   if (PRO) {
     fill_pro_tables(sm, pro, K);
     if (pro.state != nullptr) step = static_cast<unsigned>(pro.state[0]);
     __syncthreads();
   }
-  float acc[4][4];
+  float acc[RT][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  auto fa = [&](int rr, int k) -> float {
+  const bool xal = (ldx & 3) == 0 && aligned16_dev(X);
+  const bool wal = (N & 3) == 0 && aligned16_dev(W);
+  auto fa4 = [&](int rr, int k) -> float4 {
     const int r = r0 + rr;
-    if (r >= B) return 0.f;
-    const float v = X[static_cast<size_t>(r) * ldx + k];
-    return PRO ? pro_value(sm, pro, step, v, r, k) : v;
+    if (r >= B || k >= K) return f4_zero();
+    float4 v = load4_guard(X + static_cast<size_t>(r) * ldx + k, K - k, xal);
+    if (PRO) {
+      v.x = pro_value(sm, pro, step, v.x, r, k);
+      if (k + 1 < K) v.y = pro_value(sm, pro, step, v.y, r, k + 1);
+      if (k + 2 < K) v.z = pro_value(sm, pro, step, v.z, r, k + 2);
+      if (k + 3 < K) v.w = pro_value(sm, pro, step, v.w, r, k + 3);
+    }
+    return v;
   };
-  auto fb = [&](int k, int c) -> float {
+  auto fb4 = [&](int k, int c) -> float4 {
     const int n = n0 + c;
-    return n < N ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+    if (k >= K || n >= N) return f4_zero();
+    return load4_guard(W + static_cast<size_t>(k) * N + n, N - n, wal);
   };
-  gemm_32x128<true, false>(sm, K, fa, fb, acc);
+  gemm_tile_v4<RT, true, false>(sm, K, fa4, fb4, acc);
 
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty * 4 + i;
+  for (int i = 0; i < RT; ++i) {
+    const int r = r0 + ty * RT + i;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -275,6 +309,7 @@ bn_drop_apply_kernel(const float* __restrict__ A, int K, const BnDrop pro, float
 // stored activation Aprev (pro): dn = dXin * keep is stored, and its column sums
 // dbeta_prev += sum_r dn, dgamma_prev += sum_r dn * xhat_prev are accumulated for the layer below.
 // With pro.enabled == 0 (first layer) dXin is stored as is.
+template <int RT>
 __global__ void __launch_bounds__(256)
 tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W, int K,
                             const BnDrop pro, const float* __restrict__ Aprev,
@@ -282,42 +317,45 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
                             float* __restrict__ dgamma_prev, int B) {
   extern __shared__ __align__(16) uint8_t tw_smem[];
   TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
+  constexpr int BM = RT * 8;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int r0 = blockIdx.x * kTwBM, k0 = blockIdx.y * kTwBN;
+  const int r0 = blockIdx.x * BM, k0 = blockIdx.y * kTwBN;
   const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
   fill_gs_tables(sm, gs, N);
   if (pro.enabled) fill_pro_tables(sm, pro, K);
   __syncthreads();
-  float acc[4][4];
+  float acc[RT][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  auto fa = [&](int rr, int n) -> float {
+  const bool wal = (N & 3) == 0 && aligned16_dev(W);
+  auto fa4 = [&](int rr, int n) -> float4 {
     const int r = r0 + rr;
-    return r < B ? dpre_value(sm, gs, r, n) : 0.f;
+    if (r >= B || n >= N) return f4_zero();
+    return dpre4(sm, gs, r, n, N);
   };
-  auto fb = [&](int n, int c) -> float {
+  auto fb4 = [&](int n, int c) -> float4 {          // 4 consecutive n of W row (k0 + c)
     const int k = k0 + c;
-    return k < K ? __ldg(W + static_cast<size_t>(k) * N + n) : 0.f;
+    if (k >= K || n >= N) return f4_zero();
+    return load4_guard(W + static_cast<size_t>(k) * N + n, N - n, wal);
   };
-  gemm_32x128<true, true>(sm, N, fa, fb, acc);
+  gemm_tile_v4<RT, true, true>(sm, N, fa4, fb4, acc);
 
   float cb[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int k = k0 + tx * 4 + j;
     if (k >= K) continue;
+    float mu = 0.f, rstd = 0.f;
+    if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty * 4 + i;
+    for (int i = 0; i < RT; ++i) {
+      const int r = r0 + ty * RT + i;
       if (r >= B) continue;
       float v = acc[i][j];
       if (pro.enabled) {
         if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
-        // xhat = (A - mu) * rstd; sm.sc = rstd * gamma, so keep rstd separately
-        float mu, rstd;
-        bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
         const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
         cb[j] += v;
         cg[j] = fmaf(v, xhat, cg[j]);
@@ -410,17 +448,26 @@ tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, cons
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  auto fa = [&](int m, int rr) -> float {      // A[m = k index][kk = row]
+  const bool xal = (ldx & 3) == 0 && aligned16_dev(X);
+  const int nrows = rend - rbeg;
+  auto fa4 = [&](int m, int rr) -> float4 {      // 4 consecutive k of row (rbeg + rr)
     const int k = k0 + m, r = rbeg + rr;
-    if (k >= K) return 0.f;
-    const float v = X[static_cast<size_t>(r) * ldx + k];
-    return pro.enabled ? pro_value(sm, pro, step, v, r, k) : v;
+    if (k >= K || rr >= nrows) return f4_zero();
+    float4 v = load4_guard(X + static_cast<size_t>(r) * ldx + k, K - k, xal);
+    if (pro.enabled) {
+      v.x = pro_value(sm, pro, step, v.x, r, k);
+      if (k + 1 < K) v.y = pro_value(sm, pro, step, v.y, r, k + 1);
+      if (k + 2 < K) v.z = pro_value(sm, pro, step, v.z, r, k + 2);
+      if (k + 3 < K) v.w = pro_value(sm, pro, step, v.w, r, k + 3);
+    }
+    return v;
   };
-  auto fb = [&](int rr, int c) -> float {
+  auto fb4 = [&](int rr, int c) -> float4 {
     const int n = n0 + c;
-    return n < N ? dpre_value(sm, gs, rbeg + rr, n) : 0.f;
+    if (rr >= nrows || n >= N) return f4_zero();
+    return dpre4(sm, gs, rbeg + rr, n, N);
   };
-  gemm_32x128<false, false>(sm, rend - rbeg, fa, fb, acc);
+  gemm_tile_v4<4, false, false>(sm, nrows, fa4, fb4, acc);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = k0 + ty * 4 + i;
@@ -592,9 +639,12 @@ static void tower_smem_optin() {
   static bool done = false;
   if (done) return;
   const int bytes = static_cast<int>(sizeof(TowerSmem));
-  cudaFuncSetAttribute(tower_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(tower_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(tower_layer_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_fwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_fwd_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_fwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_bwd_data_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(tower_layer_bwd_data_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(tower_layer_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   done = true;
 }
@@ -635,11 +685,17 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
     CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
   }
   tower_smem_optin();
-  dim3 grid((B + kTwBM - 1) / kTwBM, (N + kTwBN - 1) / kTwBN);
-  if (has_pro)
-    tower_layer_fwd_kernel<true><<<grid, 256, sizeof(TowerSmem), st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
-  else
-    tower_layer_fwd_kernel<false><<<grid, 256, sizeof(TowerSmem), st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+  const int ny = (N + kTwBN - 1) / kTwBN;
+  const bool small = static_cast<long long>((B + 31) / 32) * ny < 2LL * sm_count();   // 16-row tiles
+  dim3 grid(small ? (B + 15) / 16 : (B + 31) / 32, ny);
+  const size_t sb = sizeof(TowerSmem);
+  if (has_pro) {
+    if (small) tower_layer_fwd_kernel<true, 2><<<grid, 256, sb, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+    else tower_layer_fwd_kernel<true, 4><<<grid, 256, sb, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+  } else {
+    if (small) tower_layer_fwd_kernel<false, 2><<<grid, 256, sb, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+    else tower_layer_fwd_kernel<false, 4><<<grid, 256, sb, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
+  }
   CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
 }
 
@@ -672,9 +728,15 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
     CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
   }
   tower_smem_optin();
-  dim3 grid((B + kTwBM - 1) / kTwBM, (K + kTwBN - 1) / kTwBN);
-  tower_layer_bwd_data_kernel<<<grid, 256, sizeof(TowerSmem), st>>>(
-      make_gs(gs, B), N, W, K, make_pro(pro, B), Aprev, dn_out, ldn, dbeta_prev, dgamma_prev, B);
+  const int ny = (K + kTwBN - 1) / kTwBN;
+  const bool small = static_cast<long long>((B + 31) / 32) * ny < 2LL * sm_count();
+  dim3 grid(small ? (B + 15) / 16 : (B + 31) / 32, ny);
+  if (small)
+    tower_layer_bwd_data_kernel<2><<<grid, 256, sizeof(TowerSmem), st>>>(
+        make_gs(gs, B), N, W, K, make_pro(pro, B), Aprev, dn_out, ldn, dbeta_prev, dgamma_prev, B);
+  else
+    tower_layer_bwd_data_kernel<4><<<grid, 256, sizeof(TowerSmem), st>>>(
+        make_gs(gs, B), N, W, K, make_pro(pro, B), Aprev, dn_out, ldn, dbeta_prev, dgamma_prev, B);
   CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
 }
 
@@ -696,7 +758,7 @@ int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_dro
   }
   tower_smem_optin();
   const int tiles = ((K + kTwBM - 1) / kTwBM) * ((N + kTwBN - 1) / kTwBN);
-  int splits = std::max(1, std::min((sm_count() * 2) / tiles, (B + 127) / 128));
+  int splits = std::max(1, std::min((sm_count() * 3) / tiles, (B + 63) / 64));
   int rps = (B + splits - 1) / splits;
   rps = (rps + kTwKC - 1) / kTwKC * kTwKC;
   splits = (B + rps - 1) / rps;
