@@ -189,3 +189,142 @@ __device__ __forceinline__ float4 load4_guard(const float* p, int valid, bool al
 }
 
 }  // namespace ctr
+
+// ------------------------------------------------------------- tensor-core variant (3xTF32)
+// Same staging pipeline; the multiply runs on the warp-level tensor-core path
+// (mma.sync.m16n8k8 tf32, fp32 accumulate) with the error-compensated split
+//   a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi,   x_hi = tf32(x), x_lo = tf32(x - x_hi)
+// which keeps fp32-grade accuracy (the dense tower must match the fp32 reference to 1e-4).
+// The split is done once per element on the way into shared memory (hi and lo tiles); the 8
+// warps each own 16 of the 128 columns and all BM rows.  This is for the small dense-tower
+// GEMMs only - the CIN contraction uses tcgen05 (cin_tc.cuh).
+namespace ctr {
+
+constexpr int kMmAP = 40, kMmBP = 136;     // pitches = 8 (mod 32): conflict-free fragment loads
+
+struct MmaSmem {
+  float Ah[2][kTwKC][kMmAP], Al[2][kTwKC][kMmAP];
+  float Bh[2][kTwKC][kMmBP], Bl[2][kTwKC][kMmBP];
+};
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+        "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
+}
+
+// acc[mt][nt][4]: C fragments of m16-tile mt (rows mt*16 + g, +8) and n8-tile nt of this warp
+// (columns warp*16 + nt*8 + 2t, +1), g = lane >> 2, t = lane & 3.   MT = BM / 16.
+template <int MT, bool A_KFAST, bool B_KFAST, typename FA, typename FB>
+__device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb4,
+                                              float (&acc)[MT][2][4]) {
+  constexpr int BM = MT * 16;
+  constexpr int NA4 = BM * kTwKC / 4;
+  constexpr int TA = (NA4 + 255) / 256;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float4 ra[TA], rb[4];
+  auto a_pos = [&](int e, int& rr, int& kk) {
+    if (A_KFAST) { rr = e >> 3; kk = (e & 7) * 4; }
+    else { kk = e / (BM / 4); rr = (e % (BM / 4)) * 4; }
+  };
+  auto b_pos = [&](int e, int& kk, int& c) {
+    if (B_KFAST) { c = e >> 3; kk = (e & 7) * 4; }
+    else { kk = e >> 5; c = (e & 31) * 4; }
+  };
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < TA; ++i) {
+      const int e = tid + 256 * i;
+      if (e < NA4) {
+        int rr, kk;
+        a_pos(e, rr, kk);
+        ra[i] = fa4(rr, k0 + kk);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int kk, c;
+      b_pos(tid + 256 * i, kk, c);
+      rb[i] = fb4(k0 + kk, c);
+    }
+  };
+  auto put = [&](float* hi, float* lo, float v) { split_tf32(v, *hi, *lo); };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < TA; ++i) {
+      const int e = tid + 256 * i;
+      if (e < NA4) {
+        int rr, kk;
+        a_pos(e, rr, kk);
+        const float v[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k2 = A_KFAST ? kk + u : kk, r2 = A_KFAST ? rr : rr + u;
+          put(&sm.Ah[buf][k2][r2], &sm.Al[buf][k2][r2], v[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int kk, c;
+      b_pos(tid + 256 * i, kk, c);
+      const float v[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k2 = B_KFAST ? kk + u : kk, c2 = B_KFAST ? c : c + u;
+        put(&sm.Bh[buf][k2][c2], &sm.Bl[buf][k2][c2], v[u]);
+      }
+    }
+  };
+  load(0);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  const int nb = warp * 16;
+  for (int k0 = 0; k0 < nk; k0 += kTwKC) {
+    const bool more = k0 + kTwKC < nk;
+    if (more) load(k0 + kTwKC);
+#pragma unroll
+    for (int ks = 0; ks < kTwKC; ks += 8) {
+      float ah[MT][4], al[MT][4], bh[2][2], bl[2][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m = mt * 16 + g;
+        ah[mt][0] = sm.Ah[buf][ks + t][m];       al[mt][0] = sm.Al[buf][ks + t][m];
+        ah[mt][1] = sm.Ah[buf][ks + t][m + 8];   al[mt][1] = sm.Al[buf][ks + t][m + 8];
+        ah[mt][2] = sm.Ah[buf][ks + t + 4][m];   al[mt][2] = sm.Al[buf][ks + t + 4][m];
+        ah[mt][3] = sm.Ah[buf][ks + t + 4][m + 8]; al[mt][3] = sm.Al[buf][ks + t + 4][m + 8];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int n = nb + nt * 8 + g;
+        bh[nt][0] = sm.Bh[buf][ks + t][n];      bl[nt][0] = sm.Bl[buf][ks + t][n];
+        bh[nt][1] = sm.Bh[buf][ks + t + 4][n];  bl[nt][1] = sm.Bl[buf][ks + t + 4][n];
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+    if (more) store(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+}  // namespace ctr

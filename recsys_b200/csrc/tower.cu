@@ -95,7 +95,7 @@ __device__ __forceinline__ void bn_consts(const float* sums, const float* mean, 
   }
 }
 
-struct TowerSmem : GemmSmem {
+struct TowerSmem : MmaSmem {
   float mu[kMaxBn], sc[kMaxBn], sh[kMaxBn];                              // prologue tables
   float gmu[kMaxBn], grs[kMaxBn], gc1[kMaxBn], gc2[kMaxBn], gsc[kMaxBn];  // gradient-source tables
   float red[2][8][kTwBN];
@@ -173,8 +173,9 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
                        float* __restrict__ out, int ldo, float* __restrict__ stats, int relu, int B) {
   extern __shared__ __align__(16) uint8_t tw_smem[];
   TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
-  constexpr int BM = RT * 8;
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  constexpr int MT = RT / 2;                 // RT = 2 -> 16-row tile, RT = 4 -> 32-row tile
+  constexpr int BM = MT * 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int r0 = blockIdx.x * BM, n0 = blockIdx.y * kTwBN;
   unsigned step = 0;
   if (PRO) {
@@ -182,11 +183,13 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
     if (pro.state != nullptr) step = static_cast<unsigned>(pro.state[0]);
     __syncthreads();
   }
-  float acc[RT][4];
+  float acc[MT][2][4];
 #pragma unroll
-  for (int i = 0; i < RT; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
   const bool xal = (ldx & 3) == 0 && aligned16_dev(X);
   const bool wal = (N & 3) == 0 && aligned16_dev(W);
   auto fa4 = [&](int rr, int k) -> float4 {
@@ -206,42 +209,43 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
     if (k >= K || n >= N) return f4_zero();
     return load4_guard(W + static_cast<size_t>(k) * N + n, N - n, wal);
   };
-  gemm_tile_v4<RT, true, false>(sm, K, fa4, fb4, acc);
+  gemm_tile_mma<MT, true, false>(sm, K, fa4, fb4, acc);
 
-  float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+  // epilogue on the C fragments: rows r0 + mt*16 + g (+8), columns n0 + warp*16 + nt*8 + 2t (+1)
 #pragma unroll
-  for (int i = 0; i < RT; ++i) {
-    const int r = r0 + ty * RT + i;
+  for (int nt = 0; nt < 2; ++nt) {
+    float cs[2] = {0.f, 0.f}, cq[2] = {0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (r < B && n < N) {
-        float v = acc[i][j] + (bias != nullptr ? __ldg(bias + n) : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
-        out[static_cast<size_t>(r) * ldo + n] = v;
-        cs[j] += v;
-        cq[j] = fmaf(v, v, cq[j]);
-      }
-    }
-  }
-  if (stats != nullptr) {
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sm.red[0][ty][tx * 4 + j] = cs[j];
-      sm.red[1][ty][tx * 4 + j] = cq[j];
-    }
-    __syncthreads();
-    if (tid < kTwBN) {
-      const int n = n0 + tid;
-      if (n < N) {
-        float a = 0.f, q = 0.f;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          a += sm.red[0][y][tid];
-          q += sm.red[1][y][tid];
+      for (int ci = 0; ci < 4; ++ci) {
+        const int r = r0 + mt * 16 + g + (ci >> 1) * 8;
+        const int n = n0 + warp * 16 + nt * 8 + 2 * t + (ci & 1);
+        if (r < B && n < N) {
+          float v = acc[mt][nt][ci] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+          if (relu) v = fmaxf(v, 0.f);
+          out[static_cast<size_t>(r) * ldo + n] = v;
+          cs[ci & 1] += v;
+          cq[ci & 1] = fmaf(v, v, cq[ci & 1]);
         }
-        red_add_f32(stats + n, a);
-        red_add_f32(stats + N + n, q);
+      }
+    if (stats != nullptr) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], o);
+        cs[1] += __shfl_xor_sync(0xffffffffu, cs[1], o);
+        cq[0] += __shfl_xor_sync(0xffffffffu, cq[0], o);
+        cq[1] += __shfl_xor_sync(0xffffffffu, cq[1], o);
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int n = n0 + warp * 16 + nt * 8 + 2 * t + j;
+          if (n < N) {
+            red_add_f32(stats + n, cs[j]);
+            red_add_f32(stats + N + n, cq[j]);
+          }
+        }
       }
     }
   }
@@ -317,18 +321,21 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
                             float* __restrict__ dgamma_prev, int B) {
   extern __shared__ __align__(16) uint8_t tw_smem[];
   TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
-  constexpr int BM = RT * 8;
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  constexpr int MT = RT / 2;
+  constexpr int BM = MT * 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int r0 = blockIdx.x * BM, k0 = blockIdx.y * kTwBN;
   const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
   fill_gs_tables(sm, gs, N);
   if (pro.enabled) fill_pro_tables(sm, pro, K);
   __syncthreads();
-  float acc[RT][4];
+  float acc[MT][2][4];
 #pragma unroll
-  for (int i = 0; i < RT; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
   const bool wal = (N & 3) == 0 && aligned16_dev(W);
   auto fa4 = [&](int rr, int n) -> float4 {
     const int r = r0 + rr;
@@ -340,61 +347,71 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
     if (k >= K || n >= N) return f4_zero();
     return load4_guard(W + static_cast<size_t>(k) * N + n, N - n, wal);
   };
-  gemm_tile_v4<RT, true, true>(sm, N, fa4, fb4, acc);
+  gemm_tile_mma<MT, true, true>(sm, N, fa4, fb4, acc);
 
-  float cb[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = k0 + tx * 4 + j;
-    if (k >= K) continue;
-    float mu = 0.f, rstd = 0.f;
-    if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+  for (int nt = 0; nt < 2; ++nt) {
+    float cb[2] = {0.f, 0.f}, cg[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < RT; ++i) {
-      const int r = r0 + ty * RT + i;
-      if (r >= B) continue;
-      float v = acc[i][j];
-      if (pro.enabled) {
-        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
-        const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
-        cb[j] += v;
-        cg[j] = fmaf(v, xhat, cg[j]);
-      }
-      dn_out[static_cast<size_t>(r) * ldn + k] = v;
-    }
-  }
-  if (pro.enabled && dbeta_prev != nullptr) {
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + warp * 16 + nt * 8 + 2 * t + j;
+      if (k >= K) continue;
+      float mu = 0.f, rstd = 0.f;
+      if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sm.red[0][ty][tx * 4 + j] = cb[j];
-      sm.red[1][ty][tx * 4 + j] = cg[j];
-    }
-    __syncthreads();
-    if (tid < kTwBN) {
-      const int k = k0 + tid;
-      if (k < K) {
-        float a = 0.f, q = 0.f;
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          a += sm.red[0][y][tid];
-          q += sm.red[1][y][tid];
+        for (int h = 0; h < 2; ++h) {
+          const int r = r0 + mt * 16 + g + h * 8;
+          if (r >= B) continue;
+          float v = acc[mt][nt][h * 2 + j];
+          if (pro.enabled) {
+            if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+            const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
+            cb[j] += v;
+            cg[j] = fmaf(v, xhat, cg[j]);
+          }
+          dn_out[static_cast<size_t>(r) * ldn + k] = v;
         }
-        red_add_f32(dbeta_prev + k, a);
-        red_add_f32(dgamma_prev + k, q);
+    }
+    if (pro.enabled && dbeta_prev != nullptr) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        cb[0] += __shfl_xor_sync(0xffffffffu, cb[0], o);
+        cb[1] += __shfl_xor_sync(0xffffffffu, cb[1], o);
+        cg[0] += __shfl_xor_sync(0xffffffffu, cg[0], o);
+        cg[1] += __shfl_xor_sync(0xffffffffu, cg[1], o);
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = k0 + warp * 16 + nt * 8 + 2 * t + j;
+          if (k < K) {
+            red_add_f32(dbeta_prev + k, cb[j]);
+            red_add_f32(dgamma_prev + k, cg[j]);
+          }
+        }
       }
     }
   }
 }
 
-// N == 1: dn[r,k] = dpre[r] * W[k] * keep, column sums for the BN below.  CTA = 64 rows x K cols.
-__global__ void __launch_bounds__(256)
-tower_out_bwd_data_kernel(const GradSrc gs, const float* __restrict__ W, int K, const BnDrop pro,
-                          const float* __restrict__ Aprev, float* __restrict__ dn_out, int ldn,
-                          float* __restrict__ dbeta_prev, float* __restrict__ dgamma_prev, int B) {
-  __shared__ float s_dp[64];
-  const int r0 = blockIdx.x * 64;
+// N == 1 (the final dense(1, relu)), both halves of its backward in one pass over the rows:
+//   dpre[r] = G[r] * 1[y[r] > 0]
+//   dW[k] += sum_r P(A)[r,k] * dpre[r];  db += sum_r dpre[r]                   (weights == true)
+//   dn[r,k] = dpre[r] * W[k] * keep;  dbeta[k] += sum_r dn;  dgamma[k] += sum_r dn * xhat  (data)
+// CTA = 16 rows x K columns (thread = column), grid = B/16: enough CTAs to hide the latency.
+constexpr int kOutRows = 16;
+template <bool WEIGHTS>
+__global__ void __launch_bounds__(128)
+tower_out_bwd_kernel(const GradSrc gs, const float* __restrict__ X, int ldx,
+                     const float* __restrict__ W, int K, const BnDrop pro, float* __restrict__ dW,
+                     float* __restrict__ db, float* __restrict__ dn_out, int ldn,
+                     float* __restrict__ dbeta_prev, float* __restrict__ dgamma_prev, int B) {
+  __shared__ float s_dp[kOutRows];
+  const int r0 = blockIdx.x * kOutRows;
   const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < kOutRows) {
     const int r = r0 + threadIdx.x;
     float v = 0.f;
     if (r < B) {
@@ -405,26 +422,53 @@ tower_out_bwd_data_kernel(const GradSrc gs, const float* __restrict__ W, int K, 
   }
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float w = W[k];
-    float mu = 0.f, rstd = 0.f;
-    if (pro.enabled) bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
-    float cb = 0.f, cg = 0.f;
-    for (int rr = 0; rr < 64; ++rr) {
+    float mu = 0.f, rstd = 0.f, sc = 1.f, sh = 0.f;
+    if (pro.enabled) {
+      bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+      sc = rstd * pro.gamma[k];
+      sh = pro.beta[k];
+    }
+    const float w = WEIGHTS ? 0.f : W[k];
+    const bool need_x = WEIGHTS || pro.enabled;
+    float xv[kOutRows];
+#pragma unroll
+    for (int rr = 0; rr < kOutRows; ++rr)
+      xv[rr] = (need_x && r0 + rr < B) ? X[static_cast<size_t>(r0 + rr) * ldx + k] : 0.f;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < kOutRows; ++rr) {
       const int r = r0 + rr;
-      if (r >= B) break;
-      float v = s_dp[rr] * w;
-      if (pro.enabled) {
-        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
-        const float xhat = (Aprev[static_cast<size_t>(r) * K + k] - mu) * rstd;
-        cb += v;
-        cg = fmaf(v, xhat, cg);
+      const float d = s_dp[rr];
+      if (r >= B || d == 0.f) {
+        if (!WEIGHTS && r < B) dn_out[static_cast<size_t>(r) * ldn + k] = 0.f;
+        continue;
       }
-      dn_out[static_cast<size_t>(r) * ldn + k] = v;
+      const float keep = (pro.enabled && pro.p > 0.f)
+                             ? drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep) : 1.f;
+      if (WEIGHTS) {
+        const float v = pro.enabled ? fmaf(xv[rr] - mu, sc, sh) * keep : xv[rr];
+        a0 = fmaf(v, d, a0);
+      } else {
+        const float v = d * w * keep;
+        dn_out[static_cast<size_t>(r) * ldn + k] = v;
+        if (pro.enabled) {
+          a0 += v;
+          a1 = fmaf(v, (xv[rr] - mu) * rstd, a1);
+        }
+      }
     }
-    if (pro.enabled && dbeta_prev != nullptr) {
-      red_add_f32(dbeta_prev + k, cb);
-      red_add_f32(dgamma_prev + k, cg);
+    if (WEIGHTS) {
+      if (a0 != 0.f) red_add_f32(dW + k, a0);
+    } else if (pro.enabled && dbeta_prev != nullptr) {
+      if (a0 != 0.f) red_add_f32(dbeta_prev + k, a0);
+      if (a1 != 0.f) red_add_f32(dgamma_prev + k, a1);
     }
+  }
+  if (WEIGHTS && db != nullptr && threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < kOutRows; ++rr) t += s_dp[rr];
+    if (t != 0.f) red_add_f32(db, t);
   }
 }
 
@@ -436,18 +480,20 @@ tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, cons
                                float* __restrict__ db, int B, int rows_per_split) {
   extern __shared__ __align__(16) uint8_t tw_smem[];
   TowerSmem& sm = *reinterpret_cast<TowerSmem*>(tw_smem);
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int k0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
   const int rbeg = blockIdx.z * rows_per_split, rend = min(B, rbeg + rows_per_split);
   const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
   fill_gs_tables(sm, gs, N);
   if (pro.enabled) fill_pro_tables(sm, pro, K);
   __syncthreads();
-  float acc[4][4];
+  float acc[2][2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
   const bool xal = (ldx & 3) == 0 && aligned16_dev(X);
   const int nrows = rend - rbeg;
   auto fa4 = [&](int m, int rr) -> float4 {      // 4 consecutive k of row (rbeg + rr)
@@ -467,17 +513,17 @@ tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, cons
     if (rr >= nrows || n >= N) return f4_zero();
     return dpre4(sm, gs, rbeg + rr, n, N);
   };
-  gemm_tile_v4<4, false, false>(sm, nrows, fa4, fb4, acc);
+  gemm_tile_mma<2, false, false>(sm, nrows, fa4, fb4, acc);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = k0 + ty * 4 + i;
-    if (k >= K) continue;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) red_add_f32(dW + static_cast<size_t>(k) * N + n, acc[i][j]);
-    }
-  }
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int k = k0 + mt * 16 + g + (ci >> 1) * 8;
+        const int n = n0 + warp * 16 + nt * 8 + 2 * t + (ci & 1);
+        if (k < K && n < N) red_add_f32(dW + static_cast<size_t>(k) * N + n, acc[mt][nt][ci]);
+      }
   if (db != nullptr) {   // column sums of dpre: this split's rows are shared out over blockIdx.x
     const int len = rend - rbeg, gx = gridDim.x;
     const int per = (len + gx - 1) / gx;
@@ -493,52 +539,6 @@ tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, cons
       const float t = sm.red[0][0][c] + sm.red[0][1][c];
       if (t != 0.f) red_add_f32(db + n, t);
     }
-  }
-}
-
-// N == 1: dW[k] += sum_r P(X)[r,k] * dpre[r]; db += sum_r dpre[r].  CTA = 128 rows x K cols.
-__global__ void __launch_bounds__(256)
-tower_out_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop pro,
-                             const GradSrc gs, float* __restrict__ dW, float* __restrict__ db, int B) {
-  __shared__ float s_dp[128];
-  const int r0 = blockIdx.x * 128;
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
-  if (threadIdx.x < 128) {
-    const int r = r0 + threadIdx.x;
-    float v = 0.f;
-    if (r < B) {
-      const float a = gs.a[static_cast<size_t>(r) * gs.lda];
-      v = a > 0.f ? gs.G[static_cast<size_t>(r) * gs.ldg] : 0.f;
-    }
-    s_dp[threadIdx.x] = v;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float mu = 0.f, rstd = 0.f, sc = 1.f, sh = 0.f;
-    if (pro.enabled) {
-      bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
-      sc = rstd * pro.gamma[k];
-      sh = pro.beta[k];
-    }
-    float acc = 0.f;
-    for (int rr = 0; rr < 128; ++rr) {
-      const int r = r0 + rr;
-      if (r >= B) break;
-      const float d = s_dp[rr];
-      if (d == 0.f) continue;
-      float v = X[static_cast<size_t>(r) * ldx + k];
-      if (pro.enabled) {
-        v = fmaf(v - mu, sc, sh);
-        if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
-      }
-      acc = fmaf(v, d, acc);
-    }
-    red_add_f32(dW + k, acc);
-  }
-  if (db != nullptr && threadIdx.x < 32) {
-    float t = s_dp[threadIdx.x] + s_dp[threadIdx.x + 32] + s_dp[threadIdx.x + 64] + s_dp[threadIdx.x + 96];
-    t = warp_sum(t);
-    if (threadIdx.x == 0) red_add_f32(db, t);
   }
 }
 
@@ -723,8 +723,9 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
   if (B == 0) return CTR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N == 1 && gs->kind == 0) {
-    tower_out_bwd_data_kernel<<<(B + 63) / 64, 128, 0, st>>>(make_gs(gs, B), W, K, make_pro(pro, B), Aprev,
-                                                            dn_out, ldn, dbeta_prev, dgamma_prev, B);
+    tower_out_bwd_kernel<false><<<(B + kOutRows - 1) / kOutRows, 128, 0, st>>>(
+        make_gs(gs, B), Aprev != nullptr ? Aprev : W, K, W, K, make_pro(pro, B), nullptr, nullptr, dn_out,
+        ldn, dbeta_prev, dgamma_prev, B);
     CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
   }
   tower_smem_optin();
@@ -752,8 +753,8 @@ int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_dro
   if (B == 0) return CTR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N == 1 && gs->kind == 0) {
-    tower_out_bwd_weights_kernel<<<(B + 127) / 128, 128, 0, st>>>(X, ldx, K, make_pro(pro, B),
-                                                                make_gs(gs, B), dW, db, B);
+    tower_out_bwd_kernel<true><<<(B + kOutRows - 1) / kOutRows, 128, 0, st>>>(
+        make_gs(gs, B), X, ldx, nullptr, K, make_pro(pro, B), dW, db, nullptr, 0, nullptr, nullptr, B);
     CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_weights");
   }
   tower_smem_optin();
