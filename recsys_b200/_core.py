@@ -117,6 +117,9 @@ class _ModelBase:
         self.dense.load(state)
 
     def dense_grads(self):
+        tw = getattr(self, "tower", None)
+        if tw is not None:
+            tw.join()
         return self.dense.grads()
 
     # EstimatorSpec --------------------------------------------------------------
@@ -202,9 +205,8 @@ class _CriteoBase(_ModelBase):
         self.ids = ops.IdPipeline(self.lay, self.device)
         self.rows = None
         # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower.
-        # Default off for the deep models until the fused GEMMs beat cuBLAS at batch 4096
-        # (profiles/r01_*tower*); FM (no tower, loss head only) always uses the fused head.
-        self.fused = bool(params.get("fused_tower", self.name == "fm"))
+        # DCN's tower has no final dense layer (its backward is not fused yet): torch tower.
+        self.fused = bool(params.get("fused_tower", self.name != "dcn"))
         self._head_anchor = torch.zeros((), device=self.device, requires_grad=True)
 
     def load_state(self, state):
@@ -231,9 +233,15 @@ class _CriteoBase(_ModelBase):
             import torch.distributed as dist
             dist.all_reduce(self.dense.grad)      # replicated dense weights: sum of per-rank grads
 
+    def _join_tower(self):
+        tw = getattr(self, "tower", None)
+        if tw is not None:
+            tw.join()
+
     def _apply_gradients(self, lr_t):
+        self.emb.adam_step(self.rows, lr_t, self.adam)     # overlaps the side-stream dW kernels
+        self._join_tower()
         self._sync_dense_grads()
-        self.emb.adam_step(self.rows, lr_t, self.adam)
         self.dense.adam_step(lr_t, self.adam)
 
 
@@ -441,10 +449,11 @@ class XDeepFMModel(_CriteoBase):
         return torch.addmm(P["head.b"], z, P["head.w"])                         # :195  [B,1]
 
     def _apply_gradients(self, lr_t):
-        self._sync_dense_grads()
         self.emb.adam_step(self.rows, lr_t, self.adam)
         if self.emb_dnn is not None:
             self.emb_dnn.adam_step(self.rows, lr_t, self.adam)
+        self._join_tower()
+        self._sync_dense_grads()
         self.dense.adam_step(lr_t, self.adam)
 
 

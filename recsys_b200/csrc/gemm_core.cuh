@@ -259,7 +259,12 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
       rb[i] = fb4(k0 + kk, c);
     }
   };
-  auto put = [&](float* hi, float* lo, float v) { split_tf32(v, *hi, *lo); };
+  auto split4 = [&](const float4& v, float4& hi, float4& lo) {
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+  };
   auto store = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < TA; ++i) {
@@ -267,11 +272,16 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
       if (e < NA4) {
         int rr, kk;
         a_pos(e, rr, kk);
-        const float v[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k2 = A_KFAST ? kk + u : kk, r2 = A_KFAST ? rr : rr + u;
-          put(&sm.Ah[buf][k2][r2], &sm.Al[buf][k2][r2], v[u]);
+        float4 hi, lo;
+        split4(ra[i], hi, lo);
+        if (A_KFAST) {          // 4 consecutive k of one row: transposing scalar stores
+          sm.Ah[buf][kk][rr] = hi.x;     sm.Al[buf][kk][rr] = lo.x;
+          sm.Ah[buf][kk + 1][rr] = hi.y; sm.Al[buf][kk + 1][rr] = lo.y;
+          sm.Ah[buf][kk + 2][rr] = hi.z; sm.Al[buf][kk + 2][rr] = lo.z;
+          sm.Ah[buf][kk + 3][rr] = hi.w; sm.Al[buf][kk + 3][rr] = lo.w;
+        } else {
+          *reinterpret_cast<float4*>(&sm.Ah[buf][kk][rr]) = hi;
+          *reinterpret_cast<float4*>(&sm.Al[buf][kk][rr]) = lo;
         }
       }
     }
@@ -279,11 +289,16 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
     for (int i = 0; i < 4; ++i) {
       int kk, c;
       b_pos(tid + 256 * i, kk, c);
-      const float v[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k2 = B_KFAST ? kk + u : kk, c2 = B_KFAST ? c : c + u;
-        put(&sm.Bh[buf][k2][c2], &sm.Bl[buf][k2][c2], v[u]);
+      float4 hi, lo;
+      split4(rb[i], hi, lo);
+      if (B_KFAST) {
+        sm.Bh[buf][kk][c] = hi.x;     sm.Bl[buf][kk][c] = lo.x;
+        sm.Bh[buf][kk + 1][c] = hi.y; sm.Bl[buf][kk + 1][c] = lo.y;
+        sm.Bh[buf][kk + 2][c] = hi.z; sm.Bl[buf][kk + 2][c] = lo.z;
+        sm.Bh[buf][kk + 3][c] = hi.w; sm.Bl[buf][kk + 3][c] = lo.w;
+      } else {
+        *reinterpret_cast<float4*>(&sm.Bh[buf][kk][c]) = hi;
+        *reinterpret_cast<float4*>(&sm.Bl[buf][kk][c]) = lo;
       }
     }
   };

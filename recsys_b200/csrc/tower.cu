@@ -17,6 +17,8 @@
 //
 // Dropout masks are counter based (Philox4x32-10 keyed by seed, layer and the device-side step
 // counter), regenerated in the backward instead of stored.
+#include <cstdlib>
+
 #include "gemm_core.cuh"
 
 namespace ctr {
@@ -686,7 +688,8 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
   }
   tower_smem_optin();
   const int ny = (N + kTwBN - 1) / kTwBN;
-  const bool small = static_cast<long long>((B + 31) / 32) * ny < 2LL * sm_count();   // 16-row tiles
+  bool small = static_cast<long long>((B + 31) / 32) * ny * 2 < sm_count();   // 16-row tiles
+  if (const char* e = getenv("CTR_TOWER_RT")) small = atoi(e) == 2;
   dim3 grid(small ? (B + 15) / 16 : (B + 31) / 32, ny);
   const size_t sb = sizeof(TowerSmem);
   if (has_pro) {
@@ -730,7 +733,8 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
   }
   tower_smem_optin();
   const int ny = (K + kTwBN - 1) / kTwBN;
-  const bool small = static_cast<long long>((B + 31) / 32) * ny < 2LL * sm_count();
+  bool small = static_cast<long long>((B + 31) / 32) * ny * 2 < sm_count();
+  if (const char* e = getenv("CTR_TOWER_RT")) small = atoi(e) == 2;
   dim3 grid(small ? (B + 15) / 16 : (B + 31) / 32, ny);
   if (small)
     tower_layer_bwd_data_kernel<2><<<grid, 256, sizeof(TowerSmem), st>>>(

@@ -548,6 +548,16 @@ class FusedTower:
         self.dense, self.prefix, self.sizes = dense, prefix, list(sizes)
         self.out_layer, self.dropout, self.adam, self.seed = out_layer, float(dropout), adam, seed
         self._anchor = torch.zeros((), device=dense.flat.device, requires_grad=True)
+        # weight-gradient kernels run on a side stream, off the critical path
+        # (dX chain -> embedding scatter -> row Adam); joined in ``join()`` before dense Adam
+        self.side = torch.cuda.Stream(device=dense.flat.device)
+        self._pending = None
+
+    def join(self):
+        """Make the current stream wait for the side-stream weight-gradient kernels."""
+        if self._pending is not None:
+            torch.cuda.current_stream().wait_event(self._pending)
+            self._pending = None
 
     def P(self, name):
         return self.dense[self.prefix + "." + name]
@@ -624,28 +634,48 @@ class _TowerFn(torch.autograd.Function):
                 g.dbeta, g.dgamma = _p(tw.G("%d.bn.beta" % l)), _p(tw.G("%d.bn.gamma" % l))
             return g
 
+        main = torch.cuda.current_stream()
+        side = tw.side
+
+        def fork():
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+
+        def weights(xin, K, pro, gs_w, H, wname, bname):
+            with torch.cuda.stream(side):
+                _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs_w), H,
+                      _p(tw.G(wname)), _p(tw.G(bname)), B, side.cuda_stream)
+
         # final dense(1, relu): dpre = dout * 1[y > 0]
         gs = grad_src(dout, 1, y, 1, 0)
         HL = tw.sizes[L]
-        _call("ctr_tower_layer_bwd_weights", _p(acts[L - 1]), HL, HL, C.byref(pros[L - 1]),
-              C.byref(gs), 1, _p(tw.G("out.w")), _p(tw.G("out.b")), B, _stream())
+        fork()
+        weights(acts[L - 1], HL, C.byref(pros[L - 1]), gs, 1, "out.w", "out.b")
         dn = torch.empty((B, HL), dtype=torch.float32, device=dev)
         _call("ctr_tower_layer_bwd_data", C.byref(gs), 1, _p(tw.P("out.w")), HL,
               C.byref(pros[L - 1]), _p(acts[L - 1]), _p(dn), HL, _p(tw.G("%d.bn.beta" % (L - 1))),
               _p(tw.G("%d.bn.gamma" % (L - 1))), B, _stream())
+        keep = [dout, dn]
         for l in range(L - 1, -1, -1):
             H, K = tw.sizes[l + 1], tw.sizes[l]
             gs = grad_src(dn, H, acts[l], H, 1, l)
             xin = acts[l - 1] if l > 0 else X
             pro = C.byref(pros[l - 1]) if l > 0 else None
-            _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs), H,
-                  _p(tw.G("%d.w" % l)), _p(tw.G("%d.b" % l)), B, _stream())
+            fork()        # dbeta_l / dgamma_l (written by the data kernel above) are ready
+            weights(xin, K, pro, gs, H, "%d.w" % l, "%d.b" % l)
             dnext = torch.empty((B, K), dtype=torch.float32, device=dev)
             _call("ctr_tower_layer_bwd_data", C.byref(gs), H, _p(tw.P("%d.w" % l)), K, pro,
                   _p(xin) if l > 0 else None, _p(dnext), K,
                   _p(tw.G("%d.bn.beta" % (l - 1))) if l > 0 else None,
                   _p(tw.G("%d.bn.gamma" % (l - 1))) if l > 0 else None, B, _stream())
             dn = dnext
+            keep.append(dn)
+        for t_ in keep + acts + [X]:           # tensors read by the side stream
+            t_.record_stream(side)
+        done = torch.cuda.Event()
+        done.record(side)
+        tw._pending = done
         return dn, None, None, None
 
 
