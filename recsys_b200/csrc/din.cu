@@ -41,6 +41,7 @@ struct DinParams {
   float* sHh;    // [B*P, E]
   float* sHQ;    // [B*P, E]
   float* sSd;    // [B, 80]  sum_p dh1
+  const int* rowbase;   // [B+1] exclusive prefix of valid positions per sample (compact rows)
   float* dW3;
   float* db3;
 };
@@ -187,12 +188,16 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
     for (int k = lane; k < kH1; k += 32) s.sd[warp][k] = 0.f;
     __syncwarp();
 
+    int row_cursor = __ldg(p.rowbase + b);
     for (int p0 = 0; p0 < p.P; p0 += 32) {
       const int pos = p0 + lane;
       const int id = pos < p.P ? __ldg(p.hist + static_cast<size_t>(b) * p.P + pos) : 0;
       const bool valid = id > 0;
-      if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
-      const size_t n = static_cast<size_t>(b) * p.P + pos;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      if (vmask == 0u) continue;
+      // compact scratch row of this position: valid positions only, in (sample, position) order
+      const size_t n = static_cast<size_t>(row_cursor + __popc(vmask & ((1u << lane) - 1u)));
+      row_cursor += __popc(vmask);
       float h[E], dh[E], tq[E];
       float h2[kH2];
       unsigned m1a = 0u, m1b = 0u, m1c = 0u;   // relu mask of h1 (80 bits)
@@ -320,62 +325,101 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
   if (lane == 0 && t3 != 0.f) red_add_f32(p.db3, t3);
 }
 
-// C[a, c] += sum over valid rows n of A[n, a] * Bm[n, c]; rowmask (nullable): row n valid iff > 0.
-// colsum (nullable): colsum[c] += sum over valid rows of Bm[n, c].  Tile 32 (a) x 128 (c), rows
-// split over gridDim.z, register-prefetch double buffering (gemm_core.cuh).
-__global__ void __launch_bounds__(256)
-xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict__ Bm, int ldb,
-           int Kb, const int* __restrict__ rowmask, long long N, float* __restrict__ C, int ldc,
-           float* __restrict__ colsum, long long rows_per_split) {
-  extern __shared__ __align__(16) uint8_t xtx_smem[];
-  GemmSmem& sm = *reinterpret_cast<GemmSmem*>(xtx_smem);
-  __shared__ float s_red[2][kTwBN];
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int a0 = blockIdx.x * kTwBM, c0 = blockIdx.y * kTwBN;
-  const long long rbeg = blockIdx.z * rows_per_split;
-  const long long rend = min(N, rbeg + rows_per_split);
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  auto ok = [&](long long r) -> bool { return rowmask == nullptr || __ldg(rowmask + r) > 0; };
-  auto fa = [&](int m, int rr) -> float {
-    const long long r = rbeg + rr;
-    const int a = a0 + m;
-    return (a < Ka && ok(r)) ? A[r * lda + a] : 0.f;
-  };
-  auto fb = [&](int rr, int c) -> float {
-    const long long r = rbeg + rr;
-    const int cc = c0 + c;
-    return (cc < Kb && ok(r)) ? Bm[r * ldb + cc] : 0.f;
-  };
-  gemm_32x128<false, false>(sm, static_cast<int>(rend - rbeg), fa, fb, acc);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int a = a0 + ty * 4 + i;
-    if (a >= Ka) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + tx * 4 + j;
-      if (c < Kb && acc[i][j] != 0.f) red_add_f32(C + static_cast<size_t>(a) * ldc + c, acc[i][j]);
+// rowbase[b] = number of valid (id > 0) history positions in samples < b; rowbase[B] = total.
+__global__ void __launch_bounds__(1024)
+din_rowbase_kernel(const int* __restrict__ hist, int B, int P, int* __restrict__ rowbase) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (B + 1023) / 1024;          // samples per thread
+  int cnt = 0;
+  for (int i = 0; i < per; ++i) {
+    const int b = tid * per + i;
+    if (b < B)
+      for (int p = 0; p < P; ++p) cnt += hist[static_cast<size_t>(b) * P + p] > 0 ? 1 : 0;
+  }
+  s_part[tid] = cnt;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {        // inclusive scan
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - cnt;                // exclusive prefix of this thread's samples
+  for (int i = 0; i < per; ++i) {
+    const int b = tid * per + i;
+    if (b < B) {
+      rowbase[b] = run;
+      int c = 0;
+      for (int p = 0; p < P; ++p) c += hist[static_cast<size_t>(b) * P + p] > 0 ? 1 : 0;
+      run += c;
     }
   }
+  if (tid == 1023) rowbase[B] = s_part[1023];
+}
+
+// C[a, c] += sum_{n < N} A[n, a] * Bm[n, c]   (N read from *n_dev when given: compact rows).
+// colsum (nullable): colsum[c] += sum_n Bm[n, c].  Tile 16|32 (a) x 128 (c), rows split over
+// gridDim.z, 3xTF32 tensor-core tile core (gemm_core.cuh).
+template <int MT>
+__global__ void __launch_bounds__(256)
+xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict__ Bm, int ldb,
+           int Kb, const int* __restrict__ n_dev, long long N, float* __restrict__ C, int ldc,
+           float* __restrict__ colsum, long long rows_per_split) {
+  extern __shared__ __align__(16) uint8_t xtx_smem[];
+  MmaSmem& sm = *reinterpret_cast<MmaSmem*>(xtx_smem);
+  __shared__ float s_red[2][kTwBN];
+  if (n_dev != nullptr) N = min(N, static_cast<long long>(*n_dev));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int a0 = blockIdx.x * (MT * 16), c0 = blockIdx.y * kTwBN;
+  const long long rbeg = blockIdx.z * rows_per_split;
+  const long long rend = min(N, rbeg + rows_per_split);
+  if (rbeg >= rend) return;
+  const int nrows = static_cast<int>(rend - rbeg);
+  float acc[MT][2][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  const bool aal = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  const bool bal = (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(Bm) & 15) == 0;
+  auto fa4 = [&](int m, int rr) -> float4 {         // 4 consecutive a of row rbeg + rr
+    const int a = a0 + m;
+    if (a >= Ka || rr >= nrows) return f4_zero();
+    return load4_guard(A + (rbeg + rr) * lda + a, Ka - a, aal);
+  };
+  auto fb4 = [&](int rr, int c) -> float4 {
+    const int cc = c0 + c;
+    if (cc >= Kb || rr >= nrows) return f4_zero();
+    return load4_guard(Bm + (rbeg + rr) * ldb + cc, Kb - cc, bal);
+  };
+  gemm_tile_mma<MT, false, false>(sm, nrows, fa4, fb4, acc, Kb - c0);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int a = a0 + mt * 16 + g + (ci >> 1) * 8;
+        const int c = c0 + warp * 16 + nt * 8 + 2 * t + (ci & 1);
+        if (a < Ka && c < Kb && acc[mt][nt][ci] != 0.f)
+          red_add_f32(C + static_cast<size_t>(a) * ldc + c, acc[mt][nt][ci]);
+      }
   if (colsum != nullptr) {   // this split's rows shared out over blockIdx.x
-    const long long len = rend - rbeg;
-    const long long per = (len + gridDim.x - 1) / gridDim.x;
+    const long long per = (nrows + gridDim.x - 1) / gridDim.x;
     const long long rb = rbeg + blockIdx.x * per, re = min(rend, rb + per);
     const int c = tid & 127, half = tid >> 7;
     const int cc = c0 + c;
     float sacc = 0.f;
     if (cc < Kb)
-      for (long long r = rb + half; r < re; r += 2)
-        if (ok(r)) sacc += Bm[r * ldb + cc];
+      for (long long r = rb + half; r < re; r += 2) sacc += Bm[r * ldb + cc];
     s_red[half][c] = sacc;
     __syncthreads();
     if (half == 0 && cc < Kb) {
-      const float t = s_red[0][c] + s_red[1][c];
-      if (t != 0.f) red_add_f32(colsum + cc, t);
+      const float v = s_red[0][c] + s_red[1][c];
+      if (v != 0.f) red_add_f32(colsum + cc, v);
     }
   }
 }
@@ -393,21 +437,28 @@ __global__ void din_assemble_dw1_kernel(const float* __restrict__ tmp, int E, fl
 }
 
 static void xtx_launch(const float* A, int lda, int Ka, const float* Bm, int ldb, int Kb,
-                       const int* mask, long long N, float* C, int ldc, float* colsum,
+                       const int* n_dev, long long N, float* C, int ldc, float* colsum,
                        cudaStream_t st) {
   static bool optin = false;
   if (!optin) {
-    cudaFuncSetAttribute(xtx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(GemmSmem)));
+    cudaFuncSetAttribute(xtx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(sizeof(MmaSmem)));
+    cudaFuncSetAttribute(xtx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(sizeof(MmaSmem)));
     optin = true;
   }
-  const int tiles = ((Ka + kTwBM - 1) / kTwBM) * ((Kb + kTwBN - 1) / kTwBN);
-  long long splits = std::max<long long>(1, std::min<long long>((sm_count() * 4) / tiles, (N + 255) / 256));
+  const int mt = Ka <= 16 ? 1 : 2;
+  const int bm = mt * 16;
+  const int tiles = ((Ka + bm - 1) / bm) * ((Kb + kTwBN - 1) / kTwBN);
+  long long splits = std::max<long long>(1, std::min<long long>((sm_count() * 2) / tiles, (N + 255) / 256));
   long long rps = (N + splits - 1) / splits;
   rps = (rps + kTwKC - 1) / kTwKC * kTwKC;
   splits = (N + rps - 1) / rps;
-  dim3 grid((Ka + kTwBM - 1) / kTwBM, (Kb + kTwBN - 1) / kTwBN, static_cast<unsigned>(splits));
-  xtx_kernel<<<grid, 256, sizeof(GemmSmem), st>>>(A, lda, Ka, Bm, ldb, Kb, mask, N, C, ldc, colsum, rps);
+  dim3 grid((Ka + bm - 1) / bm, (Kb + kTwBN - 1) / kTwBN, static_cast<unsigned>(splits));
+  if (mt == 1)
+    xtx_kernel<1><<<grid, 256, sizeof(MmaSmem), st>>>(A, lda, Ka, Bm, ldb, Kb, n_dev, N, C, ldc, colsum, rps);
+  else
+    xtx_kernel<2><<<grid, 256, sizeof(MmaSmem), st>>>(A, lda, Ka, Bm, ldb, Kb, n_dev, N, C, ldc, colsum, rps);
 }
 
 template <int E>
@@ -442,7 +493,7 @@ extern "C" {
 
 int64_t ctr_din_workspace_bytes(int B, int P, int E) {
   const int64_t n = static_cast<int64_t>(B) * P;
-  return (n * (kH1 + kH1 + kH2 + E + E) + static_cast<int64_t>(B) * kH1 + 3LL * E * kH1) * 4 + 1024;
+  return (n * (kH1 + kH1 + kH2 + E + E) + static_cast<int64_t>(B) * kH1 + 3LL * E * kH1 + B + 8) * 4 + 1024;
 }
 
 int ctr_din_att_fwd(const float* table, const int32_t* hist, const float* query, int B, int P,
@@ -501,6 +552,9 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
   p.sHQ = p.sHh + N * E;
   p.sSd = p.sHQ + N * E;
   float* tmp = p.sSd + static_cast<long long>(B) * kH1;   // [3][E][80]
+  int* rowbase = reinterpret_cast<int*>(tmp + 3 * E * kH1);   // [B+1]
+  p.rowbase = rowbase;
+  din_rowbase_kernel<<<1, 1024, 0, st>>>(hist, B, P, rowbase);
   p.dW3 = dW3; p.db3 = db3;
   cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(float) * 3 * E * kH1, st);
   if (e != cudaSuccess) return check_cuda(e, "ctr_din_att_bwd");
@@ -511,9 +565,10 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
   }
   // weight gradients: tall-skinny reductions over the valid positions; the bias gradients are
   // the column sums of the same B operands
-  xtx_launch(p.sH1, kH1, kH1, p.sdH2, kH2, kH2, hist, N, dW2, kH2, db2, st);               // dW2 = H1^T dH2
-  xtx_launch(p.sHh, E, E, p.sdH1, kH1, kH1, hist, N, tmp, kH1, nullptr, st);               // dWh = H^T dH1
-  xtx_launch(p.sHQ, E, E, p.sdH1, kH1, kH1, hist, N, tmp + E * kH1, kH1, nullptr, st);     // dWp = (H*q)^T dH1
+  const int* nvalid = rowbase + B;     // rows actually written (compact), read on the device
+  xtx_launch(p.sH1, kH1, kH1, p.sdH2, kH2, kH2, nvalid, N, dW2, kH2, db2, st);             // dW2 = H1^T dH2
+  xtx_launch(p.sHh, E, E, p.sdH1, kH1, kH1, nvalid, N, tmp, kH1, nullptr, st);             // dWh = H^T dH1
+  xtx_launch(p.sHQ, E, E, p.sdH1, kH1, kH1, nvalid, N, tmp + E * kH1, kH1, nullptr, st);   // dWp = (H*q)^T dH1
   xtx_launch(query, E, E, p.sSd, kH1, kH1, nullptr, B, tmp + 2 * E * kH1, kH1, db1, st);   // dWq = Q^T sum dH1
   din_assemble_dw1_kernel<<<(E * kH1 + 255) / 256, 256, 0, st>>>(tmp, E, dW1);
   CTR_LAUNCH_CHECK("ctr_din_att_bwd");

@@ -227,7 +227,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], con
 // (columns warp*16 + nt*8 + 2t, +1), g = lane >> 2, t = lane & 3.   MT = BM / 16.
 template <int MT, bool A_KFAST, bool B_KFAST, typename FA, typename FB>
 __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb4,
-                                              float (&acc)[MT][2][4]) {
+                                              float (&acc)[MT][2][4], int ncols = kTwBN) {
   constexpr int BM = MT * 16;
   constexpr int NA4 = BM * kTwKC / 4;
   constexpr int TA = (NA4 + 255) / 256;
@@ -310,6 +310,7 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
   for (int k0 = 0; k0 < nk; k0 += kTwKC) {
     const bool more = k0 + kTwKC < nk;
     if (more) load(k0 + kTwKC);
+    if (nb < ncols)      // warps whose 16 columns lie beyond the live columns only help staging
 #pragma unroll
     for (int ks = 0; ks < kTwKC; ks += 8) {
       float ah[MT][4], al[MT][4], bh[2][2], bl[2][2];
