@@ -325,37 +325,46 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
   if (lane == 0 && t3 != 0.f) red_add_f32(p.db3, t3);
 }
 
-// rowbase[b] = number of valid (id > 0) history positions in samples < b; rowbase[B] = total.
+// counts[b] = number of valid (id > 0) history positions of sample b: one warp per sample.
+__global__ void __launch_bounds__(256)
+din_count_kernel(const int* __restrict__ hist, int B, int P, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += gridDim.x * 8) {
+    int c = 0;
+    for (int p = lane; p < P; p += 32) c += __ldg(hist + static_cast<size_t>(b) * P + p) > 0 ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[b + 1] = c;
+  }
+}
+// in place: rowbase[0] = 0, rowbase[b+1] = sum_{i <= b} counts[i]  (single CTA, B <= 1M).
 __global__ void __launch_bounds__(1024)
-din_rowbase_kernel(const int* __restrict__ hist, int B, int P, int* __restrict__ rowbase) {
+din_scan_kernel(int* __restrict__ rowbase, int B) {
   __shared__ int s_part[1024];
   const int tid = threadIdx.x;
-  const int per = (B + 1023) / 1024;          // samples per thread
+  const int per = (B + 1023) / 1024;
   int cnt = 0;
   for (int i = 0; i < per; ++i) {
     const int b = tid * per + i;
-    if (b < B)
-      for (int p = 0; p < P; ++p) cnt += hist[static_cast<size_t>(b) * P + p] > 0 ? 1 : 0;
+    if (b < B) cnt += rowbase[b + 1];
   }
   s_part[tid] = cnt;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {        // inclusive scan
+  for (int o = 1; o < 1024; o <<= 1) {
     const int v = tid >= o ? s_part[tid - o] : 0;
     __syncthreads();
     s_part[tid] += v;
     __syncthreads();
   }
-  int run = s_part[tid] - cnt;                // exclusive prefix of this thread's samples
+  int run = s_part[tid] - cnt;
   for (int i = 0; i < per; ++i) {
     const int b = tid * per + i;
     if (b < B) {
-      rowbase[b] = run;
-      int c = 0;
-      for (int p = 0; p < P; ++p) c += hist[static_cast<size_t>(b) * P + p] > 0 ? 1 : 0;
-      run += c;
+      run += rowbase[b + 1];
+      rowbase[b + 1] = run;
     }
   }
-  if (tid == 1023) rowbase[B] = s_part[1023];
+  if (tid == 0) rowbase[0] = 0;
 }
 
 // C[a, c] += sum_{n < N} A[n, a] * Bm[n, c]   (N read from *n_dev when given: compact rows).
@@ -413,8 +422,18 @@ xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict
     const int c = tid & 127, half = tid >> 7;
     const int cc = c0 + c;
     float sacc = 0.f;
-    if (cc < Kb)
-      for (long long r = rb + half; r < re; r += 2) sacc += Bm[r * ldb + cc];
+    if (cc < Kb) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      long long r = rb + half;
+      for (; r + 6 < re; r += 8) {
+        s0 += Bm[r * ldb + cc];
+        s1 += Bm[(r + 2) * ldb + cc];
+        s2 += Bm[(r + 4) * ldb + cc];
+        s3 += Bm[(r + 6) * ldb + cc];
+      }
+      for (; r < re; r += 2) s0 += Bm[r * ldb + cc];
+      sacc = (s0 + s1) + (s2 + s3);
+    }
     s_red[half][c] = sacc;
     __syncthreads();
     if (half == 0 && cc < Kb) {
@@ -450,7 +469,7 @@ static void xtx_launch(const float* A, int lda, int Ka, const float* Bm, int ldb
   const int mt = Ka <= 16 ? 1 : 2;
   const int bm = mt * 16;
   const int tiles = ((Ka + bm - 1) / bm) * ((Kb + kTwBN - 1) / kTwBN);
-  long long splits = std::max<long long>(1, std::min<long long>((sm_count() * 2) / tiles, (N + 255) / 256));
+  long long splits = std::max<long long>(1, std::min<long long>((sm_count() * 4) / tiles, (N + 255) / 256));
   long long rps = (N + splits - 1) / splits;
   rps = (rps + kTwKC - 1) / kTwKC * kTwKC;
   splits = (N + rps - 1) / rps;
@@ -554,7 +573,8 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
   float* tmp = p.sSd + static_cast<long long>(B) * kH1;   // [3][E][80]
   int* rowbase = reinterpret_cast<int*>(tmp + 3 * E * kH1);   // [B+1]
   p.rowbase = rowbase;
-  din_rowbase_kernel<<<1, 1024, 0, st>>>(hist, B, P, rowbase);
+  din_count_kernel<<<std::min((B + 7) / 8, sm_count() * 8), 256, 0, st>>>(hist, B, P, rowbase);
+  din_scan_kernel<<<1, 1024, 0, st>>>(rowbase, B);
   p.dW3 = dW3; p.db3 = db3;
   cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(float) * 3 * E * kH1, st);
   if (e != cudaSuccess) return check_cuda(e, "ctr_din_att_bwd");

@@ -233,7 +233,7 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
   constexpr int TA = (NA4 + 255) / 256;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  float4 ra[TA], rb[4];
+  struct Regs { float4 a[TA]; float4 b[4]; };
   auto a_pos = [&](int e, int& rr, int& kk) {
     if (A_KFAST) { rr = e >> 3; kk = (e & 7) * 4; }
     else { kk = e / (BM / 4); rr = (e % (BM / 4)) * 4; }
@@ -242,21 +242,21 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
     if (B_KFAST) { c = e >> 3; kk = (e & 7) * 4; }
     else { kk = e >> 5; c = (e & 31) * 4; }
   };
-  auto load = [&](int k0) {
+  auto load = [&](int k0, Regs& R) {
 #pragma unroll
     for (int i = 0; i < TA; ++i) {
       const int e = tid + 256 * i;
       if (e < NA4) {
         int rr, kk;
         a_pos(e, rr, kk);
-        ra[i] = fa4(rr, k0 + kk);
+        R.a[i] = fa4(rr, k0 + kk);
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int kk, c;
       b_pos(tid + 256 * i, kk, c);
-      rb[i] = fb4(k0 + kk, c);
+      R.b[i] = fb4(k0 + kk, c);
     }
   };
   auto split4 = [&](const float4& v, float4& hi, float4& lo) {
@@ -265,7 +265,7 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
     split_tf32(v.z, hi.z, lo.z);
     split_tf32(v.w, hi.w, lo.w);
   };
-  auto store = [&](int buf) {
+  auto store = [&](int buf, const Regs& R) {
 #pragma unroll
     for (int i = 0; i < TA; ++i) {
       const int e = tid + 256 * i;
@@ -273,7 +273,7 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
         int rr, kk;
         a_pos(e, rr, kk);
         float4 hi, lo;
-        split4(ra[i], hi, lo);
+        split4(R.a[i], hi, lo);
         if (A_KFAST) {          // 4 consecutive k of one row: transposing scalar stores
           sm.Ah[buf][kk][rr] = hi.x;     sm.Al[buf][kk][rr] = lo.x;
           sm.Ah[buf][kk + 1][rr] = hi.y; sm.Al[buf][kk + 1][rr] = lo.y;
@@ -290,7 +290,7 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
       int kk, c;
       b_pos(tid + 256 * i, kk, c);
       float4 hi, lo;
-      split4(rb[i], hi, lo);
+      split4(R.b[i], hi, lo);
       if (B_KFAST) {
         sm.Bh[buf][kk][c] = hi.x;     sm.Bl[buf][kk][c] = lo.x;
         sm.Bh[buf][kk + 1][c] = hi.y; sm.Bl[buf][kk + 1][c] = lo.y;
@@ -302,42 +302,57 @@ __device__ __forceinline__ void gemm_tile_mma(MmaSmem& sm, int nk, FA fa4, FB fb
       }
     }
   };
-  load(0);
-  store(0);
-  __syncthreads();
-  int buf = 0;
   const int nb = warp * 16;
-  for (int k0 = 0; k0 < nk; k0 += kTwKC) {
-    const bool more = k0 + kTwKC < nk;
-    if (more) load(k0 + kTwKC);
-    if (nb < ncols)      // warps whose 16 columns lie beyond the live columns only help staging
+  auto compute = [&](int buf) {
+    if (nb < ncols) {    // warps whose 16 columns lie beyond the live columns only help staging
 #pragma unroll
-    for (int ks = 0; ks < kTwKC; ks += 8) {
-      float ah[MT][4], al[MT][4], bh[2][2], bl[2][2];
+      for (int ks = 0; ks < kTwKC; ks += 8) {
+        float ah[MT][4], al[MT][4], bh[2][2], bl[2][2];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const int m = mt * 16 + g;
-        ah[mt][0] = sm.Ah[buf][ks + t][m];       al[mt][0] = sm.Al[buf][ks + t][m];
-        ah[mt][1] = sm.Ah[buf][ks + t][m + 8];   al[mt][1] = sm.Al[buf][ks + t][m + 8];
-        ah[mt][2] = sm.Ah[buf][ks + t + 4][m];   al[mt][2] = sm.Al[buf][ks + t + 4][m];
-        ah[mt][3] = sm.Ah[buf][ks + t + 4][m + 8]; al[mt][3] = sm.Al[buf][ks + t + 4][m + 8];
-      }
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int n = nb + nt * 8 + g;
-        bh[nt][0] = sm.Bh[buf][ks + t][n];      bl[nt][0] = sm.Bl[buf][ks + t][n];
-        bh[nt][1] = sm.Bh[buf][ks + t + 4][n];  bl[nt][1] = sm.Bl[buf][ks + t + 4][n];
-      }
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m = mt * 16 + g;
+          ah[mt][0] = sm.Ah[buf][ks + t][m];         al[mt][0] = sm.Al[buf][ks + t][m];
+          ah[mt][1] = sm.Ah[buf][ks + t][m + 8];     al[mt][1] = sm.Al[buf][ks + t][m + 8];
+          ah[mt][2] = sm.Ah[buf][ks + t + 4][m];     al[mt][2] = sm.Al[buf][ks + t + 4][m];
+          ah[mt][3] = sm.Ah[buf][ks + t + 4][m + 8]; al[mt][3] = sm.Al[buf][ks + t + 4][m + 8];
+        }
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-          mma_tf32(acc[mt][nt], al[mt], bh[nt]);
-          mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
-          mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+          const int n = nb + nt * 8 + g;
+          bh[nt][0] = sm.Bh[buf][ks + t][n];      bl[nt][0] = sm.Bl[buf][ks + t][n];
+          bh[nt][1] = sm.Bh[buf][ks + t + 4][n];  bl[nt][1] = sm.Bl[buf][ks + t + 4][n];
         }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+            mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+            mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+          }
+      }
     }
-    if (more) store(buf ^ 1);
+  };
+  // Prefetch distance 2: while chunk i is multiplied from shared memory, chunk i+1 sits in one
+  // register set (loaded an iteration ago) and chunk i+2 is being loaded into the other.
+  Regs R0, R1;
+  load(0, R0);
+  store(0, R0);
+  if (kTwKC < nk) load(kTwKC, R0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < nk; k0 += 2 * kTwKC) {
+    // even step: shared[buf] = chunk k0, R0 = chunk k0 + KC
+    if (k0 + 2 * kTwKC < nk) load(k0 + 2 * kTwKC, R1);
+    compute(buf);
+    if (k0 + kTwKC < nk) store(buf ^ 1, R0);
+    __syncthreads();
+    buf ^= 1;
+    if (k0 + kTwKC >= nk) break;
+    // odd step: shared[buf] = chunk k0 + KC, R1 = chunk k0 + 2 KC
+    if (k0 + 3 * kTwKC < nk) load(k0 + 3 * kTwKC, R0);
+    compute(buf);
+    if (k0 + 2 * kTwKC < nk) store(buf ^ 1, R1);
     __syncthreads();
     buf ^= 1;
   }
