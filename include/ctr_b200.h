@@ -179,7 +179,8 @@ int ctr_transpose_df_add(const float* dXt, int ld, int B, int F, int D, float* d
  * The reference's tower is `dense(relu) -> batch_normalization -> dropout` per layer plus a
  * final dense(1, relu) (deepfm/deepfm.py:100-108, xdeepfm/xdeepfm.py:184-192,
  * dcn/dcn.py:144-149), then dense(concat[...], 1), sigmoid and the mean
- * sigmoid-cross-entropy (deepfm/deepfm.py:110-129).  fp32 CUDA-core kernels; BN and dropout are
+ * sigmoid-cross-entropy (deepfm/deepfm.py:110-129).  fp32 results from 3xTF32 tensor-core
+ * GEMMs (tcgen05 for wide first layers, mma.sync for the rest); BN and dropout are
  * never materialised: they are a prologue of the consuming GEMM, recomputed in the backward
  * (dropout masks are counter based: Philox4x32-10 over (seed, layer, step, row, col)).
  *
@@ -203,7 +204,8 @@ typedef struct {
 /* ctr_grad_src: gradient arriving at a layer's stored post-ReLU output a[r,n]:
  *   kind 0: g = G[r*ldg+n];  kind 1: g = BN-backward of the stored dn = G through the BN that
  *   follows a (needs the column sums dbeta = sum dn, dgamma = sum dn*xhat in train mode).
- *   The kernels then use dpre = g * 1[a > 0]. */
+ *   The kernels then use dpre = g * 1[a > 0].
+ *   kind 2: G already is dpre (written by ctr_tower_dpre); `a` is not read. */
 typedef struct {
   const float* G;
   const float* a;
@@ -233,6 +235,11 @@ int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out,
 int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int K,
                              const ctr_bn_drop* pro, const float* Aprev, float* dn_out, int ldn,
                              float* dbeta_prev, float* dgamma_prev, int B, ctr_stream_t stream);
+/* dpre[B,N] = g * 1[a > 0] for a kind 0/1 gradient source, written out once so that both
+ * backward GEMMs of the layer can read it as a plain tensor (kind 2);
+ * db[N] (nullable) += column sums of dpre. */
+int ctr_tower_dpre(const ctr_grad_src* gs, int N, float* dpre, int ldd, float* db, int B,
+                   ctr_stream_t stream);
 /* dW[K,N] += P(X)^T . dpre;  db[N] (nullable) += column sums of dpre. */
 int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_drop* pro,
                                 const ctr_grad_src* gs, int N, float* dW, float* db, int B,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "ctr_bn_drop_apply": (c_i, [c_f, c_i, C.POINTER(BnDrop), c_f, c_i, c_f]),
     "ctr_tower_layer_bwd_data": (c_i, [C.POINTER(GradSrc), c_i, c_f, c_i, C.POINTER(BnDrop), c_f,
                                        c_f, c_i, c_f, c_f, c_i, c_f]),
+    "ctr_tower_dpre": (c_i, [C.POINTER(GradSrc), c_i, c_f, c_i, c_f, c_i, c_f]),
     "ctr_tower_layer_bwd_weights": (c_i, [c_f, c_i, c_i, C.POINTER(BnDrop), C.POINTER(GradSrc), c_i,
                                           c_f, c_f, c_i, c_f]),
     "ctr_loss_head": (c_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i, c_i, c_f, c_f, c_f,

@@ -17,19 +17,10 @@
 //   warps 4-7 epilogue:    tcgen05.ld 32x32b (thread = row), FMA contraction in registers
 // 3xTF32 (prec 2) runs the passes (hi,hi),(lo,hi),(hi,lo) into the same accumulator.
 #pragma once
-#include <cuda.h>
-
-#include <cstdlib>
-#include <mutex>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ctr {
 
-constexpr int kTcBM = 128;          // rows per M-tile == TMEM lanes
-constexpr int kTcKB = 32;           // floats per k-block == one 128-byte swizzle span
-constexpr int kTcABytes = kTcBM * kTcKB * 4;   // 16 KB per A k-block
-constexpr int kTcBStageBytes = 256 * kTcKB * 4;  // 32 KB per B stage (NT <= 256 rows)
 constexpr int kTcMaxG = 128;        // widest per-field group the epilogue keeps in registers
 constexpr int MODE_SCALE = 0, MODE_DOT = 1;
 
@@ -43,72 +34,6 @@ struct CinTcParams {
   uint32_t idesc;
   uint64_t desc_hi;   // smem descriptor without the start address
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-template <int CW>
-__device__ __forceinline__ void tc_ld(uint32_t taddr, float* v);
-template <>
-__device__ __forceinline__ void tc_ld<8>(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-      "tcgen05.wait::ld.sync.aligned;\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tc_ld<32>(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ------------------------------------------------------------------------ kernel
 template <int MODE, int CW>
@@ -297,11 +222,6 @@ cin_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 // The tensor core reads fp32 operands as tf32 by dropping the low 13 mantissa bits
 // (truncation, biased).  Operands are therefore pre-rounded to nearest tf32 (cvt.rna) so
 // that what the MMA truncates is already zero; the 3xTF32 split keeps the remainder.
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
 // Bp[(i*Gp + g)*Kp + k] = (g < G && k < K) ? W[i*slab + g*sg + k*sk] : 0, for i < m_pad fields.
 __global__ void cin_prep_b_kernel(const float* __restrict__ W, float* __restrict__ Bp,
                                   float* __restrict__ Bp_lo, int m, int m_pad, int G, int Gp, int K,
@@ -338,46 +258,6 @@ __global__ void cin_prep_a_kernel(const float* __restrict__ A, int lda, int K, f
 // ------------------------------------------------------------------- host side
 static bool cin_dw_tc_supported(int H);
 static int64_t cin_dw_tc_ws(int M, int m, int Hp, int H, int prec);
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(f);
-  });
-  return fn;
-}
-
-// 2-D fp32 tensor [rows, cols] with row pitch ld floats; box [box_rows x 32 floats], 128B swizzle.
-static int make_map(CUtensorMap* map, const float* base, long long rows, int cols, int ld,
-                    int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  if (enc == nullptr) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return CTR_ERR_CUDA;
-  }
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcKB), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
-    return CTR_ERR_CUDA;
-  }
-  return CTR_OK;
-}
-
 struct CinTcPlan {
   int Gp, FPT, NT, n_ntiles, m_pad, nkb, Kp, NA, S, n_pass;
   size_t smem;
@@ -415,24 +295,6 @@ static CinTcPlan cin_tc_plan(int m, int G, int K, bool scale, int prec) {
   pl.ok = pl.ok && pl.S >= 2;
   pl.smem = fixed + static_cast<size_t>(pl.S) * kTcBStageBytes;
   return pl;
-}
-
-static uint64_t cin_desc_hi() {
-  // K-major, 128-byte swizzle: LBO field 1 (ignored), SBO = 8 rows * 128 B = 1024 B,
-  // descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-  uint64_t lbo = 1, sbo = 1024 >> 4, ver = 1, lay = 2;
-  if (const char* e = getenv("CTR_CIN_DESC_LBO")) lbo = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_CIN_DESC_SBO")) sbo = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_CIN_DESC_VER")) ver = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_CIN_DESC_LAYOUT")) lay = strtoull(e, nullptr, 0);
-  return (lbo << 16) | (sbo << 32) | (ver << 46) | (lay << 61);
-}
-static uint32_t cin_idesc(int N) {
-  // kind::tf32: D = F32 (1 @bit4), A = B = TF32 (2 @bits7,10), K-major both, N>>3 @17, M>>4 @24.
-  uint32_t d = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-               (static_cast<uint32_t>(kTcBM >> 4) << 24);
-  if (const char* e = getenv("CTR_CIN_IDESC_XOR")) d ^= static_cast<uint32_t>(strtoul(e, nullptr, 0));
-  return d;
 }
 
 // One GEMM+epilogue pass.  A [M, K] (pitch lda), W viewed as Wg[i][g][k] with strides, x per MODE.

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "gemm_core.cuh"
+#include "tc_gemm.cuh"
 
 namespace ctr {
 
@@ -133,6 +134,7 @@ __device__ __forceinline__ float pro_value(const TowerSmem& sm, const BnDrop& pr
 }
 // dpre[r,n] = g * 1[a > 0] with the tables in shared memory
 __device__ __forceinline__ float dpre_value(const TowerSmem& sm, const GradSrc& g, int r, int n) {
+  if (g.kind == 2) return g.G[static_cast<size_t>(r) * g.ldg + n];
   const float a = g.a[static_cast<size_t>(r) * g.lda + n];
   if (!(a > 0.f)) return 0.f;
   float v = g.G[static_cast<size_t>(r) * g.ldg + n];
@@ -148,6 +150,9 @@ __device__ __forceinline__ bool aligned16_dev(const void* p) {
 }
 // dpre for 4 consecutive columns n..n+3 of row r (columns >= N read as 0)
 __device__ __forceinline__ float4 dpre4(const TowerSmem& sm, const GradSrc& g, int r, int n, int N) {
+  if (g.kind == 2)
+    return load4_guard(g.G + static_cast<size_t>(r) * g.ldg + n, N - n,
+                       (g.ldg & 3) == 0 && aligned16_dev(g.G));
   const bool al = (g.lda & 3) == 0 && (g.ldg & 3) == 0 && aligned16_dev(g.a) && aligned16_dev(g.G);
   const float4 a = load4_guard(g.a + static_cast<size_t>(r) * g.lda + n, N - n, al);
   float4 v = load4_guard(g.G + static_cast<size_t>(r) * g.ldg + n, N - n, al);
@@ -395,6 +400,46 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
         }
       }
     }
+  }
+}
+
+// dpre[r,n] = g * 1[a > 0] written out once for both backward GEMMs of a layer (GradSrc kind 2),
+// db[n] += column sums.  Thread = column, CTA = kDpreRows rows.
+constexpr int kDpreRows = 32;
+__global__ void __launch_bounds__(256)
+tower_dpre_kernel(const GradSrc gs, int N, float* __restrict__ dpre, int ldd,
+                  float* __restrict__ db, int B) {
+  const int r0 = blockIdx.x * kDpreRows, r1 = min(B, r0 + kDpreRows);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float mu = 0.f, rstd = 0.f, c1 = 0.f, c2 = 0.f, gsc = 1.f;
+    if (gs.kind == 1) {
+      bn_consts(gs.sums, gs.mean, gs.var, n, N, gs.inv_B, gs.eps, &mu, &rstd);
+      c1 = gs.train ? gs.dbeta[n] * gs.inv_B : 0.f;
+      c2 = gs.train ? gs.dgamma[n] * gs.inv_B : 0.f;
+      gsc = rstd * gs.gamma[n];
+    }
+    float acc = 0.f;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      const float a = gs.a[static_cast<size_t>(r) * gs.lda + n];
+      float v = gs.G[static_cast<size_t>(r) * gs.ldg + n];
+      if (gs.kind == 1) v = (v - c1 - (a - mu) * rstd * c2) * gsc;
+      v = a > 0.f ? v : 0.f;
+      dpre[static_cast<size_t>(r) * ldd + n] = v;
+      acc += v;
+    }
+    if (db != nullptr && acc != 0.f) red_add_f32(db + n, acc);
+  }
+}
+
+// db[n] += sum_r D[r*ldd + n]
+__global__ void __launch_bounds__(256)
+tower_colsum_kernel(const float* __restrict__ D, int ldd, int N, float* __restrict__ db, int B) {
+  const int r0 = blockIdx.x * kDpreRows, r1 = min(B, r0 + kDpreRows);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += D[static_cast<size_t>(r) * ldd + n];
+    if (acc != 0.f) red_add_f32(db + n, acc);
   }
 }
 
@@ -651,6 +696,13 @@ static void tower_smem_optin() {
   done = true;
 }
 
+// tcgen05 path for wide layers without a BN prologue (CTR_TOWER_TC=0 forces the mma.sync path)
+static bool tower_tc() {
+  const char* e = getenv("CTR_TOWER_TC");
+  return e == nullptr || atoi(e) != 0;
+}
+static int round16(int x) { return (x + 15) / 16 * 16; }
+
 static BnDrop make_pro(const ctr_bn_drop* d, int B) {
   BnDrop p{};
   if (d == nullptr || !d->enabled) return p;
@@ -686,6 +738,16 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
     tower_out_fwd_kernel<<<g1, 256, 0, st>>>(X, ldx, K, p, W, bias, out, ldo, relu, B);
     CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
   }
+  if (!has_pro && tower_tc() && B >= 256 && K >= 64 && N >= 16 && (K & 3) == 0 && (N & 3) == 0 &&
+      (ldx & 3) == 0 && aligned16(X) && aligned16(W)) {
+    const int mtiles = (B + kTcBM - 1) / kTcBM;
+    int ntiles = (N + 127) / 128;
+    if (mtiles * ntiles * 2 <= sm_count() && N > 32) ntiles *= 2;   // few row tiles: split N
+    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
+    const int NT = std::min(128, round16((N + ntiles - 1) / ntiles));
+    return tc_gemm_launch<TCG_EPI_FWD>(X, ldx, false, W, N, true, B, N, K, NT, 1, out, ldo, bias,
+                                       stats, relu, st, "ctr_tower_layer_fwd");
+  }
   tower_smem_optin();
   const int ny = (N + kTwBN - 1) / kTwBN;
   bool small = static_cast<long long>((B + 31) / 32) * ny * 2 < sm_count();   // 16-row tiles
@@ -717,7 +779,8 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
                              const ctr_bn_drop* pro, const float* Aprev, float* dn_out, int ldn,
                              float* dbeta_prev, float* dgamma_prev, int B, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
-  CTR_REQUIRE(gs && gs->G && gs->a && W && dn_out && K > 0 && N > 0 && B >= 0 && ldn >= K,
+  CTR_REQUIRE(gs && gs->G && (gs->a || gs->kind == 2) && W && dn_out && K > 0 && N > 0 && B >= 0 &&
+                  ldn >= K,
               "ctr_tower_layer_bwd_data", "bad argument");
   const bool has_pro = pro != nullptr && pro->enabled;
   CTR_REQUIRE(!has_pro || (Aprev && K <= kMaxBn), "ctr_tower_layer_bwd_data",
@@ -730,6 +793,16 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
         make_gs(gs, B), Aprev != nullptr ? Aprev : W, K, W, K, make_pro(pro, B), nullptr, nullptr, dn_out,
         ldn, dbeta_prev, dgamma_prev, B);
     CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
+  }
+  if (gs->kind == 2 && !has_pro && tower_tc() && B >= 256 && K >= 64 && N >= 32 && (N & 3) == 0 &&
+      (gs->ldg & 3) == 0 && aligned16(gs->G) && aligned16(W)) {
+    // out[B, K] = dpre[B, N] . W[K, N]^T: both operands K-major in n
+    const int mtiles = (B + kTcBM - 1) / kTcBM;
+    int ntiles = std::max((K + 255) / 256, std::min(sm_count() / mtiles, (K + 63) / 64));
+    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max((K + 255) / 256, atoi(e));
+    const int NT = round16((K + ntiles - 1) / ntiles);
+    return tc_gemm_launch<TCG_EPI_STORE>(gs->G, gs->ldg, false, W, N, false, B, K, N, NT, 1, dn_out,
+                                         ldn, nullptr, nullptr, 0, st, "ctr_tower_layer_bwd_data");
   }
   tower_smem_optin();
   const int ny = (K + kTwBN - 1) / kTwBN;
@@ -745,11 +818,29 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
   CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_data");
 }
 
+int ctr_tower_dpre(const ctr_grad_src* gs, int N, float* dpre, int ldd, float* db, int B,
+                   ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(gs && gs->G && gs->a && dpre && N > 0 && B >= 0 && ldd >= N, "ctr_tower_dpre",
+              "bad argument");
+  CTR_REQUIRE(gs->kind == 0 || gs->kind == 1, "ctr_tower_dpre", "gradient source must be kind 0 or 1");
+  CTR_REQUIRE(gs->kind == 0 || (gs->gamma && (gs->sums || (gs->mean && gs->var))), "ctr_tower_dpre",
+              "BN gradient source needs gamma and stats");
+  CTR_REQUIRE(gs->kind == 0 || !gs->train || (gs->dbeta && gs->dgamma), "ctr_tower_dpre",
+              "BN gradient source needs dbeta / dgamma in train mode");
+  if (B == 0) return CTR_OK;
+  const int threads = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  tower_dpre_kernel<<<(B + kDpreRows - 1) / kDpreRows, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      make_gs(gs, B), N, dpre, ldd, db, B);
+  CTR_LAUNCH_CHECK("ctr_tower_dpre");
+}
+
 int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_drop* pro,
                                 const ctr_grad_src* gs, int N, float* dW, float* db, int B,
                                 ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
-  CTR_REQUIRE(X && gs && gs->G && gs->a && dW && K > 0 && N > 0 && B >= 0 && ldx >= K,
+  CTR_REQUIRE(X && gs && gs->G && (gs->a || gs->kind == 2) && dW && K > 0 && N > 0 && B >= 0 &&
+                  ldx >= K,
               "ctr_tower_layer_bwd_weights", "bad argument");
   const bool has_pro = pro != nullptr && pro->enabled;
   CTR_REQUIRE(!has_pro || K <= kMaxBn, "ctr_tower_layer_bwd_weights", "BN prologue needs K <= 256");
@@ -760,6 +851,19 @@ int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_dro
     tower_out_bwd_kernel<true><<<(B + kOutRows - 1) / kOutRows, 128, 0, st>>>(
         make_gs(gs, B), X, ldx, nullptr, K, make_pro(pro, B), dW, db, nullptr, 0, nullptr, nullptr, B);
     CTR_LAUNCH_CHECK("ctr_tower_layer_bwd_weights");
+  }
+  if (gs->kind == 2 && !has_pro && tower_tc() && B >= 1024 && K >= 64 && N >= 16 && N <= 256 &&
+      (K & 3) == 0 && (N & 3) == 0 && (ldx & 3) == 0 && (gs->ldg & 3) == 0 && aligned16(X) &&
+      aligned16(gs->G) && aligned16(dW)) {
+    // dW[K, N] += X[B, K]^T . dpre[B, N]: both operands MN-major, reduction over the rows
+    if (db != nullptr)
+      tower_colsum_kernel<<<(B + kDpreRows - 1) / kDpreRows, 256, 0, st>>>(gs->G, gs->ldg, N, db, B);
+    const int mtiles = (K + kTcBM - 1) / kTcBM;
+    int splits = std::max(1, std::min(sm_count() / mtiles, (B / kTcKB) / 4));
+    if (const char* e = getenv("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
+    return tc_gemm_launch<TCG_EPI_RED>(X, ldx, true, gs->G, gs->ldg, true, K, N, B, round16(N),
+                                       splits, dW, N, nullptr, nullptr, 0, st,
+                                       "ctr_tower_layer_bwd_weights");
   }
   tower_smem_optin();
   const int tiles = ((K + kTwBM - 1) / kTwBM) * ((N + kTwBN - 1) / kTwBN);

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -552,6 +553,9 @@ class FusedTower:
         # (dX chain -> embedding scatter -> row Adam); joined in ``join()`` before dense Adam
         self.side = torch.cuda.Stream(device=dense.flat.device)
         self._pending = None
+        # write each hidden layer's dpre once (ctr_tower_dpre) instead of re-deriving it from
+        # the BN bookkeeping inside both backward GEMMs; required for the tcgen05 path
+        self.materialise_dpre = os.environ.get("CTR_TOWER_DPRE", "1") != "0"
 
     def join(self):
         """Make the current stream wait for the side-stream weight-gradient kernels."""
@@ -645,7 +649,7 @@ class _TowerFn(torch.autograd.Function):
         def weights(xin, K, pro, gs_w, H, wname, bname):
             with torch.cuda.stream(side):
                 _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs_w), H,
-                      _p(tw.G(wname)), _p(tw.G(bname)), B, side.cuda_stream)
+                      _p(tw.G(wname)), _p(tw.G(bname)) if bname else None, B, side.cuda_stream)
 
         # final dense(1, relu): dpre = dout * 1[y > 0]
         gs = grad_src(dout, 1, y, 1, 0)
@@ -662,8 +666,16 @@ class _TowerFn(torch.autograd.Function):
             gs = grad_src(dn, H, acts[l], H, 1, l)
             xin = acts[l - 1] if l > 0 else X
             pro = C.byref(pros[l - 1]) if l > 0 else None
+            bname = "%d.b" % l
+            if tw.materialise_dpre:
+                # dpre_l written once (+ db_l), then both GEMMs read it as a plain tensor
+                dpre = torch.empty((B, H), dtype=torch.float32, device=dev)
+                _call("ctr_tower_dpre", C.byref(gs), H, _p(dpre), H, _p(tw.G(bname)), B, _stream())
+                gs = grad_src(dpre, H, None, 0, 2)
+                keep.append(dpre)
+                bname = None
             fork()        # dbeta_l / dgamma_l (written by the data kernel above) are ready
-            weights(xin, K, pro, gs, H, "%d.w" % l, "%d.b" % l)
+            weights(xin, K, pro, gs, H, "%d.w" % l, bname)
             dnext = torch.empty((B, K), dtype=torch.float32, device=dev)
             _call("ctr_tower_layer_bwd_data", C.byref(gs), H, _p(tw.P("%d.w" % l)), K, pro,
                   _p(xin) if l > 0 else None, _p(dnext), K,
