@@ -6,13 +6,14 @@
 //   backward data  dX  = dpre . W^T     A = dpre (K-major), B = W    (K-major: reduction over n)
 //   backward wts   dW += X^T . dpre     A = X  (MN-major),  B = dpre (MN-major), split over rows
 // Operand k-blocks ([128 | NT] x 32 fp32) are streamed by TMA (128-byte swizzles) through a
-// 2-3 stage ring.  tcgen05.mma.kind::tf32 reads the top 19 bits of each fp32 word, so the raw
+// 2-7 stage ring.  tcgen05.mma.kind::tf32 reads the top 19 bits of each fp32 word, so the raw
 // tile doubles as the "hi" operand; the epilogue warps compute the "lo" tiles
-// (x - trunc_tf32(x), elementwise, so the swizzled layout is irrelevant) into a second smem
-// buffer while the tensor core runs the (hi, hi) pass, then (lo, hi) and (hi, lo) follow:
+// (x - trunc_tf32(x), elementwise, so the swizzled layout is irrelevant) into a 2-slot smem
+// ring while the tensor core runs the (hi, hi) pass, then (lo, hi) and (hi, lo) follow:
 //   warp 0   TMA producer            warp 1   MMA issuer           warp 2   TMEM allocator
-//   warps 4-7  hi/lo splitter during the main loop, then the epilogue (TMEM -> registers ->
-//              bias / ReLU / BN column statistics / store, or vector RED for the split-K dW)
+//   warps 2-7  hi/lo splitter during the main loop
+//   warps 4-7  epilogue: TMEM -> registers -> bias / ReLU / BN column statistics -> smem
+//              transpose -> 128-byte row segments stored (or vector RED for the split-K dW)
 #pragma once
 #include "tc_common.cuh"
 
@@ -26,10 +27,10 @@ struct TcGemmParams {
   int a_mn, b_mn;         // operand is MN-major (else K-major)
   int kb_per_split;       // k-blocks (32 of K) per blockIdx.z
   int n_pass;             // 1 = plain tf32, 3 = 3xTF32
-  int stages;
+  int stages;             // raw (hi) ring depth, <= 8
+  int lo_slots;           // lo ring depth, 1 or 2
   uint32_t b_bytes;       // bytes of one B k-block in shared memory
-  uint32_t lo_off;        // offset of the lo tiles inside a stage (= 16 KB + max B bytes)
-  uint32_t stage_bytes;   // 2 * lo_off
+  uint32_t stage_bytes;   // 16 KB (A) + b_bytes rounded up to 1 KB; raw and lo slots alike
   uint32_t tmem_cols;
   uint32_t idesc;
   uint64_t desc_k, desc_mn;
@@ -41,9 +42,17 @@ struct TcGemmParams {
 };
 
 constexpr uint32_t kTcgMnBox = 32 * kTcKB * 4;   // one MN-major TMA box: 32 k-rows x 128 B
+constexpr int kTcgSplitThreads = 192;            // warps 2-7 compute the lo tiles
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// lo part of the 3xTF32 split: x - trunc_tf32(x) (exact), rounded to tf32 with integer ops
+// (add half an ulp of the 10-bit mantissa; the tensor core drops the low 13 bits itself).
+__device__ __forceinline__ float tcg_lo(float x) {
+  const float l = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(l) + 0x1000u);
 }
 
 // Column sums over the 32 lanes of a warp for 32 columns held as v[0..31] in every lane:
@@ -69,12 +78,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
-  uint64_t* full = bars;             // [stages] TMA landed
-  uint64_t* conv = bars + 4;         // [stages] lo tiles written
-  uint64_t* empty = bars + 8;        // [stages] MMAs retired
-  uint64_t* t_full = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint8_t* lo_ring = smem + static_cast<size_t>(p.stages) * p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + static_cast<size_t>(p.lo_slots) * p.stage_bytes);
+  uint64_t* full = bars;             // [stages]   TMA landed
+  uint64_t* empty = bars + 8;        // [stages]   MMAs that read the raw stage retired
+  uint64_t* conv = bars + 16;        // [lo_slots] lo tiles written
+  uint64_t* lo_empty = bars + 18;    // [lo_slots] MMAs that read the lo slot retired
+  uint64_t* t_full = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * p.NT;
   const int kb_total = (p.K + kTcKB - 1) / kTcKB;
@@ -85,8 +96,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], 128);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < p.lo_slots; ++s) {
+      mbar_init(&conv[s], kTcgSplitThreads);
+      mbar_init(&lo_empty[s], 1);
     }
     mbar_init(t_full, 1);
     mbar_fence_init();
@@ -143,50 +157,71 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         accum = 1;
       }
       if (p.n_pass == 3) {
-        mbar_wait(&conv[st], ph);
+        const uint32_t sl = kb % p.lo_slots, lph = (kb / p.lo_slots) & 1;
+        const uint32_t a_lo = smem_u32(lo_ring + static_cast<size_t>(sl) * p.stage_bytes);
+        const uint32_t b_lo = a_lo + kTcABytes;
+        mbar_wait(&conv[sl], lph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // (lo, hi)
-          tc_mma_tf32(tmem_base, da | (((a_addr + p.lo_off + k * sa_step) >> 4) & 0x3FFF),
+          tc_mma_tf32(tmem_base, da | (((a_lo + k * sa_step) >> 4) & 0x3FFF),
                       db | (((b_addr + k * sb_step) >> 4) & 0x3FFF), p.idesc, 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // (hi, lo)
           tc_mma_tf32(tmem_base, da | (((a_addr + k * sa_step) >> 4) & 0x3FFF),
-                      db | (((b_addr + p.lo_off + k * sb_step) >> 4) & 0x3FFF), p.idesc, 1);
+                      db | (((b_lo + k * sb_step) >> 4) & 0x3FFF), p.idesc, 1);
+        tc_commit(&lo_empty[sl]);
       }
       tc_commit(&empty[st]);
     }
     tc_commit(t_full);
-  } else if (warp >= 4) {
-    // ------------------------------------------------------- hi/lo splitter, then epilogue
-    const int ctid = threadIdx.x - 128;
+  } else if (warp >= 2) {
+    // ------------------------------------ hi/lo splitter (warps 2-7), then epilogue (warps 4-7)
     if (p.n_pass == 3) {
+      const int ctid = threadIdx.x - 64;
       const int n16 = static_cast<int>(ab_bytes >> 4);
       for (int kb = 0; kb < nkb; ++kb) {
         const uint32_t st = kb % p.stages, ph = (kb / p.stages) & 1;
+        const uint32_t sl = kb % p.lo_slots, lph = (kb / p.lo_slots) & 1;
         mbar_wait(&full[st], ph);
+        mbar_wait(&lo_empty[sl], lph ^ 1);
         const float4* hi = reinterpret_cast<const float4*>(smem + static_cast<size_t>(st) * p.stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(smem + static_cast<size_t>(st) * p.stage_bytes + p.lo_off);
-        for (int i = ctid; i < n16; i += 128) {
-          const float4 x = hi[i];
-          float4 l;
-          l.x = round_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-          l.y = round_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-          l.z = round_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-          l.w = round_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-          lo[i] = l;
+        float4* lo = reinterpret_cast<float4*>(lo_ring + static_cast<size_t>(sl) * p.stage_bytes);
+        for (int i = ctid; i < n16; i += 4 * kTcgSplitThreads) {
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = i + u * kTcgSplitThreads;
+            if (j < n16) x[u] = hi[j];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = i + u * kTcgSplitThreads;
+            if (j < n16) {
+              float4 l;
+              l.x = tcg_lo(x[u].x);
+              l.y = tcg_lo(x[u].y);
+              l.z = tcg_lo(x[u].z);
+              l.w = tcg_lo(x[u].w);
+              lo[j] = l;
+            }
+          }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&conv[st]);
+        mbar_arrive(&conv[sl]);
       }
     }
-    if (nkb > 0) {
+    if (warp >= 4 && nkb > 0) {
       const int quarter = warp & 3;
-      const int r = m0 + quarter * 32 + lane;
       mbar_wait(t_full, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const bool vec = (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+      const int r_own = m0 + quarter * 32 + lane;          // this lane's TMEM row
+      const int nlim = min(p.N, n0 + p.NT);                // first invalid output column
+      // all MMAs have retired: the raw ring is free, use it to turn the row-per-lane TMEM
+      // fragments into 128-byte row segments (4 rows x 128 B per store instruction)
+      float4* sw = reinterpret_cast<float4*>(smem + quarter * (32 * 9 * 16));
       for (int c = 0; c < p.NT; c += 32) {
         float v[32];
         tc_ld<32>(taddr + c, v);
@@ -196,32 +231,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int t = 0; t < 32; ++t) {
             const int n = nb + t;
             float x = 0.f;
-            if (r < p.M && n < p.N && c + t < p.NT) {
+            if (r_own < p.M && n < nlim) {
               x = v[t] + (p.bias != nullptr ? __ldg(p.bias + n) : 0.f);
               if (p.relu) x = fmaxf(x, 0.f);
             }
             v[t] = x;
           }
         }
-        if (r < p.M) {
-          float* o = p.out + static_cast<size_t>(r) * p.ldo + nb;
 #pragma unroll
-          for (int t = 0; t < 32; t += 4) {
-            const int lim = min(p.N - nb, p.NT - c);     // valid columns in this chunk
-            if (t + 4 <= lim && vec) {
-              const float4 q = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-              if (EPI == TCG_EPI_RED) red_add_v4(o + t, q);
-              else *reinterpret_cast<float4*>(o + t) = q;
+        for (int t = 0; t < 8; ++t)
+          sw[lane * 9 + t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3);
+          const float4 q = sw[row * 9 + (lane & 7)];
+          const int rr = m0 + quarter * 32 + row, n = nb + (lane & 7) * 4;
+          if (rr < p.M && n < nlim) {
+            float* o = p.out + static_cast<size_t>(rr) * p.ldo + n;
+            if (vec && n + 4 <= nlim) {
+              if (EPI == TCG_EPI_RED) red_add_v4(o, q);
+              else *reinterpret_cast<float4*>(o) = q;
             } else {
+              const float e[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (t + u < lim) {
-                  if (EPI == TCG_EPI_RED) red_add_f32(o + t + u, v[t + u]);
-                  else o[t + u] = v[t + u];
+                if (n + u < nlim) {
+                  if (EPI == TCG_EPI_RED) red_add_f32(o + u, e[u]);
+                  else o[u] = e[u];
                 }
             }
           }
         }
+        __syncwarp();
         if (EPI == TCG_EPI_FWD && p.stats != nullptr) {
           float q[32];
 #pragma unroll
@@ -229,7 +271,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float s1 = warp_colsum32(v, lane);
           const float s2 = warp_colsum32(q, lane);
           const int n = nb + lane;
-          if (n < p.N && c + lane < p.NT) {
+          if (n < nlim) {
             red_add_f32(p.stats + n, s1);
             red_add_f32(p.stats + p.N + n, s2);
           }
@@ -283,20 +325,20 @@ static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, i
   splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.b_bytes = b_mn ? static_cast<uint32_t>((NT + 31) / 32) * kTcgMnBox
                    : static_cast<uint32_t>(NT) * kTcKB * 4;
-  const uint32_t bmax = NT <= 128 ? 128 * kTcKB * 4 : 256 * kTcKB * 4;
-  p.lo_off = kTcABytes + bmax;
-  p.stage_bytes = 2 * p.lo_off;
-  p.stages = NT <= 128 ? 3 : 2;
+  p.stage_bytes = kTcABytes + ((p.b_bytes + 1023u) & ~1023u);
+  p.lo_slots = 2;
+  p.stages = std::max(2, std::min(8, static_cast<int>((200u * 1024u) / p.stage_bytes) - p.lo_slots));
+  if (const char* e = getenv("CTR_TCG_STAGES")) p.stages = std::max(1, std::min(p.stages, atoi(e)));
   p.tmem_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
   p.idesc = cin_idesc(NT) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u);
   p.desc_k = cin_desc_hi();
   p.desc_mn = tcg_desc_mn();
   p.out = out; p.ldo = ldo; p.bias = bias; p.stats = stats; p.relu = relu;
-  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 256 + 1024;
+  const size_t smem = static_cast<size_t>(p.stages + p.lo_slots) * p.stage_bytes + 256 + 1024;
   static bool optin = false;
   if (!optin) {
     cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(3 * 65536 + 256 + 1024));
+                         static_cast<int>(200 * 1024 + 256 + 1024));
     optin = true;
   }
   dim3 grid((M + kTcBM - 1) / kTcBM, (N + NT - 1) / NT, splits);

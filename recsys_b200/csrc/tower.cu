@@ -432,6 +432,74 @@ tower_dpre_kernel(const GradSrc gs, int N, float* __restrict__ dpre, int ldd,
   }
 }
 
+// Same, 4 columns per thread with 16-byte accesses (N % 4 == 0, pitches % 4 == 0, aligned):
+// 8 row groups x 32 column quads per CTA, 4 rows per thread all in flight at once.
+__global__ void __launch_bounds__(256)
+tower_dpre_v4_kernel(const GradSrc gs, int N, float* __restrict__ dpre, int ldd,
+                     float* __restrict__ db, int B) {
+  __shared__ float4 s_sum[8][64];
+  const int cq = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * kDpreRows;
+  const int nq = N >> 2;
+  for (int q = cq; q < nq; q += 32) {
+    const int n = q * 4;
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f},
+          c2[4] = {0.f, 0.f, 0.f, 0.f}, gsc[4] = {1.f, 1.f, 1.f, 1.f};
+    if (gs.kind == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bn_consts(gs.sums, gs.mean, gs.var, n + j, N, gs.inv_B, gs.eps, &mu[j], &rstd[j]);
+        c1[j] = gs.train ? gs.dbeta[n + j] * gs.inv_B : 0.f;
+        c2[j] = gs.train ? gs.dgamma[n + j] * gs.inv_B : 0.f;
+        gsc[j] = rstd[j] * gs.gamma[n + j];
+      }
+    }
+    float4 av[4], gv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + rg + 8 * i;
+      if (r < B) {
+        av[i] = ldg4(gs.a + static_cast<size_t>(r) * gs.lda + n);
+        gv[i] = ldg4(gs.G + static_cast<size_t>(r) * gs.ldg + n);
+      } else {
+        av[i] = f4_zero();
+        gv[i] = f4_zero();
+      }
+    }
+    float4 acc = f4_zero();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + rg + 8 * i;
+      float4 v = gv[i];
+      const float4 a = av[i];
+      if (gs.kind == 1) {
+        v.x = (v.x - c1[0] - (a.x - mu[0]) * rstd[0] * c2[0]) * gsc[0];
+        v.y = (v.y - c1[1] - (a.y - mu[1]) * rstd[1] * c2[1]) * gsc[1];
+        v.z = (v.z - c1[2] - (a.z - mu[2]) * rstd[2] * c2[2]) * gsc[2];
+        v.w = (v.w - c1[3] - (a.w - mu[3]) * rstd[3] * c2[3]) * gsc[3];
+      }
+      v.x = a.x > 0.f ? v.x : 0.f;
+      v.y = a.y > 0.f ? v.y : 0.f;
+      v.z = a.z > 0.f ? v.z : 0.f;
+      v.w = a.w > 0.f ? v.w : 0.f;
+      if (r < B) *reinterpret_cast<float4*>(dpre + static_cast<size_t>(r) * ldd + n) = v;
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (db != nullptr) {
+      s_sum[rg][q] = acc;
+    }
+  }
+  if (db != nullptr) {
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += reinterpret_cast<const float*>(&s_sum[g][0])[n];
+      if (t != 0.f) red_add_f32(db + n, t);
+    }
+  }
+}
+
 // db[n] += sum_r D[r*ldd + n]
 __global__ void __launch_bounds__(256)
 tower_colsum_kernel(const float* __restrict__ D, int ldd, int N, float* __restrict__ db, int B) {
@@ -741,8 +809,9 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
   if (!has_pro && tower_tc() && B >= 256 && K >= 64 && N >= 16 && (K & 3) == 0 && (N & 3) == 0 &&
       (ldx & 3) == 0 && aligned16(X) && aligned16(W)) {
     const int mtiles = (B + kTcBM - 1) / kTcBM;
-    int ntiles = (N + 127) / 128;
-    if (mtiles * ntiles * 2 <= sm_count() && N > 32) ntiles *= 2;   // few row tiles: split N
+    // few row tiles: split N down to 32 columns per CTA to put every SM to work (the A tiles
+    // are then re-read from L2, which is cheaper than idle SMs)
+    int ntiles = std::max((N + 127) / 128, std::min(sm_count() / mtiles, (N + 31) / 32));
     if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
     const int NT = std::min(128, round16((N + ntiles - 1) / ntiles));
     return tc_gemm_launch<TCG_EPI_FWD>(X, ldx, false, W, N, true, B, N, K, NT, 1, out, ldo, bias,
@@ -829,9 +898,15 @@ int ctr_tower_dpre(const ctr_grad_src* gs, int N, float* dpre, int ldd, float* d
   CTR_REQUIRE(gs->kind == 0 || !gs->train || (gs->dbeta && gs->dgamma), "ctr_tower_dpre",
               "BN gradient source needs dbeta / dgamma in train mode");
   if (B == 0) return CTR_OK;
-  const int threads = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
-  tower_dpre_kernel<<<(B + kDpreRows - 1) / kDpreRows, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      make_gs(gs, B), N, dpre, ldd, db, B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (B + kDpreRows - 1) / kDpreRows;
+  if ((N & 3) == 0 && N <= 256 && (ldd & 3) == 0 && (gs->ldg & 3) == 0 && (gs->lda & 3) == 0 &&
+      aligned16(dpre) && aligned16(gs->G) && aligned16(gs->a)) {
+    tower_dpre_v4_kernel<<<grid, 256, 0, st>>>(make_gs(gs, B), N, dpre, ldd, db, B);
+  } else {
+    const int threads = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    tower_dpre_kernel<<<grid, threads, 0, st>>>(make_gs(gs, B), N, dpre, ldd, db, B);
+  }
   CTR_LAUNCH_CHECK("ctr_tower_dpre");
 }
 

@@ -588,6 +588,7 @@ class FusedTower:
 class _TowerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, anchor, tw: FusedTower, training):
+        ctx.set_materialize_grads(False)
         X = X.contiguous()
         B, dev = X.shape[0], X.device
         L = len(tw.sizes) - 1
@@ -698,6 +699,7 @@ class _LossHeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, dense, names, relu0, grad_scale, labels, want_grad, *zs):
+        ctx.set_materialize_grads(False)
         B, dev = zs[0].shape[0], zs[0].device
         Cn = len(zs)
         zs = [z.contiguous().view(B) for z in zs]
