@@ -254,6 +254,67 @@ int ctr_loss_head(const float* const* z, float* const* dz, int C, int relu0, con
                   float* prob, float* loss, float* dhw, float* dhb, float* db1, float grad_scale,
                   ctr_stream_t stream);
 
+/* ctr_tower_mid: everything between the first layer's GEMM and the first layer's backward
+ * GEMMs in ONE cooperative launch (deepfm/deepfm.py:100-129, xdeepfm/xdeepfm.py:184-212):
+ * hidden layers 1..L-1 forward (BN of the previous layer's stored output + dropout as the GEMM
+ * prologue), the final dense(1, relu), the logit / sigmoid / mean-BCE head, and - in training -
+ * the whole backward down to dpre_0 = d loss / d (pre-activation of layer 0).  The whole-batch
+ * BN reductions between the pieces are grid barriers instead of kernel boundaries.
+ *   given:   act[0] [B,H[0]] (post-ReLU output of layer 0) and, training, its column sums
+ *            stats[0] = [2][H[0]]; the C-1 external head columns z[c] [B]; labels [B]
+ *   written: act[l], l >= 1; y_out / logits / prob [B] (nullable); *loss += mean BCE;
+ *   training (all accumulated with +=, buffers zero on entry except where noted):
+ *            stats[l] l >= 1 (zero on entry), dz[c] [B] (plain store), dhw[C], dhb, db1,
+ *            dw_out[H[L-1]], db_out, dbeta[l] / dgamma[l] / dbias[l] for every l,
+ *            dpre[l] [B,H[l]] (plain store; feeds ctr_tower_layer_bwd_weights / _bwd_data as a
+ *            kind-2 gradient source), dn[l] [B,H[l]] scratch.
+ * Weight gradients dW_l are NOT computed here (they are off the critical path: the caller
+ * runs ctr_tower_layer_bwd_weights on a side stream).  Hidden widths: multiples of 4, <= 128.
+ * `barrier`: 2 device words, zero-initialised once, reusable across launches. */
+#define CTR_TOWER_MID_MAX_LAYERS 4
+typedef struct {
+  int32_t L, C, relu0, training;
+  int32_t H[CTR_TOWER_MID_MAX_LAYERS];
+  const float* W[CTR_TOWER_MID_MAX_LAYERS];      /* W[l]: [H[l-1], H[l]], l >= 1 (W[0] unused) */
+  const float* b[CTR_TOWER_MID_MAX_LAYERS];      /* b[l]: [H[l]], l >= 1 */
+  const float* gamma[CTR_TOWER_MID_MAX_LAYERS];
+  const float* beta[CTR_TOWER_MID_MAX_LAYERS];
+  const float* mean[CTR_TOWER_MID_MAX_LAYERS];   /* eval only */
+  const float* var[CTR_TOWER_MID_MAX_LAYERS];
+  float* act[CTR_TOWER_MID_MAX_LAYERS];
+  float* stats[CTR_TOWER_MID_MAX_LAYERS];
+  const float* w_out;                            /* [H[L-1]] */
+  const float* b_out;
+  const float* state;                            /* device {t, lr_t}: t selects the dropout stream */
+  float eps, p_drop;
+  uint32_t seed;
+  float grad_scale;                              /* 1 / (B * world) */
+  const float* z[3];
+  const float* hw;                               /* [C], the tower's column is the last one */
+  const float* hb;
+  const float* b1;
+  const float* labels;
+  float* y_out;
+  float* logits;
+  float* prob;
+  float* loss;
+  float* dz[3];
+  float* dhw;
+  float* dhb;
+  float* db1;
+  float* dw_out;
+  float* db_out;
+  float* dgamma[CTR_TOWER_MID_MAX_LAYERS];
+  float* dbeta[CTR_TOWER_MID_MAX_LAYERS];
+  float* dbias[CTR_TOWER_MID_MAX_LAYERS];
+  float* dn[CTR_TOWER_MID_MAX_LAYERS];
+  float* dpre[CTR_TOWER_MID_MAX_LAYERS];
+  uint32_t* barrier;
+  unsigned long long* timing;                    /* nullable: 8 words, %globaltimer (ns) of block 0 at
+                                                    the phase boundaries (profiling aid) */
+} ctr_tower_mid_args;
+int ctr_tower_mid(const ctr_tower_mid_args* args, int B, ctr_stream_t stream);
+
 /* ------------------------------------------------------- row-sharded table (multi-GPU)
  * The reference only replicates (tf.distribute.MirroredStrategy, fm/fm.py:184-194); row
  * sharding is the north-star extension for tables larger than one GPU's HBM.  owner(row) =

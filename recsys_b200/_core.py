@@ -222,6 +222,18 @@ class _CriteoBase(_ModelBase):
                                            grad_scale=1.0 / (B * self.world), training=training)
         return logits.view(shape), prob.view(shape), loss
 
+    def _tower_head(self, tower, X, zs, labels, training, shape):
+        """tower(X) as the last head column: one ctr_tower_mid launch when the tower's shape
+        allows, else the per-layer kernels + ctr_loss_head."""
+        if not tower.use_mid:
+            return self._fused_head(list(zs) + [tower(X, training)], labels, training, shape)
+        B = X.shape[0]
+        if labels is None:
+            labels = torch.zeros(B, dtype=torch.float32, device=self.device)
+        loss, logits, prob = ops.tower_head(tower, X, zs, labels, relu0=True,
+                                            grad_scale=1.0 / (B * self.world), training=training)
+        return logits.view(shape), prob.view(shape), loss
+
     def backward(self, loss):
         # data parallel: the global loss is the mean over all replicas' batches (the fused loss
         # head already folds 1/world into the gradients it emits)
@@ -298,8 +310,7 @@ class DeepFMModel(_CriteoBase):
             return super().forward(features, labels, training)
         self.rows = self.ids(features)
         E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
-        y3 = self.tower(E, training)                                      # deepfm.py:100-108
-        return self._fused_head([y1s, y2, y3], labels, training, (-1,))   # :91,110-129
+        return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,))  # :91,100-129
 
     def logits(self, features, training):
         P = self.dense
@@ -415,8 +426,7 @@ class XDeepFMModel(_CriteoBase):
         cin_y = torch.relu(torch.addmm(P["cin.out.b"], pooled, P["cin.out.w"])).view(-1)  # :182
         Ed = self.emb_dnn.lookup(self.rows, want_fm=False, want_y1=False)[0] \
             if self.emb_dnn is not None else E                                    # :185
-        dnn_y = self.tower(Ed, training)                                          # :188-192
-        return self._fused_head([lin, cin_y, dnn_y], labels, training, (-1, 1))   # :131,194-212
+        return self._tower_head(self.tower, Ed, [lin, cin_y], labels, training, (-1, 1))  # :131,188-212
 
     def load_state(self, state):
         super().load_state(state)

@@ -38,6 +38,28 @@ class GradSrc(C.Structure):
                 ("kind", C.c_int32), ("train", C.c_int32), ("pad_", C.c_int32)]
 
 
+_ML = 4   # CTR_TOWER_MID_MAX_LAYERS
+
+
+class TowerMidArgs(C.Structure):
+    """ctr_tower_mid_args (include/ctr_b200.h)."""
+    _P4 = C.c_void_p * _ML
+    _fields_ = [("L", C.c_int32), ("C", C.c_int32), ("relu0", C.c_int32), ("training", C.c_int32),
+                ("H", C.c_int32 * _ML),
+                ("W", _P4), ("b", _P4), ("gamma", _P4), ("beta", _P4), ("mean", _P4), ("var", _P4),
+                ("act", _P4), ("stats", _P4),
+                ("w_out", C.c_void_p), ("b_out", C.c_void_p), ("state", C.c_void_p),
+                ("eps", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint32),
+                ("grad_scale", C.c_float),
+                ("z", C.c_void_p * 3), ("hw", C.c_void_p), ("hb", C.c_void_p), ("b1", C.c_void_p),
+                ("labels", C.c_void_p), ("y_out", C.c_void_p), ("logits", C.c_void_p),
+                ("prob", C.c_void_p), ("loss", C.c_void_p),
+                ("dz", C.c_void_p * 3), ("dhw", C.c_void_p), ("dhb", C.c_void_p),
+                ("db1", C.c_void_p), ("dw_out", C.c_void_p), ("db_out", C.c_void_p),
+                ("dgamma", _P4), ("dbeta", _P4), ("dbias", _P4), ("dn", _P4), ("dpre", _P4),
+                ("barrier", C.c_void_p), ("timing", C.c_void_p)]
+
+
 class FieldDesc(C.Structure):
     """ctr_field_desc (include/ctr_b200.h)."""
     _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("n_rows", C.c_int32),
@@ -82,6 +104,7 @@ SIGNATURES = {
                                           c_f, c_f, c_i, c_f]),
     "ctr_loss_head": (c_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i, c_i, c_f, c_f, c_f,
                             c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_fl, c_f]),
+    "ctr_tower_mid": (c_i, [C.POINTER(TowerMidArgs), c_i, c_f]),
     "ctr_shard_bucket": (c_i, [c_f, c_i64, c_i, c_i, c_f, c_f, c_f, c_f]),
     "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),
     "ctr_scatter_add_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),

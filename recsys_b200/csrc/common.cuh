@@ -81,6 +81,19 @@ __device__ __forceinline__ float4 ld4_stream(const float* p) {
                : "l"(p));
   return r;
 }
+// Plain (coherent) 16-byte / 4-byte loads that the compiler may not sink below later code.
+__device__ __forceinline__ float4 ld4_plain(const float* p) {
+  float4 r;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld1_plain(const float* p) {
+  float r;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
 // Vector float reduction into global memory: one 16-byte RED (sm_90+).
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),

@@ -312,41 +312,78 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
       accw[j] = 0.f;
     }
 
-    for (int bb = b_begin; bb < b_end; bb += RPW) {
-      const int b = bb + r;
-      const bool ok = b < b_end;
-      int rid = -1;
-      float4 g = f4_zero();
-      float gw = 0.f;
-      if (ok) rid = __ldg(p.rows + static_cast<size_t>(b) * F + f);
-      const bool live = ok && rid >= 0;   // negative ids (sharded overflow slots) are skipped
-      if (live) {
-        const size_t eo = (static_cast<size_t>(b) * F + f) * D + q * 4;
-        if (p.dE != nullptr) g = ld4_stream(p.dE + eo);
-        if (p.dy2 != nullptr) {
-          const float4 e = p.E != nullptr ? ldg4(p.E + eo)
-                                          : ldg4(p.table + static_cast<size_t>(rid) * D + q * 4);
-          const float4 s = ldg4(p.S + static_cast<size_t>(b) * D + q * 4);
-          const float cdy = __ldg(p.dy2 + b);
-          g.x = fmaf(cdy, s.x - e.x, g.x);
-          g.y = fmaf(cdy, s.y - e.y, g.y);
-          g.z = fmaf(cdy, s.z - e.z, g.z);
-          g.w = fmaf(cdy, s.w - e.w, g.w);
-        }
-        if (has_w1) gw = __ldg(p.dy1 + b);
+    // gradient of one (sample, field) slot: g = dE + dy2 * (S - E)   (fm/fm.py:123-129)
+    auto slot_grad = [&](int b, int rid, float4& g, float& gw) {
+      const size_t eo = (static_cast<size_t>(b) * F + f) * D + q * 4;
+      g = p.dE != nullptr ? ld4_stream(p.dE + eo) : f4_zero();
+      if (p.dy2 != nullptr) {
+        const float4 e = p.E != nullptr ? ldg4(p.E + eo)
+                                        : ldg4(p.table + static_cast<size_t>(rid) * D + q * 4);
+        const float4 sv = ldg4(p.S + static_cast<size_t>(b) * D + q * 4);
+        const float cdy = __ldg(p.dy2 + b);
+        g.x = fmaf(cdy, sv.x - e.x, g.x);
+        g.y = fmaf(cdy, sv.y - e.y, g.y);
+        g.z = fmaf(cdy, sv.z - e.z, g.z);
+        g.w = fmaf(cdy, sv.w - e.w, g.w);
       }
-      if (!tiny) {
-        if (live) {
-          red_add_v4(p.dtable + static_cast<size_t>(rid) * D + q * 4, g);
-          if (has_w1 && q == 0) red_add_f32(p.dw1 + rid, gw);
+      gw = has_w1 ? __ldg(p.dy1 + b) : 0.f;
+    };
+
+    if (!tiny) {
+      // UNR slots per lane in flight: all row ids first, then all operand loads, then the REDs
+      // (the RED asm is a memory barrier for the compiler, so the batching is done by hand).
+      constexpr int UNR = 4;
+      for (int bb = b_begin; bb < b_end; bb += RPW * UNR) {
+        int rid[UNR];
+        float4 g[UNR];
+        float gw[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int b = bb + u * RPW + r;
+          rid[u] = b < b_end ? __ldg(p.rows + static_cast<size_t>(b) * F + f) : -1;
         }
-      } else {
-        const int lid = live ? rid - off : -1;  // negative for inactive lanes: never matches
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          g[u] = f4_zero();
+          gw[u] = 0.f;
+          if (rid[u] >= 0) slot_grad(bb + u * RPW + r, rid[u], g[u], gw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (rid[u] >= 0) {    // negative ids (sharded overflow slots) are skipped
+            red_add_v4(p.dtable + static_cast<size_t>(rid[u]) * D + q * 4, g[u]);
+            if (has_w1 && q == 0) red_add_f32(p.dw1 + rid[u], gw[u]);
+          }
+        }
+      }
+      continue;
+    }
+
+    // tiny field: one-hot accumulation in registers; loads batched TU slots deep
+    constexpr int TU = 4;
+    for (int bb = b_begin; bb < b_end; bb += RPW * TU) {
+      int lid[TU];
+      float4 g[TU];
+      float gw[TU];
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
+        const int b = bb + u * RPW + r;
+        lid[u] = b < b_end ? __ldg(p.rows + static_cast<size_t>(b) * F + f) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
+        g[u] = f4_zero();
+        gw[u] = 0.f;
+        if (lid[u] >= 0) slot_grad(bb + u * RPW + r, lid[u], g[u], gw[u]);
+        lid[u] = lid[u] >= 0 ? lid[u] - off : -1;   // negative for inactive lanes: never matches
+      }
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
 #pragma unroll
         for (int t = 0; t < RPW; ++t) {
-          const float4 gt = f4_shfl(g, t * LPR + q);
-          const int idt = __shfl_sync(0xffffffffu, lid, t * LPR);
-          const float gwt = __shfl_sync(0xffffffffu, gw, t * LPR);
+          const float4 gt = f4_shfl(g[u], t * LPR + q);
+          const int idt = __shfl_sync(0xffffffffu, lid[u], t * LPR);
+          const float gwt = __shfl_sync(0xffffffffu, gw[u], t * LPR);
 #pragma unroll
           for (int j = 0; j < J; ++j) {
             if (idt == r + RPW * j) {
@@ -357,14 +394,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
         }
       }
     }
-    if (tiny) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int lr = r + RPW * j;
-        if (lr < nrow) {
-          red_add_v4(p.dtable + static_cast<size_t>(off + lr) * D + q * 4, acc[j]);
-          if (has_w1 && q == 0) red_add_f32(p.dw1 + off + lr, accw[j]);
-        }
+    for (int j = 0; j < J; ++j) {
+      const int lr = r + RPW * j;
+      if (lr < nrow) {
+        red_add_v4(p.dtable + static_cast<size_t>(off + lr) * D + q * 4, acc[j]);
+        if (has_w1 && q == 0) red_add_f32(p.dw1 + off + lr, accw[j]);
       }
     }
   }
@@ -588,8 +623,11 @@ __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
 }
 
 // One group of LPR lanes per lookup; the first group to tag claim[row] this step
-// owns the row's update (exactly once per distinct row).
-template <int D>
+// owns the row's update (exactly once per distinct row).  The row's g/m/v/theta
+// loads are issued together with the claim exchange (not after it) and U lookups
+// are in flight per group, so a pass costs two dependent memory round trips
+// (row id -> {claim, row data}) instead of three; losers only cost L2 hits.
+template <int D, int U>
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ th,
                  float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
@@ -603,47 +641,80 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
   constexpr int LPR = D >= 4 ? D / 4 : 1;
   const int lane = threadIdx.x & 31;
   const int q = lane % LPR;
+  const int leader = (lane / LPR) * LPR;
   const long long groups_per_block = blockDim.x / LPR;
   const long long stride = static_cast<long long>(gridDim.x) * groups_per_block;
-  const long long nr = (n + stride - 1) / stride;
-  long long i = blockIdx.x * groups_per_block + threadIdx.x / LPR;
-  for (long long k = 0; k < nr; ++k, i += stride) {
-    int rid = -1;
-    int won = 0;
-    if (i < n) {
-      rid = __ldg(rows + i);    // negative ids are padding (sharded exchange slabs)
-      if (rid >= 0 && q == 0) won = atomicExch(claim + rid, tag) != tag ? 1 : 0;
+  const long long nr = (n + stride * U - 1) / (stride * U);
+  long long i0 = blockIdx.x * groups_per_block + threadIdx.x / LPR;
+  for (long long k = 0; k < nr; ++k, i0 += stride * U) {
+    int rid[U], won[U];
+    float4 G[U], M[U], V[U], T[U];
+    float G1[U], M1[U], V1[U], T1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      rid[u] = i < n ? __ldg(rows + i) : -1;    // negative ids are padding (sharded exchange slabs)
     }
-    won = __shfl_sync(0xffffffffu, won, (lane / LPR) * LPR);
-    if (!won) continue;
-    if (D >= 4) {
-      const size_t o = static_cast<size_t>(rid) * D + q * 4;
-      float4 G = *reinterpret_cast<float4*>(g + o);
-      float4 M = *reinterpret_cast<float4*>(m + o);
-      float4 V = *reinterpret_cast<float4*>(v + o);
-      float4 T = *reinterpret_cast<float4*>(th + o);
-      CTR_ADAM1(x) CTR_ADAM1(y) CTR_ADAM1(z) CTR_ADAM1(w)
-      *reinterpret_cast<float4*>(m + o) = M;
-      *reinterpret_cast<float4*>(v + o) = V;
-      *reinterpret_cast<float4*>(th + o) = T;
-      *reinterpret_cast<float4*>(g + o) = f4_zero();
-      if (th1 != nullptr && q == 0) {   // the row's first-order weight rides on the same claim
-        const float G1 = g1[rid];
-        const float M1 = b1 * m1[rid] + (1.f - b1) * G1;
-        const float V1 = b2 * v1[rid] + (1.f - b2) * G1 * G1;
-        m1[rid] = M1;
-        v1[rid] = V1;
-        th1[rid] -= lr_t * M1 / (sqrtf(V1) + eps);
-        g1[rid] = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      won[u] = 0;
+      if (rid[u] >= 0) {
+        if (q == 0) won[u] = atomicExch(claim + rid[u], tag) != tag ? 1 : 0;
+        if (D >= 4) {
+          const size_t o = static_cast<size_t>(rid[u]) * D + q * 4;
+          G[u] = ld4_plain(g + o);
+          M[u] = ld4_plain(m + o);
+          V[u] = ld4_plain(v + o);
+          T[u] = ld4_plain(th + o);
+          if (th1 != nullptr && q == 0) {
+            G1[u] = ld1_plain(g1 + rid[u]);
+            M1[u] = ld1_plain(m1 + rid[u]);
+            V1[u] = ld1_plain(v1 + rid[u]);
+            T1[u] = ld1_plain(th1 + rid[u]);
+          }
+        } else {
+          G1[u] = ld1_plain(g + rid[u]);
+          M1[u] = ld1_plain(m + rid[u]);
+          V1[u] = ld1_plain(v + rid[u]);
+          T1[u] = ld1_plain(th + rid[u]);
+        }
       }
-    } else {
-      const float G = g[rid];
-      const float M = b1 * m[rid] + (1.f - b1) * G;
-      const float V = b2 * v[rid] + (1.f - b2) * G * G;
-      m[rid] = M;
-      v[rid] = V;
-      th[rid] -= lr_t * M / (sqrtf(V) + eps);
-      g[rid] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int w = __shfl_sync(0xffffffffu, won[u], leader);
+      if (!w) continue;
+      // Only the claim winner ever writes this row in this launch, and the values it loaded
+      // above were written by earlier kernels: the speculative loads are race free.
+      if (D >= 4) {
+        const size_t o = static_cast<size_t>(rid[u]) * D + q * 4;
+        float4 Gu = G[u], Mu = M[u], Vu = V[u], Tu = T[u];
+#define CTR_ADAM4(c)                                  \
+  Mu.c = b1 * Mu.c + (1.f - b1) * Gu.c;               \
+  Vu.c = b2 * Vu.c + (1.f - b2) * Gu.c * Gu.c;        \
+  Tu.c -= lr_t * Mu.c / (sqrtf(Vu.c) + eps);
+        CTR_ADAM4(x) CTR_ADAM4(y) CTR_ADAM4(z) CTR_ADAM4(w)
+#undef CTR_ADAM4
+        *reinterpret_cast<float4*>(m + o) = Mu;
+        *reinterpret_cast<float4*>(v + o) = Vu;
+        *reinterpret_cast<float4*>(th + o) = Tu;
+        *reinterpret_cast<float4*>(g + o) = f4_zero();
+        if (th1 != nullptr && q == 0) {   // the row's first-order weight rides on the same claim
+          const float Mn = b1 * M1[u] + (1.f - b1) * G1[u];
+          const float Vn = b2 * V1[u] + (1.f - b2) * G1[u] * G1[u];
+          m1[rid[u]] = Mn;
+          v1[rid[u]] = Vn;
+          th1[rid[u]] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
+          g1[rid[u]] = 0.f;
+        }
+      } else {
+        const float Mn = b1 * M1[u] + (1.f - b1) * G1[u];
+        const float Vn = b2 * V1[u] + (1.f - b2) * G1[u] * G1[u];
+        m[rid[u]] = Mn;
+        v[rid[u]] = Vn;
+        th[rid[u]] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
+        g[rid[u]] = 0.f;
+      }
     }
   }
 }
@@ -822,14 +893,18 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int lpr = D >= 4 ? D / 4 : 1;
   const long long gpb = 256 / lpr;
-  const int grid = static_cast<int>(std::min<long long>((n + gpb - 1) / gpb, sm_count() * 8LL));
+  constexpr int U = 2;                      // lookups in flight per lane group
+  const long long per_block = gpb * U;
+  const int grid = static_cast<int>(std::min<long long>((n + per_block - 1) / per_block, sm_count() * 8LL));
+#define CTR_AR(DD) adam_rows_kernel<DD, U><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev)
   switch (D) {
-    case 1: adam_rows_kernel<1><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
-    case 8: adam_rows_kernel<8><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
-    case 16: adam_rows_kernel<16><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
-    case 32: adam_rows_kernel<32><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev); break;
+    case 1: CTR_AR(1); break;
+    case 8: CTR_AR(8); break;
+    case 16: CTR_AR(16); break;
+    case 32: CTR_AR(32); break;
     default: return fail_arg("ctr_adam_rows", "D must be 1, 8, 16 or 32");
   }
+#undef CTR_AR
   CTR_LAUNCH_CHECK("ctr_adam_rows");
 }
 

@@ -556,6 +556,17 @@ class FusedTower:
         # write each hidden layer's dpre once (ctr_tower_dpre) instead of re-deriving it from
         # the BN bookkeeping inside both backward GEMMs; required for the tcgen05 path
         self.materialise_dpre = os.environ.get("CTR_TOWER_DPRE", "1") != "0"
+        # ctr_tower_mid: the middle of the chain (hidden layers >= 1, dense(1), head, loss and
+        # their backward) in one cooperative launch; needs every hidden width <= 128
+        self.barrier = torch.zeros(2, dtype=torch.int32, device=dense.flat.device)
+        self.timing = None      # set to an int64[8] device tensor to get the phase time stamps
+        self.last_acts = None
+        self.mid_ok = (out_layer and 1 <= len(self.sizes) - 1 <= 4
+                       and all(4 <= h <= 128 and h % 4 == 0 for h in self.sizes[1:]))
+
+    @property
+    def use_mid(self):
+        return self.mid_ok and os.environ.get("CTR_TOWER_MID", "1") != "0"
 
     def join(self):
         """Make the current stream wait for the side-stream weight-gradient kernels."""
@@ -690,6 +701,129 @@ class _TowerFn(torch.autograd.Function):
         done.record(side)
         tw._pending = done
         return dn, None, None, None
+
+
+class _TowerHeadFn(torch.autograd.Function):
+    """Tower + loss head with the middle of the chain in ONE cooperative launch (ctr_tower_mid):
+    layer-0 GEMM -> [hidden layers, dense(1), head, loss, and in training the whole backward down
+    to dpre_0] -> (backward) dX GEMM on the main stream, weight-gradient GEMMs on the side stream.
+    All parameter gradients are accumulated into the flat gradient buffer by the kernels."""
+
+    @staticmethod
+    def forward(ctx, X, anchor, tw: "FusedTower", head, labels, training, *zs):
+        ctx.set_materialize_grads(False)
+        dense = tw.dense
+        hw, hb, b1, relu0, grad_scale = head
+        X = X.contiguous()
+        B, dev = X.shape[0], X.device
+        L = len(tw.sizes) - 1
+        Hs = tw.sizes[1:]
+        zs = [z.contiguous().view(B) for z in zs]
+        labels = labels.to(dev, torch.float32).contiguous().view(B)
+        f32 = dict(dtype=torch.float32, device=dev)
+        # one zero-filled workspace per step: the BN column sums of every layer + the loss scalar
+        offs, n = [], 0
+        for H in Hs:
+            offs.append(n)
+            n += 2 * H
+        ws = torch.zeros(n + 4, **f32)
+        stats = [ws[o:o + 2 * H].view(2, H) for o, H in zip(offs, Hs)]
+        loss = ws[n:n + 1].view(())
+        acts = [torch.empty((B, H), **f32) for H in Hs]
+        logits, prob, y = (torch.empty(B, **f32) for _ in range(3))
+        _call("ctr_tower_layer_fwd", _p(X), tw.sizes[0], tw.sizes[0], None, _p(tw.P("0.w")),
+              _p(tw.P("0.b")), Hs[0], _p(acts[0]), Hs[0], _p(stats[0]) if training else None, 1, B,
+              _stream())
+        a = _lib.TowerMidArgs()
+        a.L, a.C, a.relu0, a.training = L, len(zs) + 1, 1 if relu0 else 0, 1 if training else 0
+        if training:
+            dn = [torch.empty((B, H), **f32) for H in Hs]
+            dpre = [torch.empty((B, H), **f32) for H in Hs]
+            dzs = [torch.empty(B, **f32) for _ in zs]
+        else:
+            dn = dpre = dzs = None
+        for l, H in enumerate(Hs):
+            a.H[l] = H
+            if l > 0:
+                a.W[l], a.b[l] = _p(tw.P("%d.w" % l)), _p(tw.P("%d.b" % l))
+            a.gamma[l], a.beta[l] = _p(tw.P("%d.bn.gamma" % l)), _p(tw.P("%d.bn.beta" % l))
+            a.mean[l], a.var[l] = _p(tw.P("%d.bn.mean" % l)), _p(tw.P("%d.bn.var" % l))
+            a.act[l] = _p(acts[l])
+            if training:
+                a.stats[l] = _p(stats[l])
+                a.dgamma[l], a.dbeta[l] = _p(tw.G("%d.bn.gamma" % l)), _p(tw.G("%d.bn.beta" % l))
+                a.dbias[l] = _p(tw.G("%d.b" % l))
+                a.dn[l], a.dpre[l] = _p(dn[l]), _p(dpre[l])
+        a.w_out, a.b_out = _p(tw.P("out.w")), _p(tw.P("out.b"))
+        a.state, a.eps, a.p_drop = tw.adam.state_ptr, BN_EPS, tw.dropout if training else 0.0
+        a.seed, a.grad_scale = tw.seed & 0xFFFFFFFF, float(grad_scale)
+        for c, z in enumerate(zs):
+            a.z[c] = _p(z)
+            if training:
+                a.dz[c] = _p(dzs[c])
+        a.hw, a.hb, a.b1 = _p(dense[hw]), _p(dense[hb]), _p(dense[b1]) if relu0 else None
+        a.labels, a.y_out, a.logits, a.prob, a.loss = _p(labels), _p(y), _p(logits), _p(prob), _p(loss)
+        if training:
+            a.dhw, a.dhb = _p(dense[hw].grad), _p(dense[hb].grad)
+            a.db1 = _p(dense[b1].grad) if relu0 else None
+            a.dw_out, a.db_out = _p(tw.G("out.w")), _p(tw.G("out.b"))
+            a.barrier = _p(tw.barrier)
+        a.timing = _p(tw.timing) if tw.timing is not None else None
+        _call("ctr_tower_mid", C.byref(a), B, _stream())
+        ctx.tw, ctx.training = tw, training
+        tw.last_acts = acts          # post-ReLU hidden activations of the latest call (tests)
+        ctx.saved = (X, acts, stats, dpre, dzs, dn, zs, labels, ws)
+        ctx.mark_non_differentiable(logits, prob)
+        return loss, logits, prob
+
+    @staticmethod
+    def backward(ctx, gl, _g1, _g2):
+        tw = ctx.tw
+        if not ctx.training:
+            raise RuntimeError("tower_head backward is only defined in training mode")
+        X, acts, stats, dpre, dzs, dn, zs, labels, ws = ctx.saved
+        B, dev = X.shape[0], X.device
+        L = len(tw.sizes) - 1
+        main, side = torch.cuda.current_stream(), tw.side
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+
+        def grad_src(G, H):
+            g = _lib.GradSrc()
+            g.G, g.ldg, g.a, g.lda, g.kind, g.train, g.eps = _p(G), H, None, 0, 2, 1, BN_EPS
+            return g
+
+        with torch.cuda.stream(side):       # dW_l = P(a_{l-1})^T . dpre_l, off the critical path
+            for l in range(L):
+                H, K = tw.sizes[l + 1], tw.sizes[l]
+                gs = grad_src(dpre[l], H)
+                xin = acts[l - 1] if l > 0 else X
+                pro = C.byref(tw.bn_drop(l - 1, stats[l - 1], True)) if l > 0 else None
+                _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs), H,
+                      _p(tw.G("%d.w" % l)), None, B, side.cuda_stream)
+        H0, K0 = tw.sizes[1], tw.sizes[0]
+        gs0 = grad_src(dpre[0], H0)
+        dX = torch.empty((B, K0), dtype=torch.float32, device=dev)
+        _call("ctr_tower_layer_bwd_data", C.byref(gs0), H0, _p(tw.P("0.w")), K0, None, None,
+              _p(dX), K0, None, None, B, _stream())
+        for t_ in dpre + acts + [X, ws]:        # tensors read by the side stream
+            t_.record_stream(side)
+        done = torch.cuda.Event()
+        done.record(side)
+        tw._pending = done
+        return (dX, None, None, None, None, None) + tuple(dzs)
+
+
+def tower_head(tw: "FusedTower", X, zs, labels, hw="head.w", hb="head.b", b1="b1", relu0=True,
+               grad_scale=None, training=True):
+    """loss, logits, prob of `head([zs..., tower(X)])` (deepfm/deepfm.py:100-129)."""
+    require_cuda(X, "tower input")
+    B = X.shape[0]
+    if grad_scale is None:
+        grad_scale = 1.0 / B
+    return _TowerHeadFn.apply(X, tw._anchor, tw, (hw, hb, b1, relu0, grad_scale), labels, training,
+                              *zs)
 
 
 class _LossHeadFn(torch.autograd.Function):

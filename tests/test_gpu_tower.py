@@ -112,3 +112,140 @@ def test_layer_bwd_plain(cuda, tc, B, K, N):
               K, None, None, B, ops._stream())
     _close(dX1, dpre_want @ W.double().t(), 1e-4)
     torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ ctr_tower_mid (one launch)
+def _masks(tw, B, dev):
+    """Keep masks of the current step for every hidden layer (identity-BN trick, see
+    test_gpu_models._dropout_masks)."""
+    from recsys_b200 import _lib
+    lib = _lib.load()
+    out = []
+    for l, H in enumerate(tw.sizes[1:]):
+        ones = torch.ones(B, H, device=dev)
+        res = torch.empty_like(ones)
+        zero, one = torch.zeros(H, device=dev), torch.ones(H, device=dev)
+        var = one - 1e-3
+        d = _lib.BnDrop()
+        d.sums, d.mean, d.var = None, zero.data_ptr(), var.data_ptr()
+        d.gamma, d.beta, d.state = one.data_ptr(), zero.data_ptr(), tw.adam.state_ptr
+        d.eps, d.p_drop, d.seed, d.layer, d.enabled = 1e-3, tw.dropout, tw.seed, l, 1
+        rc = lib.ctr_bn_drop_apply(ones.data_ptr(), H, C.byref(d), res.data_ptr(), B,
+                                   torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        out.append((res > 0).double())
+    return out
+
+
+def _tower_head_ref(P, X, zs, labels, sizes, masks, p, training, gates=None):
+    """float64 restatement of deepfm/deepfm.py:100-129 (dense-relu-BN-dropout stack, dense(1,relu),
+    head over [relu(z0 + b1), z1.., y], mean sigmoid cross entropy).
+
+    ``gates``: the hidden ReLUs' on/off pattern taken from the kernel's own activations.  A ReLU
+    whose pre-activation is within fp32 rounding of 0 may gate differently in fp32 and fp64 (and,
+    because the BN column sums are accumulated with atomics, from run to run); that changes the
+    forward by ~1e-7 but that row's gradient by O(1), which is a property of ReLU, not a kernel
+    error.  With the kernel's gates the comparison is between smooth functions."""
+    h = X
+    for l in range(len(sizes) - 1):
+        pre = h @ P["t.%d.w" % l] + P["t.%d.b" % l]
+        a = torch.relu(pre) if gates is None else pre * gates[l]
+        if training:
+            mu, var = a.mean(0), a.var(0, unbiased=False)
+        else:
+            mu, var = P["t.%d.bn.mean" % l], P["t.%d.bn.var" % l]
+        h = (a - mu) / torch.sqrt(var + 1e-3) * P["t.%d.bn.gamma" % l] + P["t.%d.bn.beta" % l]
+        if training and p > 0:
+            h = h * masks[l] / (1 - p)
+    y = torch.relu(h @ P["t.out.w"] + P["t.out.b"]).reshape(-1)
+    cols = [torch.relu(zs[0] + P["b1"])] + list(zs[1:]) + [y]
+    logit = torch.stack(cols, 1) @ P["head.w"].reshape(-1) + P["head.b"]
+    loss = (torch.clamp(logit, min=0) - logit * labels + torch.log1p(torch.exp(-logit.abs()))).mean()
+    return loss, logit
+
+
+@pytest.mark.parametrize("B,sizes,nz,p", [(4096, [624, 100, 100], 2, 0.5), (1000, [624, 100, 100], 2, 0.0),
+                                           (333, [96, 32, 16], 2, 0.5), (517, [64, 128], 1, 0.0),
+                                           (6000, [128, 64, 32, 16, 8], 2, 0.3)])
+def test_tower_mid_matches_float64(cuda, B, sizes, nz, p):
+    from recsys_b200 import ops
+    torch.manual_seed(B)
+    shapes = {"b1": (1,), "head.w": (nz + 1, 1), "head.b": (1,), "t.out.w": (sizes[-1], 1), "t.out.b": (1,)}
+    for l, (i, o) in enumerate(zip(sizes[:-1], sizes[1:])):
+        shapes.update({"t.%d.w" % l: (i, o), "t.%d.b" % l: (o,), "t.%d.bn.gamma" % l: (o,),
+                       "t.%d.bn.beta" % l: (o,), "t.%d.bn.mean" % l: (o,), "t.%d.bn.var" % l: (o,)})
+    frozen = [n for n in shapes if n.endswith((".bn.mean", ".bn.var"))]
+    dense = ops.DenseParams(shapes, cuda, frozen=frozen)
+    with torch.no_grad():
+        for n in dense.names:
+            v = dense[n]
+            if n.endswith(".bn.var"):
+                v.copy_(torch.rand_like(v) + 0.5)
+            elif n.endswith(".w"):
+                v.copy_(torch.randn_like(v) * (2.0 / v.shape[0]) ** 0.5)
+            else:
+                v.copy_(torch.randn_like(v) * 0.3 + (1.0 if n.endswith("gamma") else 0.0))
+    adam = ops.TFAdamState(device=cuda)
+    adam.next_lr_t()                                   # step counter 1 selects the dropout stream
+    tw = ops.FusedTower(dense, "t", sizes, True, p, adam, seed=11)
+    assert tw.use_mid
+    X = torch.randn(B, sizes[0], device=cuda, requires_grad=True)
+    zs = [torch.randn(B, device=cuda, requires_grad=True) for _ in range(nz)]
+    labels = (torch.rand(B, device=cuda) < 0.3).float()
+    masks = _masks(tw, B, cuda) if p > 0 else None
+    P64 = {n: dense[n].detach().double().requires_grad_(n not in frozen) for n in dense.names}
+    X64 = X.detach().double().requires_grad_(True)
+    zs64 = [z.detach().double().requires_grad_(True) for z in zs]
+    for training in (False, True):
+        loss, logits, prob = ops.tower_head(tw, X, zs, labels, training=training)
+        torch.cuda.synchronize()
+        gates = [(a > 0).double() for a in tw.last_acts] if training else None
+        loss64, logit64 = _tower_head_ref(P64, X64, zs64, labels.double(), sizes, masks, p, training,
+                                          gates)
+        _close(logits, logit64.detach(), 1e-4)
+        _close(prob, torch.sigmoid(logit64.detach()), 1e-4)
+        assert abs(float(loss) - float(loss64)) <= 1e-5 * max(1.0, abs(float(loss64)))
+    loss64.backward()
+    loss.backward()
+    tw.join()
+    torch.cuda.synchronize()
+    _close(X.grad, X64.grad, 1e-4)
+    for z, z64 in zip(zs, zs64):
+        _close(z.grad, z64.grad, 1e-4)
+    for n in dense.names:
+        if n not in frozen:
+            _close(dense[n].grad, P64[n].grad.reshape(dense[n].shape), 2e-4)
+
+
+def test_tower_mid_agrees_with_per_layer_kernels(cuda):
+    """Same seeds, same dropout stream: the one-launch path and the per-layer path (CTR_TOWER_MID=0)
+    of DeepFM produce the same loss and the same gradients."""
+    import numpy as np
+    import make_golden as mg
+    from oracle import models as om
+    from test_gpu_models import _build, _features_to_torch
+    from recsys_b200.deepfm import deepfm
+    spec = mg.small_spec()
+    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(100, 100), seed=5)
+    feats, batch = mg.model_batch("deepfm", 2048, 4, spec)
+    res = {}
+    for mid in ("1", "0"):
+        os.environ["CTR_TOWER_MID"] = mid
+        try:
+            m, params = _build("deepfm", spec, cuda, deep_layers="100,100", dropout=0.5)
+            m.load_state(p64)
+            sp = deepfm.model_fn(_features_to_torch(feats), batch["labels"], "train", params)
+            m.backward(m.last["loss"])
+            torch.cuda.synchronize()
+            g = {k: v.detach().clone() for k, v in m.dense_grads().items()}
+            g["emb"] = m.emb.dtable.detach().clone()
+            res[mid] = (float(sp.loss), g)
+        finally:
+            os.environ.pop("CTR_TOWER_MID", None)
+    assert abs(res["1"][0] - res["0"][0]) <= 1e-6
+    # relative Frobenius error: one ReLU gating differently within fp32 rounding (the BN sums are
+    # atomics) moves a single row's gradient, which a max-norm check would flag
+    for k, v in res["0"][1].items():
+        d = (res["1"][1][k].double() - v.double()).norm().item()
+        assert d <= 2e-3 * max(v.double().norm().item(), 1e-12), (k, d)
