@@ -161,7 +161,9 @@ class _ModelBase:
                              train_op=train_op)
 
     def backward(self, loss):
-        loss.backward()
+        if getattr(self, "_one", None) is None:        # root gradient, made once (no fill per step)
+            self._one = torch.ones((), dtype=torch.float32, device=self.device)
+        loss.backward(self._one.expand_as(loss))
         # drop the autograd graph: a live graph keeps the leaves' AccumulateGrad nodes (and the
         # stream they were created on) alive, which breaks a later CUDA-graph capture
         self.last = {k: v.detach() for k, v in self.last.items()}

@@ -84,15 +84,26 @@ __device__ __forceinline__ void mid_grid_barrier(unsigned* bar, unsigned nblocks
   __syncthreads();
 }
 
-// Ws[k][n] = W[k][n] (row-major [K, N]), zero padded to 16-row / 16-column multiples.
+// Ws[k][n] = W[k][n] (row-major [K, N]), zero padded to 16-row / 16-column multiples.  The global
+// loads are issued in batches of 4 per thread before the first shared store, so that the staging
+// costs ~2 L2 round trips instead of one per float4.
 __device__ __forceinline__ void mid_load_weights(MidSmem& sm, const float* __restrict__ W, int K,
                                                  int N) {
   const int KR = (K + 15) & ~15, NQ = ((N + 15) & ~15) >> 2;
-  for (int e = threadIdx.x; e < KR * NQ; e += kMidThreads) {
-    const int k = e / NQ, n = (e % NQ) * 4;
-    float4 v = f4_zero();
-    if (k < K && n < N) v = ldg4(W + static_cast<size_t>(k) * N + n);
-    sts4(&sm.Ws[k * kMidPB + n], v);
+  const int total = KR * NQ;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMidThreads) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kMidThreads;
+      const int k = e / NQ, n = (e % NQ) * 4;
+      v[u] = (e < total && k < K && n < N) ? ldg4(W + static_cast<size_t>(k) * N + n) : f4_zero();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kMidThreads;
+      if (e < total) sts4(&sm.Ws[(e / NQ) * kMidPB + (e % NQ) * 4], v[u]);
+    }
   }
 }
 
@@ -263,7 +274,21 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   c.step = A.state != nullptr ? static_cast<unsigned>(A.state[0]) : 0u;
   int ws_layer = -1;
   const int k4 = 4 * lane;                      // this lane's columns in the element-wise passes
+  // One tile per CTA (the usual case: B / 32 <= #SMs): everything a phase needs from an earlier
+  // one is carried in registers (a_c: the stored activation of the "current" layer for this
+  // thread's 2 rows x 4 columns, dn_c: the gradient arriving at it); the global copies are still
+  // written (the weight-gradient kernels read them) but never read back here.
+  const bool single = gridDim.x >= static_cast<unsigned>(ntiles);
+  float4 a_c[2] = {f4_zero(), f4_zero()}, dn_c[2] = {f4_zero(), f4_zero()};
+  float4 ap[2] = {f4_zero(), f4_zero()};
   mid_stamp(A, 0);
+  if (single) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = blockIdx.x * kMidBM + warp + 16 * h;
+      if (r < B && k4 < A.H[0]) a_c[h] = ldcg4(A.act[0] + static_cast<size_t>(r) * A.H[0] + k4);
+    }
+  }
 
   // ------------------------------------------------------------- forward hidden layers
   for (int l = 1; l < L; ++l) {
@@ -285,13 +310,16 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
         const int rr = warp + 16 * h, r = r0 + rr;
         if (k4 < ((K + 7) & ~7)) {
           float4 v = f4_zero(), keep;
-          if (r < B && k4 < K) v = mid_bn_drop4(sm, c, l - 1, r, k4, ldcg4(in + static_cast<size_t>(r) * K + k4), &keep);
+          if (r < B && k4 < K)
+            v = mid_bn_drop4(sm, c, l - 1, r, k4,
+                             single ? a_c[h] : ldcg4(in + static_cast<size_t>(r) * K + k4), &keep);
           sts4(&sm.Ta[rr * kMidPA + k4], v);
         }
       }
       __syncthreads();
       mid_gemm<false>(sm, (K + 7) & ~7, N);
       __syncthreads();
+      a_c[0] = a_c[1] = f4_zero();
       if (k4 < N) {
         const float4 bias = lds4(&sm.vec[k4]);
 #pragma unroll
@@ -303,6 +331,7 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
             *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * N + k4) = v;
             acc[0] = f4_add(acc[0], v);
             acc[1] = f4_fma4(v, v, acc[1]);
+            a_c[h] = v;
           }
         }
       }
@@ -319,12 +348,21 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   // ----------------------------------------------------- final dense(1, relu) + loss head
   {
     const int l = L - 1, K = A.H[l];
+    const int C = A.C;
+    // head inputs of this thread's rows (first tile): fetched ahead of the table fill
+    float zpre[2][3], lpre[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = blockIdx.x * kMidBM + warp + 16 * h;
+      lpre[h] = r < B ? A.labels[r] : 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) zpre[h][cc] = (r < B && cc < C - 1) ? A.z[cc][r] : 0.f;
+    }
     __syncthreads();
     mid_fill_bn(sm, A, c, l);
     for (int k = tid; k < K; k += kMidThreads) sm.vec[k] = A.w_out[k];
     __syncthreads();
     const float b_out = A.b_out[0];
-    const int C = A.C;
     float hw[4] = {0.f, 0.f, 0.f, 0.f};
     for (int cc = 0; cc < C; ++cc) hw[cc] = A.hw[cc];
     const float hb = A.hb[0];
@@ -341,7 +379,9 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int r = r0 + warp + 16 * h;
-        a4[h] = (on && r < B) ? ldcg4(act + static_cast<size_t>(r) * K + k4) : f4_zero();
+        a4[h] = single ? a_c[h]
+                       : (on && r < B) ? ldcg4(act + static_cast<size_t>(r) * K + k4) : f4_zero();
+        dn_c[h] = f4_zero();
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -361,14 +401,14 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
           if (cc < C) {
             float v = y;
             if (cc < C - 1) {
-              v = A.z[cc][r];
+              v = (tile == static_cast<int>(blockIdx.x) && cc < 3) ? zpre[h][cc] : A.z[cc][r];
               if (cc == 0 && A.relu0) v = fmaxf(v + b1, 0.f);
             }
             av[cc] = v;
             logit = fmaf(hw[cc], v, logit);
           }
         }
-        const float zl = A.labels[r];
+        const float zl = tile == static_cast<int>(blockIdx.x) ? lpre[h] : A.labels[r];
         const float pr = 1.f / (1.f + expf(-logit));
         // tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x z + log1p(exp(-|x|))
         const float bce = fmaxf(logit, 0.f) - logit * zl + log1pf(expf(-fabsf(logit)));
@@ -404,6 +444,7 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
             const float4 d = make_float4(dpo * w4.x * keep.x, dpo * w4.y * keep.y, dpo * w4.z * keep.z,
                                          dpo * w4.w * keep.w);
             *reinterpret_cast<float4*>(dn + static_cast<size_t>(r) * K + k4) = d;
+            dn_c[h] = d;
             acc[0] = f4_fma(dpo, hv, acc[0]);
             acc[1] = f4_add(acc[1], d);
             acc[2] = f4_fma4(d, xh, acc[2]);
@@ -439,6 +480,17 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   }
   mid_stamp(A, 3);
   if (!c.training) return;
+  // the activation below the next backward layer is final: fetch it while waiting on the barrier
+  auto prefetch_prev = [&](int lp) {
+    if (!single || lp < 0) return;
+    const int Kp = A.H[lp];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = blockIdx.x * kMidBM + warp + 16 * h;
+      ap[h] = (r < B && k4 < Kp) ? ldcg4(A.act[lp] + static_cast<size_t>(r) * Kp + k4) : f4_zero();
+    }
+  };
+  prefetch_prev(L - 2);
   mid_grid_barrier(A.barrier, gridDim.x);                          // dbeta/dgamma_{L-1} complete
   mid_stamp(A, 4);
 
@@ -461,16 +513,16 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
     float4 acc[3] = {f4_zero(), f4_zero(), f4_zero()};     // d b_l, d beta_{l-1}, d gamma_{l-1}
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int r0 = tile * kMidBM;
-      float4 ap[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int rr = warp + 16 * h, r = r0 + rr;
-        ap[h] = (r < B && k4 < K) ? ldcg4(aprev + static_cast<size_t>(r) * K + k4) : f4_zero();
+        if (!single)
+          ap[h] = (r < B && k4 < K) ? ldcg4(aprev + static_cast<size_t>(r) * K + k4) : f4_zero();
         if (k4 < ((N + 7) & ~7)) {
           float4 v = f4_zero();
           if (r < B && k4 < N) {
-            v = mid_dpre4(sm, k4, ldcg4(act + static_cast<size_t>(r) * N + k4),
-                          ldcg4(dnl + static_cast<size_t>(r) * N + k4));
+            v = mid_dpre4(sm, k4, single ? a_c[h] : ldcg4(act + static_cast<size_t>(r) * N + k4),
+                          single ? dn_c[h] : ldcg4(dnl + static_cast<size_t>(r) * N + k4));
             *reinterpret_cast<float4*>(dpre + static_cast<size_t>(r) * N + k4) = v;
             acc[0] = f4_add(acc[0], v);
           }
@@ -480,6 +532,7 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
       __syncthreads();
       mid_gemm<true>(sm, (N + 7) & ~7, K);
       __syncthreads();
+      dn_c[0] = dn_c[1] = f4_zero();
       if (k4 < K) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -491,12 +544,16 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
             *reinterpret_cast<float4*>(dnp + static_cast<size_t>(r) * K + k4) = v;
             acc[1] = f4_add(acc[1], v);
             acc[2] = f4_fma4(v, mid_xhat4(sm, k4, ap[h]), acc[2]);
+            dn_c[h] = v;
           }
         }
       }
+      a_c[0] = ap[0];                   // the layer below becomes the current one
+      a_c[1] = ap[1];
     }
     float* const dst[3] = {A.dbias[l], A.dbeta[l - 1], A.dgamma[l - 1]};
     mid_reduce_cols<3>(sm, acc, dst, N > K ? N : K);
+    prefetch_prev(l - 2);
     mid_stamp(A, 5);
     mid_grid_barrier(A.barrier, gridDim.x);                        // dbeta/dgamma_{l-1} complete
     mid_stamp(A, 6);
@@ -518,8 +575,9 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
         for (int h = 0; h < 2; ++h) {
           const int r = tile * kMidBM + warp + 16 * h;
           if (r < B) {
-            const float4 v = mid_dpre4(sm, k4, ldcg4(act + static_cast<size_t>(r) * N + k4),
-                                       ldcg4(dnl + static_cast<size_t>(r) * N + k4));
+            const float4 v = mid_dpre4(sm, k4,
+                                       single ? a_c[h] : ldcg4(act + static_cast<size_t>(r) * N + k4),
+                                       single ? dn_c[h] : ldcg4(dnl + static_cast<size_t>(r) * N + k4));
             *reinterpret_cast<float4*>(dpre + static_cast<size_t>(r) * N + k4) = v;
             acc[0] = f4_add(acc[0], v);
           }

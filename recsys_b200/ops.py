@@ -346,8 +346,9 @@ class _EmbedFn(torch.autograd.Function):
         ctx.emb, ctx.rows, ctx.E, ctx.S = emb, rows, E, S
         ctx.cross_w, ctx.cross_b = cross_w, cross_b
         ctx.flags = (want_fm, want_y1, cross)
-        outs = [E, y1 if want_y1 else E.new_zeros(()), y2 if want_fm else E.new_zeros(()),
-                xl if cross else E.new_zeros(())]
+        # placeholders for the outputs not asked for: uninitialised scalars (no fill launch)
+        outs = [E, y1 if want_y1 else E.new_empty(()), y2 if want_fm else E.new_empty(()),
+                xl if cross else E.new_empty(())]
         non_diff = [o for o, f in zip(outs[1:], (want_y1, want_fm, cross)) if not f]
         if non_diff:
             ctx.mark_non_differentiable(*non_diff)
