@@ -405,7 +405,7 @@ def time_hot_kernels(model, devb, K, W, stream):
 
         def fwd(i):
             lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rows[i % len(rows)]), B, F, D,
-                              emb.w1_fields, p(Eb), p(Sb), p(y1), p(y2), None, None, 0, None, st)
+                              emb.w1_fields, p(Eb), p(Sb), p(y1), p(y2), None, None, 0, None, None, st)
 
         def bwd(i):
             lib.ctr_embed_bwd(p(rows[i % len(rows)]), p(dE), p(Eb), p(emb.table), p(Sb), p(dy),
@@ -457,7 +457,7 @@ def time_hot_kernels(model, devb, K, W, stream):
             def fwdL(i):
                 lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rl[i % 4]), BL, F, D, emb.w1_fields,
                                   p(EL), p(SL), p(yl) if emb.w1 is not None else None, p(yl), None,
-                                  None, 0, None, st)
+                                  None, 0, None, None, st)
 
             def bwdL(i):
                 lib.ctr_embed_bwd(p(rl[i % 4]), p(dEL), p(EL), p(emb.table), p(SL), p(yl), p(yl),

@@ -82,10 +82,11 @@ int ctr_hash_strings(const uint8_t* bytes, const int32_t* offsets, int64_t N,
  *   y1[b]    = sum_{f in w1_fields} w1[rows[b,f]]   (pre-bias, pre-ReLU) (nullable)
  *   y2[b]    = 0.5 * sum_d[(sum_f E)^2 - sum_f E^2]                      (nullable)
  *   xl[b,:]  = cross stack on x0 = E[b,:]: xl <- (xl.w_l) x0 + xl + b_l  (nullable)
+ *   E_lo     = the lo half of E's 3xTF32 split (see ctr_split_lo)        (nullable)
  * D in {8,16,32}; F <= 64 and F*D <= 1280; w1_fields bit f = field f has a first-order weight. */
 int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
                   uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
-                  const float* cross_w, const float* cross_b, int cross_layers, float* xl,
+                  const float* cross_w, const float* cross_b, int cross_layers, float* xl, float* E_lo,
                   ctr_stream_t stream);
 
 /* Backward: scatter-add of the row gradients into dtable / dw1 (the IndexedSlices
@@ -254,6 +255,27 @@ int ctr_loss_head(const float* const* z, float* const* dz, int C, int relu0, con
                   float* prob, float* loss, float* dhw, float* dhb, float* db1, float grad_scale,
                   ctr_stream_t stream);
 
+/* 3xTF32 with pre-split operands.  The tower's wide first layer (624 -> H) is the one GEMM of a
+ * CTR step that belongs on tcgen05; its fp32-grade accuracy comes from
+ *   a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi,   hi = the top 19 bits of the fp32 word (what
+ *   tcgen05.mma.kind::tf32 reads), lo = tf32(x - hi).
+ * Computing lo inside the GEMM costs CUDA-core work per operand tile and per CTA; here the
+ * producer of each operand writes lo next to it (ctr_embed_fwd: E_lo; ctr_tower_mid: dpre0_lo;
+ * ctr_split_lo for the weights) and the GEMM only streams tiles by TMA into tcgen05.
+ * ctr_split_lo: lo[i] = tf32(x[i] - trunc_tf32(x[i])), n floats. */
+int ctr_split_lo(const float* x, float* lo, int64_t n, ctr_stream_t stream);
+/* The three GEMMs of a dense(relu) layer out = relu(X . W + b), X [B,K], W [K,N] (deepfm.py:101):
+ *   kind 0  forward   out[B,N] = act(X . W + bias); stats (nullable) [2][N] += colsums(out, out^2)
+ *                     A = X, B = W
+ *   kind 1  data      out[B,K] = dpre[B,N] . W^T                     A = dpre, B = W
+ *   kind 2  weights   out[K,N] += X^T . dpre   (split over the rows)  A = X,    B = dpre
+ *   kind 3  forward, split-K: out[B,N] += X . W only (out zero on entry; bias, ReLU and the
+ *                     column statistics are then applied by ctr_tower_mid, field pre0)
+ * A_lo / B_lo: the lo halves (same shapes and pitches).  Needs B >= 256, K % 4 == N % 4 == 0. */
+int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const float* Bm,
+                            const float* B_lo, int B, int K, int N, float* out, const float* bias,
+                            float* stats, int relu, ctr_stream_t stream);
+
 /* ctr_tower_mid: everything between the first layer's GEMM and the first layer's backward
  * GEMMs in ONE cooperative launch (deepfm/deepfm.py:100-129, xdeepfm/xdeepfm.py:184-212):
  * hidden layers 1..L-1 forward (BN of the previous layer's stored output + dropout as the GEMM
@@ -276,7 +298,7 @@ typedef struct {
   int32_t L, C, relu0, training;
   int32_t H[CTR_TOWER_MID_MAX_LAYERS];
   const float* W[CTR_TOWER_MID_MAX_LAYERS];      /* W[l]: [H[l-1], H[l]], l >= 1 (W[0] unused) */
-  const float* b[CTR_TOWER_MID_MAX_LAYERS];      /* b[l]: [H[l]], l >= 1 */
+  const float* b[CTR_TOWER_MID_MAX_LAYERS];      /* b[l]: [H[l]], l >= 1 (b[0] only with pre0) */
   const float* gamma[CTR_TOWER_MID_MAX_LAYERS];
   const float* beta[CTR_TOWER_MID_MAX_LAYERS];
   const float* mean[CTR_TOWER_MID_MAX_LAYERS];   /* eval only */
@@ -309,6 +331,10 @@ typedef struct {
   float* dbias[CTR_TOWER_MID_MAX_LAYERS];
   float* dn[CTR_TOWER_MID_MAX_LAYERS];
   float* dpre[CTR_TOWER_MID_MAX_LAYERS];
+  float* dpre0_lo;                               /* nullable: lo half of dpre[0] (ctr_split_lo rule) */
+  const float* pre0;                             /* nullable: X . W_0 without bias (split-K GEMM, kind 3):
+                                                    act[0] = relu(pre0 + b[0]) and stats[0] are then
+                                                    produced here (one more phase and barrier) */
   uint32_t* barrier;
   unsigned long long* timing;                    /* nullable: 8 words, %globaltimer (ns) of block 0 at
                                                     the phase boundaries (profiling aid) */

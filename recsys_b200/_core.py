@@ -224,7 +224,7 @@ class _CriteoBase(_ModelBase):
                                            grad_scale=1.0 / (B * self.world), training=training)
         return logits.view(shape), prob.view(shape), loss
 
-    def _tower_head(self, tower, X, zs, labels, training, shape):
+    def _tower_head(self, tower, X, zs, labels, training, shape, X_lo=None):
         """tower(X) as the last head column: one ctr_tower_mid launch when the tower's shape
         allows, else the per-layer kernels + ctr_loss_head."""
         if not tower.use_mid:
@@ -233,7 +233,8 @@ class _CriteoBase(_ModelBase):
         if labels is None:
             labels = torch.zeros(B, dtype=torch.float32, device=self.device)
         loss, logits, prob = ops.tower_head(tower, X, zs, labels, relu0=True,
-                                            grad_scale=1.0 / (B * self.world), training=training)
+                                            grad_scale=1.0 / (B * self.world), training=training,
+                                            X_lo=X_lo)
         return logits.view(shape), prob.view(shape), loss
 
     def backward(self, loss):
@@ -310,9 +311,13 @@ class DeepFMModel(_CriteoBase):
     def forward(self, features, labels, training):
         if not self.fused:
             return super().forward(features, labels, training)
+        self.tower.begin_step()
         self.rows = self.ids(features)
-        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
-        return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,))  # :91,100-129
+        lo = self.tower.use_presplit and self.world == 1
+        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True,
+                                        **({"want_lo": True} if lo else {}))
+        return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),
+                                X_lo=self.emb.last_E_lo if lo else None)      # :91,100-129
 
     def logits(self, features, training):
         P = self.dense

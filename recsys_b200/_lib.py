@@ -57,7 +57,7 @@ class TowerMidArgs(C.Structure):
                 ("dz", C.c_void_p * 3), ("dhw", C.c_void_p), ("dhb", C.c_void_p),
                 ("db1", C.c_void_p), ("dw_out", C.c_void_p), ("db_out", C.c_void_p),
                 ("dgamma", _P4), ("dbeta", _P4), ("dbias", _P4), ("dn", _P4), ("dpre", _P4),
-                ("barrier", C.c_void_p), ("timing", C.c_void_p)]
+                ("dpre0_lo", C.c_void_p), ("pre0", C.c_void_p), ("barrier", C.c_void_p), ("timing", C.c_void_p)]
 
 
 class FieldDesc(C.Structure):
@@ -75,7 +75,7 @@ SIGNATURES = {
     "ctr_criteo_rows": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f]),
     "ctr_hash_strings": (c_i, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
     "ctr_embed_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i,
-                            c_f, c_f]),
+                            c_f, c_f, c_f]),
     "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
                             c_i, c_i, c_f, c_f, c_f]),
     "ctr_dcn_cross_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f]),
@@ -104,6 +104,8 @@ SIGNATURES = {
                                           c_f, c_f, c_i, c_f]),
     "ctr_loss_head": (c_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i, c_i, c_f, c_f, c_f,
                             c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_fl, c_f]),
+    "ctr_split_lo": (c_i, [c_f, c_f, c_i64, c_f]),
+    "ctr_tower_gemm_presplit": (c_i, [c_i, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_i, c_f]),
     "ctr_tower_mid": (c_i, [C.POINTER(TowerMidArgs), c_i, c_f]),
     "ctr_shard_bucket": (c_i, [c_f, c_i64, c_i, c_i, c_f, c_f, c_f, c_f]),
     "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),

@@ -103,6 +103,17 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// lo part of the 3xTF32 split a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi.  tcgen05.mma.kind::tf32 reads
+// the top 19 bits of an fp32 word, so the raw value serves as "hi"; lo = x - trunc_tf32(x) (exact),
+// rounded to tf32 with integer ops (add half an ulp of the 10-bit mantissa; the tensor core drops
+// the low 13 bits itself).
+__device__ __forceinline__ float tcg_lo(float x) {
+  const float l = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(l) + 0x1000u);
+}
+__device__ __forceinline__ float4 tcg_lo4(float4 v) {
+  return make_float4(tcg_lo(v.x), tcg_lo(v.y), tcg_lo(v.z), tcg_lo(v.w));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -25,6 +25,7 @@ struct EmbedFwdParams {
   const float* w1;
   const int* rows;
   float* E;
+  float* E_lo;      // nullable: tcg_lo(E), the pre-split lo operand of the first tower GEMM
   float* S;
   float* y1;
   float* y2;
@@ -152,6 +153,13 @@ embed_fwd_kernel(const EmbedFwdParams p) {
         for (int it = 0; it < NIT; ++it)
           if (it * RPW + r < F)     // a negative row id (sharded overflow slot) reads as zeros
             *reinterpret_cast<float4*>(e + (it * 32 + lane) * 4) = v[s][it];
+        if (p.E_lo != nullptr) {
+          float* el = p.E_lo + static_cast<size_t>(b) * F * D;
+#pragma unroll
+          for (int it = 0; it < NIT; ++it)
+            if (it * RPW + r < F)
+              *reinterpret_cast<float4*>(el + (it * 32 + lane) * 4) = tcg_lo4(v[s][it]);
+        }
       }
       if (p.y1 != nullptr) {
         const float t = warp_sum(y1p[s]);
@@ -763,9 +771,11 @@ int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_c
 int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
                   uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
                   const float* cross_w, const float* cross_b, int cross_layers, float* xl,
-                  ctr_stream_t stream) {
+                  float* E_lo, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(table && rows, "ctr_embed_fwd", "null table/rows");
+  CTR_REQUIRE(E_lo == nullptr || (E != nullptr && aligned16(E_lo)), "ctr_embed_fwd",
+              "E_lo needs E and 16-byte alignment");
   CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_embed_fwd", "need 0 < F <= 64");
   CTR_REQUIRE(aligned16(table) && aligned16(rows) && aligned16(E) && aligned16(S) && aligned16(xl) &&
                   aligned16(cross_w) && aligned16(cross_b),
@@ -776,7 +786,7 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
               "xl requested without cross_w/cross_b");
   if (B == 0) return CTR_OK;
   EmbedFwdParams p;
-  p.table = table; p.w1 = w1; p.rows = rows; p.E = E; p.S = S; p.y1 = y1; p.y2 = y2;
+  p.table = table; p.w1 = w1; p.rows = rows; p.E = E; p.E_lo = E_lo; p.S = S; p.y1 = y1; p.y2 = y2;
   p.cross_w = cross_w; p.cross_b = cross_b; p.xl = xl; p.w1_fields = w1_fields;
   p.cross_layers = cross_layers; p.B = B; p.F = F;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -28,10 +28,13 @@ struct TcGemmParams {
   int kb_per_split;       // k-blocks (32 of K) per blockIdx.z
   int n_pass;             // 1 = plain tf32, 3 = 3xTF32
   int stages;             // raw (hi) ring depth, <= 8
-  int lo_slots;           // lo ring depth, 1 or 2
+  int lo_slots;           // lo ring depth, 1 or 2 (0 when the lo operands arrive pre-split)
+  int presplit;           // lo tiles are TMA-loaded from global (A_lo / B_lo), no splitter warps
   uint32_t b_bytes;       // bytes of one B k-block in shared memory
   uint32_t stage_bytes;   // 16 KB (A) + b_bytes rounded up to 1 KB; raw and lo slots alike
   uint32_t tmem_cols;
+  int n_acc;              // independent TMEM accumulators the MMAs rotate over (summed in the epilogue)
+  int acc_stride;         // TMEM columns between accumulators (NT rounded up to 32)
   uint32_t idesc;
   uint64_t desc_k, desc_mn;
   float* out;
@@ -46,13 +49,6 @@ constexpr int kTcgSplitThreads = 192;            // warps 2-7 compute the lo til
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-// lo part of the 3xTF32 split: x - trunc_tf32(x) (exact), rounded to tf32 with integer ops
-// (add half an ulp of the 10-bit mantissa; the tensor core drops the low 13 bits itself).
-__device__ __forceinline__ float tcg_lo(float x) {
-  const float l = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  return __uint_as_float(__float_as_uint(l) + 0x1000u);
 }
 
 // Column sums over the 32 lanes of a warp for 32 columns held as v[0..31] in every lane:
@@ -74,6 +70,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 template <int EPI>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -92,6 +89,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_beg = blockIdx.z * p.kb_per_split;
   const int nkb = max(0, min(kb_total, kb_beg + p.kb_per_split) - kb_beg);
   const uint32_t ab_bytes = kTcABytes + p.b_bytes;
+  // pre-split operands: a stage is [A | B | A_lo | B_lo], the lo half `lo_off` bytes in
+  const uint32_t lo_off = p.stage_bytes >> 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -122,28 +121,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int kb = 0; kb < nkb; ++kb) {
       const uint32_t st = kb % p.stages, ph = (kb / p.stages) & 1;
       mbar_wait(&empty[st], ph ^ 1);
-      mbar_expect_tx(&full[st], ab_bytes);
-      uint8_t* sa = smem + static_cast<size_t>(st) * p.stage_bytes;
-      uint8_t* sb = sa + kTcABytes;
+      mbar_expect_tx(&full[st], p.presplit ? 2 * ab_bytes : ab_bytes);
       const int kk = (kb_beg + kb) * kTcKB;
-      if (p.a_mn) {
+      for (int half = 0; half <= p.presplit; ++half) {
+        uint8_t* sa = smem + static_cast<size_t>(st) * p.stage_bytes + half * lo_off;
+        uint8_t* sb = sa + kTcABytes;
+        const CUtensorMap* mA = half ? &tmAlo : &tmA;
+        const CUtensorMap* mB = half ? &tmBlo : &tmB;
+        if (p.a_mn) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * kTcgMnBox, &tmA, m0 + 32 * j, kk, &full[st]);
-      } else {
-        tma_load_2d(sa, &tmA, kk, m0, &full[st]);
-      }
-      if (p.b_mn) {
-        const int nbox = static_cast<int>(p.b_bytes / kTcgMnBox);
-        for (int j = 0; j < nbox; ++j) tma_load_2d(sb + j * kTcgMnBox, &tmB, n0 + 32 * j, kk, &full[st]);
-      } else {
-        tma_load_2d(sb, &tmB, kk, n0, &full[st]);
+          for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * kTcgMnBox, mA, m0 + 32 * j, kk, &full[st]);
+        } else {
+          tma_load_2d(sa, mA, kk, m0, &full[st]);
+        }
+        if (p.b_mn) {
+          const int nbox = static_cast<int>(p.b_bytes / kTcgMnBox);
+          for (int j = 0; j < nbox; ++j) tma_load_2d(sb + j * kTcgMnBox, mB, n0 + 32 * j, kk, &full[st]);
+        } else {
+          tma_load_2d(sb, mB, kk, n0, &full[st]);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // -------------------------------------------------------------------- MMA issuer
     const uint64_t da = p.a_mn ? p.desc_mn : p.desc_k, db = p.b_mn ? p.desc_mn : p.desc_k;
     const uint32_t sa_step = p.a_mn ? 1024u : 32u, sb_step = p.b_mn ? 1024u : 32u;
-    uint32_t accum = 0;
+    // MMAs may rotate over n_acc independent TMEM accumulators (summed in the epilogue); with
+    // n_acc = 1 (default) this is the usual single-accumulator k loop.
+    int mi = 0;
+    auto dst = [&]() -> uint32_t { return tmem_base + static_cast<uint32_t>((mi % p.n_acc) * p.acc_stride); };
     for (int kb = 0; kb < nkb; ++kb) {
       const uint32_t st = kb % p.stages, ph = (kb / p.stages) & 1;
       const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * p.stage_bytes);
@@ -152,32 +158,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        tc_mma_tf32(tmem_base, da | (((a_addr + k * sa_step) >> 4) & 0x3FFF),
-                    db | (((b_addr + k * sb_step) >> 4) & 0x3FFF), p.idesc, accum);
-        accum = 1;
+        tc_mma_tf32(dst(), da | (((a_addr + k * sa_step) >> 4) & 0x3FFF),
+                    db | (((b_addr + k * sb_step) >> 4) & 0x3FFF), p.idesc, mi >= p.n_acc);
+        ++mi;
       }
       if (p.n_pass == 3) {
-        const uint32_t sl = kb % p.lo_slots, lph = (kb / p.lo_slots) & 1;
-        const uint32_t a_lo = smem_u32(lo_ring + static_cast<size_t>(sl) * p.stage_bytes);
+        uint32_t sl = 0, a_lo;
+        if (p.presplit) {
+          a_lo = a_addr + lo_off;            // landed together with the hi tiles
+        } else {
+          sl = kb % p.lo_slots;
+          a_lo = smem_u32(lo_ring + static_cast<size_t>(sl) * p.stage_bytes);
+          mbar_wait(&conv[sl], (kb / p.lo_slots) & 1);
+          tc_fence_after();
+        }
         const uint32_t b_lo = a_lo + kTcABytes;
-        mbar_wait(&conv[sl], lph);
-        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // (lo, hi)
-          tc_mma_tf32(tmem_base, da | (((a_lo + k * sa_step) >> 4) & 0x3FFF),
-                      db | (((b_addr + k * sb_step) >> 4) & 0x3FFF), p.idesc, 1);
+        for (int k = 0; k < 4; ++k) {  // (lo, hi)
+          tc_mma_tf32(dst(), da | (((a_lo + k * sa_step) >> 4) & 0x3FFF),
+                      db | (((b_addr + k * sb_step) >> 4) & 0x3FFF), p.idesc, mi >= p.n_acc);
+          ++mi;
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // (hi, lo)
-          tc_mma_tf32(tmem_base, da | (((a_addr + k * sa_step) >> 4) & 0x3FFF),
-                      db | (((b_lo + k * sb_step) >> 4) & 0x3FFF), p.idesc, 1);
-        tc_commit(&lo_empty[sl]);
+        for (int k = 0; k < 4; ++k) {  // (hi, lo)
+          tc_mma_tf32(dst(), da | (((a_addr + k * sa_step) >> 4) & 0x3FFF),
+                      db | (((b_lo + k * sb_step) >> 4) & 0x3FFF), p.idesc, mi >= p.n_acc);
+          ++mi;
+        }
+        if (!p.presplit) tc_commit(&lo_empty[sl]);
       }
       tc_commit(&empty[st]);
     }
     tc_commit(t_full);
   } else if (warp >= 2) {
     // ------------------------------------ hi/lo splitter (warps 2-7), then epilogue (warps 4-7)
-    if (p.n_pass == 3) {
+    if (p.n_pass == 3 && !p.presplit) {
       const int ctid = threadIdx.x - 64;
       const int n16 = static_cast<int>(ab_bytes >> 4);
       for (int kb = 0; kb < nkb; ++kb) {
@@ -222,9 +237,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // all MMAs have retired: the raw ring is free, use it to turn the row-per-lane TMEM
       // fragments into 128-byte row segments (4 rows x 128 B per store instruction)
       float4* sw = reinterpret_cast<float4*>(smem + quarter * (32 * 9 * 16));
+      const int n_used = min(p.n_acc, nkb * 4 * p.n_pass);   // accumulators that were written
       for (int c = 0; c < p.NT; c += 32) {
         float v[32];
         tc_ld<32>(taddr + c, v);
+        for (int a = 1; a < n_used; ++a) {
+          float w[32];
+          tc_ld<32>(taddr + static_cast<uint32_t>(a * p.acc_stride) + c, w);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] += w[t];
+        }
         const int nb = n0 + c;
         if (EPI == TCG_EPI_FWD) {
 #pragma unroll
@@ -303,19 +325,32 @@ static uint64_t tcg_desc_mn() {
 
 // A: K-major [M, K] pitch lda, or MN-major stored [K, M] pitch lda.  B likewise with N.
 // splits > 1 only with TCG_EPI_RED.
+// A_lo / B_lo (both or neither): the lo halves of the 3xTF32 split, same shapes and pitches as A / B,
+// produced with tcg_lo() by whoever wrote A / B; the kernel then has no CUDA-core work
+// in its main loop.
 template <int EPI>
 static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn,
                           int M, int N, int K, int NT, int splits, float* out, int ldo,
                           const float* bias, float* stats, int relu, cudaStream_t st,
-                          const char* fn) {
+                          const char* fn, const float* A_lo = nullptr, const float* B_lo = nullptr) {
   CTR_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && aligned16(A) && aligned16(Bm), fn,
               "tensor-core path needs 16-byte aligned operands");
   CTR_REQUIRE(NT % 16 == 0 && NT >= 16 && NT <= 256, fn, "bad NT");
-  CUtensorMap tA, tB;
+  const bool presplit = A_lo != nullptr && B_lo != nullptr;
+  CTR_REQUIRE(!presplit || (aligned16(A_lo) && aligned16(B_lo)), fn, "lo operands must be 16-byte aligned");
+  CUtensorMap tA, tB, tAlo, tBlo;
   int r = a_mn ? make_map(&tA, A, K, M, lda, 32, true) : make_map(&tA, A, M, K, lda, kTcBM);
   if (r != CTR_OK) return r;
   r = b_mn ? make_map(&tB, Bm, K, N, ldb, 32, true) : make_map(&tB, Bm, N, K, ldb, NT);
   if (r != CTR_OK) return r;
+  tAlo = tA;
+  tBlo = tB;
+  if (presplit) {
+    r = a_mn ? make_map(&tAlo, A_lo, K, M, lda, 32, true) : make_map(&tAlo, A_lo, M, K, lda, kTcBM);
+    if (r != CTR_OK) return r;
+    r = b_mn ? make_map(&tBlo, B_lo, K, N, ldb, 32, true) : make_map(&tBlo, B_lo, N, K, ldb, NT);
+    if (r != CTR_OK) return r;
+  }
   TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.NT = NT; p.a_mn = a_mn; p.b_mn = b_mn; p.n_pass = 3;
   if (const char* e = getenv("CTR_TCG_PASSES")) p.n_pass = atoi(e) == 1 ? 1 : 3;
@@ -327,9 +362,21 @@ static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, i
                    : static_cast<uint32_t>(NT) * kTcKB * 4;
   p.stage_bytes = kTcABytes + ((p.b_bytes + 1023u) & ~1023u);
   p.lo_slots = 2;
+  p.presplit = (presplit && p.n_pass == 3) ? 1 : 0;
+  if (p.presplit) {
+    p.stage_bytes *= 2;
+    p.lo_slots = 0;
+  }
   p.stages = std::max(2, std::min(8, static_cast<int>((200u * 1024u) / p.stage_bytes) - p.lo_slots));
   if (const char* e = getenv("CTR_TCG_STAGES")) p.stages = std::max(1, std::min(p.stages, atoi(e)));
-  p.tmem_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
+  p.acc_stride = (NT + 31) / 32 * 32;
+  // measured: one accumulator is as fast as many (the MMAs are operand-fetch bound, ~160 cycles
+  // each whatever N is), and the epilogue then has nothing to add up; CTR_TCG_NACC > 1 rotates
+  p.n_acc = 1;
+  if (const char* e = getenv("CTR_TCG_NACC"))
+    p.n_acc = std::max(1, std::min(std::min(12, 512 / p.acc_stride), atoi(e)));
+  p.tmem_cols = 32;
+  while (p.tmem_cols < static_cast<uint32_t>(p.n_acc * p.acc_stride)) p.tmem_cols <<= 1;
   p.idesc = cin_idesc(NT) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u);
   p.desc_k = cin_desc_hi();
   p.desc_mn = tcg_desc_mn();
@@ -342,7 +389,7 @@ static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, i
     optin = true;
   }
   dim3 grid((M + kTcBM - 1) / kTcBM, (N + NT - 1) / NT, splits);
-  tc_gemm_kernel<EPI><<<grid, 256, smem, st>>>(tA, tB, p);
+  tc_gemm_kernel<EPI><<<grid, 256, smem, st>>>(tA, tB, tAlo, tBlo, p);
   return check_cuda(cudaGetLastError(), fn);
 }
 

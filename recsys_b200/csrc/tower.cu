@@ -705,6 +705,16 @@ __global__ void __launch_bounds__(256) loss_head_kernel(const HeadParams p) {
   }
 }
 
+// lo[i] = tcg_lo(x[i])
+__global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ x,
+                                                       float* __restrict__ lo, long long n) {
+  const long long n4 = n >> 2, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  for (long long i = i0; i < n4; i += stride)
+    reinterpret_cast<float4*>(lo)[i] = tcg_lo4(__ldg(reinterpret_cast<const float4*>(x) + i));
+  for (long long i = (n4 << 2) + i0; i < n; i += stride) lo[i] = tcg_lo(x[i]);
+}
+
 }  // namespace ctr
 
 using namespace ctr;
@@ -792,6 +802,62 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
     else tower_layer_fwd_kernel<false, 4><<<grid, 256, sb, st>>>(X, ldx, K, p, W, bias, N, out, ldo, stats, relu, B);
   }
   CTR_LAUNCH_CHECK("ctr_tower_layer_fwd");
+}
+
+int ctr_split_lo(const float* x, float* lo, int64_t n, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(x && lo && n >= 0 && aligned16(x) && aligned16(lo), "ctr_split_lo",
+              "null / unaligned pointer");
+  if (n == 0) return CTR_OK;
+  const int grid = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, sm_count() * 4LL));
+  split_lo_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, lo, n);
+  CTR_LAUNCH_CHECK("ctr_split_lo");
+}
+
+int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const float* Bm,
+                            const float* B_lo, int B, int K, int N, float* out, const float* bias,
+                            float* stats, int relu, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(kind >= 0 && kind <= 3 && A && A_lo && Bm && B_lo && out, "ctr_tower_gemm_presplit",
+              "bad kind / null pointer");
+  CTR_REQUIRE(B >= 256 && K >= 32 && N >= 16 && (K & 3) == 0 && (N & 3) == 0, "ctr_tower_gemm_presplit",
+              "needs B >= 256, K >= 32, N >= 16, K % 4 == N % 4 == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* fn = "ctr_tower_gemm_presplit";
+  if (kind == 0) {          // out[B,N] = act(X[B,K] . W[K,N] + bias): W is MN-major (n contiguous)
+    const int mtiles = (B + kTcBM - 1) / kTcBM;
+    int ntiles = std::max((N + 127) / 128, std::min(sm_count() / mtiles, (N + 31) / 32));
+    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
+    const int NT = std::min(128, round16((N + ntiles - 1) / ntiles));
+    return tc_gemm_launch<TCG_EPI_FWD>(A, K, false, Bm, N, true, B, N, K, NT, 1, out, N, bias, stats,
+                                       relu, st, fn, A_lo, B_lo);
+  }
+  if (kind == 3) {
+    // out[B,N] += X . W, reduction split over the CTAs.  A tf32 MMA costs ~160 cycles of operand
+    // fetch whatever its N, so the cheapest schedule has the fewest MMAs per CTA: one N tile and
+    // the k-blocks shared out over sm_count / mtiles CTAs, partial sums RED'ed into `out`.
+    CTR_REQUIRE(N <= 256 && aligned16(out), fn, "split-K forward needs N <= 256 and an aligned output");
+    const int mtiles = (B + kTcBM - 1) / kTcBM;
+    int splits = std::max(1, sm_count() / mtiles);
+    if (const char* e = getenv("CTR_TCG_FWD_SPLITS")) splits = std::max(1, atoi(e));
+    return tc_gemm_launch<TCG_EPI_RED>(A, K, false, Bm, N, true, B, N, K, round16(N), splits, out, N,
+                                       nullptr, nullptr, 0, st, fn, A_lo, B_lo);
+  }
+  if (kind == 1) {          // out[B,K] = dpre[B,N] . W[K,N]^T: both K-major in n
+    const int mtiles = (B + kTcBM - 1) / kTcBM;
+    int ntiles = std::max((K + 255) / 256, std::min(sm_count() / mtiles, (K + 63) / 64));
+    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max((K + 255) / 256, atoi(e));
+    const int NT = round16((K + ntiles - 1) / ntiles);
+    return tc_gemm_launch<TCG_EPI_STORE>(A, N, false, Bm, N, false, B, K, N, NT, 1, out, K, nullptr,
+                                         nullptr, 0, st, fn, A_lo, B_lo);
+  }
+  // out[K,N] += X[B,K]^T . dpre[B,N]: both MN-major, reduction over the rows, split-K with REDs
+  CTR_REQUIRE(N <= 256 && aligned16(out), fn, "weights GEMM needs N <= 256 and an aligned output");
+  const int mtiles = (K + kTcBM - 1) / kTcBM;
+  int splits = std::max(1, std::min(sm_count() / mtiles, (B / kTcKB) / 4));
+  if (const char* e = getenv("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
+  return tc_gemm_launch<TCG_EPI_RED>(A, K, true, Bm, N, true, K, N, B, round16(N), splits, out, N,
+                                     nullptr, nullptr, 0, st, fn, A_lo, B_lo);
 }
 
 int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out, int B,

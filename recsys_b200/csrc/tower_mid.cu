@@ -282,7 +282,38 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   float4 a_c[2] = {f4_zero(), f4_zero()}, dn_c[2] = {f4_zero(), f4_zero()};
   float4 ap[2] = {f4_zero(), f4_zero()};
   mid_stamp(A, 0);
-  if (single) {
+  if (A.pre0 != nullptr) {
+    // ---------------------------------------------- layer 0 epilogue (split-K GEMM partial sums)
+    const int N = A.H[0];
+    float* __restrict__ out = A.act[0];
+    float4 acc[2] = {f4_zero(), f4_zero()};
+    if (k4 < N) {
+      const float4 bias = ldg4(A.b[0] + k4);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = tile * kMidBM + warp + 16 * h;
+          if (r < B) {
+            float4 v = f4_add(ldcg4(A.pre0 + static_cast<size_t>(r) * N + k4), bias);
+            v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * N + k4) = v;
+            acc[0] = f4_add(acc[0], v);
+            acc[1] = f4_fma4(v, v, acc[1]);
+            a_c[h] = v;
+          }
+        }
+      }
+    }
+    if (c.training) {
+      float* const dst[2] = {A.stats[0], A.stats[0] + N};
+      mid_reduce_cols<2>(sm, acc, dst, N);
+      if (L > 1) {                       // the next phase stages its weights before waiting
+        mid_load_weights(sm, A.W[1], A.H[0], A.H[1]);
+        ws_layer = 1;
+      }
+      mid_grid_barrier(A.barrier, gridDim.x);                      // stats_0 complete
+    }
+  } else if (single) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int r = blockIdx.x * kMidBM + warp + 16 * h;
@@ -294,8 +325,10 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   for (int l = 1; l < L; ++l) {
     const int K = A.H[l - 1], N = A.H[l];
     __syncthreads();
-    mid_load_weights(sm, A.W[l], K, N);
-    ws_layer = l;
+    if (ws_layer != l) {
+      mid_load_weights(sm, A.W[l], K, N);
+      ws_layer = l;
+    }
     for (int n = tid; n < N; n += kMidThreads) sm.vec[n] = A.b[l][n];
     if (c.training && l > 1) mid_grid_barrier(A.barrier, gridDim.x);   // stats_{l-1} complete
     mid_fill_bn(sm, A, c, l - 1);
@@ -568,6 +601,7 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
     const float* __restrict__ act = A.act[0];
     const float* __restrict__ dnl = A.dn[0];
     float* __restrict__ dpre = A.dpre[0];
+    float* __restrict__ dpre_lo = A.dpre0_lo;
     float4 acc[1] = {f4_zero()};
     if (k4 < N) {
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -579,6 +613,8 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
                                        single ? a_c[h] : ldcg4(act + static_cast<size_t>(r) * N + k4),
                                        single ? dn_c[h] : ldcg4(dnl + static_cast<size_t>(r) * N + k4));
             *reinterpret_cast<float4*>(dpre + static_cast<size_t>(r) * N + k4) = v;
+            if (dpre_lo != nullptr)
+              *reinterpret_cast<float4*>(dpre_lo + static_cast<size_t>(r) * N + k4) = tcg_lo4(v);
             acc[0] = f4_add(acc[0], v);
           }
         }
@@ -608,6 +644,8 @@ int ctr_tower_mid(const ctr_tower_mid_args* a, int B, ctr_stream_t stream) {
     CTR_REQUIRE(aligned16(a->act[l]), "ctr_tower_mid", "activations must be 16-byte aligned");
     CTR_REQUIRE(l == 0 || (a->W[l] && a->b[l] && aligned16(a->W[l])), "ctr_tower_mid",
                 "null / unaligned W or b");
+    CTR_REQUIRE(l != 0 || a->pre0 == nullptr || (a->b[0] && aligned16(a->b[0]) && aligned16(a->pre0)),
+                "ctr_tower_mid", "pre0 needs an aligned b[0]");
     if (a->training) {
       CTR_REQUIRE(a->stats[l] && a->dn[l] && a->dpre[l] && a->dbeta[l] && a->dgamma[l] && a->dbias[l],
                   "ctr_tower_mid", "training needs stats/dn/dpre/dbeta/dgamma/dbias per layer");

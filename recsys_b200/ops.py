@@ -293,9 +293,12 @@ class FieldEmbedding:
 
     # -- forward / backward -----------------------------------------------------
     def lookup(self, rows: torch.Tensor, want_fm: bool = True, want_y1: bool = True,
-               cross_w: Optional[torch.Tensor] = None, cross_b: Optional[torch.Tensor] = None):
-        """-> dict(E [B,F*D], y1 [B] (pre-bias), y2 [B], xl [B,F*D]) with autograd."""
+               cross_w: Optional[torch.Tensor] = None, cross_b: Optional[torch.Tensor] = None,
+               want_lo: bool = False):
+        """-> (E [B,F*D], y1 [B] (pre-bias), y2 [B], xl [B,F*D]) with autograd.  ``want_lo``: also
+        write the lo half of E's 3xTF32 split (``self.last_E_lo``) for the tower's first GEMM."""
         require_cuda(rows, "rows")
+        self._want_lo = bool(want_lo)
         return _EmbedFn.apply(self._anchor, self, rows, want_fm, want_y1 and self.with_w1,
                               cross_w, cross_b)
 
@@ -341,8 +344,10 @@ class _EmbedFn(torch.autograd.Function):
         cross = cross_w is not None
         xl = torch.empty((B, F * D), dtype=torch.float32, device=dev) if cross else None
         L = cross_w.shape[0] if cross else 0
+        E_lo = torch.empty_like(E) if getattr(emb, "_want_lo", False) else None
+        emb.last_E_lo = E_lo
         _call("ctr_embed_fwd", _p(emb.table), _p(emb.w1), _p(rows), B, F, D, emb.w1_fields, _p(E),
-              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _stream())
+              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), _stream())
         ctx.emb, ctx.rows, ctx.E, ctx.S = emb, rows, E, S
         ctx.cross_w, ctx.cross_b = cross_w, cross_b
         ctx.flags = (want_fm, want_y1, cross)
@@ -565,9 +570,35 @@ class FusedTower:
         self.mid_ok = (out_layer and 1 <= len(self.sizes) - 1 <= 4
                        and all(4 <= h <= 128 and h % 4 == 0 for h in self.sizes[1:]))
 
+        # pre-split 3xTF32 operands for the first layer's tcgen05 GEMMs (ctr_tower_gemm_presplit)
+        self.w0_lo = torch.zeros(self.sizes[0] * self.sizes[1], dtype=torch.float32,
+                                 device=dense.flat.device)
+        self._w0_ready = None
+
     @property
     def use_mid(self):
         return self.mid_ok and os.environ.get("CTR_TOWER_MID", "1") != "0"
+
+    @property
+    def use_presplit(self):
+        return (self.use_mid and os.environ.get("CTR_TOWER_PRESPLIT", "1") != "0"
+                and self.sizes[0] % 4 == 0 and self.sizes[0] >= 32 and self.sizes[1] >= 16)
+
+    def begin_step(self):
+        """Start-of-step hook: split the first layer's weights into hi/lo on the side stream
+        (they only change in the optimiser), off the critical path of the id/lookup kernels."""
+        if not self.use_presplit:
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            _call("ctr_split_lo", _p(self.P("0.w")), _p(self.w0_lo), self.w0_lo.numel(),
+                  self.side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self._w0_ready = done
 
     def join(self):
         """Make the current stream wait for the side-stream weight-gradient kernels."""
@@ -711,7 +742,7 @@ class _TowerHeadFn(torch.autograd.Function):
     All parameter gradients are accumulated into the flat gradient buffer by the kernels."""
 
     @staticmethod
-    def forward(ctx, X, anchor, tw: "FusedTower", head, labels, training, *zs):
+    def forward(ctx, X, anchor, tw: "FusedTower", head, labels, training, X_lo, *zs):
         ctx.set_materialize_grads(False)
         dense = tw.dense
         hw, hb, b1, relu0, grad_scale = head
@@ -727,26 +758,49 @@ class _TowerHeadFn(torch.autograd.Function):
         for H in Hs:
             offs.append(n)
             n += 2 * H
-        ws = torch.zeros(n + 4, **f32)
+        presplit = X_lo is not None and tw.use_presplit and B >= 256
+        splitk = presplit and os.environ.get("CTR_TOWER_SPLITK", "1") != "0"
+        # (+ with the split-K first GEMM: its zero-initialised accumulation target)
+        ws = torch.zeros(n + 4 + (B * Hs[0] if splitk else 0), **f32)
         stats = [ws[o:o + 2 * H].view(2, H) for o, H in zip(offs, Hs)]
         loss = ws[n:n + 1].view(())
+        pre0 = ws[n + 4:].view(B, Hs[0]) if splitk else None
         acts = [torch.empty((B, H), **f32) for H in Hs]
         logits, prob, y = (torch.empty(B, **f32) for _ in range(3))
-        _call("ctr_tower_layer_fwd", _p(X), tw.sizes[0], tw.sizes[0], None, _p(tw.P("0.w")),
-              _p(tw.P("0.b")), Hs[0], _p(acts[0]), Hs[0], _p(stats[0]) if training else None, 1, B,
-              _stream())
+        if presplit:
+            if tw._w0_ready is None:
+                tw.begin_step()
+            torch.cuda.current_stream().wait_event(tw._w0_ready)
+            tw._w0_ready = None
+            if splitk:      # partial sums only; bias / ReLU / column sums happen in ctr_tower_mid
+                _call("ctr_tower_gemm_presplit", 3, _p(X), _p(X_lo), _p(tw.P("0.w")), _p(tw.w0_lo),
+                      B, tw.sizes[0], Hs[0], _p(pre0), None, None, 0, _stream())
+            else:
+                _call("ctr_tower_gemm_presplit", 0, _p(X), _p(X_lo), _p(tw.P("0.w")), _p(tw.w0_lo),
+                      B, tw.sizes[0], Hs[0], _p(acts[0]), _p(tw.P("0.b")),
+                      _p(stats[0]) if training else None, 1, _stream())
+        else:
+            if tw._w0_ready is not None:       # split launched but not needed: still join the fork
+                torch.cuda.current_stream().wait_event(tw._w0_ready)
+                tw._w0_ready = None
+            _call("ctr_tower_layer_fwd", _p(X), tw.sizes[0], tw.sizes[0], None, _p(tw.P("0.w")),
+                  _p(tw.P("0.b")), Hs[0], _p(acts[0]), Hs[0], _p(stats[0]) if training else None, 1,
+                  B, _stream())
         a = _lib.TowerMidArgs()
         a.L, a.C, a.relu0, a.training = L, len(zs) + 1, 1 if relu0 else 0, 1 if training else 0
         if training:
             dn = [torch.empty((B, H), **f32) for H in Hs]
             dpre = [torch.empty((B, H), **f32) for H in Hs]
             dzs = [torch.empty(B, **f32) for _ in zs]
+            dpre0_lo = torch.empty((B, Hs[0]), **f32) if presplit else None
         else:
-            dn = dpre = dzs = None
+            dn = dpre = dzs = dpre0_lo = None
         for l, H in enumerate(Hs):
             a.H[l] = H
             if l > 0:
                 a.W[l], a.b[l] = _p(tw.P("%d.w" % l)), _p(tw.P("%d.b" % l))
+            elif splitk:
+                a.b[0], a.pre0 = _p(tw.P("0.b")), _p(pre0)
             a.gamma[l], a.beta[l] = _p(tw.P("%d.bn.gamma" % l)), _p(tw.P("%d.bn.beta" % l))
             a.mean[l], a.var[l] = _p(tw.P("%d.bn.mean" % l)), _p(tw.P("%d.bn.var" % l))
             a.act[l] = _p(acts[l])
@@ -769,11 +823,12 @@ class _TowerHeadFn(torch.autograd.Function):
             a.db1 = _p(dense[b1].grad) if relu0 else None
             a.dw_out, a.db_out = _p(tw.G("out.w")), _p(tw.G("out.b"))
             a.barrier = _p(tw.barrier)
+            a.dpre0_lo = _p(dpre0_lo)
         a.timing = _p(tw.timing) if tw.timing is not None else None
         _call("ctr_tower_mid", C.byref(a), B, _stream())
         ctx.tw, ctx.training = tw, training
         tw.last_acts = acts          # post-ReLU hidden activations of the latest call (tests)
-        ctx.saved = (X, acts, stats, dpre, dzs, dn, zs, labels, ws)
+        ctx.saved = (X, acts, stats, dpre, dzs, dn, zs, labels, ws, X_lo, dpre0_lo)
         ctx.mark_non_differentiable(logits, prob)
         return loss, logits, prob
 
@@ -782,9 +837,10 @@ class _TowerHeadFn(torch.autograd.Function):
         tw = ctx.tw
         if not ctx.training:
             raise RuntimeError("tower_head backward is only defined in training mode")
-        X, acts, stats, dpre, dzs, dn, zs, labels, ws = ctx.saved
+        X, acts, stats, dpre, dzs, dn, zs, labels, ws, X_lo, dpre0_lo = ctx.saved
         B, dev = X.shape[0], X.device
         L = len(tw.sizes) - 1
+        presplit = dpre0_lo is not None
         main, side = torch.cuda.current_stream(), tw.side
         ev = torch.cuda.Event()
         ev.record(main)
@@ -798,6 +854,10 @@ class _TowerHeadFn(torch.autograd.Function):
         with torch.cuda.stream(side):       # dW_l = P(a_{l-1})^T . dpre_l, off the critical path
             for l in range(L):
                 H, K = tw.sizes[l + 1], tw.sizes[l]
+                if l == 0 and presplit:
+                    _call("ctr_tower_gemm_presplit", 2, _p(X), _p(X_lo), _p(dpre[0]), _p(dpre0_lo),
+                          B, K, H, _p(tw.G("0.w")), None, None, 0, side.cuda_stream)
+                    continue
                 gs = grad_src(dpre[l], H)
                 xin = acts[l - 1] if l > 0 else X
                 pro = C.byref(tw.bn_drop(l - 1, stats[l - 1], True)) if l > 0 else None
@@ -806,25 +866,39 @@ class _TowerHeadFn(torch.autograd.Function):
         H0, K0 = tw.sizes[1], tw.sizes[0]
         gs0 = grad_src(dpre[0], H0)
         dX = torch.empty((B, K0), dtype=torch.float32, device=dev)
-        _call("ctr_tower_layer_bwd_data", C.byref(gs0), H0, _p(tw.P("0.w")), K0, None, None,
-              _p(dX), K0, None, None, B, _stream())
-        for t_ in dpre + acts + [X, ws]:        # tensors read by the side stream
+        if presplit:
+            _call("ctr_tower_gemm_presplit", 1, _p(dpre[0]), _p(dpre0_lo), _p(tw.P("0.w")),
+                  _p(tw.w0_lo), B, K0, H0, _p(dX), None, None, 0, _stream())
+        else:
+            _call("ctr_tower_layer_bwd_data", C.byref(gs0), H0, _p(tw.P("0.w")), K0, None, None,
+                  _p(dX), K0, None, None, B, _stream())
+        for t_ in dpre + acts + [X, ws] + ([X_lo, dpre0_lo] if presplit else []):   # read by the side stream
             t_.record_stream(side)
         done = torch.cuda.Event()
         done.record(side)
         tw._pending = done
-        return (dX, None, None, None, None, None) + tuple(dzs)
+        return (dX, None, None, None, None, None, None) + tuple(dzs)
+
+
+def split_lo(x: torch.Tensor) -> torch.Tensor:
+    """lo half of the 3xTF32 split of ``x`` (ctr_split_lo)."""
+    require_cuda(x, "x")
+    x = x.contiguous()
+    lo = torch.empty_like(x)
+    _call("ctr_split_lo", _p(x), _p(lo), x.numel(), _stream())
+    return lo
 
 
 def tower_head(tw: "FusedTower", X, zs, labels, hw="head.w", hb="head.b", b1="b1", relu0=True,
-               grad_scale=None, training=True):
-    """loss, logits, prob of `head([zs..., tower(X)])` (deepfm/deepfm.py:100-129)."""
+               grad_scale=None, training=True, X_lo=None):
+    """loss, logits, prob of `head([zs..., tower(X)])` (deepfm/deepfm.py:100-129).  ``X_lo``: the
+    lo half of X's 3xTF32 split when its producer wrote one (FieldEmbedding.lookup(want_lo=True))."""
     require_cuda(X, "tower input")
     B = X.shape[0]
     if grad_scale is None:
         grad_scale = 1.0 / B
     return _TowerHeadFn.apply(X, tw._anchor, tw, (hw, hb, b1, relu0, grad_scale), labels, training,
-                              *zs)
+                              X_lo, *zs)
 
 
 class _LossHeadFn(torch.autograd.Function):

@@ -62,7 +62,7 @@ class CudaShardOps:
         cross = cross_w is not None
         xl = torch.empty((B, F * D), dtype=torch.float32, device=dev) if cross else None
         _call("ctr_embed_fwd", _p(vec), _p(w1v), _p(slot2d), B, F, D, w1_fields, _p(E), _p(S), _p(y1),
-              _p(y2), _p(cross_w), _p(cross_b), cross_w.shape[0] if cross else 0, _p(xl), _stream())
+              _p(y2), _p(cross_w), _p(cross_b), cross_w.shape[0] if cross else 0, _p(xl), None, _stream())
         return E, S, y1, y2, xl
 
     def interact_bwd(self, slot2d, dE, E, vec, S, dy2, dy1, w1_fields, D, n_slots):

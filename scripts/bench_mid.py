@@ -111,7 +111,7 @@ def table_sweep(B=4096, F=39, D=16):
             r = rows[it[0] % nb]
             it[0] += 1
             lib.ctr_embed_fwd(table.data_ptr(), w1.data_ptr(), r.data_ptr(), B, F, D, mask, E.data_ptr(),
-                              S.data_ptr(), y1.data_ptr(), y2.data_ptr(), None, None, 0, None, st)
+                              S.data_ptr(), y1.data_ptr(), y2.data_ptr(), None, None, 0, None, None, st)
 
         def bwd():
             r = rows[it[0] % nb]

@@ -195,13 +195,13 @@ def test_embed_rejects_bad_arguments(cuda):
     t = torch.zeros(10, 16, device=cuda)
     rows = torch.zeros(4, 3, dtype=torch.int32, device=cuda)
     rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 4, 3, 12, 0, None, None, None, None,
-                           None, None, 0, None, None)
+                           None, None, 0, None, None, None)
     assert rc == -1 and "D must be" in _lib.last_error()
     rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 4, 65, 16, 0, None, None, None, None,
-                           None, None, 0, None, None)
+                           None, None, 0, None, None, None)
     assert rc == -1
     rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 0, 3, 16, 0, None, None, None, None,
-                           None, None, 0, None, None)
+                           None, None, 0, None, None, None)
     assert rc == 0                                                 # empty batch is a no-op
 
 

@@ -165,10 +165,11 @@ def _tower_head_ref(P, X, zs, labels, sizes, masks, p, training, gates=None):
     return loss, logit
 
 
+@pytest.mark.parametrize("presplit", [False, True])
 @pytest.mark.parametrize("B,sizes,nz,p", [(4096, [624, 100, 100], 2, 0.5), (1000, [624, 100, 100], 2, 0.0),
                                            (333, [96, 32, 16], 2, 0.5), (517, [64, 128], 1, 0.0),
                                            (6000, [128, 64, 32, 16, 8], 2, 0.3)])
-def test_tower_mid_matches_float64(cuda, B, sizes, nz, p):
+def test_tower_mid_matches_float64(cuda, B, sizes, nz, p, presplit):
     from recsys_b200 import ops
     torch.manual_seed(B)
     shapes = {"b1": (1,), "head.w": (nz + 1, 1), "head.b": (1,), "t.out.w": (sizes[-1], 1), "t.out.b": (1,)}
@@ -198,7 +199,8 @@ def test_tower_mid_matches_float64(cuda, B, sizes, nz, p):
     X64 = X.detach().double().requires_grad_(True)
     zs64 = [z.detach().double().requires_grad_(True) for z in zs]
     for training in (False, True):
-        loss, logits, prob = ops.tower_head(tw, X, zs, labels, training=training)
+        X_lo = ops.split_lo(X.detach()) if presplit else None   # first-layer GEMMs on pre-split operands
+        loss, logits, prob = ops.tower_head(tw, X, zs, labels, training=training, X_lo=X_lo)
         torch.cuda.synchronize()
         gates = [(a > 0).double() for a in tw.last_acts] if training else None
         loss64, logit64 = _tower_head_ref(P64, X64, zs64, labels.double(), sizes, masks, p, training,
