@@ -405,12 +405,13 @@ def time_hot_kernels(model, devb, K, W, stream):
 
         def fwd(i):
             lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rows[i % len(rows)]), B, F, D,
-                              emb.w1_fields, p(Eb), p(Sb), p(y1), p(y2), None, None, 0, None, None, st)
+                              emb.w1_fields, p(Eb), p(Sb), p(y1), p(y2), None, None, 0, None, None,
+                              emb.ld, emb.ld1, st)
 
         def bwd(i):
             lib.ctr_embed_bwd(p(rows[i % len(rows)]), p(dE), p(Eb), p(emb.table), p(Sb), p(dy),
                               p(dy), emb.w1_fields, emb._offsets_host, B, F, D, p(emb.dtable),
-                              p(emb.dw1), st)
+                              p(emb.dw1), emb.ld, emb.ld1, st)
 
         emb._ensure_adam()
 
@@ -419,20 +420,34 @@ def time_hot_kernels(model, devb, K, W, stream):
             lib.ctr_adam_rows(p(rows[i % len(rows)]), B * F, D, p(emb.table), p(emb._m), p(emb._v),
                               p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
                               p(getattr(emb, "_v1", None)), p(emb.dw1),
-                              p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, st)
+                              p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, emb.ld, emb.ld1,
+                              emb.ldc, st)
 
-        def timeit(fn):
-            for i in range(W):
+        def timeit(fn, once=False):
+            """Per-launch device time: the launches (one per distinct id batch) are captured into a
+            CUDA graph and replayed, so the host's ctypes call rate cannot bound the number.
+            ``once``: capture all K launches and replay a single time (the row optimiser's claim
+            tags are baked in at capture, so a second replay would find every row claimed)."""
+            nb = K if once else len(rows)
+            for i in range(max(W, 1)):
                 fn(i)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(nb):
+                    fn(W + i)
+            reps = 1 if once else max(1, (K + nb - 1) // nb)
+            if not once:
+                g.replay()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for i in range(K):
-                fn(W + i)
+            for _ in range(reps):
+                g.replay()
             e1.record(stream)
             e1.synchronize()
-            return e0.elapsed_time(e1) * 1e3 / K
+            return e0.elapsed_time(e1) * 1e3 / (reps * nb)
 
-        res = {"fwd_us": timeit(fwd), "bwd_us": timeit(bwd), "adam_us": timeit(adam)}
+        res = {"fwd_us": timeit(fwd), "bwd_us": timeit(bwd), "adam_us": timeit(adam, once=True)}
         ops.LAUNCHES["n"] += 3 * (K + W)
         # bytes the implementation actually moves per sample (DESIGN.md "data layout")
         res["fwd_moved"] = 156 + 2496 + 156 + 2496 + 64 + 8          # ids, rows, w1, E, S, y1/y2
@@ -457,12 +472,12 @@ def time_hot_kernels(model, devb, K, W, stream):
             def fwdL(i):
                 lib.ctr_embed_fwd(p(emb.table), p(emb.w1), p(rl[i % 4]), BL, F, D, emb.w1_fields,
                                   p(EL), p(SL), p(yl) if emb.w1 is not None else None, p(yl), None,
-                                  None, 0, None, None, st)
+                                  None, 0, None, None, emb.ld, emb.ld1, st)
 
             def bwdL(i):
                 lib.ctr_embed_bwd(p(rl[i % 4]), p(dEL), p(EL), p(emb.table), p(SL), p(yl), p(yl),
                                   emb.w1_fields, emb._offsets_host, BL, F, D, p(emb.dtable),
-                                  p(emb.dw1), st)
+                                  p(emb.dw1), emb.ld, emb.ld1, st)
             tf_, tb_ = timeit(fwdL), timeit(bwdL)
             res["large"] = {"batch": BL, "fwd_us": tf_, "bwd_us": tb_,
                             "alg_GBps": ALG_BYTES * BL / (tf_ + tb_) / 1e3,

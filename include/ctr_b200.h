@@ -87,7 +87,7 @@ int ctr_hash_strings(const uint8_t* bytes, const int32_t* offsets, int64_t N,
 int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
                   uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
                   const float* cross_w, const float* cross_b, int cross_layers, float* xl, float* E_lo,
-                  ctr_stream_t stream);
+                  int64_t row_stride, int64_t w1_stride, ctr_stream_t stream);
 
 /* Backward: scatter-add of the row gradients into dtable / dw1 (the IndexedSlices
  * gradient of the gathers, fm/fm.py:162-163), field-major, contention-free for
@@ -98,7 +98,7 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
 int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const float* table,
                   const float* S, const float* dy2, const float* dy1, uint64_t w1_fields,
                   const int64_t* row_offsets_host, int B, int F, int D, float* dtable, float* dw1,
-                  ctr_stream_t stream);
+                  int64_t row_stride, int64_t w1_stride, ctr_stream_t stream);
 
 /* DCN cross stack, stand-alone (dcn/dcn.py:132-142) on x0[B,W] (W = F*D, W%4==0, W<=1280). */
 int ctr_dcn_cross_fwd(const float* x0, const float* w, const float* b, int L, int B, int W,
@@ -124,11 +124,21 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
 /* Lazy variant: exactly one update per distinct row in rows[n] (claim[R] int32
  * scratch, tag must differ from the previous call's), then zeroes the row of g.  Negative
  * row ids are skipped.  theta1/m1/v1/g1 (nullable): a per-row scalar parameter indexed by the
- * same rows (the first-order weights w1) updated under the same claim. */
+ * same rows (the first-order weights w1) updated under the same claim.
+ *
+ * Row strides (ctr_embed_fwd / ctr_embed_bwd / ctr_adam_rows; 0 = planar defaults D, 1, 1): the
+ * distance in floats between consecutive rows of table / m / v / g (row_stride), of the
+ * first-order arrays (w1_stride) and of claim (claim_stride).  With the ROW-RECORD layout
+ *   record[r] = { theta[D] | m[D] | v[D] | g[D] | theta1 m1 v1 g1 | claim, pad[3] }   (4D+8 floats)
+ * all pointers address one array with one stride, so everything the optimiser touches for a row
+ * sits in one DRAM page (1 activate per row instead of 9: random row access is bounded by the
+ * HBM activate rate long before its bandwidth), and the lookup's first-order weight shares the
+ * page of the row it just read. */
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
                   float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
                   int32_t tag, float lr_t, float beta1, float beta2, float eps,
-                  const float* state_dev, ctr_stream_t stream);
+                  const float* state_dev, int64_t row_stride, int64_t w1_stride,
+                  int64_t claim_stride, ctr_stream_t stream);
 
 /* -------------------------------------------------------- DIN activation unit
  * din/din.py:103-125 `_attention`: for each sample b and position p with hist[b,p] > 0

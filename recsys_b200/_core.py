@@ -496,8 +496,10 @@ class DINModel(_ModelBase):
         self.lay = fc.Layout(cols, ["i_id", "i_cate"], [n_items, n_cates],
                              [0, n_items, n_items + n_cates], E)
         seed = int(params.get("seed", 0))
+        # planar tables: the activation-unit kernels (din.cu) index rows with stride E
         self.emb = ops.FieldEmbedding(self.lay, self.device, with_w1=True, w1_fields=0b01,
-                                      adam_mode=params.get("embedding_adam", "exact_tf"), seed=seed)
+                                      adam_mode=params.get("embedding_adam", "exact_tf"), seed=seed,
+                                      record=False)
         g = torch.Generator().manual_seed(seed)
         with torch.no_grad():   # glorot_normal tables, zero item bias (din/din.py:88-90)
             self.emb.table[:n_items].copy_(_glorot_normal((n_items, E), g))

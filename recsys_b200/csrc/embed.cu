@@ -33,6 +33,8 @@ struct EmbedFwdParams {
   const float* cross_b;
   float* xl;
   unsigned long long w1_fields;
+  long long ld;     // floats between consecutive table rows (D: planar table; 4D+4: row records)
+  long long ld1;    // floats between consecutive first-order weights (1 or the record stride)
   int cross_layers;
   int B;
   int F;
@@ -126,7 +128,7 @@ embed_fwd_kernel(const EmbedFwdParams p) {
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         v[s][it] = rid[s][it] >= 0
-                       ? ldg4(p.table + static_cast<size_t>(rid[s][it]) * D + q * 4)
+                       ? ldg4(p.table + static_cast<size_t>(rid[s][it]) * p.ld + q * 4)
                        : f4_zero();
       }
     }
@@ -138,7 +140,7 @@ embed_fwd_kernel(const EmbedFwdParams p) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
           const int f = it * RPW + r;
-          if (rid[s][it] >= 0 && ((p.w1_fields >> f) & 1ull)) y1p[s] += __ldg(p.w1 + rid[s][it]);
+          if (rid[s][it] >= 0 && ((p.w1_fields >> f) & 1ull)) y1p[s] += __ldg(p.w1 + static_cast<size_t>(rid[s][it]) * p.ld1);
         }
       }
     }
@@ -281,6 +283,8 @@ struct EmbedBwdParams {
   float* dtable;
   float* dw1;
   unsigned long long w1_fields;
+  long long ld;     // row stride of table / dtable (floats)
+  long long ld1;    // stride of dw1 (floats)
   int B;
   int F;
   int chunk;
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
       g = p.dE != nullptr ? ld4_stream(p.dE + eo) : f4_zero();
       if (p.dy2 != nullptr) {
         const float4 e = p.E != nullptr ? ldg4(p.E + eo)
-                                        : ldg4(p.table + static_cast<size_t>(rid) * D + q * 4);
+                                        : ldg4(p.table + static_cast<size_t>(rid) * p.ld + q * 4);
         const float4 sv = ldg4(p.S + static_cast<size_t>(b) * D + q * 4);
         const float cdy = __ldg(p.dy2 + b);
         g.x = fmaf(cdy, sv.x - e.x, g.x);
@@ -359,8 +363,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           if (rid[u] >= 0) {    // negative ids (sharded overflow slots) are skipped
-            red_add_v4(p.dtable + static_cast<size_t>(rid[u]) * D + q * 4, g[u]);
-            if (has_w1 && q == 0) red_add_f32(p.dw1 + rid[u], gw[u]);
+            red_add_v4(p.dtable + static_cast<size_t>(rid[u]) * p.ld + q * 4, g[u]);
+            if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(rid[u]) * p.ld1, gw[u]);
           }
         }
       }
@@ -406,8 +410,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
     for (int j = 0; j < J; ++j) {
       const int lr = r + RPW * j;
       if (lr < nrow) {
-        red_add_v4(p.dtable + static_cast<size_t>(off + lr) * D + q * 4, acc[j]);
-        if (has_w1 && q == 0) red_add_f32(p.dw1 + off + lr, accw[j]);
+        red_add_v4(p.dtable + static_cast<size_t>(off + lr) * p.ld + q * 4, acc[j]);
+        if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(off + lr) * p.ld1, accw[j]);
       }
     }
   }
@@ -641,7 +645,7 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
                  float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
                  float* __restrict__ th1, float* __restrict__ m1, float* __restrict__ v1,
                  float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
-                 float b2, float eps, const float* __restrict__ state) {
+                 float b2, float eps, const float* __restrict__ state, long long ld, long long ld1, long long ldc) {
   if (state != nullptr) {
     tag = static_cast<int>(state[0]);
     lr_t = state[1];
@@ -667,24 +671,26 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
     for (int u = 0; u < U; ++u) {
       won[u] = 0;
       if (rid[u] >= 0) {
-        if (q == 0) won[u] = atomicExch(claim + rid[u], tag) != tag ? 1 : 0;
+        if (q == 0) won[u] = atomicExch(claim + static_cast<size_t>(rid[u]) * ldc, tag) != tag ? 1 : 0;
         if (D >= 4) {
-          const size_t o = static_cast<size_t>(rid[u]) * D + q * 4;
+          const size_t o = static_cast<size_t>(rid[u]) * ld + q * 4;
           G[u] = ld4_plain(g + o);
           M[u] = ld4_plain(m + o);
           V[u] = ld4_plain(v + o);
           T[u] = ld4_plain(th + o);
           if (th1 != nullptr && q == 0) {
-            G1[u] = ld1_plain(g1 + rid[u]);
-            M1[u] = ld1_plain(m1 + rid[u]);
-            V1[u] = ld1_plain(v1 + rid[u]);
-            T1[u] = ld1_plain(th1 + rid[u]);
+            const size_t o1 = static_cast<size_t>(rid[u]) * ld1;
+            G1[u] = ld1_plain(g1 + o1);
+            M1[u] = ld1_plain(m1 + o1);
+            V1[u] = ld1_plain(v1 + o1);
+            T1[u] = ld1_plain(th1 + o1);
           }
         } else {
-          G1[u] = ld1_plain(g + rid[u]);
-          M1[u] = ld1_plain(m + rid[u]);
-          V1[u] = ld1_plain(v + rid[u]);
-          T1[u] = ld1_plain(th + rid[u]);
+          const size_t o1 = static_cast<size_t>(rid[u]) * ld;
+          G1[u] = ld1_plain(g + o1);
+          M1[u] = ld1_plain(m + o1);
+          V1[u] = ld1_plain(v + o1);
+          T1[u] = ld1_plain(th + o1);
         }
       }
     }
@@ -695,7 +701,7 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
       // Only the claim winner ever writes this row in this launch, and the values it loaded
       // above were written by earlier kernels: the speculative loads are race free.
       if (D >= 4) {
-        const size_t o = static_cast<size_t>(rid[u]) * D + q * 4;
+        const size_t o = static_cast<size_t>(rid[u]) * ld + q * 4;
         float4 Gu = G[u], Mu = M[u], Vu = V[u], Tu = T[u];
 #define CTR_ADAM4(c)                                  \
   Mu.c = b1 * Mu.c + (1.f - b1) * Gu.c;               \
@@ -710,18 +716,20 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
         if (th1 != nullptr && q == 0) {   // the row's first-order weight rides on the same claim
           const float Mn = b1 * M1[u] + (1.f - b1) * G1[u];
           const float Vn = b2 * V1[u] + (1.f - b2) * G1[u] * G1[u];
-          m1[rid[u]] = Mn;
-          v1[rid[u]] = Vn;
-          th1[rid[u]] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
-          g1[rid[u]] = 0.f;
+          const size_t o1 = static_cast<size_t>(rid[u]) * ld1;
+          m1[o1] = Mn;
+          v1[o1] = Vn;
+          th1[o1] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
+          g1[o1] = 0.f;
         }
       } else {
         const float Mn = b1 * M1[u] + (1.f - b1) * G1[u];
         const float Vn = b2 * V1[u] + (1.f - b2) * G1[u] * G1[u];
-        m[rid[u]] = Mn;
-        v[rid[u]] = Vn;
-        th[rid[u]] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
-        g[rid[u]] = 0.f;
+        const size_t o1 = static_cast<size_t>(rid[u]) * ld;
+        m[o1] = Mn;
+        v[o1] = Vn;
+        th[o1] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
+        g[o1] = 0.f;
       }
     }
   }
@@ -771,7 +779,7 @@ int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_c
 int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
                   uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
                   const float* cross_w, const float* cross_b, int cross_layers, float* xl,
-                  float* E_lo, ctr_stream_t stream) {
+                  float* E_lo, int64_t row_stride, int64_t w1_stride, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(table && rows, "ctr_embed_fwd", "null table/rows");
   CTR_REQUIRE(E_lo == nullptr || (E != nullptr && aligned16(E_lo)), "ctr_embed_fwd",
@@ -781,6 +789,10 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
                   aligned16(cross_w) && aligned16(cross_b),
               "ctr_embed_fwd", "pointers must be 16-byte aligned");
   CTR_REQUIRE(y1 == nullptr || w1 != nullptr, "ctr_embed_fwd", "y1 requested without w1");
+  if (row_stride <= 0) row_stride = D;
+  if (w1_stride <= 0) w1_stride = 1;
+  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, "ctr_embed_fwd",
+              "row_stride must be >= D and a multiple of 4 floats");
   const bool cross = xl != nullptr;
   CTR_REQUIRE(!cross || (cross_w && cross_b && cross_layers >= 0), "ctr_embed_fwd",
               "xl requested without cross_w/cross_b");
@@ -788,7 +800,7 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
   EmbedFwdParams p;
   p.table = table; p.w1 = w1; p.rows = rows; p.E = E; p.E_lo = E_lo; p.S = S; p.y1 = y1; p.y2 = y2;
   p.cross_w = cross_w; p.cross_b = cross_b; p.xl = xl; p.w1_fields = w1_fields;
-  p.cross_layers = cross_layers; p.B = B; p.F = F;
+  p.cross_layers = cross_layers; p.B = B; p.F = F; p.ld = row_stride; p.ld1 = w1_stride;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int r = cross ? dispatch_fwd<true>(p, D, st) : dispatch_fwd<false>(p, D, st);
   if (r != CTR_OK) return r;
@@ -798,7 +810,7 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
 int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const float* table,
                   const float* S, const float* dy2, const float* dy1, uint64_t w1_fields,
                   const int64_t* row_offsets_host, int B, int F, int D, float* dtable, float* dw1,
-                  ctr_stream_t stream) {
+                  int64_t row_stride, int64_t w1_stride, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(rows && dtable && row_offsets_host, "ctr_embed_bwd", "null rows/dtable/row_offsets");
   CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_embed_bwd", "need 0 < F <= 64");
@@ -807,10 +819,15 @@ int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const fl
   CTR_REQUIRE(aligned16(dE) && aligned16(E) && aligned16(table) && aligned16(S) && aligned16(dtable),
               "ctr_embed_bwd", "pointers must be 16-byte aligned");
   CTR_REQUIRE(row_offsets_host[F] < (1LL << 31), "ctr_embed_bwd", "table too large for int32 rows");
+  if (row_stride <= 0) row_stride = D;
+  if (w1_stride <= 0) w1_stride = 1;
+  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, "ctr_embed_bwd",
+              "row_stride must be >= D and a multiple of 4 floats");
   if (B == 0) return CTR_OK;
   EmbedBwdParams p;
   p.rows = rows; p.dE = dE; p.E = E; p.table = table; p.S = S; p.dy2 = dy2; p.dy1 = dy1;
   p.dtable = dtable; p.dw1 = dw1; p.w1_fields = w1_fields; p.B = B; p.F = F;
+  p.ld = row_stride; p.ld1 = w1_stride;
   for (int f = 0; f <= F; ++f) p.off[f] = static_cast<int>(row_offsets_host[f]);
   // chunk: enough warp-tasks to fill the machine, few enough tiny-field flushes.
   int chunk = 64;
@@ -892,13 +909,19 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
                   float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
                   int32_t tag, float lr_t, float beta1, float beta2, float eps,
-                  const float* state_dev, ctr_stream_t stream) {
+                  const float* state_dev, int64_t row_stride, int64_t w1_stride, int64_t claim_stride,
+                  ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(rows && theta && m && v && g && claim && n >= 0, "ctr_adam_rows", "null pointer");
   CTR_REQUIRE(theta1 == nullptr || (m1 && v1 && g1 && D >= 4), "ctr_adam_rows",
               "first-order vector needs m1/v1/g1 and a D >= 4 table");
   CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_rows",
               "pointers must be 16-byte aligned");
+  if (row_stride <= 0) row_stride = D;
+  if (w1_stride <= 0) w1_stride = 1;
+  if (claim_stride <= 0) claim_stride = 1;
+  CTR_REQUIRE(row_stride >= D && (D < 4 || (row_stride & 3) == 0), "ctr_adam_rows",
+              "row_stride must be >= D and a multiple of 4 floats");
   if (n == 0) return CTR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int lpr = D >= 4 ? D / 4 : 1;
@@ -906,7 +929,7 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
   constexpr int U = 2;                      // lookups in flight per lane group
   const long long per_block = gpb * U;
   const int grid = static_cast<int>(std::min<long long>((n + per_block - 1) / per_block, sm_count() * 8LL));
-#define CTR_AR(DD) adam_rows_kernel<DD, U><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev)
+#define CTR_AR(DD) adam_rows_kernel<DD, U><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev, row_stride, w1_stride, claim_stride)
   switch (D) {
     case 1: CTR_AR(1); break;
     case 8: CTR_AR(8); break;

@@ -245,31 +245,57 @@ class FieldEmbedding:
     """
 
     def __init__(self, lay: fc.Layout, device, with_w1: bool = True, w1_fields: int = 0,
-                 adam_mode: str = "lazy", seed: int = 0):
+                 adam_mode: str = "lazy", seed: int = 0, record: Optional[bool] = None):
         self.lay, self.device = lay, device
         self.D, self.F, self.R = lay.dimension, lay.F, lay.total_rows
         if self.D not in (8, 16, 32):
             raise ValueError("embedding_size must be 8, 16 or 32 (got %d)" % self.D)
         if self.F > 64:
             raise ValueError("at most 64 fields")
+        D, R = self.D, self.R
+        # Row-record layout (include/ctr_b200.h, "Row strides"): one [R, 4D+8] array holding
+        # theta | m | v | g | theta1 m1 v1 g1 | claim per row, so that a lookup's first-order weight
+        # and everything the lazy optimiser touches for a row share one DRAM page.  ``table``,
+        # ``dtable``, ``w1`` ... are strided views of it.  The dense (exact_tf) optimiser streams
+        # whole arrays and keeps the planar layout.
+        if record is None:
+            record = adam_mode == "lazy" and os.environ.get("CTR_ROW_RECORDS", "1") != "0"
+        self.record = bool(record)
         g = torch.Generator(device=device).manual_seed(seed)
+        if self.record:
+            S = 4 * D + 8
+            self.rec = torch.zeros(R, S, dtype=torch.float32, device=device)
+            self.table, self._m = self.rec[:, 0:D], self.rec[:, D:2 * D]
+            self._v, self.dtable = self.rec[:, 2 * D:3 * D], self.rec[:, 3 * D:4 * D]
+            self.w1, self._m1 = self.rec[:, 4 * D], self.rec[:, 4 * D + 1]
+            self._v1, self.dw1 = self.rec[:, 4 * D + 2], self.rec[:, 4 * D + 3]
+            self._claim = self.rec[:, 4 * D + 4].view(torch.int32)
+            self.ld = self.ld1 = self.ldc = S
+        else:
+            self.rec = None
+            self.table = torch.empty(R, D, dtype=torch.float32, device=device)
+            self.dtable = torch.zeros_like(self.table)
+            self.w1 = torch.empty(R, dtype=torch.float32, device=device) if with_w1 else None
+            self.dw1 = torch.zeros_like(self.w1) if with_w1 else None
+            self._m = self._v = self._m1 = self._v1 = self._claim = None
+            self.ld, self.ld1, self.ldc = D, 1, 1
         # embedding_column default initialiser: truncated normal, stddev 1/sqrt(D) [TF-sem];
-        # drawn on the device (the R-full table is 2 GB)
-        self.table = torch.empty(self.R, self.D, dtype=torch.float32, device=device)
-        torch.nn.init.trunc_normal_(self.table, std=self.D ** -0.5, a=-2 * self.D ** -0.5,
-                                    b=2 * self.D ** -0.5, generator=g)
-        self.dtable = torch.zeros_like(self.table)
+        # drawn on the device (the R-full table is 2 GB), in row chunks so that the strided view
+        # of a record array needs no table-sized temporary
+        std = D ** -0.5
+        step = 1 << 22
+        for r0 in range(0, R, step):
+            blk = torch.empty(min(step, R - r0), D, dtype=torch.float32, device=device)
+            torch.nn.init.trunc_normal_(blk, std=std, a=-2 * std, b=2 * std, generator=g)
+            self.table[r0:r0 + blk.shape[0]].copy_(blk)
         self.with_w1 = with_w1
         self.w1_fields = w1_fields
         if with_w1:
-            lim = math.sqrt(6.0 / (self.R + 1))        # dense(onehot,1) glorot-uniform kernel
-            self.w1 = (torch.rand(self.R, generator=g, device=device) * 2 - 1) * lim
-            self.dw1 = torch.zeros_like(self.w1)
-        else:
-            self.w1 = self.dw1 = None
+            lim = math.sqrt(6.0 / (R + 1))             # dense(onehot,1) glorot-uniform kernel
+            self.w1.copy_((torch.rand(R, generator=g, device=device) * 2 - 1) * lim)
+        elif self.record:
+            self.w1 = self.dw1 = self._m1 = self._v1 = None
         self.adam_mode = adam_mode
-        self._m = self._v = self._m1 = self._v1 = None
-        self._claim = self._claim1 = None
         self._tag = 0
         self._offsets_host = (C.c_int64 * (self.F + 1))(*lay.offsets)
         self._anchor = torch.zeros((), device=device, requires_grad=True)
@@ -325,7 +351,7 @@ class FieldEmbedding:
         _call("ctr_adam_rows", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
               _p(self.dtable), _p(self.w1) if w else None, _p(self._m1) if w else None,
               _p(self._v1) if w else None, _p(self.dw1) if w else None, _p(self._claim), self._tag,
-              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, _stream())
+              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, self.ld, self.ld1, self.ldc, _stream())
 
 
 class _EmbedFn(torch.autograd.Function):
@@ -347,7 +373,8 @@ class _EmbedFn(torch.autograd.Function):
         E_lo = torch.empty_like(E) if getattr(emb, "_want_lo", False) else None
         emb.last_E_lo = E_lo
         _call("ctr_embed_fwd", _p(emb.table), _p(emb.w1), _p(rows), B, F, D, emb.w1_fields, _p(E),
-              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), _stream())
+              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld, emb.ld1,
+              _stream())
         ctx.emb, ctx.rows, ctx.E, ctx.S = emb, rows, E, S
         ctx.cross_w, ctx.cross_b = cross_w, cross_b
         ctx.flags = (want_fm, want_y1, cross)
@@ -379,7 +406,8 @@ class _EmbedFn(torch.autograd.Function):
         dy1 = dy1.contiguous() if (want_y1 and dy1 is not None) else None
         if dE is not None or dy2 is not None:
             _call("ctr_embed_bwd", _p(rows), _p(dE), _p(E), _p(emb.table), _p(S), _p(dy2), _p(dy1),
-                  emb.w1_fields, emb._offsets_host, B, F, D, _p(emb.dtable), _p(emb.dw1), _stream())
+                  emb.w1_fields, emb._offsets_host, B, F, D, _p(emb.dtable), _p(emb.dw1), emb.ld,
+                  emb.ld1, _stream())
         return None, None, None, None, None, dcw, dcb
 
 

@@ -62,7 +62,7 @@ class CudaShardOps:
         cross = cross_w is not None
         xl = torch.empty((B, F * D), dtype=torch.float32, device=dev) if cross else None
         _call("ctr_embed_fwd", _p(vec), _p(w1v), _p(slot2d), B, F, D, w1_fields, _p(E), _p(S), _p(y1),
-              _p(y2), _p(cross_w), _p(cross_b), cross_w.shape[0] if cross else 0, _p(xl), None, _stream())
+              _p(y2), _p(cross_w), _p(cross_b), cross_w.shape[0] if cross else 0, _p(xl), None, 0, 0, _stream())
         return E, S, y1, y2, xl
 
     def interact_bwd(self, slot2d, dE, E, vec, S, dy2, dy1, w1_fields, D, n_slots):
@@ -73,7 +73,7 @@ class CudaShardOps:
         # slots are unique per lookup: no field is "tiny" (fake offsets 1000 apart)
         offs = (C.c_int64 * (F + 1))(*[1000 * f for f in range(F + 1)])
         _call("ctr_embed_bwd", _p(slot2d), _p(dE), _p(E), _p(vec), _p(S), _p(dy2), _p(dy1),
-              w1_fields, offs, B, F, D, _p(gsend), _p(gw1), _stream())
+              w1_fields, offs, B, F, D, _p(gsend), _p(gw1), 0, 0, _stream())
         return gsend, gw1
 
 
@@ -178,7 +178,7 @@ class ShardedFieldEmbedding:
         _call("ctr_adam_rows", _p(ids), ids.numel(), self.D, _p(self.table), _p(self._m),
               _p(self._v), _p(self.dtable), _p(self.w1) if w else None, _p(self._m1) if w else None,
               _p(self._v1) if w else None, _p(self.dw1) if w else None, _p(self._claim), self._tag,
-              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, _stream())
+              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, 0, 0, 0, _stream())
 
 
 class _ShardedEmbedFn(torch.autograd.Function):

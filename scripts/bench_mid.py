@@ -111,14 +111,14 @@ def table_sweep(B=4096, F=39, D=16):
             r = rows[it[0] % nb]
             it[0] += 1
             lib.ctr_embed_fwd(table.data_ptr(), w1.data_ptr(), r.data_ptr(), B, F, D, mask, E.data_ptr(),
-                              S.data_ptr(), y1.data_ptr(), y2.data_ptr(), None, None, 0, None, None, st)
+                              S.data_ptr(), y1.data_ptr(), y2.data_ptr(), None, None, 0, None, None, 0, 0, st)
 
         def bwd():
             r = rows[it[0] % nb]
             it[0] += 1
             lib.ctr_embed_bwd(r.data_ptr(), dE.data_ptr(), E.data_ptr(), table.data_ptr(), S.data_ptr(),
                               dy.data_ptr(), dy.data_ptr(), mask, offs_c, B, F, D, dt.data_ptr(),
-                              dw1.data_ptr(), st)
+                              dw1.data_ptr(), 0, 0, st)
 
         def adam():
             r = rows[it[0] % nb]
@@ -126,7 +126,7 @@ def table_sweep(B=4096, F=39, D=16):
             tag[0] += 1
             lib.ctr_adam_rows(r.data_ptr(), B * F, D, table.data_ptr(), m.data_ptr(), v.data_ptr(),
                               dt.data_ptr(), w1.data_ptr(), m1.data_ptr(), v1.data_ptr(), dw1.data_ptr(),
-                              claim.data_ptr(), tag[0], 1e-3, 0.9, 0.999, 1e-8, None, st)
+                              claim.data_ptr(), tag[0], 1e-3, 0.9, 0.999, 1e-8, None, 0, 0, 0, st)
 
         print("R=%9d rows (%.2f GB table): fwd %.1f us  bwd %.1f us  adam_rows %.1f us" % (
             R, R * D * 4 / 1e9, ev_time(fwd, 64), ev_time(bwd, 64), ev_time(adam, 64)))

@@ -111,7 +111,8 @@ def _rand_rows(B, offsets, seed, hot=False):
 
 @pytest.mark.parametrize("B,F,D", [(1, 39, 16), (5, 39, 16), (16, 39, 16), (4096, 39, 16),
                                    (333, 2, 32), (130, 39, 32), (257, 64, 8), (64, 7, 16)])
-def test_embed_fwd_matches_oracle(cuda, B, F, D):
+@pytest.mark.parametrize("record", [True, False])
+def test_embed_fwd_matches_oracle(cuda, B, F, D, record):
     ops = _ops()
     from recsys_b200 import feature_column as fc
     rng = np.random.default_rng(B + F + D)
@@ -120,7 +121,7 @@ def test_embed_fwd_matches_oracle(cuda, B, F, D):
             for i, n in enumerate(nrows)]
     lay = fc.layout(cols)
     mask = (int.from_bytes(rng.bytes(8), "little") & ((1 << F) - 1)) | 1
-    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask)
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask, record=record)
     rows_np = _rand_rows(B, lay.offsets, seed=B, hot=True)
     rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
     with torch.no_grad():
@@ -139,7 +140,8 @@ def test_embed_fwd_matches_oracle(cuda, B, F, D):
     (1, 16, True, True, False), (77, 16, True, True, False), (4096, 16, True, True, False),
     (300, 16, False, True, True), (300, 16, True, False, False), (515, 32, True, True, False),
     (129, 8, True, True, True)])
-def test_embed_bwd_matches_oracle(cuda, B, D, use_dE, use_fm, regather):
+@pytest.mark.parametrize("record", [True, False])
+def test_embed_bwd_matches_oracle(cuda, B, D, use_dE, use_fm, regather, record):
     """dtable / dw1 against the dense autograd gradient of the oracle; includes fields with
     3..32 rows (register one-hot path), a field where every sample hits one row, and big fields."""
     ops = _ops()
@@ -151,7 +153,7 @@ def test_embed_bwd_matches_oracle(cuda, B, D, use_dE, use_fm, regather):
             for i, n in enumerate(nrows)]
     lay = fc.layout(cols)
     mask = 0b10110101101
-    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask)
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask, record=record)
     rows_np = _rand_rows(B, lay.offsets, seed=B + D, hot=True)
     rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
     g = torch.Generator().manual_seed(B)
@@ -167,7 +169,7 @@ def test_embed_bwd_matches_oracle(cuda, B, D, use_dE, use_fm, regather):
     dEc, dy2c, dy1c = dE.to(cuda), dy2.to(cuda), dy1.to(cuda)
     rc = lib.ctr_embed_bwd(p(rows), p(dEc) if use_dE else None, None if regather else p(E),
                            p(emb.table), p(S) if use_fm else None, p(dy2c) if use_fm else None,
-                           p(dy1c), mask, offs, B, F, D, p(emb.dtable), p(emb.dw1),
+                           p(dy1c), mask, offs, B, F, D, p(emb.dtable), p(emb.dw1), emb.ld, emb.ld1,
                            torch.cuda.current_stream().cuda_stream)
     assert rc == 0, _lib.last_error()
     torch.cuda.synchronize()
@@ -195,13 +197,13 @@ def test_embed_rejects_bad_arguments(cuda):
     t = torch.zeros(10, 16, device=cuda)
     rows = torch.zeros(4, 3, dtype=torch.int32, device=cuda)
     rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 4, 3, 12, 0, None, None, None, None,
-                           None, None, 0, None, None, None)
+                           None, None, 0, None, None, 0, 0, None)
     assert rc == -1 and "D must be" in _lib.last_error()
     rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 4, 65, 16, 0, None, None, None, None,
-                           None, None, 0, None, None, None)
+                           None, None, 0, None, None, 0, 0, None)
     assert rc == -1
     rc = lib.ctr_embed_fwd(t.data_ptr(), None, rows.data_ptr(), 0, 3, 16, 0, None, None, None, None,
-                           None, None, 0, None, None, None)
+                           None, None, 0, None, None, 0, 0, None)
     assert rc == 0                                                 # empty batch is a no-op
 
 
@@ -244,8 +246,12 @@ def test_adam_rows_and_dense_match_tf_rule(cuda):
     cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("a", 50), D),
             fc.embedding_column(fc.categorical_column_with_hash_bucket("b", 5000), D)]
     lay = fc.layout(cols)
-    for mode in ("lazy", "exact_tf"):
-        emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=0b11, adam_mode=mode, seed=1)
+    for mode in ("lazy", "lazy-planar", "exact_tf"):      # row records / planar arrays / dense apply
+        record = {"lazy": True, "lazy-planar": False, "exact_tf": None}[mode]
+        mode = mode.split("-")[0]
+        emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=0b11, adam_mode=mode, seed=1,
+                                 record=record)
+        assert emb.record == (record is True)
         p = {"emb": emb.table.double().cpu().clone(), "w1": emb.w1.double().cpu().clone()}
         opt = tfsem.TFAdam(p, lr=1e-2)
         st = ops.TFAdamState(lr=1e-2, device=cuda if mode == "lazy" else None)
@@ -428,7 +434,7 @@ def test_din_attention_fwd_bwd(cuda, B, P, E):
         feats["u_iid_seq"][1] = 0                       # a sample whose whole history is padding
     cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("i_id", n_items), E)]
     lay = fc.Layout(cols, ["i_id"], [n_items], [0, n_items], E)
-    emb = ops.FieldEmbedding(lay, cuda, with_w1=False, seed=2)
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=False, seed=2, record=False)   # din.cu: planar rows
     g = torch.Generator().manual_seed(B)
     p64 = {}
     sizes = [4 * E, 80, 40, 1]
