@@ -420,6 +420,7 @@ class XDeepFMModel(_CriteoBase):
         if not self.fused:
             return super().forward(features, labels, training)
         P = self.dense
+        self.tower.begin_step()
         want_num = len(self.numeric_linear) > 0
         if want_num:
             self.rows, logx = self.ids(features, want_logx=True)
@@ -431,9 +432,14 @@ class XDeepFMModel(_CriteoBase):
         bs = [P[f"cin.{k}.b"] for k in range(len(self.cin_layers))]
         pooled = ops.cin(E, self.F, self.D, Ws, bs, self.cin_precision)          # :135-181
         cin_y = torch.relu(torch.addmm(P["cin.out.b"], pooled, P["cin.out.w"])).view(-1)  # :182
-        Ed = self.emb_dnn.lookup(self.rows, want_fm=False, want_y1=False)[0] \
-            if self.emb_dnn is not None else E                                    # :185
-        return self._tower_head(self.tower, Ed, [lin, cin_y], labels, training, (-1, 1))  # :131,188-212
+        lo = self.tower.use_presplit and self.world == 1 and self.emb_dnn is not None
+        if self.emb_dnn is not None:
+            Ed = self.emb_dnn.lookup(self.rows, want_fm=False, want_y1=False,
+                                     **({"want_lo": True} if lo else {}))[0]       # :185
+        else:
+            Ed = E
+        return self._tower_head(self.tower, Ed, [lin, cin_y], labels, training, (-1, 1),
+                                X_lo=self.emb_dnn.last_E_lo if lo else None)      # :131,188-212
 
     def load_state(self, state):
         super().load_state(state)

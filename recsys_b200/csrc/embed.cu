@@ -671,7 +671,10 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
     for (int u = 0; u < U; ++u) {
       won[u] = 0;
       if (rid[u] >= 0) {
-        if (q == 0) won[u] = atomicExch(claim + static_cast<size_t>(rid[u]) * ldc, tag) != tag ? 1 : 0;
+        // claim word read with a plain L2 load first (same sector as the first-order group in the
+        // record layout): a row that is already claimed - every later lookup of a hot row - is
+        // dropped without an atomic, so same-address atomics no longer serialise at the L2.
+        if (q == 0) won[u] = __ldcg(claim + static_cast<size_t>(rid[u]) * ldc) != tag ? 1 : 0;
         if (D >= 4) {
           const size_t o = static_cast<size_t>(rid[u]) * ld + q * 4;
           G[u] = ld4_plain(g + o);
@@ -694,6 +697,9 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
         }
       }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)     // candidates race for the claim; exactly one wins per row
+      if (won[u]) won[u] = atomicExch(claim + static_cast<size_t>(rid[u]) * ldc, tag) != tag ? 1 : 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int w = __shfl_sync(0xffffffffu, won[u], leader);

@@ -65,21 +65,31 @@ __device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) {   // a
   return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
 }
 
-// Sense-reversing grid barrier on {count, generation}; every CTA of the (cooperative) grid calls it.
+// Grid barrier on {count, generation}; every CTA of the (cooperative) grid calls it.  Release /
+// acquire operations at gpu scope instead of __threadfence() (a sequentially consistent MEMBAR):
+// bar.sync makes the CTA's writes visible to thread 0, whose release-add publishes them; the
+// waiters' acquire-load of the generation word, followed by bar.sync, hands them to the CTA.
+__device__ __forceinline__ unsigned mid_atom_add_release(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned mid_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mid_grid_barrier(unsigned* bar, unsigned nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned* genp = bar + 1;
-    const unsigned gen = *genp;
-    __threadfence();
-    if (atomicAdd(bar, 1u) == nblocks - 1) {
-      bar[0] = 0;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
+    const unsigned gen = mid_ld_acquire(bar + 1);
+    if (mid_atom_add_release(bar, 1u) == nblocks - 1) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+      mid_atom_add_release(bar + 1, 1u);
     } else {
-      while (*genp == gen) __nanosleep(20);
+      while (mid_ld_acquire(bar + 1) == gen) {
+      }
     }
-    __threadfence();
   }
   __syncthreads();
 }
