@@ -179,11 +179,14 @@ class Estimator:
 class GraphedTrainStep:
     """One whole train step - ``spec = model_fn(features, labels, TRAIN, params);
     spec.train_op()`` - captured once into a CUDA graph over static device input
-    buffers and replayed per batch.  ``__call__(features, labels)`` copies the
-    batch (pinned host or device ``PackedFeatures``) into the static buffers on the
-    step stream, replays the graph and returns the device loss tensor without
-    synchronising; ``losses_to_host`` streams losses into a pinned ring so that
-    reading them does not stall the pipeline."""
+    buffers and replayed per batch.
+
+    ``__call__(features, labels)`` with HOST tensors (pinned for real overlap) copies the batch
+    to a device staging blob on a copy stream - which runs while the previous step's graph is
+    still executing - then, on the step stream, moves it into the static buffers with ONE
+    device-to-device copy and replays the graph; device tensors are copied straight into the
+    static buffers.  It returns the device loss tensor without synchronising; ``loss_to_host``
+    reads it back on a third stream so that the read does not sit between two replays."""
 
     def __init__(self, model_fn, params, example_features, example_labels, warmup: int = 3):
         from .ops import PackedFeatures
@@ -193,17 +196,29 @@ class GraphedTrainStep:
         # capture on the caller's stream when it is already a side stream (keeps every autograd
         # node on one stream); the legacy default stream cannot be captured
         self.stream = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.d2h_stream = torch.cuda.Stream(device=dev)
         f = example_features
-        if isinstance(f, PackedFeatures):
-            self._static = {"cont": torch.empty_like(f.cont, device=dev),
-                            "cat": torch.empty_like(f.cat, device=dev)}
+        self._packed = isinstance(f, PackedFeatures)
+        ex = {"cont": f.cont, "cat": f.cat} if self._packed else \
+            {k: torch.as_tensor(v) for k, v in f.items()}
+        ex["__labels__"] = example_labels
+        # static inputs (what the graph reads) and the staging copy, each ONE blob with views
+        self._blob, self._static = self._make_blob(ex, dev)
+        self._stage_blob, self._stage = self._make_blob(ex, dev)
+        self.labels = self._static.pop("__labels__")
+        if self._packed:
             self.features = PackedFeatures(self._static["cont"], self._static["cat"], f.cont_keys,
                                            f.cat_keys)
         else:       # plain dict of tensors (e.g. the DIN features)
-            self._static = {k: torch.empty_like(torch.as_tensor(v), device=dev) for k, v in f.items()}
             self.features = dict(self._static)
-        self.labels = torch.empty_like(example_labels, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self._h2d_done = torch.cuda.Event()
+        self._stage_free = torch.cuda.Event()
+        self._loss_ready = torch.cuda.Event()
+        self._loss_read = torch.cuda.Event()
+        self._stage_free.record(self.stream)
+        self._loss_read.record(self.stream)
         self._load(example_features, example_labels)
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):                 # allocator + lazy-init warm-up, eager
@@ -216,24 +231,51 @@ class GraphedTrainStep:
             self._eager()
         self.stream.synchronize()
 
+    @staticmethod
+    def _make_blob(example: dict, dev):
+        offs, n = {}, 0
+        for k, t in example.items():
+            offs[k] = n
+            n += (t.numel() * t.element_size() + 255) // 256 * 256
+        blob = torch.empty(max(n, 256), dtype=torch.uint8, device=dev)
+        views = {k: blob[offs[k]:offs[k] + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+                 for k, t in example.items()}
+        return blob, views
+
     def _eager(self):
         spec = self.model_fn(self.features, self.labels, ModeKeys.TRAIN, self.params)
         spec.train_op()
         self.loss.copy_(spec.loss)
 
+    def _sources(self, features, labels):
+        src = {"cont": features.cont, "cat": features.cat} if self._packed else \
+            {k: torch.as_tensor(features[k]) for k in self._static}
+        src["__labels__"] = labels
+        return src
+
     def _load(self, features, labels):
-        from .ops import PackedFeatures
+        src = self._sources(features, labels)
+        dst = dict(self._static)
+        dst["__labels__"] = self.labels
+        if all(t.is_cuda for t in src.values()):
+            with torch.cuda.stream(self.stream):     # already in HBM: straight into the static views
+                for k, t in src.items():
+                    dst[k].copy_(t, non_blocking=True)
+            return
+        cs = self.copy_stream
+        cs.wait_event(self._stage_free)              # the previous batch has left the staging blob
+        with torch.cuda.stream(cs):
+            for k, t in src.items():
+                self._stage[k].copy_(t, non_blocking=True)
+            self._h2d_done.record(cs)
+        self.stream.wait_event(self._h2d_done)
         with torch.cuda.stream(self.stream):
-            if isinstance(features, PackedFeatures):
-                self._static["cont"].copy_(features.cont, non_blocking=True)
-                self._static["cat"].copy_(features.cat, non_blocking=True)
-            else:
-                for k, dst in self._static.items():
-                    dst.copy_(torch.as_tensor(features[k]), non_blocking=True)
-            self.labels.copy_(labels, non_blocking=True)
+            self._blob.copy_(self._stage_blob, non_blocking=True)
+            self._stage_free.record(self.stream)
 
     def __call__(self, features, labels):
         self._load(features, labels)
+        self.stream.wait_event(self._loss_read)      # the previous loss has been read back
         with torch.cuda.stream(self.stream):
             self.graph.replay()
         return self.loss
@@ -245,5 +287,8 @@ class GraphedTrainStep:
         return self.loss
 
     def loss_to_host(self, pinned_slot: torch.Tensor):
-        with torch.cuda.stream(self.stream):
+        self._loss_ready.record(self.stream)
+        self.d2h_stream.wait_event(self._loss_ready)
+        with torch.cuda.stream(self.d2h_stream):
             pinned_slot.copy_(self.loss, non_blocking=True)
+            self._loss_read.record(self.d2h_stream)

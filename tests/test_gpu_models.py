@@ -269,3 +269,46 @@ def test_din_matches_oracle(cuda, B, P):
     for k, gg in g64.items():
         if k in dg:
             close(dg[k], gg.reshape(dg[k].shape), k)
+
+
+def test_graphed_step_with_host_batches_follows_the_oracle(cuda):
+    """estimator.GraphedTrainStep fed from pinned host batches (the bench's e2e path: H2D on a
+    copy stream overlapped with the previous replay, one D2D into the static buffers, loss read
+    back on a third stream): the per-step losses follow the oracle's TF-Adam trajectory."""
+    from recsys_b200.deepfm import deepfm
+    from recsys_b200.estimator import GraphedTrainStep
+    spec = mg.small_spec()
+    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
+    train = {k: v for k, v in p64.items() if not k.endswith((".bn.mean", ".bn.var"))}
+    opt = tfsem.TFAdam(train, lr=1e-2)
+    nsteps, B = 6, 256
+    data = [mg.model_batch("deepfm", B, 40 + s, spec) for s in range(nsteps)]
+    host = [({k: v.pin_memory() for k, v in _features_to_torch(f).items()},
+             torch.as_tensor(b["labels"]).pin_memory()) for f, b in data]
+    side = torch.cuda.Stream(device=cuda)
+    with torch.cuda.stream(side):
+        m, params = _build("deepfm", spec, cuda, learning_rate=1e-2)
+        m.load_state(p64)
+        step = GraphedTrainStep(deepfm.model_fn, params, host[0][0], host[0][1], warmup=1)
+        # the warm-up ran one real training step: put parameters and optimiser state back
+        assert m.emb.record
+        D = m.emb.D
+        m.emb.rec[:, D:4 * D].zero_()           # m | v | g
+        m.emb.rec[:, 4 * D + 1:].zero_()        # m1 v1 g1 | claim
+        m.dense.m.zero_()
+        m.dense.v.zero_()
+        m.dense.grad.zero_()
+        m.adam.t = 0
+        m.adam.state.zero_()
+        m.load_state(p64)
+        losses = torch.zeros(nsteps).pin_memory()
+        for s in range(nsteps):
+            step(*host[s])
+            step.loss_to_host(losses[s:s + 1].view(()))
+    torch.cuda.synchronize()
+    for s in range(nsteps):
+        out, g = om.loss_and_grads("deepfm", p64, data[s][1])
+        assert abs(float(losses[s]) - float(out["loss"])) <= 3e-4 * (1 + s), (s, float(losses[s]))
+        opt.step(train, g, lazy_rows={"emb": data[s][1]["rows"].reshape(-1),
+                                      "w1": data[s][1]["rows"].reshape(-1)})
+        p64.update(train)
