@@ -30,7 +30,7 @@ ALG_BYTES_BWD = 5460          # ids 156 + table-grad RMW 2*2496 + w1-grad RMW 2*
 ALG_BYTES = ALG_BYTES_FWD + ALG_BYTES_BWD   # 8276 B / sample, F=39, D=16
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (debug)")
     ap.add_argument("--cin-precision", default="tf32", choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--fused-tower", type=int, default=None, help="1/0: force the fused tower kernels")
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 # ------------------------------------------------------------------------ clocks
@@ -87,6 +87,20 @@ class ClockSampler:
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
                 "reasons": reasons, "samples": len(self.rows)}
+
+
+def ncu_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the lookup forward + scatter
+    backward pair, from the committed `ncu --set full` capture (profiles/r01_ncu_traffic.json,
+    written by scripts/summarise_ncu.py).  None when the capture is for another batch size."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        if int(d.get("batch", -1)) != int(batch):
+            return None
+        return float(d["embed_fwd"]["dram_bytes"]) + float(d["embed_bwd"]["dram_bytes"])
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -231,8 +245,11 @@ def run_ours(args):
         return sharded.bench_main(args, rank, local, world)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    # everything (variables, autograd nodes, capture) lives on one side stream
-    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    # everything (variables, autograd nodes, capture) lives on one side stream; high priority, so
+    # that the critical path's CTAs are scheduled ahead of the weight-gradient kernels that the
+    # tower runs concurrently on its own (default-priority) stream
+    PRIO = int(os.environ.get("CTR_MAIN_PRIO", "-1"))
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=PRIO))
     from recsys_b200 import _lib, ops
     from recsys_b200 import feature_column as fc
     from recsys_b200.data import SyntheticCriteo
@@ -272,13 +289,16 @@ def run_ours(args):
             torch.cuda.synchronize()
     torch.cuda.synchronize()
 
+    dev_blobs = [step.to_device_batch(f, l) for f, l in devb] if step is not None else None
+
     def resident_step(i):
-        f, l = devb[i % len(devb)]
         if step is None:
+            f, l = devb[i % len(devb)]
             sp = mod.model_fn(f, l, "train", params)
             sp.train_op()
             return sp.loss
-        return step(f, l)     # device->device copy of the batch into the static buffers + replay
+        # one device->device copy of the resident batch into the static buffers + replay
+        return step.run_device_batch(dev_blobs[i % len(dev_blobs)])
 
     def e2e_step(i, slot):
         f, l = host_batches[i % len(host_batches)]
@@ -353,8 +373,11 @@ def run_ours(args):
         ach = ALG_BYTES * B / (t_pair * 1e-6) / 1e9
         line["roofline"] = {
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src,
-            "kernel": "embed_fwd_kernel<16,5,false> + embed_bwd_kernel<16> (one pair per step)",
+            "traffic": ncu_traffic(B), "peak_source": peak_src,
+            "traffic_note": "ncu --set full, caches flushed before each kernel (dE / E / S of the "
+                            "backward are L2 hits inside a real step); per launch pair, bytes",
+            "kernel": "embed_fwd_kernel<16,5,false> + embed_bwd_kernel<16> (one pair per step), "
+                      "each timed alone as 32 launches on distinct id batches inside a CUDA graph",
             "algorithmic_bytes_per_launch_pair": ALG_BYTES * B,
             "fwd": {"us": kern["fwd_us"], "GBps": ALG_BYTES_FWD * B / kern["fwd_us"] / 1e3,
                     "moved_GBps": kern["fwd_moved"] * B / kern["fwd_us"] / 1e3},

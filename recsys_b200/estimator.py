@@ -195,7 +195,8 @@ class GraphedTrainStep:
         cur = torch.cuda.current_stream(dev)
         # capture on the caller's stream when it is already a side stream (keeps every autograd
         # node on one stream); the legacy default stream cannot be captured
-        self.stream = cur if cur != torch.cuda.default_stream(dev) else torch.cuda.Stream(device=dev)
+        self.stream = cur if cur != torch.cuda.default_stream(dev) else \
+            torch.cuda.Stream(device=dev, priority=-1)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.d2h_stream = torch.cuda.Stream(device=dev)
         f = example_features
@@ -277,6 +278,24 @@ class GraphedTrainStep:
         self._load(features, labels)
         self.stream.wait_event(self._loss_read)      # the previous loss has been read back
         with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        return self.loss
+
+    def to_device_batch(self, features, labels) -> torch.Tensor:
+        """Lay a batch out on the device exactly like the static input blob (for batches that are
+        kept resident in HBM); ``run_device_batch`` then needs one D2D copy per step."""
+        src = self._sources(features, labels)
+        ex = dict(self._static)
+        ex["__labels__"] = self.labels
+        blob, views = self._make_blob(ex, self._blob.device)
+        with torch.cuda.stream(self.stream):
+            for k, t in src.items():
+                views[k].copy_(t, non_blocking=True)
+        return blob
+
+    def run_device_batch(self, blob: torch.Tensor):
+        with torch.cuda.stream(self.stream):
+            self._blob.copy_(blob, non_blocking=True)
             self.graph.replay()
         return self.loss
 

@@ -283,7 +283,7 @@ def bench_main(args, rank, local, world):
         host.append((PackedFeatures(cont, cat, [], keys), lab))
         devb.append((PackedFeatures(cont.to(dev), cat.to(dev), [], keys), lab.to(dev)))
     from .estimator import GraphedTrainStep
-    torch.cuda.set_stream(torch.cuda.Stream(device=dev))     # one side stream for everything
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))   # one (high-priority) stream
     n0 = ops.LAUNCHES["n"]
     sp = deepfm.model_fn(devb[0][0], devb[0][1], "train", params)
     sp.train_op()

@@ -1,0 +1,80 @@
+"""Kernel timeline of graph-replayed train steps via torch.profiler (CUPTI): per-kernel device
+time inside the replay and the idle gaps between consecutive kernels."""
+import json
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="deepfm")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=6)
+    a = ap.parse_args()
+    args = bench.parse(["--model", a.model] + (["--batch", str(a.batch)] if a.batch else []))
+    if args.batch is None:
+        args.batch = 8192 if args.model == "xdeepfm" else 4096
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=int(os.environ.get("CTR_MAIN_PRIO", "-1"))))
+    from recsys_b200 import ops
+    from recsys_b200 import feature_column as fc
+    from recsys_b200.data import SyntheticCriteo
+    from recsys_b200.estimator import GraphedTrainStep
+    mod, params = bench.build_model(args, dev)
+    lay = fc.layout(params["embedding_feature_columns"])
+    host = SyntheticCriteo(lay, args.batch, 8, dist="uniform", seed=0, device=None).batches
+    sp = mod.model_fn(ops.PackedFeatures(host[0][0].cont.to(dev), host[0][0].cat.to(dev), host[0][0].cont_keys,
+                                         host[0][0].cat_keys), host[0][1].to(dev), "train", params)
+    sp.train_op()
+    step = GraphedTrainStep(mod.model_fn, params, host[0][0], host[0][1], warmup=3)
+    for i in range(5):
+        step(*host[i % 8])
+    torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for i in range(a.steps):
+            step(*host[i % 8])
+        torch.cuda.synchronize()
+    path = os.path.join(tempfile.gettempdir(), "trace.json")
+    prof.export_chrome_trace(path)
+    ev = [e for e in json.load(open(path))["traceEvents"]
+          if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e]
+    ev.sort(key=lambda e: e["ts"])
+    if not ev:
+        print("no device activity records (CUPTI unavailable?)")
+        return
+    # split into steps at the blob D2D copy (first memcpy DtoD of each step)
+    per = {}
+    order = []
+    last_end = None
+    gaps = []
+    t_first, t_last = ev[0]["ts"], ev[-1]["ts"] + ev[-1]["dur"]
+    for e in ev:
+        name = e["name"][:70]
+        if name not in per:
+            per[name] = [0.0, 0]
+            order.append(name)
+        per[name][0] += e["dur"]
+        per[name][1] += 1
+        if last_end is not None:
+            gaps.append(max(0.0, e["ts"] - last_end))
+        last_end = max(last_end or 0, e["ts"] + e["dur"])
+    n = a.steps
+    print("%d steps, span %.1f us/step, busy %.1f us/step, idle gaps %.1f us/step (%d records)" % (
+        n, (t_last - t_first) / n, sum(v[0] for v in per.values()) / n, sum(gaps) / n, len(ev)))
+    for name in order:
+        tot, cnt = per[name]
+        print("  %7.2f us x %4.1f/step  %s" % (tot / cnt, cnt / n, name))
+
+
+if __name__ == "__main__":
+    main()
