@@ -362,12 +362,17 @@ int ctr_tower_mid(const ctr_tower_mid_args* args, int B, ctr_stream_t stream);
  *   lookups for that owner (> capacity means overflow: those lookups got slot -1). */
 int ctr_shard_bucket(const int32_t* rows, int64_t n, int G, int capacity, int32_t* send_local,
                      int32_t* slot, int32_t* counts, ctr_stream_t stream);
-/* Owner side: out[i,:] = table[ids[i],:] (zeros for ids[i] < 0); out_w1[i] = w1[ids[i]]. */
+/* Owner side: out[i,:] = table[ids[i],:] (zeros for ids[i] < 0); out_w1[i] = w1[ids[i]].
+ * Strides in floats, 0 = planar (D, 1): with out_stride = out_w1_stride = D+4 and out_w1 = out + D the
+ * row and its first-order weight travel in ONE exchange slab (one all-to-all instead of two); the
+ * table side takes the row-record stride. */
 int ctr_gather_rows(const float* table, const float* w1, const int32_t* ids, int64_t n, int D,
-                    float* out, float* out_w1, ctr_stream_t stream);
+                    float* out, float* out_w1, int64_t table_stride, int64_t w1_stride,
+                    int64_t out_stride, int64_t out_w1_stride, ctr_stream_t stream);
 /* Owner side: dtable[ids[i],:] += g[i,:]; dw1[ids[i]] += gw1[i]; ids < 0 skipped. */
 int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, int64_t n, int D,
-                         float* dtable, float* dw1, ctr_stream_t stream);
+                         float* dtable, float* dw1, int64_t g_stride, int64_t gw1_stride,
+                         int64_t dtable_stride, int64_t dw1_stride, ctr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -313,7 +313,7 @@ class DeepFMModel(_CriteoBase):
             return super().forward(features, labels, training)
         self.tower.begin_step()
         self.rows = self.ids(features)
-        lo = self.tower.use_presplit and self.world == 1
+        lo = self.tower.use_presplit and (self.world == 1 or getattr(self.emb.ops, "packed", False))
         E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True,
                                         **({"want_lo": True} if lo else {}))
         return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),

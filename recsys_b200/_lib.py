@@ -108,8 +108,9 @@ SIGNATURES = {
     "ctr_tower_gemm_presplit": (c_i, [c_i, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_i, c_f]),
     "ctr_tower_mid": (c_i, [C.POINTER(TowerMidArgs), c_i, c_f]),
     "ctr_shard_bucket": (c_i, [c_f, c_i64, c_i, c_i, c_f, c_f, c_f, c_f]),
-    "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),
-    "ctr_scatter_add_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f]),
+    "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f]),
+    "ctr_scatter_add_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_i64, c_i64, c_i64, c_i64,
+                                   c_f]),
     "ctr_transpose_fd": (c_i, [c_f, c_i, c_i, c_i, c_f, c_i, c_f]),
     "ctr_transpose_df_add": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
 }

@@ -42,16 +42,18 @@ template <int D>
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ table, const float* __restrict__ w1,
                    const int* __restrict__ ids, long long n, float* __restrict__ out,
-                   float* __restrict__ out_w1) {
+                   float* __restrict__ out_w1, long long lt, long long lw, long long lo,
+                   long long low) {
   constexpr int LPR = D / 4;
   const long long gpb = blockDim.x / LPR;
   const int q = threadIdx.x % LPR;
   for (long long i = blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += gridDim.x * gpb) {
     const int id = __ldg(ids + i);
     float4 v = f4_zero();
-    if (id >= 0) v = ldg4(table + static_cast<size_t>(id) * D + q * 4);
-    *reinterpret_cast<float4*>(out + static_cast<size_t>(i) * D + q * 4) = v;
-    if (out_w1 != nullptr && q == 0) out_w1[i] = id >= 0 ? __ldg(w1 + id) : 0.f;
+    if (id >= 0) v = ldg4(table + static_cast<size_t>(id) * lt + q * 4);
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(i) * lo + q * 4) = v;
+    if (out_w1 != nullptr && q == 0)
+      out_w1[static_cast<size_t>(i) * low] = id >= 0 ? __ldg(w1 + static_cast<size_t>(id) * lw) : 0.f;
   }
 }
 
@@ -59,16 +61,18 @@ template <int D>
 __global__ void __launch_bounds__(256)
 scatter_add_rows_kernel(const int* __restrict__ ids, const float* __restrict__ g,
                         const float* __restrict__ gw1, long long n, float* __restrict__ dtable,
-                        float* __restrict__ dw1) {
+                        float* __restrict__ dw1, long long lg, long long lgw, long long ld,
+                        long long ldw) {
   constexpr int LPR = D / 4;
   const long long gpb = blockDim.x / LPR;
   const int q = threadIdx.x % LPR;
   for (long long i = blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += gridDim.x * gpb) {
     const int id = __ldg(ids + i);
     if (id < 0) continue;
-    red_add_v4(dtable + static_cast<size_t>(id) * D + q * 4,
-               ld4_stream(g + static_cast<size_t>(i) * D + q * 4));
-    if (dw1 != nullptr && q == 0) red_add_f32(dw1 + id, gw1[i]);
+    red_add_v4(dtable + static_cast<size_t>(id) * ld + q * 4,
+               ld4_stream(g + static_cast<size_t>(i) * lg + q * 4));
+    if (dw1 != nullptr && q == 0)
+      red_add_f32(dw1 + static_cast<size_t>(id) * ldw, gw1[static_cast<size_t>(i) * lgw]);
   }
 }
 
@@ -94,39 +98,49 @@ int ctr_shard_bucket(const int32_t* rows, int64_t n, int G, int capacity, int32_
 }
 
 int ctr_gather_rows(const float* table, const float* w1, const int32_t* ids, int64_t n, int D,
-                    float* out, float* out_w1, ctr_stream_t stream) {
+                    float* out, float* out_w1, int64_t table_stride, int64_t w1_stride,
+                    int64_t out_stride, int64_t out_w1_stride, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(table && ids && out && n >= 0, "ctr_gather_rows", "null pointer");
   CTR_REQUIRE(out_w1 == nullptr || w1 != nullptr, "ctr_gather_rows", "out_w1 without w1");
   CTR_REQUIRE(aligned16(table) && aligned16(out), "ctr_gather_rows", "pointers must be 16-byte aligned");
+  const long long lt = table_stride > 0 ? table_stride : D, lw = w1_stride > 0 ? w1_stride : 1;
+  const long long lo = out_stride > 0 ? out_stride : D, low = out_w1_stride > 0 ? out_w1_stride : 1;
+  CTR_REQUIRE((lt & 3) == 0 && (lo & 3) == 0 && lt >= D && lo >= D, "ctr_gather_rows",
+              "row strides must be >= D and multiples of 4 floats");
   if (n == 0) return CTR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long gpb = 256 / (D / 4 > 0 ? D / 4 : 1);
   const int grid = static_cast<int>(std::min<long long>((n + gpb - 1) / gpb, sm_count() * 8LL));
   switch (D) {
-    case 8: gather_rows_kernel<8><<<grid, 256, 0, st>>>(table, w1, ids, n, out, out_w1); break;
-    case 16: gather_rows_kernel<16><<<grid, 256, 0, st>>>(table, w1, ids, n, out, out_w1); break;
-    case 32: gather_rows_kernel<32><<<grid, 256, 0, st>>>(table, w1, ids, n, out, out_w1); break;
+    case 8: gather_rows_kernel<8><<<grid, 256, 0, st>>>(table, w1, ids, n, out, out_w1, lt, lw, lo, low); break;
+    case 16: gather_rows_kernel<16><<<grid, 256, 0, st>>>(table, w1, ids, n, out, out_w1, lt, lw, lo, low); break;
+    case 32: gather_rows_kernel<32><<<grid, 256, 0, st>>>(table, w1, ids, n, out, out_w1, lt, lw, lo, low); break;
     default: return fail_arg("ctr_gather_rows", "D must be 8, 16 or 32");
   }
   CTR_LAUNCH_CHECK("ctr_gather_rows");
 }
 
 int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, int64_t n, int D,
-                         float* dtable, float* dw1, ctr_stream_t stream) {
+                         float* dtable, float* dw1, int64_t g_stride, int64_t gw1_stride,
+                         int64_t dtable_stride, int64_t dw1_stride, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(ids && g && dtable && n >= 0, "ctr_scatter_add_rows", "null pointer");
   CTR_REQUIRE(dw1 == nullptr || gw1 != nullptr, "ctr_scatter_add_rows", "dw1 without gw1");
   CTR_REQUIRE(aligned16(g) && aligned16(dtable), "ctr_scatter_add_rows",
               "pointers must be 16-byte aligned");
+  const long long lg = g_stride > 0 ? g_stride : D, lgw = gw1_stride > 0 ? gw1_stride : 1;
+  const long long ld = dtable_stride > 0 ? dtable_stride : D, ldw = dw1_stride > 0 ? dw1_stride : 1;
+  CTR_REQUIRE((lg & 3) == 0 && (ld & 3) == 0 && lg >= D && ld >= D, "ctr_scatter_add_rows",
+              "row strides must be >= D and multiples of 4 floats");
   if (n == 0) return CTR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long gpb = 256 / (D / 4 > 0 ? D / 4 : 1);
   const int grid = static_cast<int>(std::min<long long>((n + gpb - 1) / gpb, sm_count() * 8LL));
   switch (D) {
-    case 8: scatter_add_rows_kernel<8><<<grid, 256, 0, st>>>(ids, g, gw1, n, dtable, dw1); break;
-    case 16: scatter_add_rows_kernel<16><<<grid, 256, 0, st>>>(ids, g, gw1, n, dtable, dw1); break;
-    case 32: scatter_add_rows_kernel<32><<<grid, 256, 0, st>>>(ids, g, gw1, n, dtable, dw1); break;
+    case 8: scatter_add_rows_kernel<8><<<grid, 256, 0, st>>>(ids, g, gw1, n, dtable, dw1, lg, lgw, ld, ldw); break;
+    case 16: scatter_add_rows_kernel<16><<<grid, 256, 0, st>>>(ids, g, gw1, n, dtable, dw1, lg, lgw, ld, ldw); break;
+    case 32: scatter_add_rows_kernel<32><<<grid, 256, 0, st>>>(ids, g, gw1, n, dtable, dw1, lg, lgw, ld, ldw); break;
     default: return fail_arg("ctr_scatter_add_rows", "D must be 8, 16 or 32");
   }
   CTR_LAUNCH_CHECK("ctr_scatter_add_rows");
