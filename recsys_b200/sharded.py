@@ -353,7 +353,9 @@ def bench_main(args, rank, local, world):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    total_rows = int(os.environ.get("CTR_SHARDED_ROWS", "1000000000"))
+    # weak scaling: 125 M rows (36 GB of row records) per GPU, i.e. the 1 B-row table of BASELINE
+    # config 5 at 8 GPUs; CTR_SHARDED_ROWS overrides the total
+    total_rows = int(os.environ.get("CTR_SHARDED_ROWS", str(125_000_000 * world)))
     lin, emb = sharded_columns(total_rows, 16)
     params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
               "learning_rate": 1e-3, "dropout": 0.5, "deep_layers": "100,100", "device": dev,
