@@ -302,7 +302,9 @@ int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const f
  *            kind-2 gradient source), dn[l] [B,H[l]] scratch.
  * Weight gradients dW_l are NOT computed here (they are off the critical path: the caller
  * runs ctr_tower_layer_bwd_weights on a side stream).  Hidden widths: multiples of 4, <= 128.
- * `barrier`: 2 device words, zero-initialised once, reusable across launches. */
+ * `barrier`: CTR_TOWER_MID_BARRIER_WORDS device words, zero-initialised once, reusable across
+ * launches ({arrival count, generation}; the rest is reserved). */
+#define CTR_TOWER_MID_BARRIER_WORDS 320
 #define CTR_TOWER_MID_MAX_LAYERS 4
 typedef struct {
   int32_t L, C, relu0, training;

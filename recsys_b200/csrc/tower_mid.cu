@@ -69,9 +69,9 @@ __device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) {   // a
 // acquire operations at gpu scope instead of __threadfence() (a sequentially consistent MEMBAR):
 // bar.sync makes the CTA's writes visible to thread 0, whose release-add publishes them; the
 // waiters' acquire-load of the generation word, followed by bar.sync, hands them to the CTA.
-__device__ __forceinline__ unsigned mid_atom_add_release(unsigned* p, unsigned v) {
+__device__ __forceinline__ unsigned mid_atom_add_acq_rel(unsigned* p, unsigned v) {
   unsigned old;
-  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
 __device__ __forceinline__ unsigned mid_ld_acquire(const unsigned* p) {
@@ -79,13 +79,15 @@ __device__ __forceinline__ unsigned mid_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// (Measured and rejected: a two-level arrival - 8 group counters, then a top counter - to avoid 128
+// same-address atomics; the extra dependent L2 round trip cost more, 3.3 us against 2.4 us.)
 __device__ __forceinline__ void mid_grid_barrier(unsigned* bar, unsigned nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned gen = mid_ld_acquire(bar + 1);
-    if (mid_atom_add_release(bar, 1u) == nblocks - 1) {
+    if (mid_atom_add_acq_rel(bar, 1u) == nblocks - 1) {
       asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
-      mid_atom_add_release(bar + 1, 1u);
+      mid_atom_add_acq_rel(bar + 1, 1u);
     } else {
       while (mid_ld_acquire(bar + 1) == gen) {
       }

@@ -592,7 +592,7 @@ class FusedTower:
         self.materialise_dpre = os.environ.get("CTR_TOWER_DPRE", "1") != "0"
         # ctr_tower_mid: the middle of the chain (hidden layers >= 1, dense(1), head, loss and
         # their backward) in one cooperative launch; needs every hidden width <= 128
-        self.barrier = torch.zeros(2, dtype=torch.int32, device=dense.flat.device)
+        self.barrier = torch.zeros(320, dtype=torch.int32, device=dense.flat.device)   # CTR_TOWER_MID_BARRIER_WORDS
         self.timing = None      # set to an int64[8] device tensor to get the phase time stamps
         self.last_acts = None
         self.mid_ok = (out_layer and 1 <= len(self.sizes) - 1 <= 4
