@@ -89,6 +89,17 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
                   const float* cross_w, const float* cross_b, int cross_layers, float* xl, float* E_lo,
                   int64_t row_stride, int64_t w1_stride, ctr_stream_t stream);
 
+/* Same, with the id pipeline of ctr_criteo_rows fused in front (one launch instead of two): every
+ * CTA computes the row ids of its sample tile from the raw features straight into shared memory
+ * and writes them to rows_out [B,F] for the backward / optimiser.  boundaries: n_boundaries <= 512. */
+int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, int n_cont,
+                      const int64_t* xcat, int n_cat, const ctr_field_desc* fields_dev,
+                      const float* boundaries_dev, int n_boundaries, int32_t* rows_out, float* logx,
+                      int32_t* status, int B, int F, int D, uint64_t w1_fields, float* E, float* S,
+                      float* y1, float* y2, const float* cross_w, const float* cross_b,
+                      int cross_layers, float* xl, float* E_lo, int64_t row_stride,
+                      int64_t w1_stride, ctr_stream_t stream);
+
 /* Backward: scatter-add of the row gradients into dtable / dw1 (the IndexedSlices
  * gradient of the gathers, fm/fm.py:162-163), field-major, contention-free for
  * fields with <= 32 rows.

@@ -215,6 +215,18 @@ class _CriteoBase(_ModelBase):
         super().load_state(state)
         self.emb.load(state.get("emb"), state.get("w1"))
 
+    def _lookup(self, features, want_logx=False, **kw):
+        """ids + fused lookup.  One launch (ctr_embed_fwd_raw) for the unsharded table; the sharded
+        table needs the ids on their own (they are bucketed by owner first).
+        -> (logx or None, lookup outputs...); sets ``self.rows``."""
+        if self.world == 1 and hasattr(self.emb, "lookup_features"):
+            out = self.emb.lookup_features(self.ids, features, want_logx=want_logx, **kw)
+            self.rows = out[0]
+            return out[1:]
+        r = self.ids(features, want_logx=want_logx)
+        self.rows, logx = r if want_logx else (r, None)
+        return (logx,) + tuple(self.emb.lookup(self.rows, **kw))
+
     def _fused_head(self, zs, labels, training, shape):
         """ctr_loss_head over the columns ``zs`` (column 0 = pre-bias first-order sum)."""
         B = zs[0].shape[0]
@@ -283,8 +295,7 @@ class FMModel(_CriteoBase):
     def forward(self, features, labels, training):
         if not self.fused:
             return super().forward(features, labels, training)
-        self.rows = self.ids(features)
-        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True)
+        _, E, y1s, y2, _ = self._lookup(features, want_fm=True, want_y1=True)
         return self._fused_head([y1s, y2], labels, training, (-1, 1))     # fm/fm.py:121-149
 
 
@@ -312,9 +323,8 @@ class DeepFMModel(_CriteoBase):
         if not self.fused:
             return super().forward(features, labels, training)
         self.tower.begin_step()
-        self.rows = self.ids(features)
         lo = self.tower.use_presplit and (self.world == 1 or getattr(self.emb.ops, "packed", False))
-        E, y1s, y2, _ = self.emb.lookup(self.rows, want_fm=True, want_y1=True,
+        _, E, y1s, y2, _ = self._lookup(features, want_fm=True, want_y1=True,
                                         **({"want_lo": True} if lo else {}))
         return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),
                                 X_lo=self.emb.last_E_lo if lo else None)      # :91,100-129
@@ -369,8 +379,7 @@ class DCNModel(_CriteoBase):
 
     def logits(self, features, training):
         P = self.dense
-        self.rows = self.ids(features)
-        E, _, _, xl = self.emb.lookup(self.rows, want_fm=False, want_y1=False,
+        _, E, _, _, xl = self._lookup(features, want_fm=False, want_y1=False,
                                       cross_w=P["cross.w"], cross_b=P["cross.b"])
         h = self._tower(E, "dnn", len(self.layers), training)             # dcn.py:144-149
         z = torch.cat([h, xl], 1)                                         # :151
@@ -422,11 +431,7 @@ class XDeepFMModel(_CriteoBase):
         P = self.dense
         self.tower.begin_step()
         want_num = len(self.numeric_linear) > 0
-        if want_num:
-            self.rows, logx = self.ids(features, want_logx=True)
-        else:
-            self.rows, logx = self.ids(features), None
-        E, y1s, _, _ = self.emb.lookup(self.rows, want_fm=False, want_y1=True)
+        logx, E, y1s, _, _ = self._lookup(features, want_logx=want_num, want_fm=False, want_y1=True)
         lin = y1s + logx @ P["wnum"] if want_num else y1s                        # :82
         Ws = [P[f"cin.{k}.w"] for k in range(len(self.cin_layers))]
         bs = [P[f"cin.{k}.b"] for k in range(len(self.cin_layers))]

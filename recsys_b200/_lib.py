@@ -76,6 +76,8 @@ SIGNATURES = {
     "ctr_hash_strings": (c_i, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
     "ctr_embed_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i,
                             c_f, c_f, c_i64, c_i64, c_f]),
+    "ctr_embed_fwd_raw": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i,
+                                c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
                             c_i, c_i, c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_dcn_cross_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f]),

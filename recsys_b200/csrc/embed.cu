@@ -19,6 +19,33 @@
 
 namespace ctr {
 
+// One row id of the Criteo id pipeline (fm/fm.py:76-80,89): numeric fields log -> Bucketize
+// (upper_bound), categorical fields offset + range check.  Shared by criteo_rows_kernel and the
+// lookup kernel's fused id stage, so both produce bit-identical ids.
+__device__ __forceinline__ int criteo_row_id(const ctr_field_desc& fd, const float* __restrict__ bnd,
+                                             const float* __restrict__ xcont, int n_cont,
+                                             const long long* __restrict__ xcat, int n_cat, int b,
+                                             float* __restrict__ logx, int* __restrict__ status) {
+  int id;
+  if (fd.kind == 0) {
+    // fm/fm.py:76-79: tf.log(x + off) in fp32, then Bucketize == upper_bound.
+    const float v = logf(xcont[static_cast<size_t>(b) * n_cont + fd.src] + fd.log_offset);
+    if (logx != nullptr) logx[static_cast<size_t>(b) * n_cont + fd.src] = v;
+    id = 0;
+    for (int k = 0; k < fd.bnd_count; ++k) id += (bnd[fd.bnd_begin + k] <= v) ? 1 : 0;
+    if (v != v) id = fd.bnd_count;
+  } else {
+    long long raw = xcat[static_cast<size_t>(b) * n_cat + fd.src];
+    if (raw < 0 || raw >= fd.n_rows) {
+      if (status != nullptr) atomicOr(status, 1);
+      raw %= fd.n_rows;
+      if (raw < 0) raw += fd.n_rows;
+    }
+    id = static_cast<int>(raw);
+  }
+  return fd.row_offset + id;
+}
+
 // ------------------------------------------------------------------ forward
 struct EmbedFwdParams {
   const float* table;
@@ -33,6 +60,15 @@ struct EmbedFwdParams {
   const float* cross_b;
   float* xl;
   unsigned long long w1_fields;
+  // fused id stage (RAW kernels): raw features in, row ids out (rows_out feeds the backward)
+  const float* xcont;
+  const long long* xcat;
+  const ctr_field_desc* fields;
+  const float* bnd;
+  int* rows_out;
+  float* logx;
+  int* status;
+  int n_cont, n_cat, n_bnd;
   long long ld;     // floats between consecutive table rows (D: planar table; 4D+4: row records)
   long long ld1;    // floats between consecutive first-order weights (1 or the record stride)
   int cross_layers;
@@ -44,15 +80,20 @@ constexpr int kFwdWarps = 8;
 constexpr int kFwdSPW = 2;                      // samples per warp per tile
 constexpr int kFwdTB = kFwdWarps * kFwdSPW;     // samples per tile (multiple of 4)
 
+constexpr int kFwdMaxBnd = 512;      // boundaries staged in shared memory by the RAW kernels
+
 template <int D, int NIT, bool CROSS>
 __global__ void __launch_bounds__(kFwdWarps * 32)
 embed_fwd_kernel(const EmbedFwdParams p) {
+  const bool RAW = p.fields != nullptr;     // fused id stage (ctr_embed_fwd_raw), block-uniform
   constexpr int LPR = D / 4;
   constexpr int RPW = 32 / LPR;
   constexpr int SPW = kFwdSPW;
   constexpr int TB = kFwdTB;
   __shared__ __align__(128) int s_rows[2][TB * CTR_MAX_FIELDS];
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ ctr_field_desc s_fields[CTR_MAX_FIELDS];
+  __shared__ float s_bnd[kFwdMaxBnd];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -67,6 +108,10 @@ embed_fwd_kernel(const EmbedFwdParams p) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     mbar_fence_init();
+  }
+  if (RAW) {
+    for (int i = tid; i < F; i += blockDim.x) s_fields[i] = p.fields[i];
+    for (int i = tid; i < p.n_bnd; i += blockDim.x) s_bnd[i] = p.bnd[i];
   }
   __syncthreads();
 
@@ -88,13 +133,25 @@ embed_fwd_kernel(const EmbedFwdParams p) {
   uint32_t phase0 = 0, phase1 = 0;
   int buf = 0;
   int tile = blockIdx.x;
-  if (tile < ntiles) prefetch(tile, 0);
+  if (!RAW && tile < ntiles) prefetch(tile, 0);
 
   for (; tile < ntiles; tile += gridDim.x) {
     const int nxt = tile + gridDim.x;
-    if (nxt < ntiles) prefetch(nxt, buf ^ 1);
+    if (!RAW && nxt < ntiles) prefetch(nxt, buf ^ 1);
     const int b0 = tile * TB;
-    if (tile_bulk(tile)) {
+    if (RAW) {
+      // fused id stage: this tile's ids straight from the raw features into shared memory (and
+      // out to rows_out for the backward / optimiser) - no separate id kernel, no id round trip
+      const int n = min(TB, B - b0) * F;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const int bl = i / F, f = i - bl * F;
+        const int id = criteo_row_id(s_fields[f], s_bnd, p.xcont, p.n_cont, p.xcat, p.n_cat, b0 + bl,
+                                     p.logx, p.status);
+        s_rows[buf][i] = id;
+        p.rows_out[static_cast<size_t>(b0) * F + i] = id;
+      }
+      __syncthreads();
+    } else if (tile_bulk(tile)) {
       if (buf == 0) {
         mbar_wait(&s_bar[0], phase0);
         phase0 ^= 1;
@@ -567,24 +624,7 @@ __global__ void criteo_rows_kernel(const float* __restrict__ xcont, int n_cont,
     const int b = static_cast<int>(i / F);
     const int f = static_cast<int>(i % F);
     const ctr_field_desc fd = fields[f];
-    int id;
-    if (fd.kind == 0) {
-      // fm/fm.py:76-79: tf.log(x + off) in fp32, then Bucketize == upper_bound.
-      const float v = logf(xcont[static_cast<size_t>(b) * n_cont + fd.src] + fd.log_offset);
-      if (logx != nullptr) logx[static_cast<size_t>(b) * n_cont + fd.src] = v;
-      id = 0;
-      for (int k = 0; k < fd.bnd_count; ++k) id += (bnd[fd.bnd_begin + k] <= v) ? 1 : 0;
-      if (v != v) id = fd.bnd_count;
-    } else {
-      long long raw = xcat[static_cast<size_t>(b) * n_cat + fd.src];
-      if (raw < 0 || raw >= fd.n_rows) {
-        if (status != nullptr) atomicOr(status, 1);
-        raw %= fd.n_rows;
-        if (raw < 0) raw += fd.n_rows;
-      }
-      id = static_cast<int>(raw);
-    }
-    rows[i] = fd.row_offset + id;
+    rows[i] = criteo_row_id(fd, bnd, xcont, n_cont, xcat, n_cat, b, logx, status);
   }
 }
 
@@ -782,35 +822,65 @@ int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_c
   CTR_LAUNCH_CHECK("ctr_criteo_rows");
 }
 
-int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
-                  uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
-                  const float* cross_w, const float* cross_b, int cross_layers, float* xl,
-                  float* E_lo, int64_t row_stride, int64_t w1_stride, ctr_stream_t stream) {
+static int embed_fwd_impl(const char* fn, const float* table, const float* w1, const int32_t* rows,
+                          int B, int F, int D, uint64_t w1_fields, float* E, float* S, float* y1,
+                          float* y2, const float* cross_w, const float* cross_b, int cross_layers,
+                          float* xl, float* E_lo, int64_t row_stride, int64_t w1_stride,
+                          const EmbedFwdParams* raw, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
-  CTR_REQUIRE(table && rows, "ctr_embed_fwd", "null table/rows");
-  CTR_REQUIRE(E_lo == nullptr || (E != nullptr && aligned16(E_lo)), "ctr_embed_fwd",
+  CTR_REQUIRE(table && (rows || raw), fn, "null table/rows");
+  CTR_REQUIRE(E_lo == nullptr || (E != nullptr && aligned16(E_lo)), fn,
               "E_lo needs E and 16-byte alignment");
-  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_embed_fwd", "need 0 < F <= 64");
+  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, fn, "need 0 < F <= 64");
   CTR_REQUIRE(aligned16(table) && aligned16(rows) && aligned16(E) && aligned16(S) && aligned16(xl) &&
                   aligned16(cross_w) && aligned16(cross_b),
-              "ctr_embed_fwd", "pointers must be 16-byte aligned");
-  CTR_REQUIRE(y1 == nullptr || w1 != nullptr, "ctr_embed_fwd", "y1 requested without w1");
+              fn, "pointers must be 16-byte aligned");
+  CTR_REQUIRE(y1 == nullptr || w1 != nullptr, fn, "y1 requested without w1");
   if (row_stride <= 0) row_stride = D;
   if (w1_stride <= 0) w1_stride = 1;
-  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, "ctr_embed_fwd",
+  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, fn,
               "row_stride must be >= D and a multiple of 4 floats");
   const bool cross = xl != nullptr;
-  CTR_REQUIRE(!cross || (cross_w && cross_b && cross_layers >= 0), "ctr_embed_fwd",
+  CTR_REQUIRE(!cross || (cross_w && cross_b && cross_layers >= 0), fn,
               "xl requested without cross_w/cross_b");
   if (B == 0) return CTR_OK;
-  EmbedFwdParams p;
+  EmbedFwdParams p{};
+  if (raw != nullptr) p = *raw;
   p.table = table; p.w1 = w1; p.rows = rows; p.E = E; p.E_lo = E_lo; p.S = S; p.y1 = y1; p.y2 = y2;
   p.cross_w = cross_w; p.cross_b = cross_b; p.xl = xl; p.w1_fields = w1_fields;
   p.cross_layers = cross_layers; p.B = B; p.F = F; p.ld = row_stride; p.ld1 = w1_stride;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int r = cross ? dispatch_fwd<true>(p, D, st) : dispatch_fwd<false>(p, D, st);
   if (r != CTR_OK) return r;
-  CTR_LAUNCH_CHECK("ctr_embed_fwd");
+  return check_cuda(cudaGetLastError(), fn);
+}
+
+int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int B, int F, int D,
+                  uint64_t w1_fields, float* E, float* S, float* y1, float* y2,
+                  const float* cross_w, const float* cross_b, int cross_layers, float* xl,
+                  float* E_lo, int64_t row_stride, int64_t w1_stride, ctr_stream_t stream) {
+  return embed_fwd_impl("ctr_embed_fwd", table, w1, rows, B, F, D, w1_fields, E, S, y1, y2, cross_w,
+                        cross_b, cross_layers, xl, E_lo, row_stride, w1_stride, nullptr, stream);
+}
+
+int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, int n_cont,
+                      const int64_t* xcat, int n_cat, const ctr_field_desc* fields_dev,
+                      const float* boundaries_dev, int n_boundaries, int32_t* rows_out, float* logx,
+                      int32_t* status, int B, int F, int D, uint64_t w1_fields, float* E, float* S,
+                      float* y1, float* y2, const float* cross_w, const float* cross_b,
+                      int cross_layers, float* xl, float* E_lo, int64_t row_stride,
+                      int64_t w1_stride, ctr_stream_t stream) {
+  CTR_REQUIRE(fields_dev && rows_out, "ctr_embed_fwd_raw", "null fields/rows_out");
+  CTR_REQUIRE(n_cont == 0 || (xcont && boundaries_dev), "ctr_embed_fwd_raw", "null xcont/boundaries");
+  CTR_REQUIRE(n_cat == 0 || xcat, "ctr_embed_fwd_raw", "null xcat");
+  CTR_REQUIRE(n_boundaries >= 0 && n_boundaries <= kFwdMaxBnd, "ctr_embed_fwd_raw",
+              "at most 512 bucket boundaries in total");
+  EmbedFwdParams raw{};
+  raw.xcont = xcont; raw.xcat = reinterpret_cast<const long long*>(xcat); raw.fields = fields_dev;
+  raw.bnd = boundaries_dev; raw.rows_out = rows_out; raw.logx = logx; raw.status = status;
+  raw.n_cont = n_cont; raw.n_cat = n_cat; raw.n_bnd = n_boundaries;
+  return embed_fwd_impl("ctr_embed_fwd_raw", table, w1, nullptr, B, F, D, w1_fields, E, S, y1, y2,
+                        cross_w, cross_b, cross_layers, xl, E_lo, row_stride, w1_stride, &raw, stream);
 }
 
 int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const float* table,

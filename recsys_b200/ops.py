@@ -86,6 +86,7 @@ class IdPipeline:
         raw = bytes(descs)
         self.fields_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
         self.bnd_dev = torch.tensor(bnd if bnd else [0.0], dtype=torch.float32, device=device)
+        self.n_bnd = len(bnd)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.n_buckets_dev = torch.tensor(lay.rows, dtype=torch.int32, device=device)
         self.row_offset_dev = torch.tensor(lay.offsets[:-1], dtype=torch.int32, device=device)
@@ -328,6 +329,25 @@ class FieldEmbedding:
         return _EmbedFn.apply(self._anchor, self, rows, want_fm, want_y1 and self.with_w1,
                               cross_w, cross_b)
 
+    def lookup_features(self, idp: "IdPipeline", features, want_logx: bool = False, **kw):
+        """``lookup(idp(features))`` in ONE launch (ctr_embed_fwd_raw): the id pipeline runs as the
+        first stage of the lookup kernel.  -> (rows, logx or None, lookup outputs...)."""
+        if idp.n_bnd > 512 or os.environ.get("CTR_FUSED_IDS", "1") == "0":
+            r = idp(features, want_logx=want_logx)
+            rows, logx = r if want_logx else (r, None)
+            return (rows, logx) + tuple(self.lookup(rows, **kw))
+        cont, cat = idp.pack(features)
+        B = (cont if cont is not None else cat).shape[0]
+        rows = torch.empty((B, self.F), dtype=torch.int32, device=self.device)
+        logx = torch.empty((B, len(idp.cont_keys)), dtype=torch.float32, device=self.device) \
+            if want_logx else None
+        self._raw = (idp, cont, cat, logx)
+        try:
+            outs = self.lookup(rows, **kw)
+        finally:
+            self._raw = None
+        return (rows, logx) + tuple(outs)
+
     def zero_grad(self):
         self.dtable.zero_()
         if self.with_w1:
@@ -372,9 +392,17 @@ class _EmbedFn(torch.autograd.Function):
         L = cross_w.shape[0] if cross else 0
         E_lo = torch.empty_like(E) if getattr(emb, "_want_lo", False) else None
         emb.last_E_lo = E_lo
-        _call("ctr_embed_fwd", _p(emb.table), _p(emb.w1), _p(rows), B, F, D, emb.w1_fields, _p(E),
-              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld, emb.ld1,
-              _stream())
+        raw = getattr(emb, "_raw", None)
+        if raw is not None:       # id pipeline fused in front: fills ``rows`` (and logx) as well
+            idp, cont, cat, logx = raw
+            _call("ctr_embed_fwd_raw", _p(emb.table), _p(emb.w1), _p(cont), len(idp.cont_keys),
+                  _p(cat), len(idp.cat_keys), _p(idp.fields_dev), _p(idp.bnd_dev), idp.n_bnd,
+                  _p(rows), _p(logx), _p(idp.status), B, F, D, emb.w1_fields, _p(E), _p(S), _p(y1),
+                  _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld, emb.ld1, _stream())
+        else:
+            _call("ctr_embed_fwd", _p(emb.table), _p(emb.w1), _p(rows), B, F, D, emb.w1_fields, _p(E),
+                  _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld,
+                  emb.ld1, _stream())
         ctx.emb, ctx.rows, ctx.E, ctx.S = emb, rows, E, S
         ctx.cross_w, ctx.cross_b = cross_w, cross_b
         ctx.flags = (want_fm, want_y1, cross)

@@ -59,6 +59,31 @@ def test_criteo_rows_bit_exact(cuda, B):
     assert int(pipe.status.item()) == 0
 
 
+@pytest.mark.parametrize("B", [1, 7, 256, 4099])
+@pytest.mark.parametrize("record", [True, False])
+def test_fused_ids_and_lookup_equal_the_two_launch_path(cuda, B, record):
+    """ctr_embed_fwd_raw (id pipeline as the first stage of the lookup kernel) against
+    ctr_criteo_rows + ctr_embed_fwd: identical ids, logx and lookup outputs, bit for bit."""
+    ops = _ops()
+    lay, _ = _criteo_layout()
+    spec = criteo.CriteoSpec()
+    feats, _ = criteo.synthetic_features(B, seed=B + 1, spec=spec, dist="zipf")
+    tf = _to_torch_features(feats)
+    pipe = ops.IdPipeline(lay, cuda)
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=(1 << 39) - 1, record=record)
+    with torch.no_grad():
+        rows_a, logx_a = pipe(tf, want_logx=True)
+        Ea, y1a, y2a, _ = emb.lookup(rows_a, want_lo=True)
+        Elo_a = emb.last_E_lo
+        rows_b, logx_b, Eb, y1b, y2b, _ = emb.lookup_features(pipe, tf, want_logx=True, want_lo=True)
+        Elo_b = emb.last_E_lo
+    torch.cuda.synchronize()
+    assert torch.equal(rows_a, rows_b) and torch.equal(logx_a, logx_b)
+    assert torch.equal(Ea, Eb) and torch.equal(y1a, y1b) and torch.equal(y2a, y2b)
+    assert torch.equal(Elo_a, Elo_b)
+    assert int(pipe.status.item()) == 0
+
+
 def test_criteo_rows_real_shard_strings(cuda):
     """Raw byte strings (b'NULL' default included) hashed on the device == oracle == fixture."""
     ops = _ops()
