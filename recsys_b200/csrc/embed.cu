@@ -355,7 +355,10 @@ template <int D>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) {
   constexpr int LPR = D / 4;
   constexpr int RPW = 32 / LPR;
-  constexpr int J = kTinyRows / RPW;  // one-hot accumulators per lane
+  constexpr int J = kTinyRows / RPW;  // rows per lane group in the tiny-field flush
+  constexpr int PT = D + 4;           // pitch of the tiny-field tile (floats): conflict-free float4 rows
+  __shared__ __align__(16) float s_tiny[8 * kTinyRows * PT];
+  __shared__ float s_tinyw[8 * kTinyRows];
   const int lane = threadIdx.x & 31;
   const int r = lane / LPR;
   const int q = lane % LPR;
@@ -372,14 +375,6 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
     const int nrow = p.off[f + 1] - off;
     const bool tiny = nrow <= kTinyRows;
     const bool has_w1 = p.dw1 != nullptr && p.dy1 != nullptr && ((p.w1_fields >> f) & 1ull);
-
-    float4 acc[J];
-    float accw[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      acc[j] = f4_zero();
-      accw[j] = 0.f;
-    }
 
     // gradient of one (sample, field) slot: g = dE + dy2 * (S - E)   (fm/fm.py:123-129)
     auto slot_grad = [&](int b, int rid, float4& g, float& gw) {
@@ -428,7 +423,18 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
       continue;
     }
 
-    // tiny field: one-hot accumulation in registers; loads batched TU slots deep
+    // Tiny field (<= 32 rows: the 13 bucketised numerics, the small hashed fields): the chunk's
+    // gradients are summed per row in a warp-private shared-memory tile and flushed with <= 32
+    // vector REDs.  A slot adds its float4 with a plain read-modify-write; slots of one warp
+    // instruction that hit the same row take turns (rank within their __match_any group), so a
+    // field that puts every sample in one row (_c5) costs 8 rounds and an all-distinct
+    // one a single round.  (The earlier register one-hot form broadcast every slot to every lane:
+    // 30 instructions per slot, 44 % of the kernel's issue slots.)
+    float* sacc = &s_tiny[(threadIdx.x >> 5) * kTinyRows * PT];
+    float* saccw = &s_tinyw[(threadIdx.x >> 5) * kTinyRows];
+    for (int i = lane; i < kTinyRows * PT / 4; i += 32) reinterpret_cast<float4*>(sacc)[i] = f4_zero();
+    saccw[lane] = 0.f;
+    __syncwarp();
     constexpr int TU = 4;
     for (int bb = b_begin; bb < b_end; bb += RPW * TU) {
       int lid[TU];
@@ -444,22 +450,22 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
         g[u] = f4_zero();
         gw[u] = 0.f;
         if (lid[u] >= 0) slot_grad(bb + u * RPW + r, lid[u], g[u], gw[u]);
-        lid[u] = lid[u] >= 0 ? lid[u] - off : -1;   // negative for inactive lanes: never matches
+        lid[u] = lid[u] >= 0 ? lid[u] - off : -1;
       }
 #pragma unroll
       for (int u = 0; u < TU; ++u) {
-#pragma unroll
-        for (int t = 0; t < RPW; ++t) {
-          const float4 gt = f4_shfl(g[u], t * LPR + q);
-          const int idt = __shfl_sync(0xffffffffu, lid[u], t * LPR);
-          const float gwt = __shfl_sync(0xffffffffu, gw[u], t * LPR);
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            if (idt == r + RPW * j) {
-              acc[j] = f4_add(acc[j], gt);
-              accw[j] += gwt;
-            }
+        const bool live = lid[u] >= 0 && lid[u] < kTinyRows;
+        const unsigned peers = __match_any_sync(0xffffffffu, live ? lid[u] : -1 - r);
+        // slots with the same row before mine (each slot is LPR lanes)
+        const int rank = live ? __popc(peers & ((1u << (lane - q)) - 1u)) / LPR : 0;
+        const int rounds = __reduce_max_sync(0xffffffffu, rank) + 1;
+        for (int k = 0; k < rounds; ++k) {
+          if (live && rank == k) {
+            float4* dst = reinterpret_cast<float4*>(&sacc[lid[u] * PT + q * 4]);
+            *dst = f4_add(*dst, g[u]);
+            if (q == 0) saccw[lid[u]] += gw[u];
           }
+          __syncwarp();
         }
       }
     }
@@ -467,10 +473,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
     for (int j = 0; j < J; ++j) {
       const int lr = r + RPW * j;
       if (lr < nrow) {
-        red_add_v4(p.dtable + static_cast<size_t>(off + lr) * p.ld + q * 4, acc[j]);
-        if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(off + lr) * p.ld1, accw[j]);
+        red_add_v4(p.dtable + static_cast<size_t>(off + lr) * p.ld + q * 4,
+                   *reinterpret_cast<const float4*>(&sacc[lr * PT + q * 4]));
+        if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(off + lr) * p.ld1, saccw[lr]);
       }
     }
+    __syncwarp();
   }
 }
 
