@@ -65,7 +65,39 @@ class TorchShardOps:
         return gsend, gw1
 
 
-def _worker(rank, world, port, q):
+class TorchPackedShardOps(TorchShardOps):
+    """Doubles for the packed exchange (one [D+4] slab record = row | w1 | pad per lookup, and
+    the same for the gradients): the 3-all-to-all path that CudaShardOps takes."""
+    packed = True
+
+    def gather_packed(self, table, w1, ids):
+        D = table.shape[1]
+        vec, w1v = self.gather(table, w1, ids)
+        slab = torch.zeros(ids.numel(), D + 4)
+        slab[:, :D] = vec
+        if w1v is not None:
+            slab[:, D] = w1v
+        return slab
+
+    def scatter_add_packed(self, ids, gslab, D, dtable, dw1):
+        self.scatter_add(ids, gslab[:, :D].contiguous(), gslab[:, D].contiguous(), dtable, dw1)
+
+    def interact_fwd_packed(self, slab, slot2d, D, w1_fields, want_fm, want_y1, cross_w, cross_b,
+                            want_lo=False):
+        E, S, y1, y2, xl = self.interact_fwd(slab[:, :D], slab[:, D], slot2d, D, w1_fields, want_fm,
+                                             want_y1, cross_w, cross_b)
+        return E, S, y1, y2, xl, None
+
+    def interact_bwd_packed(self, slot2d, dE, E, slab, S, dy2, dy1, w1_fields, D, n_slots):
+        gsend, gw1 = self.interact_bwd(slot2d, dE, E, slab[:, :D], S, dy2, dy1, w1_fields, D, n_slots)
+        gslab = torch.zeros(n_slots, D + 4)
+        gslab[:, :D] = gsend
+        if gw1 is not None:
+            gslab[:, D] = gw1
+        return gslab
+
+
+def _worker(rank, world, port, q, packed=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -81,7 +113,8 @@ def _worker(rank, world, port, q):
         full_table = torch.randn(R, D, generator=g)
         full_w1 = torch.randn(R, generator=g)
         emb = sharded.ShardedFieldEmbedding(lay, torch.device("cpu"), with_w1=True, w1_fields=0b1011,
-                                            shard_ops=TorchShardOps(), capacity=34 * len(nrows))
+                                            shard_ops=TorchPackedShardOps() if packed else TorchShardOps(),
+                                            capacity=34 * len(nrows))
         emb.load(full_table, full_w1)
         assert emb.table.shape[0] == (R - rank + world - 1) // world
         B = 33 + rank                                   # ragged: ranks hold different batch sizes
@@ -126,11 +159,11 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_exchange_world2():
+def test_sharded_exchange_world2(packed=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 300 + (300 if packed else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, packed)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
@@ -147,3 +180,8 @@ def test_slab_capacity_and_overflow_flag():
     rows = torch.zeros(10, dtype=torch.int32)          # every lookup goes to owner 0
     send, slot, counts = ops.bucket(rows, 2, 4)
     assert counts.tolist() == [10, 0] and (slot[4:] == -1).all() and (send[4:] == -1).all()
+
+
+def test_sharded_packed_exchange_world2():
+    """The packed-slab routing (3 all-to-alls per step: ids, row|w1 slab, gradient slab)."""
+    test_sharded_exchange_world2(packed=True)
