@@ -623,6 +623,7 @@ class FusedTower:
         self.barrier = torch.zeros(320, dtype=torch.int32, device=dense.flat.device)   # CTR_TOWER_MID_BARRIER_WORDS
         self.timing = None      # set to an int64[8] device tensor to get the phase time stamps
         self.last_acts = None
+        self.last_y = None
         self.mid_ok = (out_layer and 1 <= len(self.sizes) - 1 <= 4
                        and all(4 <= h <= 128 and h % 4 == 0 for h in self.sizes[1:]))
 
@@ -884,6 +885,7 @@ class _TowerHeadFn(torch.autograd.Function):
         _call("ctr_tower_mid", C.byref(a), B, _stream())
         ctx.tw, ctx.training = tw, training
         tw.last_acts = acts          # post-ReLU hidden activations of the latest call (tests)
+        tw.last_y = y                # and the tower's output relu(h . w_out + b_out)
         ctx.saved = (X, acts, stats, dpre, dzs, dn, zs, labels, ws, X_lo, dpre0_lo)
         ctx.mark_non_differentiable(logits, prob)
         return loss, logits, prob

@@ -34,7 +34,7 @@ def run(B, sizes, nz, p):
     zs64 = [z.detach().double().requires_grad_(True) for z in zs]
     loss, logits, prob = ops.tower_head(tw, X, zs, labels, training=True)
     torch.cuda.synchronize()
-    gates = [(a > 0).double() for a in tw.last_acts]
+    gates = [(a > 0).double() for a in tw.last_acts] + [(tw.last_y > 0).double()]
     loss64, logit64 = T._tower_head_ref(P64, X64, zs64, labels.double(), sizes, masks, p, True, gates)
     loss64.backward(); loss.backward(); tw.join(); torch.cuda.synchronize()
     def rep(name, got, want):

@@ -150,7 +150,7 @@ def _tower_head_ref(P, X, zs, labels, sizes, masks, p, training, gates=None):
     h = X
     for l in range(len(sizes) - 1):
         pre = h @ P["t.%d.w" % l] + P["t.%d.b" % l]
-        a = torch.relu(pre) if gates is None else pre * gates[l]
+        a = torch.relu(pre) if gates is None else pre * gates[l]      # gates[-1]: the output ReLU
         if training:
             mu, var = a.mean(0), a.var(0, unbiased=False)
         else:
@@ -158,7 +158,8 @@ def _tower_head_ref(P, X, zs, labels, sizes, masks, p, training, gates=None):
         h = (a - mu) / torch.sqrt(var + 1e-3) * P["t.%d.bn.gamma" % l] + P["t.%d.bn.beta" % l]
         if training and p > 0:
             h = h * masks[l] / (1 - p)
-    y = torch.relu(h @ P["t.out.w"] + P["t.out.b"]).reshape(-1)
+    pre_y = (h @ P["t.out.w"] + P["t.out.b"]).reshape(-1)
+    y = torch.relu(pre_y) if gates is None else pre_y * gates[-1]
     cols = [torch.relu(zs[0] + P["b1"])] + list(zs[1:]) + [y]
     logit = torch.stack(cols, 1) @ P["head.w"].reshape(-1) + P["head.b"]
     loss = (torch.clamp(logit, min=0) - logit * labels + torch.log1p(torch.exp(-logit.abs()))).mean()
@@ -202,7 +203,8 @@ def test_tower_mid_matches_float64(cuda, B, sizes, nz, p, presplit):
         X_lo = ops.split_lo(X.detach()) if presplit else None   # first-layer GEMMs on pre-split operands
         loss, logits, prob = ops.tower_head(tw, X, zs, labels, training=training, X_lo=X_lo)
         torch.cuda.synchronize()
-        gates = [(a > 0).double() for a in tw.last_acts] if training else None
+        gates = [(a > 0).double() for a in tw.last_acts] + [(tw.last_y > 0).double()] \
+            if training else None
         loss64, logit64 = _tower_head_ref(P64, X64, zs64, labels.double(), sizes, masks, p, training,
                                           gates)
         _close(logits, logit64.detach(), 1e-4)
