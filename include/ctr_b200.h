@@ -91,14 +91,16 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
 
 /* Same, with the id pipeline of ctr_criteo_rows fused in front (one launch instead of two): every
  * CTA computes the row ids of its sample tile from the raw features straight into shared memory
- * and writes them to rows_out [B,F] for the backward / optimiser.  boundaries: n_boundaries <= 512. */
+ * and writes them to rows_out [B,F] for the backward / optimiser.  boundaries: n_boundaries <= 512.
+ * zero_buf (nullable) / zero_n floats: a buffer the launch clears on the side (the tower's
+ * per-step accumulators: BN column sums, loss, split-K target), sparing the step a memset. */
 int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, int n_cont,
                       const int64_t* xcat, int n_cat, const ctr_field_desc* fields_dev,
                       const float* boundaries_dev, int n_boundaries, int32_t* rows_out, float* logx,
                       int32_t* status, int B, int F, int D, uint64_t w1_fields, float* E, float* S,
                       float* y1, float* y2, const float* cross_w, const float* cross_b,
                       int cross_layers, float* xl, float* E_lo, int64_t row_stride,
-                      int64_t w1_stride, ctr_stream_t stream);
+                      int64_t w1_stride, float* zero_buf, int64_t zero_n, ctr_stream_t stream);
 
 /* Backward: scatter-add of the row gradients into dtable / dw1 (the IndexedSlices
  * gradient of the gathers, fm/fm.py:162-163), field-major, contention-free for
@@ -122,15 +124,19 @@ int ctr_dcn_cross_bwd(const float* x0, const float* w, const float* b, int L, in
 /* ------------------------------------------------------------------ optimiser
  * tf.train.AdamOptimizer semantics (fm/fm.py:162): eps outside the sqrt,
  *   lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t).
- * The schedule can live on the device so that a captured CUDA graph advances it on
- * replay: state_dev = float[2] {t, lr_t}; ctr_adam_tick does t += 1 and recomputes lr_t.
- * When state_dev is non-null the kernels read lr_t (and the claim tag = t) from it and
- * ignore the by-value arguments.
+ * The schedule can live on the device so that a captured CUDA graph advances it on replay:
+ * state_dev = float[4] {t = optimiser steps completed, lr_t of the step in progress (step t+1),
+ * lr, block counter}.  When state_dev is non-null the kernels of a step read lr_t (and the claim
+ * tag = t+1) from it and ignore the by-value arguments; the step's LAST optimiser launch -
+ * ctr_adam_dense with advance_state != 0 - moves the schedule on (its last block to finish does
+ * t += 1 and recomputes lr_t), so advancing costs no launch.  ctr_adam_tick(state, lr, ...) sets lr
+ * and advances once: from {-1,0,0,0} it initialises the schedule at t = 0; it is also the way to
+ * advance for a caller whose step does not end with ctr_adam_dense.
  * ctr_adam_dense: every element (TF's sparse apply decays m, v of every row [TF-sem]).
  * g is zeroed afterwards when zero_g != 0. */
 int ctr_adam_tick(float* state_dev, float lr, float beta1, float beta2, ctr_stream_t stream);
 int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
-                   float beta2, float eps, int zero_g, const float* state_dev,
+                   float beta2, float eps, int zero_g, float* state_dev, int advance_state,
                    ctr_stream_t stream);
 /* Lazy variant: exactly one update per distinct row in rows[n] (claim[R] int32
  * scratch, tag must differ from the previous call's), then zeroes the row of g.  Negative

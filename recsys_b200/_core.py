@@ -215,14 +215,25 @@ class _CriteoBase(_ModelBase):
         super().load_state(state)
         self.emb.load(state.get("emb"), state.get("w1"))
 
-    def _lookup(self, features, want_logx=False, **kw):
+    @staticmethod
+    def _batch_size(features):
+        if isinstance(features, ops.PackedFeatures):
+            t = features.cat if features.cat is not None else features.cont
+            return int(t.shape[0])
+        return int(torch.as_tensor(next(iter(features.values()))).shape[0])
+
+    def _lookup(self, features, want_logx=False, zero_buf=None, **kw):
         """ids + fused lookup.  One launch (ctr_embed_fwd_raw) for the unsharded table; the sharded
-        table needs the ids on their own (they are bucketed by owner first).
+        table needs the ids on their own (they are bucketed by owner first).  ``zero_buf``: a
+        buffer to clear on the way (the tower's per-step accumulators).
         -> (logx or None, lookup outputs...); sets ``self.rows``."""
         if self.world == 1 and hasattr(self.emb, "lookup_features"):
-            out = self.emb.lookup_features(self.ids, features, want_logx=want_logx, **kw)
+            out = self.emb.lookup_features(self.ids, features, want_logx=want_logx,
+                                           zero_buf=zero_buf, **kw)
             self.rows = out[0]
             return out[1:]
+        if zero_buf is not None:
+            zero_buf.zero_()
         r = self.ids(features, want_logx=want_logx)
         self.rows, logx = r if want_logx else (r, None)
         return (logx,) + tuple(self.emb.lookup(self.rows, **kw))
@@ -322,9 +333,9 @@ class DeepFMModel(_CriteoBase):
     def forward(self, features, labels, training):
         if not self.fused:
             return super().forward(features, labels, training)
-        self.tower.begin_step()
         lo = self.tower.use_presplit and (self.world == 1 or getattr(self.emb.ops, "packed", False))
-        _, E, y1s, y2, _ = self._lookup(features, want_fm=True, want_y1=True,
+        ws = self.tower.begin_step(self._batch_size(features), expect_lo=lo)
+        _, E, y1s, y2, _ = self._lookup(features, zero_buf=ws, want_fm=True, want_y1=True,
                                         **({"want_lo": True} if lo else {}))
         return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),
                                 X_lo=self.emb.last_E_lo if lo else None)      # :91,100-129
@@ -429,15 +440,16 @@ class XDeepFMModel(_CriteoBase):
         if not self.fused:
             return super().forward(features, labels, training)
         P = self.dense
-        self.tower.begin_step()
+        lo = self.tower.use_presplit and self.world == 1 and self.emb_dnn is not None
+        ws = self.tower.begin_step(self._batch_size(features), expect_lo=lo)
         want_num = len(self.numeric_linear) > 0
-        logx, E, y1s, _, _ = self._lookup(features, want_logx=want_num, want_fm=False, want_y1=True)
+        logx, E, y1s, _, _ = self._lookup(features, want_logx=want_num, zero_buf=ws, want_fm=False,
+                                          want_y1=True)
         lin = y1s + logx @ P["wnum"] if want_num else y1s                        # :82
         Ws = [P[f"cin.{k}.w"] for k in range(len(self.cin_layers))]
         bs = [P[f"cin.{k}.b"] for k in range(len(self.cin_layers))]
         pooled = ops.cin(E, self.F, self.D, Ws, bs, self.cin_precision)          # :135-181
         cin_y = torch.relu(torch.addmm(P["cin.out.b"], pooled, P["cin.out.w"])).view(-1)  # :182
-        lo = self.tower.use_presplit and self.world == 1 and self.emb_dnn is not None
         if self.emb_dnn is not None:
             Ed = self.emb_dnn.lookup(self.rows, want_fm=False, want_y1=False,
                                      **({"want_lo": True} if lo else {}))[0]       # :185

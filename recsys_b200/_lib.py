@@ -77,13 +77,14 @@ SIGNATURES = {
     "ctr_embed_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i,
                             c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_embed_fwd_raw": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i,
-                                c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i64, c_i64, c_f]),
+                                c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i64, c_i64, c_f, c_i64,
+                                c_f]),
     "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
                             c_i, c_i, c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_dcn_cross_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f]),
     "ctr_dcn_cross_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "ctr_adam_tick": (c_i, [c_f, c_fl, c_fl, c_fl, c_f]),
-    "ctr_adam_dense": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_i, c_f, c_f]),
+    "ctr_adam_dense": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_i, c_f, c_i, c_f]),
     "ctr_adam_rows": (c_i, [c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                             C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_f]),
     "ctr_din_att_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,

@@ -68,6 +68,8 @@ struct EmbedFwdParams {
   int* rows_out;
   float* logx;
   int* status;
+  float* zero_buf;        // nullable: a buffer this launch also clears (the tower's per-step sums)
+  long long zero_n4;      // its length in float4
   int n_cont, n_cat, n_bnd;
   long long ld;     // floats between consecutive table rows (D: planar table; 4D+4: row records)
   long long ld1;    // floats between consecutive first-order weights (1 or the record stride)
@@ -112,6 +114,10 @@ embed_fwd_kernel(const EmbedFwdParams p) {
   if (RAW) {
     for (int i = tid; i < F; i += blockDim.x) s_fields[i] = p.fields[i];
     for (int i = tid; i < p.n_bnd; i += blockDim.x) s_bnd[i] = p.bnd[i];
+    if (p.zero_buf != nullptr)
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + tid; i < p.zero_n4;
+           i += static_cast<long long>(gridDim.x) * blockDim.x)
+        reinterpret_cast<float4*>(p.zero_buf)[i] = f4_zero();
   }
   __syncthreads();
 
@@ -637,20 +643,29 @@ __global__ void criteo_rows_kernel(const float* __restrict__ xcont, int n_cont,
 }
 
 // ----------------------------------------------------------------------- Adam
-// state (nullable, device): [0] = step count t (as float), [1] = lr_t; written by
-// adam_tick_kernel so that a captured CUDA graph advances the schedule on replay.
+// Device-side Adam schedule (nullable `state`, 4 floats) so that a captured CUDA graph advances it
+// on replay:  [0] = t, optimiser steps completed so far;  [1] = lr_t of the step in progress
+// (step t+1: lr * sqrt(1 - b2^(t+1)) / (1 - b1^(t+1)));  [2] = lr;  [3] = block counter (as u32).
+// The kernels of step t+1 read tag = t+1 and lr_t = [1]; the LAST optimiser kernel of the step
+// (ctr_adam_dense with advance_state) moves the schedule on, so no launch is spent on it.
+__device__ __forceinline__ void adam_advance(float* __restrict__ state, float b1, float b2) {
+  const float t = state[0] + 1.f;
+  const float tn = t + 1.f;
+  state[0] = t;
+  state[1] = state[2] * sqrtf(1.f - powf(b2, tn)) / (1.f - powf(b1, tn));
+}
+// ctr_adam_tick: set lr and advance once (from t = -1 this initialises the schedule at t = 0).
 __global__ void adam_tick_kernel(float* __restrict__ state, float lr, float b1, float b2) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const float t = state[0] + 1.f;
-    state[0] = t;
-    state[1] = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+    state[2] = lr;
+    adam_advance(state, b1, b2);
   }
 }
 
 __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
                                   float* __restrict__ v, float* __restrict__ g, long long n,
                                   float lr_t, float b1, float b2, float eps, int zero_g,
-                                  const float* __restrict__ state) {
+                                  float* __restrict__ state, int advance) {
   if (state != nullptr) lr_t = state[1];
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -680,6 +695,18 @@ __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
     th[i] -= lr_t * M / (sqrtf(V) + eps);
     if (zero_g) g[i] = 0.f;
   }
+  if (advance && state != nullptr) {
+    // every block read lr_t when it started; the last one to finish moves the schedule on
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* cnt = reinterpret_cast<unsigned*>(state + 3);
+      __threadfence();
+      if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+        *cnt = 0u;
+        adam_advance(state, b1, b2);
+      }
+    }
+  }
 }
 
 // One group of LPR lanes per lookup; the first group to tag claim[row] this step
@@ -695,7 +722,7 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
                  float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
                  float b2, float eps, const float* __restrict__ state, long long ld, long long ld1, long long ldc) {
   if (state != nullptr) {
-    tag = static_cast<int>(state[0]);
+    tag = static_cast<int>(state[0]) + 1;      // the step in progress
     lr_t = state[1];
   }
   constexpr int LPR = D >= 4 ? D / 4 : 1;
@@ -877,8 +904,10 @@ int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, i
                       int32_t* status, int B, int F, int D, uint64_t w1_fields, float* E, float* S,
                       float* y1, float* y2, const float* cross_w, const float* cross_b,
                       int cross_layers, float* xl, float* E_lo, int64_t row_stride,
-                      int64_t w1_stride, ctr_stream_t stream) {
+                      int64_t w1_stride, float* zero_buf, int64_t zero_n, ctr_stream_t stream) {
   CTR_REQUIRE(fields_dev && rows_out, "ctr_embed_fwd_raw", "null fields/rows_out");
+  CTR_REQUIRE(zero_buf == nullptr || (aligned16(zero_buf) && zero_n >= 0 && (zero_n & 3) == 0),
+              "ctr_embed_fwd_raw", "zero_buf must be 16-byte aligned, zero_n a multiple of 4");
   CTR_REQUIRE(n_cont == 0 || (xcont && boundaries_dev), "ctr_embed_fwd_raw", "null xcont/boundaries");
   CTR_REQUIRE(n_cat == 0 || xcat, "ctr_embed_fwd_raw", "null xcat");
   CTR_REQUIRE(n_boundaries >= 0 && n_boundaries <= kFwdMaxBnd, "ctr_embed_fwd_raw",
@@ -887,6 +916,7 @@ int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, i
   raw.xcont = xcont; raw.xcat = reinterpret_cast<const long long*>(xcat); raw.fields = fields_dev;
   raw.bnd = boundaries_dev; raw.rows_out = rows_out; raw.logx = logx; raw.status = status;
   raw.n_cont = n_cont; raw.n_cat = n_cat; raw.n_bnd = n_boundaries;
+  raw.zero_buf = zero_n > 0 ? zero_buf : nullptr; raw.zero_n4 = zero_n >> 2;
   return embed_fwd_impl("ctr_embed_fwd_raw", table, w1, nullptr, B, F, D, w1_fields, E, S, y1, y2,
                         cross_w, cross_b, cross_layers, xl, E_lo, row_stride, w1_stride, &raw, stream);
 }
@@ -977,7 +1007,7 @@ int ctr_adam_tick(float* state_dev, float lr, float beta1, float beta2, ctr_stre
 }
 
 int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
-                   float beta2, float eps, int zero_g, const float* state_dev,
+                   float beta2, float eps, int zero_g, float* state_dev, int advance_state,
                    ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(theta && m && v && g && n >= 0, "ctr_adam_dense", "null pointer / negative n");
@@ -986,7 +1016,7 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
   if (n == 0) return CTR_OK;
   const int grid = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, sm_count() * 8LL));
   adam_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g, state_dev);
+      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g, state_dev, advance_state);
   CTR_LAUNCH_CHECK("ctr_adam_dense");
 }
 

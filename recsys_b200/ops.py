@@ -157,20 +157,35 @@ def hash_strings(strings: Sequence[bytes], n_buckets: int, device) -> torch.Tens
 # ---------------------------------------------------------------- Adam (TF rule)
 class TFAdamState:
     """Step counter + lr_t of tf.train.AdamOptimizer (fm/fm.py:162):
-    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), eps outside the sqrt.  The schedule
-    lives on the device ({t, lr_t}, advanced by ctr_adam_tick) so a captured CUDA
-    graph of the train step stays correct on replay."""
+    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), eps outside the sqrt.  The schedule lives on the
+    device (``state`` = {t completed, lr_t of the step in progress, lr, counter}; see
+    include/ctr_b200.h "optimiser") so a captured CUDA graph of the train step stays correct on
+    replay.  It is advanced by the step's last optimiser launch (``DenseParams.adam_step``); a
+    caller whose step has no dense parameters calls ``advance()`` itself."""
 
     def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, device=None):
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.t = 0
-        self.state = torch.zeros(2, dtype=torch.float32, device=device) if device is not None \
-            else None
+        self.state = None
+        if device is not None:
+            self.state = torch.zeros(4, dtype=torch.float32, device=device)
+            self.reset()
 
-    def next_lr_t(self) -> float:
-        self.t += 1
+    def reset(self):
+        """Back to t = 0 (tests; re-initialises the device schedule)."""
+        self.t = 0
+        if self.state is not None:
+            self.state.copy_(torch.tensor([-1.0, 0.0, 0.0, 0.0]))
+            self.advance()
+
+    def advance(self):
         if self.state is not None:
             _call("ctr_adam_tick", _p(self.state), self.lr, self.beta1, self.beta2, _stream())
+
+    def next_lr_t(self) -> float:
+        """Host-side lr_t of the step that starts now (the device copy needs no launch: it was
+        prepared when the previous step's optimiser finished)."""
+        self.t += 1
         return self.lr * math.sqrt(1 - self.beta2 ** self.t) / (1 - self.beta1 ** self.t)
 
     @property
@@ -231,7 +246,7 @@ class DenseParams:
         """One launch over the flat buffer; frozen slots have zero gradient and
         zero moments, so the rule leaves them untouched."""
         _call("ctr_adam_dense", _p(self.flat), _p(self.m), _p(self.v), _p(self.grad), self.numel,
-              lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
+              lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, 1, _stream())   # ends the step
 
 
 # ------------------------------------------------------- fused multi-field lookup
@@ -329,10 +344,14 @@ class FieldEmbedding:
         return _EmbedFn.apply(self._anchor, self, rows, want_fm, want_y1 and self.with_w1,
                               cross_w, cross_b)
 
-    def lookup_features(self, idp: "IdPipeline", features, want_logx: bool = False, **kw):
+    def lookup_features(self, idp: "IdPipeline", features, want_logx: bool = False,
+                        zero_buf: Optional[torch.Tensor] = None, **kw):
         """``lookup(idp(features))`` in ONE launch (ctr_embed_fwd_raw): the id pipeline runs as the
-        first stage of the lookup kernel.  -> (rows, logx or None, lookup outputs...)."""
+        first stage of the lookup kernel, which also clears ``zero_buf`` (the tower's per-step
+        accumulators) on the side.  -> (rows, logx or None, lookup outputs...)."""
         if idp.n_bnd > 512 or os.environ.get("CTR_FUSED_IDS", "1") == "0":
+            if zero_buf is not None:
+                zero_buf.zero_()
             r = idp(features, want_logx=want_logx)
             rows, logx = r if want_logx else (r, None)
             return (rows, logx) + tuple(self.lookup(rows, **kw))
@@ -341,7 +360,7 @@ class FieldEmbedding:
         rows = torch.empty((B, self.F), dtype=torch.int32, device=self.device)
         logx = torch.empty((B, len(idp.cont_keys)), dtype=torch.float32, device=self.device) \
             if want_logx else None
-        self._raw = (idp, cont, cat, logx)
+        self._raw = (idp, cont, cat, logx, zero_buf)
         try:
             outs = self.lookup(rows, **kw)
         finally:
@@ -359,10 +378,10 @@ class FieldEmbedding:
         self._ensure_adam()
         if self.adam_mode == "exact_tf":
             _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
-                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
+                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, 0, _stream())
             if self.with_w1:
                 _call("ctr_adam_dense", _p(self.w1), _p(self._m1), _p(self._v1), _p(self.dw1),
-                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr,
+                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, 0,
                       _stream())
             return
         self._tag += 1
@@ -394,11 +413,12 @@ class _EmbedFn(torch.autograd.Function):
         emb.last_E_lo = E_lo
         raw = getattr(emb, "_raw", None)
         if raw is not None:       # id pipeline fused in front: fills ``rows`` (and logx) as well
-            idp, cont, cat, logx = raw
+            idp, cont, cat, logx, zbuf = raw
             _call("ctr_embed_fwd_raw", _p(emb.table), _p(emb.w1), _p(cont), len(idp.cont_keys),
                   _p(cat), len(idp.cat_keys), _p(idp.fields_dev), _p(idp.bnd_dev), idp.n_bnd,
                   _p(rows), _p(logx), _p(idp.status), B, F, D, emb.w1_fields, _p(E), _p(S), _p(y1),
-                  _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld, emb.ld1, _stream())
+                  _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld, emb.ld1, _p(zbuf),
+                  zbuf.numel() if zbuf is not None else 0, _stream())
         else:
             _call("ctr_embed_fwd", _p(emb.table), _p(emb.w1), _p(rows), B, F, D, emb.w1_fields, _p(E),
                   _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), L, _p(xl), _p(E_lo), emb.ld,
@@ -631,6 +651,7 @@ class FusedTower:
         self.w0_lo = torch.zeros(self.sizes[0] * self.sizes[1], dtype=torch.float32,
                                  device=dense.flat.device)
         self._w0_ready = None
+        self._ws = None
 
     @property
     def use_mid(self):
@@ -641,9 +662,32 @@ class FusedTower:
         return (self.use_mid and os.environ.get("CTR_TOWER_PRESPLIT", "1") != "0"
                 and self.sizes[0] % 4 == 0 and self.sizes[0] >= 32 and self.sizes[1] >= 16)
 
-    def begin_step(self):
-        """Start-of-step hook: split the first layer's weights into hi/lo on the side stream
-        (they only change in the optimiser), off the critical path of the id/lookup kernels."""
+    def ws_numel(self, B, splitk):
+        """Floats of the per-step workspace: BN column sums of every layer | loss (+3 pad) |
+        (split-K first GEMM) its [B, H0] accumulation target."""
+        return 2 * sum(self.sizes[1:]) + 4 + (B * self.sizes[1] if splitk else 0)
+
+    def splitk_for(self, B, have_lo):
+        return bool(have_lo) and self.use_presplit and B >= 256 and \
+            os.environ.get("CTR_TOWER_SPLITK", "1") != "0"
+
+    def begin_step(self, B=None, expect_lo=False):
+        """Start-of-step hook.  (1) Split the first layer's weights into hi/lo on the side stream
+        (they only change in the optimiser), off the critical path of the id/lookup kernels.
+        (2) With ``B``: allocate the step's workspace and return it, so that the caller can have
+        the lookup kernel clear it (``FieldEmbedding.lookup_features(zero_buf=...)``); the tower
+        then takes it as already zeroed."""
+        self._ws = None
+        ws = None
+        if B is not None and self.use_mid:
+            splitk = self.splitk_for(B, expect_lo)
+            ws = torch.empty(self.ws_numel(B, splitk), dtype=torch.float32,
+                             device=self.dense.flat.device)
+            self._ws = (ws, B, splitk)
+        self._begin_split()
+        return ws
+
+    def _begin_split(self):
         if not self.use_presplit:
             return
         main = torch.cuda.current_stream()
@@ -816,9 +860,14 @@ class _TowerHeadFn(torch.autograd.Function):
             offs.append(n)
             n += 2 * H
         presplit = X_lo is not None and tw.use_presplit and B >= 256
-        splitk = presplit and os.environ.get("CTR_TOWER_SPLITK", "1") != "0"
-        # (+ with the split-K first GEMM: its zero-initialised accumulation target)
-        ws = torch.zeros(n + 4 + (B * Hs[0] if splitk else 0), **f32)
+        splitk = tw.splitk_for(B, X_lo is not None)
+        # (+ with the split-K first GEMM: its zero-initialised accumulation target).  Taken from
+        # begin_step() when the lookup kernel has already cleared it, else one fill launch here.
+        pre, tw._ws = tw._ws, None
+        if pre is not None and pre[1] == B and pre[2] == splitk and pre[0].numel() == tw.ws_numel(B, splitk):
+            ws = pre[0]
+        else:
+            ws = torch.zeros(tw.ws_numel(B, splitk), **f32)
         stats = [ws[o:o + 2 * H].view(2, H) for o, H in zip(offs, Hs)]
         loss = ws[n:n + 1].view(())
         pre0 = ws[n + 4:].view(B, Hs[0]) if splitk else None

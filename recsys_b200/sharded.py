@@ -238,10 +238,10 @@ class ShardedFieldEmbedding:
                 self._m1, self._v1 = torch.zeros_like(self.w1), torch.zeros_like(self.w1)
         if self.adam_mode == "exact_tf":
             _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
-                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
+                  self.table.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, 0, _stream())
             if self.with_w1:
                 _call("ctr_adam_dense", _p(self.w1), _p(self._m1), _p(self._v1), _p(self.dw1),
-                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, _stream())
+                      self.w1.numel(), lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, 0, _stream())
             return
         self._tag += 1
         ids = self.recv_ids
@@ -377,6 +377,8 @@ def bench_main(args, rank, local, world):
         devb.append((PackedFeatures(cont.to(dev), cat.to(dev), [], keys), lab.to(dev)))
     from .estimator import GraphedTrainStep
     torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))   # one (high-priority) stream
+    sp = deepfm.model_fn(devb[0][0], devb[0][1], "train", params)      # creates the variables
+    sp.train_op()
     n0 = ops.LAUNCHES["n"]
     sp = deepfm.model_fn(devb[0][0], devb[0][1], "train", params)
     sp.train_op()

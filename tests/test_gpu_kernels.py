@@ -293,6 +293,7 @@ def test_adam_rows_and_dense_match_tf_rule(cuda):
             emb.dtable.copy_(g)
             emb.dw1.copy_(g1)
             emb.adam_step(rows, st.next_lr_t(), st)
+            st.advance()        # no dense parameters here: the caller moves the device schedule on
             lazy = {"emb": torch.from_numpy(rows_np).reshape(-1),
                     "w1": torch.from_numpy(rows_np).reshape(-1)} if mode == "lazy" else None
             opt.step(p, {"emb": g.double(), "w1": g1.double()}, lazy_rows=lazy)

@@ -298,8 +298,7 @@ def test_graphed_step_with_host_batches_follows_the_oracle(cuda):
         m.dense.m.zero_()
         m.dense.v.zero_()
         m.dense.grad.zero_()
-        m.adam.t = 0
-        m.adam.state.zero_()
+        m.adam.reset()
         m.load_state(p64)
         losses = torch.zeros(nsteps).pin_memory()
         for s in range(nsteps):
