@@ -52,3 +52,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the C ABI, as gcc lays them out from
+    include/ctr_b200.h, against the ctypes mirrors in recsys_b200/_lib.py."""
+    import subprocess
+    from recsys_b200 import _lib
+    checks = {
+        "ctr_field_desc": (_lib.FieldDesc, ["kind", "n_rows", "bnd_count", "log_offset"]),
+        "ctr_bn_drop": (_lib.BnDrop, ["sums", "gamma", "state", "eps", "seed", "enabled"]),
+        "ctr_grad_src": (_lib.GradSrc, ["G", "a", "dgamma", "ldg", "eps", "train"]),
+        "ctr_tower_mid_args": (_lib.TowerMidArgs, ["L", "H", "W", "act", "stats", "w_out", "eps", "seed",
+                                                   "grad_scale", "z", "labels", "loss", "dz", "dw_out",
+                                                   "dgamma", "dpre", "dpre0_lo", "pre0", "barrier",
+                                                   "timing"]),
+    }
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "ctr_b200.h"', "int main(void) {"]
+    for cname, (_, fields) in checks.items():
+        lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in fields:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(l.rsplit(" ", 1) for l in out.strip().splitlines())
+    for cname, (cls, fields) in checks.items():
+        assert int(got[cname + ".sizeof"]) == ctypes.sizeof(cls), cname
+        for f in fields:
+            assert int(got["%s.%s" % (cname, f)]) == getattr(cls, f).offset, (cname, f)
