@@ -84,3 +84,38 @@ def test_ctypes_structs_match_the_header(tmp_path):
         assert int(got[cname + ".sizeof"]) == ctypes.sizeof(cls), cname
         for f in fields:
             assert int(got["%s.%s" % (cname, f)]) == getattr(cls, f).offset, (cname, f)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/ctr_b200.h against recsys_b200/_lib.SIGNATURES: argument count
+    and, per argument, the ctypes class (pointer / int / int64 / uint64 / float) - a mismatch
+    here would corrupt the call frame silently."""
+    from recsys_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "ctr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char\s*\*)\s+(ctr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) >= 30
+
+    def kind(arg):
+        arg = " ".join(arg.split())
+        if arg in ("void", ""):
+            return None
+        if "*" in arg or arg.startswith("ctr_stream_t"):
+            return "ptr"
+        t = arg.rsplit(" ", 1)[0].replace("const ", "").strip()
+        return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "float": "f32",
+                "uint32_t": "u32"}[t]
+
+    def ckind(ct):
+        if ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents"):
+            return "ptr"
+        return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_int64: "i64",
+                ctypes.c_uint64: "u64", ctypes.c_float: "f32", ctypes.c_uint32: "u32"}[ct]
+
+    seen = set()
+    for name, args in protos:
+        kinds = [k for k in (kind(a) for a in args.split(",")) if k is not None]
+        res, argtypes = _lib.SIGNATURES[name]
+        assert [ckind(t) for t in argtypes] == kinds, (name, kinds, [ckind(t) for t in argtypes])
+        seen.add(name)
+    assert seen == set(_lib.SIGNATURES)
