@@ -62,6 +62,7 @@ def test_graphed_step_blob_layout():
         assert off % 256 == 0 and off >= end          # slots in order, 256-byte aligned
         end = off + t.numel() * t.element_size()
     assert end <= blob.numel()
+    blob.zero_()
     views["cat"].fill_(7)
     views["cont"].fill_(1.5)                          # neighbours do not overlap
     assert int(views["cat"].min()) == 7 and float(views["__labels__"].abs().sum()) == 0.0
