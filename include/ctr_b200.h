@@ -221,7 +221,7 @@ typedef struct {
   const float* var;
   const float* gamma;  /* device [K]                                                 */
   const float* beta;
-  const float* state;  /* device {t, lr_t} (ctr_adam_tick): t selects the dropout stream; NULL -> 0 */
+  const float* state;  /* device Adam schedule (see "optimiser"): [0] = t selects the dropout stream; NULL -> 0 */
   float eps;           /* 1e-3 (tf.layers.batch_normalization default)               */
   float p_drop;        /* dropout rate, 0 disables                                   */
   uint32_t seed;
@@ -336,7 +336,7 @@ typedef struct {
   float* stats[CTR_TOWER_MID_MAX_LAYERS];
   const float* w_out;                            /* [H[L-1]] */
   const float* b_out;
-  const float* state;                            /* device {t, lr_t}: t selects the dropout stream */
+  const float* state;                            /* device Adam schedule: [0] = t selects the dropout stream */
   float eps, p_drop;
   uint32_t seed;
   float grad_scale;                              /* 1 / (B * world) */
