@@ -242,6 +242,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from recsys_b200 import sharded
+        args.clock_sampler = ClockSampler          # rank 0 samples nvidia-smi during the timed region
         return sharded.bench_main(args, rank, local, world)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)

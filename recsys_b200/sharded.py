@@ -431,8 +431,21 @@ def bench_main(args, rank, local, world):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
 
+    clk = None
+    try:                                            # clocks / throttle reasons during the timed region
+        cs = getattr(args, "clock_sampler", None)
+        clk = cs(local).__enter__() if (cs is not None and rank == 0) else None
+    except Exception:
+        clk = None
     ms, _ = timed(devb, False)
     ms_e2e, wall_e2e = timed(host, True)
+    clocks = None
+    if clk is not None:
+        try:
+            clk.__exit__(None, None, None)
+            clocks = clk.summary()
+        except Exception:
+            clocks = None
     model.emb.check_overflow()
     if os.environ.get("CTR_TRACE"):         # in-graph kernel timeline of a few steps (every rank
         from torch.profiler import ProfilerActivity, profile   # runs them; rank 0 prints)
@@ -475,6 +488,7 @@ def bench_main(args, rank, local, world):
                     "api": "estimator.GraphedTrainStep(deepfm.model_fn, params)(pinned PackedFeatures, "
                            "labels)" if graphed is not None else
                            "deepfm.model_fn(pinned PackedFeatures, labels, 'train', params).train_op()"},
+            "clocks": clocks,
             "gpu_launches": per_step_launches * K * world, "gpu_launches_per_step": per_step_launches,
             "nvlink_bytes_per_gpu_per_step": int((G - 1) / G * B * 39 * (4 + 64 + 64 + 8)),
             "launch_mode": mode,
