@@ -72,6 +72,11 @@ int ctr_hash_strings(const uint8_t* bytes, const int32_t* offsets, int64_t N,
                      const int32_t* field_of, const int32_t* n_buckets_dev,
                      const int32_t* row_offset_dev, int32_t* out, ctr_stream_t stream);
 
+/* categorical_column_with_hash_bucket(dtype=int64) (deepfm/deepfm.py:41,46) [TF-sem]: the key is
+ * formatted as_string ("%lld") and hashed: out[i] = Fingerprint64(decimal(ids[i])) mod n_buckets. */
+int ctr_hash_int64(const int64_t* ids, int64_t N, int32_t n_buckets, int64_t* out,
+                   ctr_stream_t stream);
+
 /* --------------------------------------------------- fused multi-field lookup
  * Forward.  Replaces input_layer(embedding columns) + input_layer(indicator
  * columns) + the FM second-order block + (optionally) the DCN cross stack:
@@ -163,10 +168,30 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
  *   out[b,:] = sum_p w * h        (no softmax; padding id 0 is masked out)
  * W1 [4E,H1], W2 [H1,H2], W3 [H2] row-major as tf.layers.dense kernels.  E in {8,16,32};
  * H1 <= 128, H2 <= 64.  att_w (nullable) [B,P] receives the raw position weights. */
+/* ctr_din_opts (nullable everywhere = no dropout, no range check):
+ *  - dropout after each of the two hidden attention layers (din/din.py:118, default rate 0.5 at :15):
+ *    inverted dropout, keep iff a 16-bit uniform >= p_drop * 65536, uniforms from Philox4x32-10 with
+ *    counter (b*P + pos, column / 8, 0x100 + 2*unit + layer, step) and key (seed, 0xD1A7); step =
+ *    state[0] (the device Adam schedule, so that a captured CUDA graph draws a fresh mask on every
+ *    replay); the backward regenerates the same bits.  ctr_din_dropout_mask writes the keep scales
+ *    (0 or 1/(1-p)) of one layer for n_rows positions, [n_rows, H] (H = 80 for layer 0, 40 for
+ *    layer 1) - what the parity tests inject into the oracle.
+ *  - table_rows > 0: history ids outside [0, table_rows) read as padding instead of out of bounds
+ *    and set bit 1 of *status (nullable device int) - tf.gather raises on CPU and zero-fills on GPU. */
+typedef struct {
+  const float* state;
+  float p_drop;
+  uint32_t seed;
+  uint32_t unit;        /* which attention unit: 0 = item history, 1 = category history */
+  int32_t table_rows;
+  int32_t* status;
+} ctr_din_opts;
 int ctr_din_att_fwd(const float* table, const int32_t* hist, const float* query, int B, int P,
                     int E, const float* W1, const float* b1, int H1, const float* W2,
                     const float* b2, int H2, const float* W3, const float* b3, float* out,
-                    float* att_w, ctr_stream_t stream);
+                    float* att_w, const ctr_din_opts* opts, ctr_stream_t stream);
+int ctr_din_dropout_mask(const ctr_din_opts* opts, int layer, int64_t n_rows, int H, float* out,
+                         ctr_stream_t stream);
 /* Backward of the above: dtable rows += (RED scatter), dquery[B,E] written, weight and bias
  * gradients (dW1..dW3, db1..db3) accumulated (+=).  workspace: ctr_din_workspace_bytes(B,P,E)
  * bytes of scratch (per-position h1/dh1/dh2/h rows feeding the tall-skinny dW reductions). */
@@ -176,7 +201,7 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
                     const float* b2, int H2, const float* W3, const float* b3, const float* dout,
                     float* dtable, float* dquery, float* dW1, float* db1, float* dW2, float* db2,
                     float* dW3, float* db3, void* workspace, int64_t workspace_bytes,
-                    ctr_stream_t stream);
+                    const ctr_din_opts* opts, ctr_stream_t stream);
 
 /* --------------------------------------------------------------- xDeepFM CIN
  * One CIN layer (xdeepfm/xdeepfm.py:145-169):
@@ -257,6 +282,19 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
 /* out[B,K] = P(A): the last BN+dropout of a tower that does not end in a dense layer (DCN). */
 int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out, int B,
                       ctr_stream_t stream);
+/* Backward of ctr_bn_drop_apply (dcn/dcn.py:146-149, the tower that ends in BN + dropout):
+ * dn[B,K] = dout * keep; dbeta[K] += colsum(dn); dgamma[K] += colsum(dn * xhat(A)) (both nullable).
+ * The layer's dpre then follows from a kind-1 gradient source over dn. */
+int ctr_bn_drop_apply_bwd(const float* dout, int ldd, const float* A, int K, const ctr_bn_drop* pro,
+                          float* dn, float* dbeta, float* dgamma, int B, ctr_stream_t stream);
+/* DCN head + loss in one launch (dcn/dcn.py:151-153,166-169): logit = [h | xl] . w + hb with
+ * h [B,H] the tower output and xl [B,W] the cross output (H % 4 == W % 4 == 0, H + W <= 1536);
+ * logits / prob (nullable) written, *loss += mean BCE.  With dh != NULL the gradients come out of
+ * the same launch: dh [B,H], dxl [B,W] written; dw [H+W], dhb accumulated; all scaled by
+ * grad_scale * B (grad_scale = 1/(B*world)). */
+int ctr_dcn_head(const float* h, int H, const float* xl, int W, const float* w, const float* hb,
+                 const float* labels, int B, float* logits, float* prob, float* loss, float* dh,
+                 float* dxl, float* dw, float* dhb, float grad_scale, ctr_stream_t stream);
 /* dn_out[B,K] = (dpre[B,N] . W[K,N]^T) * keep  (keep from `pro`, the prologue that produced this
  * layer's input from Aprev); dbeta_prev/dgamma_prev [K] += column sums of dn, dn*xhat(Aprev).
  * pro disabled (first layer): dn_out = dpre . W^T, nothing else. */

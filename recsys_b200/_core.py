@@ -137,11 +137,37 @@ class _ModelBase:
         loss = bce_with_logits_mean(logits, labels) if labels is not None else None
         return logits, pred, loss
 
+    # A sticky device word collects what the kernels cannot raise themselves: bit 0 = a categorical
+    # id outside [0, n_rows) (wrapped by modulo), bit 1 = a DIN history id outside its table (read
+    # as padding), bit 2 = a sharded exchange slab overflowed (lookups dropped).  It is read - one
+    # 4-byte D2H copy and a synchronisation - on every eval / predict call and every
+    # ``status_every`` (default 256) train calls, never inside a CUDA-graph capture.
+    STATUS_TEXT = {1: "categorical id outside [0, num_buckets) (wrapped by modulo; hash raw ids first)",
+                   2: "DIN history id outside its table (treated as padding)",
+                   4: "sharded exchange slab overflow: lookups were dropped (raise shard_slack)"}
+
+    def status_word(self) -> Optional[torch.Tensor]:
+        ids = getattr(self, "ids", None)
+        return None if ids is None else ids.status
+
+    def check_status(self):
+        w = self.status_word()
+        if w is None or torch.cuda.is_current_stream_capturing():
+            return
+        v = int(w.item())
+        if v:
+            w.zero_()
+            raise RuntimeError("recsys_b200 %s: %s" % (self.name, "; ".join(
+                t for b, t in self.STATUS_TEXT.items() if v & b)))
+
     def spec(self, features, labels, mode) -> EstimatorSpec:
         training = mode == ModeKeys.TRAIN
         with torch.set_grad_enabled(training):
             logits, pred, loss = self.forward(features, None if mode == ModeKeys.PREDICT else labels,
                                               training)
+        self._calls = getattr(self, "_calls", 0) + 1
+        if not training or self._calls % int(self.params.get("status_every", 256)) == 0:
+            self.check_status()
         predictions = {"prob": pred}
         export_outputs = {DEFAULT_SERVING_SIGNATURE_DEF_KEY: PredictOutput(predictions)}
         if mode == ModeKeys.PREDICT:
@@ -206,9 +232,8 @@ class _CriteoBase(_ModelBase):
                                           adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
         self.ids = ops.IdPipeline(self.lay, self.device)
         self.rows = None
-        # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower.
-        # DCN's tower has no final dense layer (its backward is not fused yet): torch tower.
-        self.fused = bool(params.get("fused_tower", self.name != "dcn"))
+        # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower
+        self.fused = bool(params.get("fused_tower", True))
         self._head_anchor = torch.zeros((), device=self.device, requires_grad=True)
 
     def load_state(self, state):
@@ -368,6 +393,26 @@ class DCNModel(_CriteoBase):
         frozen = [n for n in shapes if n.endswith((".bn.mean", ".bn.var"))]
         self.dense = ops.DenseParams(shapes, self.device, frozen=frozen)
         self._init_dense(int(params.get("seed", 0)) + 1)
+        # dense(relu) -> BN -> dropout per layer, no final dense layer (dcn/dcn.py:144-149)
+        self.tower = ops.FusedTower(self.dense, "dnn", [W] + self.layers, False, self.dropout,
+                                    self.adam, seed=int(params.get("seed", 0)))
+
+    _uses_fused_head = True
+
+    def forward(self, features, labels, training):
+        if not self.fused:
+            return super().forward(features, labels, training)
+        P = self.dense
+        _, E, _, _, xl = self._lookup(features, want_fm=False, want_y1=False,
+                                      cross_w=P["cross.w"], cross_b=P["cross.b"])   # dcn.py:123-142
+        h = self.tower(E, training)                                                  # :144-149
+        B = E.shape[0]
+        if labels is None:
+            labels = torch.zeros(B, dtype=torch.float32, device=self.device)
+        loss, logits, prob = ops.dcn_head(self._head_anchor, P, h, xl, labels,
+                                          grad_scale=1.0 / (B * self.world),
+                                          training=training)                        # :151-153,166
+        return logits.view(-1, 1), prob.view(-1, 1), loss
 
     def _init_weight(self, name, shape, g):
         if name == "cross.w":
@@ -535,8 +580,21 @@ class DINModel(_ModelBase):
         shapes.update({"mlp.out.w": (DIN_MLP_LAYERS[-1], 1), "mlp.out.b": (1,)})
         self.dense = ops.DenseParams(shapes, self.device)
         self._init_dense(seed + 1)
-        self.n_items = n_items
+        self.n_items, self.n_cates = n_items, n_cates
         self.rows = None
+        self.seed = seed
+        self.fused = bool(params.get("fused_tower", True))
+        # target ids -> rows of the concatenated table, range-checked on the device
+        self.ids = ops.IdPipeline(self.lay, self.device)
+        # MLP 100-50-20 (ReLU + dropout, no BN) + dense(1) without activation (din/din.py:133-139)
+        self.tower = ops.FusedTower(self.dense, "mlp", [3 * E] + DIN_MLP_LAYERS, True, self.dropout,
+                                    self.adam, seed=seed, bn=False, out_relu=False, layer_base=8)
+        # logit = mlp_out + i_b (:140) through ctr_loss_head: constant head weights [1, 1], bias 0;
+        # their "gradients" land in a scratch buffer that nothing reads
+        self._head_w = torch.ones(2, dtype=torch.float32, device=self.device)
+        self._head_b = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._head_scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._head_anchor = torch.zeros((), device=self.device, requires_grad=True)
 
     def load_state(self, state):
         super().load_state(state)
@@ -546,30 +604,53 @@ class DINModel(_ModelBase):
                             torch.zeros(self.lay.rows[1], dtype=state["i_item"].dtype)])
             self.emb.load(tab, w1)
 
-    def _att(self, prefix, field, hist, query):
+    def att_opts(self, unit, training):
+        """ctr_din_opts of attention unit ``unit``: the dropout of din/din.py:118 (training only)
+        and the id range check against the unit's table."""
+        return ops.din_opts(unit, self.lay.rows[unit], self.dropout if training else 0.0, self.seed,
+                            self.adam.state_ptr, self.ids.status)
+
+    def _att(self, prefix, field, hist, query, training):
         P = self.dense
         return ops.din_attention(self.emb, field, hist, query, P[f"{prefix}.0.w"], P[f"{prefix}.0.b"],
                                  P[f"{prefix}.1.w"], P[f"{prefix}.1.b"], P[f"{prefix}.2.w"],
-                                 P[f"{prefix}.2.b"])
+                                 P[f"{prefix}.2.b"], self.att_opts(field, training))
 
-    def logits(self, features, training):
-        if training and self.dropout > 0.0:
-            raise NotImplementedError(
-                "dropout inside the fused DIN activation unit is not implemented; use dropout=0")
-        P = self.dense
+    def _net(self, features, training):
+        """-> (net [B, 3E], i_b [B]): target embeddings + the two attended histories (:91-131)."""
         dev = self.device
-        i_id = torch.as_tensor(features["i_id"]).to(dev, non_blocking=True).reshape(-1)
-        i_cate = torch.as_tensor(features["i_cate"]).to(dev, non_blocking=True).reshape(-1)
         h_iid = torch.as_tensor(features["u_iid_seq"]).to(dev, non_blocking=True).to(torch.int32)
         h_cat = torch.as_tensor(features["u_icat_seq"]).to(dev, non_blocking=True).to(torch.int32)
-        self.rows = torch.stack([i_id, i_cate + self.n_items], 1).to(torch.int32)
+        self.rows = self.ids({"i_id": torch.as_tensor(features["i_id"]).reshape(-1, 1),
+                              "i_cate": torch.as_tensor(features["i_cate"]).reshape(-1, 1)})
         self.hist = (h_iid, h_cat)
         Ecat, i_b, _, _ = self.emb.lookup(self.rows, want_fm=False, want_y1=True)   # :91-99
         E = self.E
         pkg_emb, pkgc_emb = Ecat[:, :E], Ecat[:, E:]
-        pkg_h = self._att("att_iid", 0, h_iid, pkg_emb)                             # :127
-        pkgc_h = self._att("att_cat", 1, h_cat, pkgc_emb)                           # :128
-        net = torch.cat([pkg_emb, pkg_h, pkgc_h], 1)                                # :131
+        pkg_h = self._att("att_iid", 0, h_iid, pkg_emb, training)                   # :127
+        pkgc_h = self._att("att_cat", 1, h_cat, pkgc_emb, training)                 # :128
+        return torch.cat([pkg_emb, pkg_h, pkgc_h], 1), i_b                          # :131
+
+    def forward(self, features, labels, training):
+        if not self.fused:
+            return super().forward(features, labels, training)
+        net, i_b = self._net(features, training)
+        y = self.tower(net, training)                                               # :133-139
+        if labels is None:
+            labels = torch.zeros(net.shape[0], dtype=torch.float32, device=self.device)
+        loss, logits, prob = ops.loss_head(
+            self._head_anchor, self.dense, [y, i_b], labels,
+            hw=(self._head_w, self._head_scratch[0:2]), hb=(self._head_b, self._head_scratch[2:3]),
+            b1=(None, None), relu0=False, training=training)                        # :140-141,166
+        return logits, prob, loss
+
+    def logits(self, features, training):
+        """The torch (cuBLAS) MLP of params['fused_tower'] = False; no dropout there."""
+        if training and self.dropout > 0.0:
+            raise NotImplementedError("the torch MLP path has no device-side dropout stream; use "
+                                      "the default fused_tower=True")
+        P = self.dense
+        net, i_b = self._net(features, training)
         net = self._tower(net, "mlp", len(DIN_MLP_LAYERS), training, bn=False)      # :133-137
         out = torch.addmm(P["mlp.out.b"], net, P["mlp.out.w"])                      # :139
         return out.reshape(-1) + i_b                                                # :140
@@ -582,4 +663,5 @@ class DINModel(_ModelBase):
             touched = torch.cat([self.rows.reshape(-1), h_iid.reshape(-1),
                                  (h_cat + self.n_items).reshape(-1)])
             self.emb.adam_step(touched, lr_t, self.adam)
+        self.tower.join()
         self.dense.adam_step(lr_t, self.adam)

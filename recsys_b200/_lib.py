@@ -60,6 +60,12 @@ class TowerMidArgs(C.Structure):
                 ("dpre0_lo", C.c_void_p), ("pre0", C.c_void_p), ("barrier", C.c_void_p), ("timing", C.c_void_p)]
 
 
+class DinOpts(C.Structure):
+    """ctr_din_opts (include/ctr_b200.h)."""
+    _fields_ = [("state", C.c_void_p), ("p_drop", C.c_float), ("seed", C.c_uint32),
+                ("unit", C.c_uint32), ("table_rows", C.c_int32), ("status", C.c_void_p)]
+
+
 class FieldDesc(C.Structure):
     """ctr_field_desc (include/ctr_b200.h)."""
     _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("n_rows", C.c_int32),
@@ -74,6 +80,7 @@ SIGNATURES = {
     "ctr_device_check": (c_i, []),
     "ctr_criteo_rows": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f]),
     "ctr_hash_strings": (c_i, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "ctr_hash_int64": (c_i, [c_f, c_i64, C.c_int32, c_f, c_f]),
     "ctr_embed_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i,
                             c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_embed_fwd_raw": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i,
@@ -88,10 +95,12 @@ SIGNATURES = {
     "ctr_adam_rows": (c_i, [c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                             C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_f]),
     "ctr_din_att_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,
-                              c_f, c_f, c_f]),
+                              c_f, c_f, C.POINTER(DinOpts), c_f]),
+    "ctr_din_dropout_mask": (c_i, [C.POINTER(DinOpts), c_i, c_i64, c_i, c_f, c_f]),
     "ctr_din_workspace_bytes": (c_i64, [c_i, c_i, c_i]),
     "ctr_din_att_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,
-                              c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_f]),
+                              c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i64,
+                              C.POINTER(DinOpts), c_f]),
     "ctr_cin_workspace_bytes": (c_i64, [c_i, c_i, c_i, c_i, c_i, c_i]),
     "ctr_cin_layer_fwd": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_i,
                                 c_f, c_i64, c_f]),
@@ -100,6 +109,9 @@ SIGNATURES = {
     "ctr_tower_layer_fwd": (c_i, [c_f, c_i, c_i, C.POINTER(BnDrop), c_f, c_f, c_i, c_f, c_i, c_f, c_i,
                                   c_i, c_f]),
     "ctr_bn_drop_apply": (c_i, [c_f, c_i, C.POINTER(BnDrop), c_f, c_i, c_f]),
+    "ctr_bn_drop_apply_bwd": (c_i, [c_f, c_i, c_f, c_i, C.POINTER(BnDrop), c_f, c_f, c_f, c_i, c_f]),
+    "ctr_dcn_head": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                           c_fl, c_f]),
     "ctr_tower_layer_bwd_data": (c_i, [C.POINTER(GradSrc), c_i, c_f, c_i, C.POINTER(BnDrop), c_f,
                                        c_f, c_i, c_f, c_f, c_i, c_f]),
     "ctr_tower_dpre": (c_i, [C.POINTER(GradSrc), c_i, c_f, c_i, c_f, c_i, c_f]),

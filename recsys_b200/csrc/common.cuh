@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -29,6 +30,15 @@ int sm_count();         // multiprocessors of the current device (cached)
 #define CTR_LAUNCH_CHECK(fn) return ::ctr::check_cuda(cudaGetLastError(), fn)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Developer knobs (environment overrides of tcgen05 descriptor bits, tile schedules, launch modes)
+// exist only in a build made with -DCTR_DEBUG_KNOBS=1 (CTR_DEBUG_KNOBS=1 python -m recsys_b200.build):
+// the product library never reads them, so a stray variable cannot change - or corrupt - results.
+#ifdef CTR_DEBUG_KNOBS
+static inline const char* ctr_knob(const char* name) { return getenv(name); }
+#else
+static inline const char* ctr_knob(const char*) { return nullptr; }
+#endif
 
 // ------------------------------------------------------------------ device side
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

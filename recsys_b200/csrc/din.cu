@@ -12,6 +12,7 @@
 // (`xtx`: C += A^T B over the valid rows) forms dW1/dW2 as tall-skinny reductions.
 // FP32 CUDA-core work, compute-bound: padding positions are skipped.
 #include "gemm_core.cuh"
+#include "tower_common.cuh"
 
 namespace ctr {
 
@@ -44,7 +45,40 @@ struct DinParams {
   const int* rowbase;   // [B+1] exclusive prefix of valid positions per sample (compact rows)
   float* dW3;
   float* db3;
+  // dropout after each of the two hidden attention layers (din/din.py:118)
+  const float* dstate;      // device Adam schedule: [0] = t selects the dropout stream (nullable -> 0)
+  float inv_keep;
+  unsigned thr;             // keep iff a 16-bit uniform >= thr = p * 65536
+  unsigned seed, unit;      // unit: which attention unit (0 = att_iid, 1 = att_cat)
+  int n_rows;               // rows of `table`: ids outside [0, n_rows) are treated as padding ...
+  int* status;              // ... and set bit 1 of *status (nullable)
 };
+
+__device__ __forceinline__ bool din_valid_id(const DinParams& p, int id) {
+  if (id > 0 && id < p.n_rows) return true;      // din/din.py:107 mask: id > 0
+  if (id != 0 && p.status != nullptr) atomicOr(p.status, 2);
+  return false;
+}
+
+// Keep bits of the 8 consecutive columns [8*blk, 8*blk+8) of attention layer `layer` (0: the 80-wide
+// one, 1: the 40-wide one) at history position `row` = b*P + pos: one Philox4x32-10 block =
+// 8 x 16-bit uniforms, counter (row, blk, 0x100 + 2*unit + layer, step), key (seed, 0xD1A7).  The
+// backward regenerates the same bits; nothing is stored.
+__device__ __forceinline__ unsigned din_keep8(const DinParams& p, unsigned step, unsigned row,
+                                              unsigned layer, unsigned blk) {
+  const uint4 r = philox4x32_10(make_uint4(row, blk, 0x100u + 2u * p.unit + layer, step),
+                                make_uint2(p.seed, 0xD1A7u));
+  unsigned bits = 0u;
+  bits |= (r.x & 0xFFFFu) >= p.thr ? 1u : 0u;
+  bits |= (r.x >> 16) >= p.thr ? 2u : 0u;
+  bits |= (r.y & 0xFFFFu) >= p.thr ? 4u : 0u;
+  bits |= (r.y >> 16) >= p.thr ? 8u : 0u;
+  bits |= (r.z & 0xFFFFu) >= p.thr ? 16u : 0u;
+  bits |= (r.z >> 16) >= p.thr ? 32u : 0u;
+  bits |= (r.w & 0xFFFFu) >= p.thr ? 64u : 0u;
+  bits |= (r.w >> 16) >= p.thr ? 128u : 0u;
+  return bits;
+}
 
 template <int E>
 struct DinSmem {
@@ -90,7 +124,7 @@ __device__ __forceinline__ void din_fold_sample(DinSmem<E>& s, int warp, int lan
   }
 }
 
-template <int E>
+template <int E, bool DROP>
 __global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
   extern __shared__ __align__(16) uint8_t din_smem_raw[];
   DinSmem<E>& s = *reinterpret_cast<DinSmem<E>*>(din_smem_raw);
@@ -98,6 +132,7 @@ __global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
   din_load_weights<E>(s, p);
   __syncthreads();
   const float b3 = p.b3[0];
+  const unsigned step = (DROP && p.dstate != nullptr) ? static_cast<unsigned>(p.dstate[0]) : 0u;
 
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
     float q[E];
@@ -116,7 +151,7 @@ __global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
     for (int p0 = 0; p0 < p.P; p0 += 32) {
       const int pos = p0 + lane;
       const int id = pos < p.P ? __ldg(p.hist + static_cast<size_t>(b) * p.P + pos) : 0;
-      const bool valid = id > 0;                       // din/din.py:107 mask
+      const bool valid = din_valid_id(p, id);
       if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
       float w = 0.f;
       if (valid) {
@@ -129,20 +164,34 @@ __global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
         float h2[kH2];
 #pragma unroll
         for (int j = 0; j < kH2; ++j) h2[j] = s.b2[j];
+        const unsigned row = static_cast<unsigned>(b) * p.P + pos;
+        for (int kb = 0; kb < kH1 / 8; ++kb) {
+          const unsigned keep = DROP ? din_keep8(p, step, row, 0u, kb) : 0xFFu;
 #pragma unroll 2
-        for (int k = 0; k < kH1; ++k) {
-          float a = s.cq[warp][k];
-          const float* we = &s.Weff[warp][k * E];
+          for (int u = 0; u < 8; ++u) {
+            const int k = kb * 8 + u;
+            float a = s.cq[warp][k];
+            const float* we = &s.Weff[warp][k * E];
 #pragma unroll
-          for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
-          a = fmaxf(a, 0.f);
-          const float* w2 = &s.W2[k * kH2];
+            for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
+            a = fmaxf(a, 0.f);
+            if (DROP) a = ((keep >> u) & 1u) ? a * p.inv_keep : 0.f;
+            const float* w2 = &s.W2[k * kH2];
 #pragma unroll
-          for (int j = 0; j < kH2; ++j) h2[j] = fmaf(a, w2[j], h2[j]);
+            for (int j = 0; j < kH2; ++j) h2[j] = fmaf(a, w2[j], h2[j]);
+          }
         }
         w = b3;
 #pragma unroll
-        for (int j = 0; j < kH2; ++j) w = fmaf(fmaxf(h2[j], 0.f), s.W3[j], w);
+        for (int jb = 0; jb < kH2 / 8; ++jb) {
+          const unsigned keep = DROP ? din_keep8(p, step, row, 1u, jb) : 0xFFu;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float r = fmaxf(h2[jb * 8 + u], 0.f);
+            if (DROP) r = ((keep >> u) & 1u) ? r * p.inv_keep : 0.f;
+            w = fmaf(r, s.W3[jb * 8 + u], w);
+          }
+        }
 #pragma unroll
         for (int e = 0; e < E; ++e) o[e] = fmaf(w, h[e], o[e]);
       }
@@ -159,7 +208,7 @@ __global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
   }
 }
 
-template <int E>
+template <int E, bool DROP>
 __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
   extern __shared__ __align__(16) uint8_t din_smem_raw[];
   DinSmem<E>& s = *reinterpret_cast<DinSmem<E>*>(din_smem_raw);
@@ -171,6 +220,7 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 #pragma unroll
   for (int j = 0; j < kH2; ++j) dW3acc[j] = 0.f;
   float db3acc = 0.f;
+  const unsigned step = (DROP && p.dstate != nullptr) ? static_cast<unsigned>(p.dstate[0]) : 0u;
 
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
     float q[E], g[E], dq[E];
@@ -192,7 +242,7 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
     for (int p0 = 0; p0 < p.P; p0 += 32) {
       const int pos = p0 + lane;
       const int id = pos < p.P ? __ldg(p.hist + static_cast<size_t>(b) * p.P + pos) : 0;
-      const bool valid = id > 0;
+      const bool valid = din_valid_id(p, id);
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       if (vmask == 0u) continue;
       // compact scratch row of this position: valid positions only, in (sample, position) order
@@ -200,7 +250,9 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
       row_cursor += __popc(vmask);
       float h[E], dh[E], tq[E];
       float h2[kH2];
-      unsigned m1a = 0u, m1b = 0u, m1c = 0u;   // relu mask of h1 (80 bits)
+      unsigned m1a = 0u, m1b = 0u, m1c = 0u;   // relu (and dropout keep) mask of h1 (80 bits)
+      unsigned long long keep2 = ~0ull;        // dropout keep bits of h2 (40 bits)
+      const unsigned row = static_cast<unsigned>(b) * p.P + pos;
       float w = 0.f, dw = 0.f;
       if (valid) {
 #pragma unroll
@@ -211,8 +263,11 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 #pragma unroll
         for (int j = 0; j < kH2; ++j) h2[j] = s.b2[j];
         float* oh1 = p.sH1 + n * kH1;
+        unsigned keep8 = 0xFFu;
         for (int k4 = 0; k4 < kH1; k4 += 4) {
           float a4[4];
+          if (DROP && (k4 & 4) == 0) keep8 = din_keep8(p, step, row, 0u, k4 >> 3);
+          const unsigned keep = (keep8 >> (k4 & 4)) & 0xFu;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = k4 + u;
@@ -221,6 +276,7 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 #pragma unroll
             for (int e = 0; e < E; ++e) a = fmaf(h[e], we[e], a);
             a = fmaxf(a, 0.f);
+            if (DROP) a = ((keep >> u) & 1u) ? a * p.inv_keep : 0.f;
             a4[u] = a;
             const float* w2 = &s.W2[k * kH2];
 #pragma unroll
@@ -233,9 +289,17 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
           else m1c |= bits << (k4 - 64);
           *reinterpret_cast<float4*>(oh1 + k4) = make_float4(a4[0], a4[1], a4[2], a4[3]);
         }
+        if (DROP) {
+          keep2 = 0ull;
+#pragma unroll
+          for (int jb = 0; jb < kH2 / 8; ++jb)
+            keep2 |= static_cast<unsigned long long>(din_keep8(p, step, row, 1u, jb)) << (8 * jb);
+        }
+        const float ik = DROP ? p.inv_keep : 1.f;
         w = b3;
 #pragma unroll
-        for (int j = 0; j < kH2; ++j) w = fmaf(fmaxf(h2[j], 0.f), s.W3[j], w);
+        for (int j = 0; j < kH2; ++j)
+          w = fmaf(((keep2 >> j) & 1ull) ? fmaxf(h2[j], 0.f) * ik : 0.f, s.W3[j], w);
         // out = sum_p w h  ->  dw = g . h
 #pragma unroll
         for (int e = 0; e < E; ++e) dw = fmaf(g[e], h[e], dw);
@@ -243,9 +307,10 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
         float* odh2 = p.sdH2 + n * kH2;
 #pragma unroll
         for (int j = 0; j < kH2; ++j) {
-          const float r = fmaxf(h2[j], 0.f);
+          const bool kp = (keep2 >> j) & 1ull;
+          const float r = kp ? fmaxf(h2[j], 0.f) * ik : 0.f;
           dW3acc[j] = fmaf(dw, r, dW3acc[j]);
-          h2[j] = h2[j] > 0.f ? dw * s.W3[j] : 0.f;    // h2 now holds dh2
+          h2[j] = (h2[j] > 0.f && kp) ? dw * s.W3[j] * ik : 0.f;    // h2 now holds dh2
         }
 #pragma unroll
         for (int j = 0; j < kH2; j += 4)
@@ -269,6 +334,7 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
             const float* w2 = &s.W2[k * kH2];
 #pragma unroll
             for (int j = 0; j < kH2; ++j) d1 = fmaf(h2[j], w2[j], d1);
+            if (DROP) d1 *= p.inv_keep;      // the mask bit already includes the keep decision
             const float* we = &s.Weff[warp][k * E];
             const float* wp = &s.Wp[k * E];
 #pragma unroll
@@ -327,11 +393,14 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 
 // counts[b] = number of valid (id > 0) history positions of sample b: one warp per sample.
 __global__ void __launch_bounds__(256)
-din_count_kernel(const int* __restrict__ hist, int B, int P, int* __restrict__ counts) {
+din_count_kernel(const int* __restrict__ hist, int B, int P, int n_rows, int* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += gridDim.x * 8) {
     int c = 0;
-    for (int p = lane; p < P; p += 32) c += __ldg(hist + static_cast<size_t>(b) * P + p) > 0 ? 1 : 0;
+    for (int p = lane; p < P; p += 32) {
+      const int id = __ldg(hist + static_cast<size_t>(b) * P + p);
+      c += (id > 0 && id < n_rows) ? 1 : 0;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) counts[b + 1] = c;
@@ -480,28 +549,68 @@ static void xtx_launch(const float* A, int lda, int Ka, const float* Bm, int ldb
     xtx_kernel<2><<<grid, 256, sizeof(MmaSmem), st>>>(A, lda, Ka, Bm, ldb, Kb, n_dev, N, C, ldc, colsum, rps);
 }
 
-template <int E>
-static int din_fwd_launch(const DinParams& p, cudaStream_t st) {
+template <int E, bool DROP>
+static int din_fwd_launch2(const DinParams& p, cudaStream_t st) {
   const size_t smem = sizeof(DinSmem<E>);
-  cudaFuncSetAttribute(din_att_fwd_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(din_att_fwd_kernel<E, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(smem));
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, din_att_fwd_kernel<E>, 256, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, din_att_fwd_kernel<E, DROP>, 256, smem);
   const int grid = std::min((p.B + 7) / 8, sm_count() * std::max(1, occ));
-  din_att_fwd_kernel<E><<<grid, 256, smem, st>>>(p);
+  din_att_fwd_kernel<E, DROP><<<grid, 256, smem, st>>>(p);
   return CTR_OK;
 }
-
 template <int E>
-static int din_bwd_launch(const DinParams& p, cudaStream_t st) {
+static int din_fwd_launch(const DinParams& p, cudaStream_t st) {
+  return p.thr > 0u ? din_fwd_launch2<E, true>(p, st) : din_fwd_launch2<E, false>(p, st);
+}
+
+template <int E, bool DROP>
+static int din_bwd_launch2(const DinParams& p, cudaStream_t st) {
   const size_t smem = sizeof(DinSmem<E>);
-  cudaFuncSetAttribute(din_att_bwd_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(din_att_bwd_kernel<E, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(smem));
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, din_att_bwd_kernel<E>, 256, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, din_att_bwd_kernel<E, DROP>, 256, smem);
   const int grid = std::min((p.B + 7) / 8, sm_count() * std::max(1, occ));
-  din_att_bwd_kernel<E><<<grid, 256, smem, st>>>(p);
+  din_att_bwd_kernel<E, DROP><<<grid, 256, smem, st>>>(p);
   return CTR_OK;
+}
+template <int E>
+static int din_bwd_launch(const DinParams& p, cudaStream_t st) {
+  return p.thr > 0u ? din_bwd_launch2<E, true>(p, st) : din_bwd_launch2<E, false>(p, st);
+}
+
+// keep scale (0 or 1/(1-p)) of every (position row, column) of one attention layer, for tests that
+// inject the kernel's masks into the oracle.
+__global__ void din_dropout_mask_kernel(const DinParams p, unsigned layer, long long n_rows, int H,
+                                        float* __restrict__ out) {
+  const unsigned step = p.dstate != nullptr ? static_cast<unsigned>(p.dstate[0]) : 0u;
+  const int nb = (H + 7) / 8;
+  const long long n = n_rows * nb;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / nb;
+    const int blk = static_cast<int>(i % nb);
+    const unsigned keep = din_keep8(p, step, static_cast<unsigned>(row), layer, blk);
+    for (int u = 0; u < 8 && blk * 8 + u < H; ++u)
+      out[row * H + blk * 8 + u] = ((keep >> u) & 1u) ? p.inv_keep : 0.f;
+  }
+}
+
+static bool din_set_opts(DinParams& p, const ctr_din_opts* d) {
+  p.thr = 0u; p.inv_keep = 1.f; p.dstate = nullptr; p.seed = 0u; p.unit = 0u;
+  p.n_rows = 0x7FFFFFFF; p.status = nullptr;
+  if (d == nullptr) return true;
+  if (d->table_rows > 0) p.n_rows = d->table_rows;
+  p.status = d->status;
+  if (!(d->p_drop > 0.f)) return true;
+  if (!(d->p_drop < 1.f)) return false;
+  p.thr = static_cast<unsigned>(d->p_drop * 65536.f);
+  if (p.thr == 0u) p.thr = 1u;
+  p.inv_keep = 1.f / (1.f - d->p_drop);
+  p.dstate = d->state; p.seed = d->seed; p.unit = d->unit;
+  return true;
 }
 
 }  // namespace ctr
@@ -518,7 +627,7 @@ int64_t ctr_din_workspace_bytes(int B, int P, int E) {
 int ctr_din_att_fwd(const float* table, const int32_t* hist, const float* query, int B, int P,
                     int E, const float* W1, const float* b1, int H1, const float* W2,
                     const float* b2, int H2, const float* W3, const float* b3, float* out,
-                    float* att_w, ctr_stream_t stream) {
+                    float* att_w, const ctr_din_opts* opts, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(table && hist && query && W1 && b1 && W2 && b2 && W3 && b3 && out, "ctr_din_att_fwd",
               "null pointer");
@@ -531,6 +640,7 @@ int ctr_din_att_fwd(const float* table, const int32_t* hist, const float* query,
   DinParams p{};
   p.table = table; p.hist = hist; p.query = query; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
   p.W3 = W3; p.b3 = b3; p.B = B; p.P = P; p.out = out; p.att_w = att_w;
+  CTR_REQUIRE(din_set_opts(p, opts), "ctr_din_att_fwd", "p_drop must be < 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (E) {
     case 8: din_fwd_launch<8>(p, st); break;
@@ -546,7 +656,7 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
                     const float* b2, int H2, const float* W3, const float* b3, const float* dout,
                     float* dtable, float* dquery, float* dW1, float* db1, float* dW2, float* db2,
                     float* dW3, float* db3, void* workspace, int64_t workspace_bytes,
-                    ctr_stream_t stream) {
+                    const ctr_din_opts* opts, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(table && hist && query && W1 && b1 && W2 && b2 && W3 && b3 && dout && dtable &&
                   dquery && dW1 && db1 && dW2 && db2 && dW3 && db3,
@@ -564,6 +674,7 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
   DinParams p{};
   p.table = table; p.hist = hist; p.query = query; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
   p.W3 = W3; p.b3 = b3; p.B = B; p.P = P; p.dout = dout; p.dtable = dtable; p.dquery = dquery;
+  CTR_REQUIRE(din_set_opts(p, opts), "ctr_din_att_bwd", "p_drop must be < 1");
   p.sH1 = ws;
   p.sdH1 = p.sH1 + N * kH1;
   p.sdH2 = p.sdH1 + N * kH1;
@@ -573,7 +684,7 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
   float* tmp = p.sSd + static_cast<long long>(B) * kH1;   // [3][E][80]
   int* rowbase = reinterpret_cast<int*>(tmp + 3 * E * kH1);   // [B+1]
   p.rowbase = rowbase;
-  din_count_kernel<<<std::min((B + 7) / 8, sm_count() * 8), 256, 0, st>>>(hist, B, P, rowbase);
+  din_count_kernel<<<std::min((B + 7) / 8, sm_count() * 8), 256, 0, st>>>(hist, B, P, p.n_rows, rowbase);
   din_scan_kernel<<<1, 1024, 0, st>>>(rowbase, B);
   p.dW3 = dW3; p.db3 = db3;
   cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(float) * 3 * E * kH1, st);
@@ -592,6 +703,21 @@ int ctr_din_att_bwd(const float* table, const int32_t* hist, const float* query,
   xtx_launch(query, E, E, p.sSd, kH1, kH1, nullptr, B, tmp + 2 * E * kH1, kH1, db1, st);   // dWq = Q^T sum dH1
   din_assemble_dw1_kernel<<<(E * kH1 + 255) / 256, 256, 0, st>>>(tmp, E, dW1);
   CTR_LAUNCH_CHECK("ctr_din_att_bwd");
+}
+
+int ctr_din_dropout_mask(const ctr_din_opts* opts, int layer, int64_t n_rows, int H, float* out,
+                         ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(opts && out && (layer == 0 || layer == 1) && n_rows >= 0 && H > 0,
+              "ctr_din_dropout_mask", "bad argument");
+  DinParams p{};
+  CTR_REQUIRE(din_set_opts(p, opts), "ctr_din_dropout_mask", "p_drop must be < 1");
+  if (n_rows == 0) return CTR_OK;
+  const long long n = n_rows * ((H + 7) / 8);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 8LL));
+  din_dropout_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, static_cast<unsigned>(layer), n_rows, H, out);
+  CTR_LAUNCH_CHECK("ctr_din_dropout_mask");
 }
 
 }  // extern "C"

@@ -146,7 +146,41 @@ __global__ void hash_strings_kernel(const uint8_t* __restrict__ bytes,
   }
 }
 
+// categorical_column_with_hash_bucket(dtype=int64) (deepfm/deepfm.py:41,46) [TF-sem]: the integer key
+// is formatted with as_string ("%lld") and hashed like any other string.
+__global__ void hash_int64_kernel(const long long* __restrict__ ids, long long N, int n_buckets,
+                                  long long* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < N;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint8_t buf[24];
+    const long long v = ids[i];
+    u64 mag = v < 0 ? 0ull - static_cast<u64>(v) : static_cast<u64>(v);
+    int n = 0;
+    uint8_t rev[20];
+    do {
+      rev[n++] = static_cast<uint8_t>('0' + mag % 10ull);
+      mag /= 10ull;
+    } while (mag != 0ull);
+    int len = 0;
+    if (v < 0) buf[len++] = '-';
+    while (n > 0) buf[len++] = rev[--n];
+    out[i] = static_cast<long long>(fingerprint64(buf, len) % static_cast<u64>(n_buckets));
+  }
+}
+
 }  // namespace ctr
+
+extern "C" int ctr_hash_int64(const int64_t* ids, int64_t N, int32_t n_buckets, int64_t* out,
+                              ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(ids && out && N >= 0 && n_buckets > 0, "ctr_hash_int64", "bad argument");
+  if (N == 0) return CTR_OK;
+  const int grid =
+      static_cast<int>(std::min<long long>((N + 255) / 256, ctr::sm_count() * 8LL));
+  ctr::hash_int64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), N, n_buckets, reinterpret_cast<long long*>(out));
+  CTR_LAUNCH_CHECK("ctr_hash_int64");
+}
 
 extern "C" int ctr_hash_strings(const uint8_t* bytes, const int32_t* offsets, int64_t N,
                                 const int32_t* field_of, const int32_t* n_buckets_dev,

@@ -135,17 +135,17 @@ static uint64_t cin_desc_hi() {
   // K-major, 128-byte swizzle: LBO field 1 (ignored), SBO = 8 rows * 128 B = 1024 B,
   // descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
   uint64_t lbo = 1, sbo = 1024 >> 4, ver = 1, lay = 2;
-  if (const char* e = getenv("CTR_CIN_DESC_LBO")) lbo = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_CIN_DESC_SBO")) sbo = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_CIN_DESC_VER")) ver = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_CIN_DESC_LAYOUT")) lay = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_CIN_DESC_LBO")) lbo = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_CIN_DESC_SBO")) sbo = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_CIN_DESC_VER")) ver = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_CIN_DESC_LAYOUT")) lay = strtoull(e, nullptr, 0);
   return (lbo << 16) | (sbo << 32) | (ver << 46) | (lay << 61);
 }
 static uint32_t cin_idesc(int N) {
   // kind::tf32: D = F32 (1 @bit4), A = B = TF32 (2 @bits7,10), K-major both, N>>3 @17, M>>4 @24.
   uint32_t d = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
                (static_cast<uint32_t>(kTcBM >> 4) << 24);
-  if (const char* e = getenv("CTR_CIN_IDESC_XOR")) d ^= static_cast<uint32_t>(strtoul(e, nullptr, 0));
+  if (const char* e = ctr_knob("CTR_CIN_IDESC_XOR")) d ^= static_cast<uint32_t>(strtoul(e, nullptr, 0));
   return d;
 }
 

@@ -317,9 +317,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // TMA box), SBO = distance between 4-row k groups.
 static uint64_t tcg_desc_mn() {
   uint64_t lbo = kTcgMnBox >> 4, sbo = 512 >> 4, ver = 1, lay = 1;
-  if (const char* e = getenv("CTR_TCG_MN_LAYOUT")) lay = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_TCG_MN_LBO")) lbo = strtoull(e, nullptr, 0);
-  if (const char* e = getenv("CTR_TCG_MN_SBO")) sbo = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_TCG_MN_LAYOUT")) lay = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_TCG_MN_LBO")) lbo = strtoull(e, nullptr, 0);
+  if (const char* e = ctr_knob("CTR_TCG_MN_SBO")) sbo = strtoull(e, nullptr, 0);
   return (lbo << 16) | (sbo << 32) | (ver << 46) | (lay << 61);
 }
 
@@ -353,7 +353,7 @@ static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, i
   }
   TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.NT = NT; p.a_mn = a_mn; p.b_mn = b_mn; p.n_pass = 3;
-  if (const char* e = getenv("CTR_TCG_PASSES")) p.n_pass = atoi(e) == 1 ? 1 : 3;
+  if (const char* e = ctr_knob("CTR_TCG_PASSES")) p.n_pass = atoi(e) == 1 ? 1 : 3;
   const int kb_total = (K + kTcKB - 1) / kTcKB;
   splits = std::max(1, std::min(splits, kb_total));
   p.kb_per_split = (kb_total + splits - 1) / splits;
@@ -368,12 +368,12 @@ static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, i
     p.lo_slots = 0;
   }
   p.stages = std::max(2, std::min(8, static_cast<int>((200u * 1024u) / p.stage_bytes) - p.lo_slots));
-  if (const char* e = getenv("CTR_TCG_STAGES")) p.stages = std::max(1, std::min(p.stages, atoi(e)));
+  if (const char* e = ctr_knob("CTR_TCG_STAGES")) p.stages = std::max(1, std::min(p.stages, atoi(e)));
   p.acc_stride = (NT + 31) / 32 * 32;
   // measured: one accumulator is as fast as many (the MMAs are operand-fetch bound, ~160 cycles
   // each whatever N is), and the epilogue then has nothing to add up; CTR_TCG_NACC > 1 rotates
   p.n_acc = 1;
-  if (const char* e = getenv("CTR_TCG_NACC"))
+  if (const char* e = ctr_knob("CTR_TCG_NACC"))
     p.n_acc = std::max(1, std::min(std::min(12, 512 / p.acc_stride), atoi(e)));
   p.tmem_cols = 32;
   while (p.tmem_cols < static_cast<uint32_t>(p.n_acc * p.acc_stride)) p.tmem_cols <<= 1;

@@ -276,6 +276,112 @@ bn_drop_apply_kernel(const float* __restrict__ A, int K, const BnDrop pro, float
   }
 }
 
+// Backward of bn_drop_apply (the last BN + dropout of a tower that ends without a dense layer,
+// dcn/dcn.py:146-149): dn[r,k] = dout[r,k] * keep(r,k), dbeta[k] += sum_r dn, dgamma[k] += sum_r
+// dn * xhat(A[r,k]) - the same bookkeeping tower_layer_bwd_data leaves for the layer below, so
+// the layer's dpre follows from a kind-1 gradient source over dn.  CTA = 32 rows, thread = column.
+__global__ void __launch_bounds__(256)
+bn_drop_apply_bwd_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ A, int K,
+                         const BnDrop pro, float* __restrict__ dn, float* __restrict__ dbeta,
+                         float* __restrict__ dgamma, int B) {
+  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const int r0 = blockIdx.x * 32, r1 = min(B, r0 + 32);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float mu, rstd;
+    bn_consts(pro.sums, pro.mean, pro.var, k, K, pro.inv_B, pro.eps, &mu, &rstd);
+    float cb = 0.f, cg = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float v = dout[static_cast<size_t>(r) * ldd + k];
+      if (pro.p > 0.f) v *= drop_scale(pro.seed, pro.layer, step, r, k, pro.p, pro.inv_keep);
+      dn[static_cast<size_t>(r) * K + k] = v;
+      cb += v;
+      cg = fmaf(v, (A[static_cast<size_t>(r) * K + k] - mu) * rstd, cg);
+    }
+    if (dbeta != nullptr && cb != 0.f) red_add_f32(dbeta + k, cb);
+    if (dgamma != nullptr && cg != 0.f) red_add_f32(dgamma + k, cg);
+  }
+}
+
+// ------------------------------------------------------------------------- DCN head
+// dcn/dcn.py:151-153 + the loss block :166-169 in one launch: logit[b] = [h[b,:H] | xl[b,:W]] . w
+// + hb, prob, mean BCE, and (training) dh = dl * w[:H], dxl = dl * w[H:], dw += sum_b dl * [h|xl],
+// dhb += sum_b dl with dl = (prob - z) * grad_scale.  Warp per sample; lane l owns the float4
+// columns l, l+32, ... of the concatenated row in every sample its warp visits, so the weight
+// gradient accumulates in registers and is flushed once per warp.
+constexpr int kDcnHeadNIT = 12;      // (H + W) / 4 <= 32 * 12
+struct DcnHeadParams {
+  const float* h; const float* xl; const float* w; const float* hb; const float* labels;
+  float* logits; float* prob; float* loss; float* dh; float* dxl; float* dw; float* dhb;
+  float loss_scale, grad_scale;
+  int H, W, B, want_grad;
+};
+__global__ void __launch_bounds__(256) dcn_head_kernel(const DcnHeadParams p) {
+  __shared__ float s_red[8][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HQ = p.H >> 2, NQ = (p.H + p.W) >> 2;
+  float4 wv[kDcnHeadNIT], dwv[kDcnHeadNIT];
+#pragma unroll
+  for (int it = 0; it < kDcnHeadNIT; ++it) {
+    const int q = it * 32 + lane;
+    wv[it] = q < NQ ? ldg4(p.w + q * 4) : f4_zero();
+    dwv[it] = f4_zero();
+  }
+  const float hb = p.hb[0];
+  float a_loss = 0.f, a_hb = 0.f;
+  for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
+    float4 x[kDcnHeadNIT];
+    float dot = 0.f;
+#pragma unroll
+    for (int it = 0; it < kDcnHeadNIT; ++it) {
+      const int q = it * 32 + lane;
+      x[it] = f4_zero();
+      if (q < HQ) x[it] = ldg4(p.h + static_cast<size_t>(b) * p.H + q * 4);
+      else if (q < NQ) x[it] = ldg4(p.xl + static_cast<size_t>(b) * p.W + (q - HQ) * 4);
+      dot += f4_dot(x[it], wv[it]);
+    }
+    const float logit = warp_sum(dot) + hb;
+    const float z = p.labels[b];
+    const float pr = 1.f / (1.f + expf(-logit));
+    if (lane == 0) {
+      if (p.logits != nullptr) p.logits[b] = logit;
+      if (p.prob != nullptr) p.prob[b] = pr;
+      a_loss += fmaxf(logit, 0.f) - logit * z + log1pf(expf(-fabsf(logit)));
+    }
+    if (p.want_grad) {
+      const float dl = (pr - z) * p.grad_scale;
+      if (lane == 0) a_hb += dl;
+#pragma unroll
+      for (int it = 0; it < kDcnHeadNIT; ++it) {
+        const int q = it * 32 + lane;
+        if (q >= NQ) continue;
+        dwv[it] = f4_fma(dl, x[it], dwv[it]);
+        const float4 g = make_float4(dl * wv[it].x, dl * wv[it].y, dl * wv[it].z, dl * wv[it].w);
+        if (q < HQ) *reinterpret_cast<float4*>(p.dh + static_cast<size_t>(b) * p.H + q * 4) = g;
+        else *reinterpret_cast<float4*>(p.dxl + static_cast<size_t>(b) * p.W + (q - HQ) * 4) = g;
+      }
+    }
+  }
+  if (p.want_grad) {
+#pragma unroll
+    for (int it = 0; it < kDcnHeadNIT; ++it) {
+      const int q = it * 32 + lane;
+      if (q < NQ) red_add_v4(p.dw + q * 4, dwv[it]);
+    }
+  }
+  if (lane == 0) {
+    s_red[warp][0] = a_loss;
+    s_red[warp][1] = a_hb;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
+    if (threadIdx.x == 0) red_add_f32(p.loss, t * p.loss_scale);
+    else if (p.want_grad) red_add_f32(p.dhb, t);
+  }
+}
+
 // -------------------------------------------------------------------------- backward
 // dXin[r,k] = sum_n dpre[r,n] * W[k,n]; then through the dropout + BN that produced Xin from the
 // stored activation Aprev (pro): dn = dXin * keep is stored, and its column sums
@@ -783,7 +889,7 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
     // few row tiles: split N down to 32 columns per CTA to put every SM to work (the A tiles
     // are then re-read from L2, which is cheaper than idle SMs)
     int ntiles = std::max((N + 127) / 128, std::min(sm_count() / mtiles, (N + 31) / 32));
-    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
+    if (const char* e = ctr_knob("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
     const int NT = std::min(128, round16((N + ntiles - 1) / ntiles));
     return tc_gemm_launch<TCG_EPI_FWD>(X, ldx, false, W, N, true, B, N, K, NT, 1, out, ldo, bias,
                                        stats, relu, st, "ctr_tower_layer_fwd");
@@ -791,7 +897,7 @@ int ctr_tower_layer_fwd(const float* X, int ldx, int K, const ctr_bn_drop* pro, 
   tower_smem_optin();
   const int ny = (N + kTwBN - 1) / kTwBN;
   bool small = static_cast<long long>((B + 31) / 32) * ny * 2 < sm_count();   // 16-row tiles
-  if (const char* e = getenv("CTR_TOWER_RT")) small = atoi(e) == 2;
+  if (const char* e = ctr_knob("CTR_TOWER_RT")) small = atoi(e) == 2;
   dim3 grid(small ? (B + 15) / 16 : (B + 31) / 32, ny);
   const size_t sb = sizeof(TowerSmem);
   if (has_pro) {
@@ -827,7 +933,7 @@ int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const f
   if (kind == 0) {          // out[B,N] = act(X[B,K] . W[K,N] + bias): W is MN-major (n contiguous)
     const int mtiles = (B + kTcBM - 1) / kTcBM;
     int ntiles = std::max((N + 127) / 128, std::min(sm_count() / mtiles, (N + 31) / 32));
-    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
+    if (const char* e = ctr_knob("CTR_TCG_NTILES")) ntiles = std::max(1, atoi(e));
     const int NT = std::min(128, round16((N + ntiles - 1) / ntiles));
     return tc_gemm_launch<TCG_EPI_FWD>(A, K, false, Bm, N, true, B, N, K, NT, 1, out, N, bias, stats,
                                        relu, st, fn, A_lo, B_lo);
@@ -839,14 +945,14 @@ int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const f
     CTR_REQUIRE(N <= 256 && aligned16(out), fn, "split-K forward needs N <= 256 and an aligned output");
     const int mtiles = (B + kTcBM - 1) / kTcBM;
     int splits = std::max(1, sm_count() / mtiles);
-    if (const char* e = getenv("CTR_TCG_FWD_SPLITS")) splits = std::max(1, atoi(e));
+    if (const char* e = ctr_knob("CTR_TCG_FWD_SPLITS")) splits = std::max(1, atoi(e));
     return tc_gemm_launch<TCG_EPI_RED>(A, K, false, Bm, N, true, B, N, K, round16(N), splits, out, N,
                                        nullptr, nullptr, 0, st, fn, A_lo, B_lo);
   }
   if (kind == 1) {          // out[B,K] = dpre[B,N] . W[K,N]^T: both K-major in n
     const int mtiles = (B + kTcBM - 1) / kTcBM;
     int ntiles = std::max((K + 255) / 256, std::min(sm_count() / mtiles, (K + 63) / 64));
-    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max((K + 255) / 256, atoi(e));
+    if (const char* e = ctr_knob("CTR_TCG_NTILES")) ntiles = std::max((K + 255) / 256, atoi(e));
     const int NT = round16((K + ntiles - 1) / ntiles);
     return tc_gemm_launch<TCG_EPI_STORE>(A, N, false, Bm, N, false, B, K, N, NT, 1, out, K, nullptr,
                                          nullptr, 0, st, fn, A_lo, B_lo);
@@ -855,7 +961,7 @@ int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const f
   CTR_REQUIRE(N <= 256 && aligned16(out), fn, "weights GEMM needs N <= 256 and an aligned output");
   const int mtiles = (K + kTcBM - 1) / kTcBM;
   int splits = std::max(1, std::min(sm_count() / mtiles, (B / kTcKB) / 4));
-  if (const char* e = getenv("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
+  if (const char* e = ctr_knob("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
   return tc_gemm_launch<TCG_EPI_RED>(A, K, true, Bm, N, true, K, N, B, round16(N), splits, out, N,
                                      nullptr, nullptr, 0, st, fn, A_lo, B_lo);
 }
@@ -869,6 +975,43 @@ int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out,
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 8LL));
   bn_drop_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, K, make_pro(pro, B), out, B);
   CTR_LAUNCH_CHECK("ctr_bn_drop_apply");
+}
+
+int ctr_bn_drop_apply_bwd(const float* dout, int ldd, const float* A, int K, const ctr_bn_drop* pro,
+                          float* dn, float* dbeta, float* dgamma, int B, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(dout && A && dn && pro && pro->enabled && K > 0 && B >= 0 && ldd >= K,
+              "ctr_bn_drop_apply_bwd", "bad argument");
+  CTR_REQUIRE(pro->gamma && pro->beta && (pro->sums || (pro->mean && pro->var)),
+              "ctr_bn_drop_apply_bwd", "BN needs gamma/beta and stats");
+  if (B == 0) return CTR_OK;
+  const int threads = K <= 32 ? 32 : K <= 64 ? 64 : K <= 128 ? 128 : 256;
+  bn_drop_apply_bwd_kernel<<<(B + 31) / 32, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dout, ldd, A, K, make_pro(pro, B), dn, dbeta, dgamma, B);
+  CTR_LAUNCH_CHECK("ctr_bn_drop_apply_bwd");
+}
+
+int ctr_dcn_head(const float* h, int H, const float* xl, int W, const float* w, const float* hb,
+                 const float* labels, int B, float* logits, float* prob, float* loss, float* dh,
+                 float* dxl, float* dw, float* dhb, float grad_scale, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(h && xl && w && hb && labels && loss && B >= 0, "ctr_dcn_head", "null pointer");
+  CTR_REQUIRE(H > 0 && W > 0 && (H & 3) == 0 && (W & 3) == 0 && (H + W) / 4 <= 32 * kDcnHeadNIT,
+              "ctr_dcn_head", "need H % 4 == W % 4 == 0 and H + W <= 1536");
+  CTR_REQUIRE(aligned16(h) && aligned16(xl) && aligned16(w) && aligned16(dh) && aligned16(dxl) &&
+                  aligned16(dw),
+              "ctr_dcn_head", "pointers must be 16-byte aligned");
+  const bool want_grad = dh != nullptr;
+  CTR_REQUIRE(!want_grad || (dxl && dw && dhb), "ctr_dcn_head", "missing gradient outputs");
+  if (B == 0) return CTR_OK;
+  DcnHeadParams p{};
+  p.h = h; p.xl = xl; p.w = w; p.hb = hb; p.labels = labels; p.logits = logits; p.prob = prob;
+  p.loss = loss; p.dh = dh; p.dxl = dxl; p.dw = dw; p.dhb = dhb;
+  p.loss_scale = 1.f / static_cast<float>(B); p.grad_scale = grad_scale;
+  p.H = H; p.W = W; p.B = B; p.want_grad = want_grad ? 1 : 0;
+  const int grid = std::min((B + 7) / 8, sm_count() * 2);
+  dcn_head_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CTR_LAUNCH_CHECK("ctr_dcn_head");
 }
 
 int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int K,
@@ -895,7 +1038,7 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
     // out[B, K] = dpre[B, N] . W[K, N]^T: both operands K-major in n
     const int mtiles = (B + kTcBM - 1) / kTcBM;
     int ntiles = std::max((K + 255) / 256, std::min(sm_count() / mtiles, (K + 63) / 64));
-    if (const char* e = getenv("CTR_TCG_NTILES")) ntiles = std::max((K + 255) / 256, atoi(e));
+    if (const char* e = ctr_knob("CTR_TCG_NTILES")) ntiles = std::max((K + 255) / 256, atoi(e));
     const int NT = round16((K + ntiles - 1) / ntiles);
     return tc_gemm_launch<TCG_EPI_STORE>(gs->G, gs->ldg, false, W, N, false, B, K, N, NT, 1, dn_out,
                                          ldn, nullptr, nullptr, 0, st, "ctr_tower_layer_bwd_data");
@@ -903,7 +1046,7 @@ int ctr_tower_layer_bwd_data(const ctr_grad_src* gs, int N, const float* W, int 
   tower_smem_optin();
   const int ny = (K + kTwBN - 1) / kTwBN;
   bool small = static_cast<long long>((B + 31) / 32) * ny * 2 < sm_count();
-  if (const char* e = getenv("CTR_TOWER_RT")) small = atoi(e) == 2;
+  if (const char* e = ctr_knob("CTR_TOWER_RT")) small = atoi(e) == 2;
   dim3 grid(small ? (B + 15) / 16 : (B + 31) / 32, ny);
   if (small)
     tower_layer_bwd_data_kernel<2><<<grid, 256, sizeof(TowerSmem), st>>>(
@@ -962,7 +1105,7 @@ int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_dro
       tower_colsum_kernel<<<(B + kDpreRows - 1) / kDpreRows, 256, 0, st>>>(gs->G, gs->ldg, N, db, B);
     const int mtiles = (K + kTcBM - 1) / kTcBM;
     int splits = std::max(1, std::min(sm_count() / mtiles, (B / kTcKB) / 4));
-    if (const char* e = getenv("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
+    if (const char* e = ctr_knob("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
     return tc_gemm_launch<TCG_EPI_RED>(X, ldx, true, gs->G, gs->ldg, true, K, N, B, round16(N),
                                        splits, dW, N, nullptr, nullptr, 0, st,
                                        "ctr_tower_layer_bwd_weights");

@@ -694,7 +694,7 @@ int ctr_tower_mid(const ctr_tower_mid_args* a, int B, ctr_stream_t stream) {
   // could occupy an SM ever waits on this kernel), for drivers that cannot capture cooperative
   // launches into a CUDA graph.
   static const bool coop = [] {
-    const char* v = getenv("CTR_MID_COOP");
+    const char* v = ctr_knob("CTR_MID_COOP");
     return v == nullptr || atoi(v) != 0;
   }();
   if (a->training && coop) {

@@ -65,6 +65,7 @@ class IdPipeline:
         self.device = device
         self.cont_keys: List[str] = []
         self.cat_keys: List[str] = []
+        self.raw_int64: Dict[str, bool] = {}      # columns fed raw int64 keys (hashed here)
         descs = (_lib.FieldDesc * lay.F)()
         bnd: List[float] = []
         for f, col in enumerate(lay.columns):
@@ -83,6 +84,7 @@ class IdPipeline:
             else:
                 d.kind, d.src = 1, len(self.cat_keys)
                 self.cat_keys.append(cc.key)
+                self.raw_int64[cc.key] = getattr(cc, "dtype", "string") == "int64"
         raw = bytes(descs)
         self.fields_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
         self.bnd_dev = torch.tensor(bnd if bnd else [0.0], dtype=torch.float32, device=device)
@@ -94,7 +96,7 @@ class IdPipeline:
     def pack(self, features) -> tuple:
         """-> (cont f32 [B,n_cont], cat i64 [B,n_cat]) on the device."""
         if isinstance(features, PackedFeatures) and features.cont_keys == self.cont_keys \
-                and features.cat_keys == self.cat_keys:
+                and features.cat_keys == self.cat_keys and not any(self.raw_int64.values()):
             cont, cat = features.cont, features.cat
         else:
             cont = torch.cat([torch.as_tensor(features[k]).reshape(-1, 1).float()
@@ -102,8 +104,15 @@ class IdPipeline:
             cats = []
             for k in self.cat_keys:
                 v = features[k]
-                if not torch.is_tensor(v):
+                if not torch.is_tensor(v) and not _is_int_array(v):
                     v = self.hash_strings_host(k, v)
+                elif self.raw_int64[k]:
+                    # categorical_column_with_hash_bucket(dtype=int64): raw keys, hashed as their
+                    # decimal strings on the device (deepfm/deepfm.py:41,46) [TF-sem]
+                    v = hash_int64(torch.as_tensor(v), self.lay.rows[self.lay.field_of(k)],
+                                   self.device)
+                else:
+                    v = torch.as_tensor(v)
                 cats.append(v.reshape(-1, 1).long())
             cat = torch.cat(cats, 1) if cats else None
         if cont is not None:
@@ -128,6 +137,19 @@ class IdPipeline:
               _p(self.fields_dev), _p(self.bnd_dev), B, self.lay.F, _p(rows), _p(logx),
               _p(self.status), _stream())
         return (rows, logx) if want_logx else rows
+
+
+def _is_int_array(v) -> bool:
+    import numpy as np
+    return isinstance(v, np.ndarray) and v.dtype.kind in "iu"
+
+
+def hash_int64(ids: torch.Tensor, n_buckets: int, device) -> torch.Tensor:
+    """Fingerprint64(as_string(id)) mod n_buckets on the device (ctr_hash_int64)."""
+    ids = ids.to(device, torch.int64).contiguous()
+    out = torch.empty_like(ids)
+    _call("ctr_hash_int64", _p(ids), ids.numel(), int(n_buckets), _p(out), _stream())
+    return out
 
 
 def _flatten(values):
@@ -577,22 +599,23 @@ class _DinAttFn(torch.autograd.Function):
     first row; the table gradient is RED-accumulated there, not returned."""
 
     @staticmethod
-    def forward(ctx, anchor, table, dtable, hist, query, W1, b1, W2, b2, W3, b3):
+    def forward(ctx, anchor, table, dtable, hist, query, W1, b1, W2, b2, W3, b3, opts):
         B, P = hist.shape
         E = query.shape[1]
         hist = hist.contiguous()
         query = query.contiguous()
         out = torch.empty((B, E), dtype=torch.float32, device=query.device)
         _call("ctr_din_att_fwd", _p(table), _p(hist), _p(query), B, P, E, _p(W1), _p(b1),
-              W1.shape[1], _p(W2), _p(b2), W2.shape[1], _p(W3), _p(b3), _p(out), None, _stream())
+              W1.shape[1], _p(W2), _p(b2), W2.shape[1], _p(W3), _p(b3), _p(out), None,
+              C.byref(opts) if opts is not None else None, _stream())
         ctx.save_for_backward(hist, query, W1, b1, W2, b2, W3, b3)
-        ctx.tabs = (table, dtable)
+        ctx.tabs = (table, dtable, opts)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         hist, query, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
-        table, dtable = ctx.tabs
+        table, dtable, opts = ctx.tabs
         B, P = hist.shape
         E = query.shape[1]
         lib = _lib.load()
@@ -603,17 +626,40 @@ class _DinAttFn(torch.autograd.Function):
         _call("ctr_din_att_bwd", _p(table), _p(hist), _p(query), B, P, E, _p(W1), _p(b1),
               W1.shape[1], _p(W2), _p(b2), W2.shape[1], _p(W3), _p(b3), _p(dout.contiguous()),
               _p(dtable), _p(dq), _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(g[5]),
-              _p(ws), ws.numel(), _stream())
-        return (None, None, None, None, dq) + tuple(g)
+              _p(ws), ws.numel(), C.byref(opts) if opts is not None else None, _stream())
+        return (None, None, None, None, dq) + tuple(g) + (None,)
 
 
-def din_attention(emb: "FieldEmbedding", field: int, hist, query, W1, b1, W2, b2, W3, b3):
+def din_opts(unit: int, n_rows: int, p_drop: float = 0.0, seed: int = 0, state_ptr=None,
+             status: Optional[torch.Tensor] = None) -> "_lib.DinOpts":
+    """ctr_din_opts: dropout stream + id range check of one attention unit."""
+    o = _lib.DinOpts()
+    o.state, o.p_drop, o.seed, o.unit = state_ptr, float(p_drop), seed & 0xFFFFFFFF, unit
+    o.table_rows, o.status = int(n_rows), _p(status)
+    return o
+
+
+def din_attention(emb: "FieldEmbedding", field: int, hist, query, W1, b1, W2, b2, W3, b3,
+                  opts=None):
     """Attention of ``query`` over the history ids ``hist`` (local ids of sub-table
-    ``field`` of ``emb``; 0 = padding)."""
+    ``field`` of ``emb``; 0 = padding).  ``opts``: ``din_opts(...)`` (dropout, id range check)."""
     require_cuda(hist, "hist")
     lo, hi = emb.lay.offsets[field], emb.lay.offsets[field + 1]
+    if opts is None:
+        opts = din_opts(field, hi - lo)
     return _DinAttFn.apply(emb._anchor, emb.table[lo:hi], emb.dtable[lo:hi], hist, query,
-                           W1.contiguous(), b1, W2.contiguous(), b2, W3.reshape(-1), b3)
+                           W1.contiguous(), b1, W2.contiguous(), b2, W3.reshape(-1), b3, opts)
+
+
+def din_dropout_masks(opts, n_rows: int, device):
+    """Keep scales (0 or 1/(1-p)) the attention kernels use at the current step:
+    ([n_rows, 80], [n_rows, 40]) - what the parity tests inject into the oracle."""
+    outs = []
+    for layer, H in ((0, 80), (1, 40)):
+        o = torch.empty((n_rows, H), dtype=torch.float32, device=device)
+        _call("ctr_din_dropout_mask", C.byref(opts), layer, n_rows, H, _p(o), _stream())
+        outs.append(o)
+    return outs
 
 
 # ------------------------------------------------------- fused dense tower + loss head
@@ -627,9 +673,20 @@ class FusedTower:
     flat gradient buffer by the backward kernels (no per-parameter autograd adds)."""
 
     def __init__(self, dense: "DenseParams", prefix: str, sizes, out_layer: bool, dropout: float,
-                 adam: "TFAdamState", seed: int = 0):
+                 adam: "TFAdamState", seed: int = 0, bn: bool = True, out_relu: bool = True,
+                 layer_base: int = 0):
+        """``bn=False``: dense(relu) -> dropout without batch normalisation (DIN's MLP,
+        din/din.py:133-137).  ``out_relu=False``: the final dense(1) has no activation
+        (din/din.py:139).  ``layer_base``: offset of this tower's layers in the dropout
+        counter space, so that two towers of one model draw independent masks."""
         self.dense, self.prefix, self.sizes = dense, prefix, list(sizes)
         self.out_layer, self.dropout, self.adam, self.seed = out_layer, float(dropout), adam, seed
+        self.bn, self.out_relu, self.layer_base = bool(bn), bool(out_relu), int(layer_base)
+        if not self.bn:     # identity "BN" constants for the prologue descriptors
+            w = max(self.sizes)
+            self._zeros = torch.zeros(w, dtype=torch.float32, device=dense.flat.device)
+            self._ones = torch.ones(w, dtype=torch.float32, device=dense.flat.device)
+        self._ones_col = {}
         self._anchor = torch.zeros((), device=dense.flat.device, requires_grad=True)
         # weight-gradient kernels run on a side stream, off the critical path
         # (dX chain -> embedding scatter -> row Adam); joined in ``join()`` before dense Adam
@@ -644,7 +701,7 @@ class FusedTower:
         self.timing = None      # set to an int64[8] device tensor to get the phase time stamps
         self.last_acts = None
         self.last_y = None
-        self.mid_ok = (out_layer and 1 <= len(self.sizes) - 1 <= 4
+        self.mid_ok = (out_layer and self.bn and self.out_relu and 1 <= len(self.sizes) - 1 <= 4
                        and all(4 <= h <= 128 and h % 4 == 0 for h in self.sizes[1:]))
 
         # pre-split 3xTF32 operands for the first layer's tcgen05 GEMMs (ctr_tower_gemm_presplit)
@@ -711,7 +768,15 @@ class FusedTower:
         return self.dense[self.prefix + "." + name]
 
     def G(self, name):
-        return self.dense[self.prefix + "." + name].grad
+        key = self.prefix + "." + name
+        return self.dense[key].grad if key in self.dense else None
+
+    def ones_col(self, B):
+        t = self._ones_col.get(B)
+        if t is None:
+            t = self._ones_col[B] = torch.ones(B, 1, dtype=torch.float32,
+                                               device=self.dense.flat.device)
+        return t
 
     def __call__(self, X, training: bool):
         require_cuda(X, "tower input")
@@ -719,13 +784,19 @@ class FusedTower:
 
     def bn_drop(self, l, sums, training):
         d = _lib.BnDrop()
-        d.sums = _p(sums) if training else None
-        d.mean, d.var = _p(self.P("%d.bn.mean" % l)), _p(self.P("%d.bn.var" % l))
-        d.gamma, d.beta = _p(self.P("%d.bn.gamma" % l)), _p(self.P("%d.bn.beta" % l))
         d.state = self.adam.state_ptr
-        d.eps = BN_EPS
         d.p_drop = self.dropout if training else 0.0
-        d.seed, d.layer, d.enabled = self.seed & 0xFFFFFFFF, l, 1
+        d.seed, d.layer = self.seed & 0xFFFFFFFF, self.layer_base + l
+        if self.bn:
+            d.sums = _p(sums) if training else None
+            d.mean, d.var = _p(self.P("%d.bn.mean" % l)), _p(self.P("%d.bn.var" % l))
+            d.gamma, d.beta = _p(self.P("%d.bn.gamma" % l)), _p(self.P("%d.bn.beta" % l))
+            d.eps, d.enabled = BN_EPS, 1
+        else:       # x' = x * keep: mean 0, var 1, eps 0, gamma 1, beta 0; nothing at all in eval
+            d.sums = None
+            d.mean, d.var = _p(self._zeros), _p(self._ones)
+            d.gamma, d.beta = _p(self._ones), _p(self._zeros)
+            d.eps, d.enabled = 0.0, 1 if d.p_drop > 0.0 else 0
         return d
 
 
@@ -741,7 +812,7 @@ class _TowerFn(torch.autograd.Function):
         for l in range(L):
             H = tw.sizes[l + 1]
             a = torch.empty((B, H), dtype=torch.float32, device=dev)
-            st = torch.zeros((2, H), dtype=torch.float32, device=dev) if training else None
+            st = torch.zeros((2, H), dtype=torch.float32, device=dev) if (training and tw.bn) else None
             _call("ctr_tower_layer_fwd", _p(x), K, K, C.byref(pro) if pro is not None else None,
                   _p(tw.P("%d.w" % l)), _p(tw.P("%d.b" % l)), H, _p(a), H, _p(st), 1, B, _stream())
             pro = tw.bn_drop(l, st, training)
@@ -752,12 +823,14 @@ class _TowerFn(torch.autograd.Function):
         if tw.out_layer:
             y = torch.empty((B, 1), dtype=torch.float32, device=dev)
             _call("ctr_tower_layer_fwd", _p(x), K, K, C.byref(pro), _p(tw.P("out.w")),
-                  _p(tw.P("out.b")), 1, _p(y), 1, None, 1, B, _stream())
+                  _p(tw.P("out.b")), 1, _p(y), 1, None, 1 if tw.out_relu else 0, B, _stream())
             out = y.view(B)
-        else:
+        elif pro.enabled:
             y = None
             out = torch.empty((B, K), dtype=torch.float32, device=dev)
             _call("ctr_bn_drop_apply", _p(x), K, C.byref(pro), _p(out), B, _stream())
+        else:
+            y, out = None, x.clone()
         ctx.tw, ctx.training = tw, training
         ctx.saved = (X, acts, stats, pros, y)
         return out
@@ -768,13 +841,13 @@ class _TowerFn(torch.autograd.Function):
         X, acts, stats, pros, y = ctx.saved
         if not ctx.training:
             raise RuntimeError("FusedTower backward is only defined in training mode")
-        if not tw.out_layer:
-            raise NotImplementedError("backward of a tower without a final dense layer")
         B, dev = X.shape[0], X.device
         L = len(tw.sizes) - 1
-        dout = dout.contiguous().view(B, 1)
+        dout = dout.contiguous().view(B, -1)
 
         def grad_src(G, ldg, a, lda, kind, l=None):
+            if kind == 1 and not tw.bn:
+                kind = 0          # no BN after the layer: the stored dn is the gradient itself
             g = _lib.GradSrc()
             g.G, g.ldg, g.a, g.lda, g.kind, g.train, g.eps = _p(G), ldg, _p(a), lda, kind, 1, BN_EPS
             if kind == 1:
@@ -796,15 +869,25 @@ class _TowerFn(torch.autograd.Function):
                 _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs_w), H,
                       _p(tw.G(wname)), _p(tw.G(bname)) if bname else None, B, side.cuda_stream)
 
-        # final dense(1, relu): dpre = dout * 1[y > 0]
-        gs = grad_src(dout, 1, y, 1, 0)
         HL = tw.sizes[L]
-        fork()
-        weights(acts[L - 1], HL, C.byref(pros[L - 1]), gs, 1, "out.w", "out.b")
         dn = torch.empty((B, HL), dtype=torch.float32, device=dev)
-        _call("ctr_tower_layer_bwd_data", C.byref(gs), 1, _p(tw.P("out.w")), HL,
-              C.byref(pros[L - 1]), _p(acts[L - 1]), _p(dn), HL, _p(tw.G("%d.bn.beta" % (L - 1))),
-              _p(tw.G("%d.bn.gamma" % (L - 1))), B, _stream())
+        if tw.out_layer:
+            # final dense(1, relu): dpre = dout * 1[y > 0]; without the ReLU (DIN) dpre = dout, which
+            # the same kernels produce when the "activation" they gate on is a column of ones
+            gs = grad_src(dout, 1, y if tw.out_relu else tw.ones_col(B), 1, 0)
+            fork()
+            weights(acts[L - 1], HL, C.byref(pros[L - 1]), gs, 1, "out.w", "out.b")
+            _call("ctr_tower_layer_bwd_data", C.byref(gs), 1, _p(tw.P("out.w")), HL,
+                  C.byref(pros[L - 1]), _p(acts[L - 1]), _p(dn), HL,
+                  _p(tw.G("%d.bn.beta" % (L - 1))), _p(tw.G("%d.bn.gamma" % (L - 1))), B, _stream())
+        elif pros[L - 1].enabled:
+            # the tower ends in BN + dropout (dcn/dcn.py:146-149): through the dropout, and the BN
+            # column sums of the last layer
+            _call("ctr_bn_drop_apply_bwd", _p(dout), HL, _p(acts[L - 1]), HL, C.byref(pros[L - 1]),
+                  _p(dn), _p(tw.G("%d.bn.beta" % (L - 1))), _p(tw.G("%d.bn.gamma" % (L - 1))), B,
+                  _stream())
+        else:
+            dn = dout
         keep = [dout, dn]
         for l in range(L - 1, -1, -1):
             H, K = tw.sizes[l + 1], tw.sizes[l]
@@ -987,6 +1070,43 @@ class _TowerHeadFn(torch.autograd.Function):
         return (dX, None, None, None, None, None, None) + tuple(dzs)
 
 
+class _DcnHeadFn(torch.autograd.Function):
+    """ctr_dcn_head: logit = [h | xl] . w + b, prob, mean BCE and - in training - dh, dxl, dw, db in
+    the same launch (dcn/dcn.py:151-153,166-169)."""
+
+    @staticmethod
+    def forward(ctx, h, xl, anchor, w, dw, hb, dhb, labels, grad_scale, training):
+        ctx.set_materialize_grads(False)
+        h, xl = h.contiguous(), xl.contiguous()
+        B, dev = h.shape[0], h.device
+        labels = labels.to(dev, torch.float32).contiguous().view(B)
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        prob = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        dh = torch.empty_like(h) if training else None
+        dxl = torch.empty_like(xl) if training else None
+        _call("ctr_dcn_head", _p(h), h.shape[1], _p(xl), xl.shape[1], _p(w), _p(hb), _p(labels), B,
+              _p(logits), _p(prob), _p(loss), _p(dh), _p(dxl), _p(dw) if training else None,
+              _p(dhb) if training else None, float(grad_scale), _stream())
+        ctx.g = (dh, dxl)
+        ctx.mark_non_differentiable(logits, prob)
+        return loss, logits, prob
+
+    @staticmethod
+    def backward(ctx, gl, _g1, _g2):
+        dh, dxl = ctx.g       # produced with the final scale; the caller backpropagates the loss itself
+        return (dh, dxl) + (None,) * 8
+
+
+def dcn_head(anchor, dense: "DenseParams", h, xl, labels, hw="head.w", hb="head.b", grad_scale=None,
+             training=True):
+    require_cuda(h, "tower output")
+    if grad_scale is None:
+        grad_scale = 1.0 / h.shape[0]
+    return _DcnHeadFn.apply(h, xl, anchor, dense[hw], dense[hw].grad, dense[hb], dense[hb].grad,
+                            labels, grad_scale, training)
+
+
 def split_lo(x: torch.Tensor) -> torch.Tensor:
     """lo half of the 3xTF32 split of ``x`` (ctr_split_lo)."""
     require_cuda(x, "x")
@@ -1026,11 +1146,14 @@ class _LossHeadFn(torch.autograd.Function):
         zp = (C.c_void_p * Cn)(*[z.data_ptr() for z in zs])
         dzs = [torch.empty(B, dtype=torch.float32, device=dev) for _ in zs] if want_grad else None
         dzp = (C.c_void_p * Cn)(*[d.data_ptr() for d in dzs]) if want_grad else None
-        hw, hb, b1 = names
-        _call("ctr_loss_head", zp, dzp, Cn, 1 if relu0 else 0, _p(dense[hw]), _p(dense[hb]),
-              _p(dense[b1]) if relu0 else None, _p(labels), B, _p(logits), _p(prob), _p(loss),
-              _p(dense[hw].grad) if want_grad else None, _p(dense[hb].grad) if want_grad else None,
-              _p(dense[b1].grad) if (want_grad and relu0) else None, float(grad_scale), _stream())
+        # a head parameter is a name in ``dense`` or an explicit (value, gradient) tensor pair
+        (hw, dhw), (hb, dhb), (b1, db1) = [
+            n if isinstance(n, tuple) else (dense[n], dense[n].grad) if n in dense else (None, None)
+            for n in names]
+        _call("ctr_loss_head", zp, dzp, Cn, 1 if relu0 else 0, _p(hw), _p(hb),
+              _p(b1) if relu0 else None, _p(labels), B, _p(logits), _p(prob), _p(loss),
+              _p(dhw) if want_grad else None, _p(dhb) if want_grad else None,
+              _p(db1) if (want_grad and relu0) else None, float(grad_scale), _stream())
         ctx.dzs = dzs
         ctx.mark_non_differentiable(logits, prob)
         return loss, logits, prob

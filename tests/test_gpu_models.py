@@ -67,7 +67,7 @@ def _check_grads(m, grads64, tol=1e-3):
 
 
 @pytest.mark.parametrize("model", ["fm", "deepfm", "dcn", "xdeepfm", "xdeepfm-fp32", "fm-torch",
-                                   "deepfm-torch", "xdeepfm-torch"])
+                                   "deepfm-torch", "xdeepfm-torch", "dcn-torch"])
 @pytest.mark.parametrize("B", [64, 1000])
 def test_criteo_models_match_oracle(cuda, model, B):
     """Default = fused tower / loss-head kernels; ``-torch`` = the torch (cuBLAS) tower."""
@@ -110,7 +110,7 @@ def _dropout_masks(m, B):
         d = _lib.BnDrop()
         d.sums, d.mean, d.var = None, zero.data_ptr(), (one - 1e-3).data_ptr()
         d.gamma, d.beta, d.state = one.data_ptr(), zero.data_ptr(), tw.adam.state_ptr
-        d.eps, d.p_drop, d.seed, d.layer, d.enabled = 1e-3, tw.dropout, tw.seed, l, 1
+        d.eps, d.p_drop, d.seed, d.layer, d.enabled = 1e-3, tw.dropout, tw.seed, tw.layer_base + l, 1
         var = one - 1e-3
         d.var = var.data_ptr()
         rc = lib.ctr_bn_drop_apply(ones.data_ptr(), H, C.byref(d), out.data_ptr(), B,
@@ -123,21 +123,22 @@ def _dropout_masks(m, B):
     return masks
 
 
-def test_fused_tower_dropout_matches_oracle_with_same_masks(cuda):
+@pytest.mark.parametrize("model", ["deepfm", "dcn"])
+def test_fused_tower_dropout_matches_oracle_with_same_masks(cuda, model):
     """dropout 0.5 (the reference's training default): the fused kernels regenerate the mask in
     the backward from (seed, layer, step); with those masks injected into the oracle, logits,
-    loss and every gradient agree; the keep rate is ~0.5 and masks differ between layers/steps."""
-    from recsys_b200.deepfm import deepfm
+    loss and every gradient agree; the keep rate is ~0.5 and masks differ between layers/steps.
+    DCN: the tower ends in BN + dropout (no final dense layer, dcn/dcn.py:144-149)."""
     spec = mg.small_spec()
     B = 512
-    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
-    feats, batch = mg.model_batch("deepfm", B, 9, spec)
-    m, params = _build("deepfm", spec, cuda, dropout=0.5, fused_tower=True)
+    p64 = om.init_params(model, spec.total_rows, deep_layers=(32, 16), seed=3)
+    feats, batch = mg.model_batch(model, B, 9, spec)
+    m, params = _build(model, spec, cuda, dropout=0.5, fused_tower=True)
     m.load_state(p64)
     masks = _dropout_masks(m, B)
     assert all(0.4 < float(k.mean()) < 0.6 for k in masks) and not torch.equal(masks[0][:, :16], masks[1])
-    out64, g64 = om.loss_and_grads("deepfm", p64, batch, dropout=0.5, masks=[k.double() for k in masks])
-    sp = deepfm.model_fn(_features_to_torch(feats), batch["labels"], "train", params)
+    out64, g64 = om.loss_and_grads(model, p64, batch, dropout=0.5, masks=[k.double() for k in masks])
+    sp = _model_fn(model)(_features_to_torch(feats), batch["labels"], "train", params)
     logits = m.last["logits"].detach().cpu().double().reshape(-1)
     ref = out64["logits"].reshape(-1)
     assert float(((logits - ref).abs() / (ref.abs() + 0.1)).max()) <= 1e-4
@@ -269,6 +270,121 @@ def test_din_matches_oracle(cuda, B, P):
     for k, gg in g64.items():
         if k in dg:
             close(dg[k], gg.reshape(dg[k].shape), k)
+
+
+def test_din_dropout_matches_oracle_with_same_masks(cuda):
+    """din/din.py:15,118,136: the reference's default dropout 0.5 sits inside both activation
+    units (after the 80- and the 40-wide layer, per history position) and after every MLP layer.
+    The kernels draw counter-based masks (Philox) and regenerate them in the backward; with the
+    same masks injected into the oracle, logits, loss and every gradient agree."""
+    from recsys_b200 import _core, ops
+    from recsys_b200.din import din
+    from recsys_b200.estimator import VariableStore
+    B, P = 192, 40
+    feats, labels = synth.synthetic_din(B, P=P, seed=6, n_items=500, n_cates=50)
+    p64 = om.init_params("din", D=16, seed=4, din_items=500, din_cates=50)
+    g = torch.Generator().manual_seed(2)
+    p64["i_item"] = torch.randn(500, generator=g, dtype=torch.float64) * 0.1
+    for k in list(p64):
+        if k.endswith(".b"):
+            p64[k] = torch.randn(p64[k].shape, generator=g, dtype=torch.float64) * 0.05
+    params = {"embedding_size": 16, "learning_rate": 1e-3, "dropout": 0.5, "din_items": 500,
+              "din_cates": 50, "variable_store": VariableStore(), "device": cuda}
+    m = params["variable_store"].get("din", lambda: _core.DINModel(params))
+    m.load_state(p64)
+    masks = {}
+    for unit, name in enumerate(("att_iid", "att_cat")):
+        scales = ops.din_dropout_masks(m.att_opts(unit, True), B * P, cuda)
+        masks[name] = [(s > 0).double().cpu() for s in scales]
+        assert all(torch.allclose(s[s > 0], torch.full_like(s[s > 0], 2.0)) for s in scales)
+        assert all(0.45 < float(k.mean()) < 0.55 for k in masks[name])
+    assert not torch.equal(masks["att_iid"][0], masks["att_cat"][0])
+    masks["mlp"] = [k.double() for k in _dropout_masks(m, B)]
+    assert all(0.4 < float(k.mean()) < 0.6 for k in masks["mlp"])
+    batch = {k: torch.from_numpy(v) for k, v in feats.items()}
+    batch["labels"] = torch.from_numpy(labels)
+    out64, g64 = om.loss_and_grads("din", p64, batch, dropout=0.5, masks=masks)
+    sp = din.model_fn({k: torch.from_numpy(v) for k, v in feats.items()}, torch.from_numpy(labels),
+                      "train", params)
+    logits = m.last["logits"].detach().cpu().double()
+    ref = out64["logits"]
+    assert float(((logits - ref).abs() / (ref.abs() + 0.1)).max()) <= 1e-4
+    assert abs(float(sp.loss) - float(out64["loss"])) <= 1e-5
+    m.backward(m.last["loss"])
+
+    def close(a, b, what, tol=1e-3):
+        err = float((a.detach().cpu().double() - b).abs().max())
+        s = float(b.abs().max()) + 1e-12
+        assert err <= tol * s + 1e-7, "%s: err %.3e scale %.3e" % (what, err, s)
+    close(m.emb.dtable[:500], g64["i_id"], "d i_id")
+    close(m.emb.dtable[500:], g64["i_cate"], "d i_cate")
+    dg = m.dense_grads()
+    for k, gg in g64.items():
+        if k in dg:
+            close(dg[k], gg.reshape(dg[k].shape), k)
+    # eval mode: no dropout, deterministic
+    e1 = din.model_fn({k: torch.from_numpy(v) for k, v in feats.items()}, torch.from_numpy(labels),
+                      "eval", params)
+    o = om.din(p64, **batch, training=False)
+    assert torch.allclose(e1.predictions["prob"].cpu().double(), o["prob"], rtol=1e-4, atol=1e-6)
+
+
+def test_din_out_of_range_ids_are_flagged_not_read(cuda):
+    """ids >= table rows must not read / RED out of bounds.  History ids outside the
+    table are treated as padding, target ids are wrapped, and the sticky status word makes the
+    next eval call raise."""
+    from recsys_b200 import _core
+    from recsys_b200.din import din
+    from recsys_b200.estimator import VariableStore
+    B, P = 64, 12
+    feats, labels = synth.synthetic_din(B, P=P, seed=7, n_items=500, n_cates=50)
+    params = {"embedding_size": 16, "learning_rate": 1e-3, "dropout": 0.0, "din_items": 500,
+              "din_cates": 50, "variable_store": VariableStore(), "device": cuda}
+    tf = {k: torch.from_numpy(v.copy()) for k, v in feats.items()}
+    clean = din.model_fn(tf, torch.from_numpy(labels), "eval", params).predictions["prob"].clone()
+    m = params["variable_store"]._objs["din"]
+    bad = {k: v.clone() for k, v in tf.items()}
+    was_pad = bad["u_iid_seq"][:, 3] == 0
+    bad["u_iid_seq"][:, 3] = torch.where(was_pad, torch.tensor(10 ** 7), bad["u_iid_seq"][:, 3])
+    assert bool(was_pad.any())
+    with torch.no_grad():        # the out-of-range ids replaced padding and are read as padding
+        _, prob, _ = m.forward(bad, torch.from_numpy(labels), False)
+    assert torch.equal(clean, prob)
+    with pytest.raises(RuntimeError, match="history id outside"):
+        m.check_status()
+    assert int(m.ids.status.item()) == 0          # reading the word clears it
+    bad2 = {k: v.clone() for k, v in tf.items()}
+    bad2["i_id"][0] = 500
+    with pytest.raises(RuntimeError, match="categorical id outside"):
+        din.model_fn(bad2, torch.from_numpy(labels), "eval", params)
+
+
+def test_deepfm_two_field_int64_keys_are_hashed(cuda):
+    """deepfm/deepfm.py:37-51: u_id / i_id are int64 keys; categorical_column_with_hash_bucket
+    hashes their decimal strings (as_string + Fingerprint64) [TF-sem].  The ids the model looks
+    up must be hash(str(key)) % buckets, not key % buckets."""
+    from recsys_b200 import _core
+    from recsys_b200.deepfm import deepfm
+    from recsys_b200.estimator import VariableStore
+    from oracle import farmhash
+    lin, emb = deepfm.build_model_columns(16)
+    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
+              "learning_rate": 1e-3, "dropout": 0.0, "deep_layers": "32,16",
+              "variable_store": VariableStore(), "device": cuda}
+    rng = np.random.default_rng(0)
+    u = rng.integers(-5, 10 ** 12, size=(300, 1))
+    i = rng.integers(0, 10 ** 6, size=(300, 1))
+    u[0, 0], u[1, 0] = 0, -17
+    feats = {"u_id": torch.from_numpy(u), "i_id": torch.from_numpy(i)}
+    sp = deepfm.model_fn(feats, torch.zeros(300), "eval", params)
+    m = params["variable_store"]._objs["deepfm"]
+    order = [c.key for c in m.lay.columns]
+    want = {"u_id": [farmhash.fingerprint64(str(int(v)).encode()) % 500000 for v in u[:, 0]],
+            "i_id": [farmhash.fingerprint64(str(int(v)).encode()) % 100000 for v in i[:, 0]]}
+    rows = m.rows.cpu().numpy()
+    for f, k in enumerate(order):
+        assert (rows[:, f] - m.lay.offsets[f] == np.array(want[k])).all(), k
+    assert sp.predictions["prob"].shape == (300,)
 
 
 def test_graphed_step_with_host_batches_follows_the_oracle(cuda):

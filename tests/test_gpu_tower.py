@@ -253,3 +253,87 @@ def test_tower_mid_agrees_with_per_layer_kernels(cuda):
     for k, v in res["0"][1].items():
         d = (res["1"][1][k].double() - v.double()).norm().item()
         assert d <= 2e-3 * max(v.double().norm().item(), 1e-12), (k, d)
+
+
+@pytest.mark.parametrize("B,H,W", [(4096, 100, 624), (77, 32, 64), (1000, 16, 1280)])
+def test_dcn_head_matches_float64(cuda, B, H, W):
+    """ctr_dcn_head (dcn/dcn.py:151-153,166-169): logits, prob, mean BCE and every gradient in
+    one launch, against float64 autograd."""
+    from recsys_b200 import ops
+    g = torch.Generator().manual_seed(B + H + W)
+    h = torch.randn(B, H, generator=g)
+    xl = torch.randn(B, W, generator=g)
+    w = torch.randn(H + W, generator=g) / (H + W) ** 0.5
+    hb = torch.tensor([0.3])
+    z = (torch.rand(B, generator=g) < 0.3).float()
+    d = {k: v.to(cuda).contiguous() for k, v in dict(h=h, xl=xl, w=w, hb=hb, z=z).items()}
+    logits, prob = torch.empty(B, device=cuda), torch.empty(B, device=cuda)
+    loss = torch.zeros((), device=cuda)
+    dh, dxl = torch.empty(B, H, device=cuda), torch.empty(B, W, device=cuda)
+    dw, dhb = torch.zeros(H + W, device=cuda), torch.zeros(1, device=cuda)
+    ops._call("ctr_dcn_head", d["h"].data_ptr(), H, d["xl"].data_ptr(), W, d["w"].data_ptr(),
+              d["hb"].data_ptr(), d["z"].data_ptr(), B, logits.data_ptr(), prob.data_ptr(),
+              loss.data_ptr(), dh.data_ptr(), dxl.data_ptr(), dw.data_ptr(), dhb.data_ptr(),
+              1.0 / B, ops._stream())
+    h64, xl64 = h.double().requires_grad_(True), xl.double().requires_grad_(True)
+    w64, hb64 = w.double().requires_grad_(True), hb.double().requires_grad_(True)
+    lg = torch.cat([h64, xl64], 1) @ w64 + hb64
+    ls = torch.nn.functional.binary_cross_entropy_with_logits(lg, z.double())
+    ls.backward()
+    _close(logits, lg.detach(), 1e-5)
+    _close(prob, torch.sigmoid(lg.detach()), 1e-5)
+    assert abs(loss.item() - ls.item()) <= 1e-6
+    _close(dh, h64.grad, 1e-5)
+    _close(dxl, xl64.grad, 1e-5)
+    _close(dw, w64.grad, 2e-5)
+    _close(dhb, hb64.grad, 2e-5)
+    # inference flavour: no gradient outputs
+    loss2 = torch.zeros((), device=cuda)
+    ops._call("ctr_dcn_head", d["h"].data_ptr(), H, d["xl"].data_ptr(), W, d["w"].data_ptr(),
+              d["hb"].data_ptr(), d["z"].data_ptr(), B, logits.data_ptr(), None, loss2.data_ptr(),
+              None, None, None, None, 1.0 / B, ops._stream())
+    assert abs(loss2.item() - ls.item()) <= 1e-6
+
+
+@pytest.mark.parametrize("B,K,p", [(4096, 100, 0.5), (130, 36, 0.0), (512, 256, 0.3)])
+def test_bn_drop_apply_and_its_backward(cuda, B, K, p):
+    """ctr_bn_drop_apply / ctr_bn_drop_apply_bwd: out = dropout(BN_train(A)); the backward hands
+    dn = dout * keep and the BN column sums to a kind-1 gradient source, whose dpre must equal
+    float64 autograd through relu -> batch-norm (batch statistics) -> the same dropout mask."""
+    from recsys_b200 import _lib, ops
+    g = torch.Generator().manual_seed(B + K)
+    pre = torch.randn(B, K, generator=g)
+    A = torch.relu(pre).to(cuda)
+    gamma = (torch.rand(K, generator=g) + 0.5).to(cuda)
+    beta = torch.randn(K, generator=g).to(cuda)
+    dout = torch.randn(B, K, generator=g).to(cuda)
+    sums = torch.stack([A.sum(0), (A * A).sum(0)]).contiguous()
+    d = _lib.BnDrop()
+    d.sums, d.gamma, d.beta, d.state = sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), None
+    d.eps, d.p_drop, d.seed, d.layer, d.enabled = 1e-3, p, 5, 1, 1
+    out = torch.empty(B, K, device=cuda)
+    ops._call("ctr_bn_drop_apply", A.data_ptr(), K, C.byref(d), out.data_ptr(), B, ops._stream())
+    a64 = pre.double().requires_grad_(True)
+    r = torch.relu(a64)
+    mu, var = r.mean(0), r.var(0, unbiased=False)
+    bn = (r - mu) / torch.sqrt(var + 1e-3) * gamma.cpu().double() + beta.cpu().double()
+    # the mask the kernel used: where the output is exactly zero although bn is not
+    keep = torch.ones(B, K, dtype=torch.float64)
+    if p > 0:
+        keep = (out.cpu().double() != 0).double()
+        assert abs(keep.mean().item() - (1 - p)) < 0.03
+    want = bn * keep / (1 - p)
+    _close(out, want.detach(), 2e-5)
+    want.backward(dout.cpu().double())
+    dn = torch.empty(B, K, device=cuda)
+    dbeta, dgamma = torch.zeros(K, device=cuda), torch.zeros(K, device=cuda)
+    ops._call("ctr_bn_drop_apply_bwd", dout.data_ptr(), K, A.data_ptr(), K, C.byref(d),
+              dn.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), B, ops._stream())
+    _close(dn, dout.cpu().double() * keep / (1 - p), 1e-6)
+    gs = _lib.GradSrc()
+    gs.G, gs.ldg, gs.a, gs.lda, gs.kind, gs.train, gs.eps = dn.data_ptr(), K, A.data_ptr(), K, 1, 1, 1e-3
+    gs.sums, gs.gamma = sums.data_ptr(), gamma.data_ptr()
+    gs.dbeta, gs.dgamma = dbeta.data_ptr(), dgamma.data_ptr()
+    dpre = torch.empty(B, K, device=cuda)
+    ops._call("ctr_tower_dpre", C.byref(gs), K, dpre.data_ptr(), K, None, B, ops._stream())
+    _close(dpre, a64.grad, 5e-5)
