@@ -30,6 +30,7 @@ extern "C" {
 #define CTR_ERR_ARG (-1)   /* bad argument (null, misaligned, unsupported size) */
 #define CTR_ERR_CUDA (-2)  /* CUDA runtime error, text in ctr_last_error()      */
 #define CTR_ERR_ARCH (-3)  /* current device is not sm_100                      */
+#define CTR_ERR_DATA (-4)  /* corrupt / malformed input records (host-side input pipeline) */
 
 #define CTR_MAX_FIELDS 64
 
@@ -76,6 +77,42 @@ int ctr_hash_strings(const uint8_t* bytes, const int32_t* offsets, int64_t N,
  * formatted as_string ("%lld") and hashed: out[i] = Fingerprint64(decimal(ids[i])) mod n_buckets. */
 int ctr_hash_int64(const int64_t* ids, int64_t N, int32_t n_buckets, int64_t* out,
                    ctr_stream_t stream);
+
+/* The same hash over fixed-width slots, the layout ctr_criteo_parse produces: string i occupies
+ * bytes[i*slot, i*slot + lens[i]) and belongs to field i % n_fields;
+ * out[i] = Fingerprint64 mod n_buckets[field] as int64 - directly the xcat operand [B, n_fields] of
+ * ctr_criteo_rows / ctr_embed_fwd_raw. */
+int ctr_hash_slots(const uint8_t* bytes, int slot, const int32_t* lens, int64_t N, int n_fields,
+                   const int32_t* n_buckets_dev, int64_t* out, ctr_stream_t stream);
+
+/* ------------------------------------------------- input pipeline (HOST side, no GPU needed)
+ * Replaces TFRecordDataset + parse_single_example + batch of `input_fn` (fm/fm.py:100-112,
+ * din/din.py:52-80) with a multi-threaded decoder that fills caller-owned (pinned) batch buffers.
+ * All pointers are HOST pointers.
+ *
+ * ctr_tfrecord_scan: walk a buffer of TFRecord frames {u64 len | u32 masked crc32c(len) | payload |
+ *   u32 masked crc32c(payload)}; payload_off/payload_len (nullable) receive the first max_records
+ *   frames.  Returns the number of frames, or CTR_ERR_DATA (truncated frame; crc mismatch when
+ *   verify_crc != 0).  ctr_masked_crc32c is the checksum it verifies.
+ * ctr_criteo_parse: decode n tf.train.Example payloads with the Criteo feature_description
+ *   (fm/fm.py:39-44): labels[n] = _c0; cont[n,13] = _c1.._c13; the 26 strings _c14.._c39 go to
+ *   cat_bytes[n,26,slot] (zero padded) with cat_len[n,26]; a missing / empty string feature gets the
+ *   default 'NULL' (fm/fm.py:44); a missing float feature is an error, as in TF.  slot: multiple
+ *   of 8 in [8,64].  n_threads <= 0: all hardware threads.
+ * ctr_din_parse: decode n payloads with DIN's feature_description (din/din.py:43-50).  With
+ *   labels == NULL it only returns the history length of the first record; otherwise fills labels,
+ *   i_id, i_cate [n] and the densified histories u_iid_seq, u_icat_seq [n,P]; every record must
+ *   carry exactly P ids in both histories (the reference uses .batch(), not padded_batch,
+ *   din/din.py:73), else CTR_ERR_DATA. */
+int64_t ctr_tfrecord_scan(const uint8_t* buf, int64_t nbytes, int verify_crc, int64_t* payload_off,
+                          int32_t* payload_len, int64_t max_records);
+uint32_t ctr_masked_crc32c(const uint8_t* data, int64_t n);
+int ctr_criteo_parse(const uint8_t* buf, const int64_t* payload_off, const int32_t* payload_len,
+                     int64_t n, int n_threads, float* labels, float* cont, uint8_t* cat_bytes,
+                     int32_t* cat_len, int slot);
+int64_t ctr_din_parse(const uint8_t* buf, const int64_t* payload_off, const int32_t* payload_len,
+                      int64_t n, int n_threads, int64_t P, int64_t* labels, int64_t* i_id,
+                      int64_t* i_cate, int64_t* u_iid_seq, int64_t* u_icat_seq);
 
 /* --------------------------------------------------- fused multi-field lookup
  * Forward.  Replaces input_layer(embedding columns) + input_layer(indicator

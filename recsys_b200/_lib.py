@@ -81,6 +81,11 @@ SIGNATURES = {
     "ctr_criteo_rows": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f]),
     "ctr_hash_strings": (c_i, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
     "ctr_hash_int64": (c_i, [c_f, c_i64, C.c_int32, c_f, c_f]),
+    "ctr_hash_slots": (c_i, [c_f, c_i, c_f, c_i64, c_i, c_f, c_f, c_f]),
+    "ctr_tfrecord_scan": (c_i64, [c_f, c_i64, c_i, c_f, c_f, c_i64]),
+    "ctr_masked_crc32c": (C.c_uint32, [c_f, c_i64]),
+    "ctr_criteo_parse": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_i]),
+    "ctr_din_parse": (c_i64, [c_f, c_f, c_f, c_i64, c_i, c_i64, c_f, c_f, c_f, c_f, c_f]),
     "ctr_embed_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i,
                             c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_embed_fwd_raw": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i,

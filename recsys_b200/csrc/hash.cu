@@ -168,7 +168,35 @@ __global__ void hash_int64_kernel(const long long* __restrict__ ids, long long N
   }
 }
 
+// Fixed-width string slots as the record parser (records.cu) lays them out: string i occupies
+// bytes[i*slot, i*slot + lens[i]), belongs to field i % n_fields; out = local id as int64, i.e.
+// directly the `xcat` operand of the id pipeline.
+__global__ void hash_slots_kernel(const uint8_t* __restrict__ bytes, int slot,
+                                  const int* __restrict__ lens, long long N, int n_fields,
+                                  const int* __restrict__ n_buckets, long long* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < N;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int f = static_cast<int>(i % n_fields);
+    const u64 h = fingerprint64(bytes + i * slot, min(max(lens[i], 0), slot));
+    out[i] = static_cast<long long>(h % static_cast<u64>(n_buckets[f]));
+  }
+}
+
 }  // namespace ctr
+
+extern "C" int ctr_hash_slots(const uint8_t* bytes, int slot, const int32_t* lens, int64_t N,
+                              int n_fields, const int32_t* n_buckets_dev, int64_t* out,
+                              ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(bytes && lens && n_buckets_dev && out && N >= 0 && slot > 0 && n_fields > 0,
+              "ctr_hash_slots", "bad argument");
+  if (N == 0) return CTR_OK;
+  const int grid =
+      static_cast<int>(std::min<long long>((N + 255) / 256, ctr::sm_count() * 8LL));
+  ctr::hash_slots_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bytes, slot, lens, N, n_fields, n_buckets_dev, reinterpret_cast<long long*>(out));
+  CTR_LAUNCH_CHECK("ctr_hash_slots");
+}
 
 extern "C" int ctr_hash_int64(const int64_t* ids, int64_t N, int32_t n_buckets, int64_t* out,
                               ctr_stream_t stream) {

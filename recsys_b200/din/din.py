@@ -19,32 +19,10 @@ feature_description = {
 
 def input_fn(filenames, batch_size, num_epochs=-1, need_shuffle=False):
     """din/din.py:63-80: VarLen sequences densified per record, ``.batch()`` (not
-    padded_batch), so every record of a file must carry the same history length."""
-    from ..data import iter_tfrecords, parse_example
-
-    def gen():
-        epoch = 0
-        while num_epochs < 0 or epoch < num_epochs:
-            buf = []
-            for fn in filenames:
-                for rec in iter_tfrecords(fn):
-                    buf.append(parse_example(rec))
-                    if len(buf) == batch_size:
-                        yield _to_batch(buf)
-                        buf = []
-            if buf:
-                yield _to_batch(buf)
-            epoch += 1
-
-    def _to_batch(exs):
-        feats = {k: torch.tensor([e[k][0] for e in exs], dtype=torch.int64)
-                 for k in ("i_id", "i_cate")}
-        for k in ("u_iid_seq", "u_icat_seq"):
-            feats[k] = torch.tensor([e.get(k) or [] for e in exs], dtype=torch.int64)
-        labels = torch.tensor([e["label"][0] for e in exs], dtype=torch.int64)
-        return feats, labels
-
-    return gen()
+    padded_batch), so every record of a batch must carry the same history length.
+    Decoded by the library's multi-threaded host decoder (data.din_input_fn)."""
+    from ..data import din_input_fn
+    return din_input_fn(filenames, batch_size, num_epochs, need_shuffle)
 
 
 def model_fn(features, labels, mode, params):

@@ -93,8 +93,41 @@ class IdPipeline:
         self.n_buckets_dev = torch.tensor(lay.rows, dtype=torch.int32, device=device)
         self.row_offset_dev = torch.tensor(lay.offsets[:-1], dtype=torch.int32, device=device)
 
+    def _raw_order(self):
+        """Column permutations from the decoder's raw order (_c1.._c13 / _c14.._c39) to this
+        pipeline's packed order, and the bucket counts in raw order (device tensors, cached)."""
+        if getattr(self, "_raw_perm", None) is None:
+            ci = [int(k[2:]) - 1 for k in self.cont_keys]
+            ki = [int(k[2:]) - 14 for k in self.cat_keys]
+            nb = [1] * 26
+            for k, j in zip(self.cat_keys, ki):
+                nb[j] = self.lay.rows[self.lay.field_of(k)]
+            dev = self.device
+            self._raw_perm = (torch.tensor(ci, dtype=torch.long, device=dev),
+                         torch.tensor(ki, dtype=torch.long, device=dev),
+                         torch.tensor(nb, dtype=torch.int32, device=dev))
+        return self._raw_perm
+
+    def pack_raw(self, batch) -> tuple:
+        """A ``data.CriteoRawBatch`` (decoder output: numerics + fixed-width string slots) ->
+        (cont, cat) on the device; the strings are fingerprinted there (ctr_hash_slots)."""
+        ci, ki, nb = self._raw_order()
+        dev = self.device
+        cont = batch.cont.to(dev, non_blocking=True).index_select(1, ci) if self.cont_keys else None
+        cat = None
+        if self.cat_keys:
+            cb = batch.cat_bytes.to(dev, non_blocking=True)
+            cl = batch.cat_len.to(dev, non_blocking=True)
+            B, nf, slot = cb.shape
+            ids = torch.empty((B, nf), dtype=torch.int64, device=dev)
+            _call("ctr_hash_slots", _p(cb), slot, _p(cl), B * nf, nf, _p(nb), _p(ids), _stream())
+            cat = ids.index_select(1, ki)
+        return cont, cat
+
     def pack(self, features) -> tuple:
         """-> (cont f32 [B,n_cont], cat i64 [B,n_cat]) on the device."""
+        if hasattr(features, "cat_bytes") and hasattr(features, "cat_len"):
+            return self.pack_raw(features)
         if isinstance(features, PackedFeatures) and features.cont_keys == self.cont_keys \
                 and features.cat_keys == self.cat_keys and not any(self.raw_int64.values()):
             cont, cat = features.cont, features.cat

@@ -3,6 +3,7 @@
 Run in the authoring container (needs /root/reference for the real shard):
     python scripts/make_golden.py
 
+  criteo_shard256.tfrecord  the first 256 TFRecord frames of the shard, byte for byte
   criteo_shard256.npz   first 256 records of the reference's only data fixture,
                         xdeepfm/part-r-00000, parsed by oracle/tfrecord.py (crc-verified):
                         13 numerics, 26 raw byte strings ('NULL' default), labels - plus the
@@ -82,6 +83,19 @@ def main():
             save[k] = np.array([bytes(v) for v in feats[k].reshape(-1)], dtype="S8")
         np.savez_compressed(os.path.join(OUT, "criteo_shard256.npz"), **save)
         print("criteo_shard256.npz", rows.shape, float(labels.mean()))
+        # the same 256 records as raw TFRecord frames (byte copy of the head of the shard), so the
+        # product's decoder (recsys_b200/data.py, csrc/records.cu) can be tested where
+        # /root/reference is absent
+        import struct
+        with open(SHARD, "rb") as f:
+            blob = bytearray()
+            for _ in range(256):
+                hdr = f.read(12)
+                (n,) = struct.unpack("<Q", hdr[:8])
+                blob += hdr + f.read(n + 4)
+        with open(os.path.join(OUT, "criteo_shard256.tfrecord"), "wb") as f:
+            f.write(bytes(blob))
+        print("criteo_shard256.tfrecord", len(blob), "bytes")
     spec = small_spec()
     for model in ("fm", "deepfm", "xdeepfm", "dcn"):
         kw = {}

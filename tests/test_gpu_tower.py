@@ -26,7 +26,7 @@ def _restore_env():
 
 
 def _close(got, want, tol=2e-5):
-    want = want.to(torch.float64)
+    want = want.to(torch.float64).to(got.device)
     err = (got.to(torch.float64) - want).abs().max().item()
     ref = max(want.abs().max().item(), 1e-6)
     assert err <= tol * ref, "max err %.3e vs scale %.3e" % (err, ref)
