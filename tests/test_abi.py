@@ -63,6 +63,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "ctr_field_desc": (_lib.FieldDesc, ["kind", "n_rows", "bnd_count", "log_offset"]),
         "ctr_bn_drop": (_lib.BnDrop, ["sums", "gamma", "state", "eps", "seed", "enabled"]),
         "ctr_grad_src": (_lib.GradSrc, ["G", "a", "dgamma", "ldg", "eps", "train"]),
+        "ctr_din_opts": (_lib.DinOpts, ["state", "p_drop", "seed", "unit", "table_rows", "status"]),
         "ctr_tower_mid_args": (_lib.TowerMidArgs, ["L", "H", "W", "act", "stats", "w_out", "eps", "seed",
                                                    "grad_scale", "z", "labels", "loss", "dz", "dw_out",
                                                    "dgamma", "dpre", "dpre0_lo", "pre0", "barrier",
@@ -93,7 +94,7 @@ def test_ctypes_signatures_match_the_header_prototypes():
     from recsys_b200 import _lib
     src = open(os.path.join(ROOT, "include", "ctr_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    protos = re.findall(r"\b(?:int|int64_t|const char\s*\*)\s+(ctr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|uint32_t|const char\s*\*)\s+(ctr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
     assert len(protos) >= 30
 
     def kind(arg):
