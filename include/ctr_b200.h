@@ -188,7 +188,8 @@ int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float 
  * Row strides (ctr_embed_fwd / ctr_embed_bwd / ctr_adam_rows; 0 = planar defaults D, 1, 1): the
  * distance in floats between consecutive rows of table / m / v / g (row_stride), of the
  * first-order arrays (w1_stride) and of claim (claim_stride).  With the ROW-RECORD layout
- *   record[r] = { theta[D] | m[D] | v[D] | g[D] | theta1 m1 v1 g1 | claim, pad[3] }   (4D+8 floats)
+ *   record[r] = { theta[D] | m[D] | v[D] | g[D] | theta1 m1 v1 g1 | claim, cnt, c, pad }   (4D+8 floats;
+ *   cnt / c: lookup count and sum of dy2 of the fused scatter + optimiser pass, ctr_embed_bwd_adam)
  * all pointers address one array with one stride, so everything the optimiser touches for a row
  * sits in one DRAM page (1 activate per row instead of 9: random row access is bounded by the
  * HBM activate rate long before its bandwidth), and the lookup's first-order weight shares the
@@ -198,6 +199,27 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
                   int32_t tag, float lr_t, float beta1, float beta2, float eps,
                   const float* state_dev, int64_t row_stride, int64_t w1_stride,
                   int64_t claim_stride, ctr_stream_t stream);
+
+/* Scatter-add and row optimiser in ONE pass (row-record layout only; rec = the record array,
+ * row_stride >= 4D+8).  The unfused pair ctr_embed_bwd + ctr_adam_rows visits every touched record
+ * twice; here the lookup that completes a row's gradient applies the update while the record is
+ * still in L2:
+ *   ctr_count_rows      cnt[row] += 1 for every entry of rows[n] (the record's `cnt` word; zero
+ *                       before and after a step).  Launch it before the backward, e.g. on a side
+ *                       stream beside the tower's backward GEMMs.
+ *   ctr_embed_bwd_adam  per slot: g[row] += dE[b,f,:] + dy2[b]*S[b,:], c[row] += dy2[b],
+ *                       g1[row] += dy1[b]; then cnt[row] -= multiplicity; the slot that takes cnt
+ *                       to zero reads the record back, forms the gradient g - c*theta (which equals
+ *                       sum dE + dy2*(S - E), fm/fm.py:123-129, without re-reading E), applies
+ *                       TF-Adam to theta (and theta1), and clears g / c / g1.  Duplicates inside a
+ *                       warp instruction are summed in registers (__match_any_sync), fields with
+ *                       <= 32 rows per sample chunk in shared memory.  lr_t etc. as ctr_adam_rows. */
+int ctr_count_rows(const int32_t* rows, int64_t n, int D, float* rec, int64_t row_stride,
+                   ctr_stream_t stream);
+int ctr_embed_bwd_adam(const int32_t* rows, const float* dE, const float* S, const float* dy2,
+                       const float* dy1, uint64_t w1_fields, const int64_t* row_offsets_host, int B,
+                       int F, int D, float* rec, int64_t row_stride, float lr_t, float beta1,
+                       float beta2, float eps, const float* state_dev, ctr_stream_t stream);
 
 /* -------------------------------------------------------- DIN activation unit
  * din/din.py:103-125 `_attention`: for each sample b and position p with hist[b,p] > 0

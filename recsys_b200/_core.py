@@ -179,8 +179,12 @@ class _ModelBase:
                                  eval_metric_ops=ops_)
 
         def train_op():
+            lr_t = self.adam.next_lr_t()
+            self._arm_row_optimiser(lr_t)     # scatter-add + Adam of the tables in one pass
             self.backward(loss)
-            self.apply_gradients()
+            self._apply_gradients(lr_t)
+            if self.store is not None:
+                self.store.global_step += 1
 
         self.last = {"loss": loss, "logits": logits}
         return EstimatorSpec(mode=mode, predictions=predictions, loss=loss.detach(),
@@ -194,7 +198,16 @@ class _ModelBase:
         # stream they were created on) alive, which breaks a later CUDA-graph capture
         self.last = {k: v.detach() for k, v in self.last.items()}
 
+    def _arm_row_optimiser(self, lr_t):
+        """Tables that support it run their scatter-add and row Adam fused in the backward."""
+        for emb in (getattr(self, "emb", None), getattr(self, "emb_dnn", None)):
+            if emb is not None and getattr(emb, "can_fuse", False) and self.rows is not None \
+                    and self.params.get("fused_row_adam", True):
+                emb.arm_fused(self.rows, lr_t, self.adam)
+
     def apply_gradients(self):
+        """The unfused optimiser step (after a plain ``backward``): Adam over the accumulated
+        gradients.  ``train_op`` fuses the tables' share into the backward instead."""
         lr_t = self.adam.next_lr_t()
         self._apply_gradients(lr_t)
         if self.store is not None:

@@ -93,6 +93,9 @@ SIGNATURES = {
                                 c_f]),
     "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
                             c_i, c_i, c_f, c_f, c_i64, c_i64, c_f]),
+    "ctr_count_rows": (c_i, [c_f, c_i64, c_i, c_f, c_i64, c_f]),
+    "ctr_embed_bwd_adam": (c_i, [c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i, c_i, c_i,
+                                 c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_f, c_f]),
     "ctr_dcn_cross_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f]),
     "ctr_dcn_cross_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "ctr_adam_tick": (c_i, [c_f, c_fl, c_fl, c_fl, c_f]),

@@ -370,6 +370,13 @@ class FieldEmbedding:
         self._tag = 0
         self._offsets_host = (C.c_int64 * (self.F + 1))(*lay.offsets)
         self._anchor = torch.zeros((), device=device, requires_grad=True)
+        # fused scatter + row optimiser (ctr_embed_bwd_adam): armed by ``arm_fused`` right before
+        # the backward of a train step, consumed by the backward, acknowledged by ``adam_step``
+        self.can_fuse = self.record and adam_mode == "lazy" and \
+            os.environ.get("CTR_FUSED_ROW_ADAM", "1") != "0"
+        self._fused = None
+        self._fused_done = False
+        self._side = None
 
     # -- state ------------------------------------------------------------------
     def load(self, table=None, w1=None):
@@ -427,9 +434,37 @@ class FieldEmbedding:
         if self.with_w1:
             self.dw1.zero_()
 
+    def arm_fused(self, rows: torch.Tensor, lr_t: float, st: TFAdamState) -> bool:
+        """Train step, right before the backward: count the batch's lookups per row
+        (ctr_count_rows, on a side stream beside the tower's backward GEMMs) so that the
+        backward can run scatter-add and Adam in one pass (ctr_embed_bwd_adam)."""
+        if not self.can_fuse:
+            return False
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        rows = rows.contiguous()
+        with torch.cuda.stream(self._side):
+            _call("ctr_count_rows", _p(rows), rows.numel(), self.D, _p(self.rec), self.ld,
+                  self._side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        rows.record_stream(self._side)
+        self._fused = (lr_t, st, done)
+        return True
+
     def adam_step(self, rows: torch.Tensor, lr_t: float, st: TFAdamState):
         """Consume (and re-zero) the accumulated gradients.  ``lazy``: one update per
         touched row (LazyAdam); ``exact_tf``: every row, as TF's sparse apply does."""
+        if self._fused_done:          # the backward already applied the update (ctr_embed_bwd_adam)
+            self._fused_done = False
+            return
+        if self._fused is not None:   # armed, but no gradient reached the table: undo the counts
+            raise RuntimeError("fused row optimiser was armed but the backward never reached the "
+                               "embedding table")
         self._ensure_adam()
         if self.adam_mode == "exact_tf":
             _call("ctr_adam_dense", _p(self.table), _p(self._m), _p(self._v), _p(self.dtable),
@@ -507,7 +542,15 @@ class _EmbedFn(torch.autograd.Function):
         dE = None if dE is None else dE.contiguous()
         dy2 = dy2.contiguous() if (want_fm and dy2 is not None) else None
         dy1 = dy1.contiguous() if (want_y1 and dy1 is not None) else None
-        if dE is not None or dy2 is not None:
+        fused, emb._fused = emb._fused, None
+        if fused is not None and (dE is not None or dy2 is not None):
+            lr_t, st, counted = fused
+            torch.cuda.current_stream().wait_event(counted)
+            _call("ctr_embed_bwd_adam", _p(rows), _p(dE), _p(S), _p(dy2), _p(dy1), emb.w1_fields,
+                  emb._offsets_host, B, F, D, _p(emb.rec), emb.ld, lr_t, st.beta1, st.beta2, st.eps,
+                  st.state_ptr, _stream())
+            emb._fused_done = True
+        elif dE is not None or dy2 is not None:
             _call("ctr_embed_bwd", _p(rows), _p(dE), _p(E), _p(emb.table), _p(S), _p(dy2), _p(dy1),
                   emb.w1_fields, emb._offsets_host, B, F, D, _p(emb.dtable), _p(emb.dw1), emb.ld,
                   emb.ld1, _stream())

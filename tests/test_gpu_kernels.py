@@ -216,6 +216,85 @@ def test_embed_bwd_matches_oracle(cuda, B, D, use_dE, use_fm, regather, record):
     assert float((emb.dw1.cpu().double() - w.grad).abs().max()) <= 1e-5 * float(w.grad.abs().max()) + 1e-5
 
 
+@pytest.mark.parametrize("B,D,use_dE,use_fm", [(1, 16, True, True), (77, 16, True, True),
+                                               (4096, 16, True, True), (300, 16, False, True),
+                                               (300, 16, True, False), (515, 32, True, True),
+                                               (129, 8, True, True)])
+def test_fused_scatter_adam_matches_tf_adam_on_the_oracle_gradient(cuda, B, D, use_dE, use_fm):
+    """ctr_count_rows + ctr_embed_bwd_adam (scatter-add and row optimiser in one pass): three
+    steps against the dense autograd gradient of the oracle fed to tfsem.TFAdam (lazy rows).
+    Fields with 3..32 rows (shared-memory tile), a field where every sample hits one row,
+    in-warp duplicates (match-any aggregation) and big fields; afterwards the records'
+    accumulators and lookup counts are all zero again."""
+    ops = _ops()
+    from recsys_b200 import _lib
+    from recsys_b200 import feature_column as fc
+    nrows = [3, 10, 32, 33, 7, 1000, 50000, 4, 64, 31, 200]
+    F = len(nrows)
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("k%02d" % i, n), D)
+            for i, n in enumerate(nrows)]
+    lay = fc.layout(cols)
+    mask = 0b10110101101
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask, adam_mode="lazy", seed=2)
+    assert emb.record and emb.can_fuse
+    p64 = {"emb": emb.table.double().cpu().clone(), "w1": emb.w1.double().cpu().clone()}
+    opt = tfsem.TFAdam(p64, lr=1e-2)
+    st = ops.TFAdamState(lr=1e-2, device=cuda)
+    lib = _lib.load()
+    offs = (C.c_int64 * (F + 1))(*lay.offsets)
+    P = ops._p
+    fm_mask = torch.tensor([(mask >> f) & 1 for f in range(F)], dtype=torch.float64)
+    for step in range(3):
+        rows_np = _rand_rows(B, lay.offsets, seed=B + D + step, hot=True)
+        rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
+        g = torch.Generator().manual_seed(B + step)
+        dE = torch.randn(B, F * D, generator=g)
+        dy1 = torch.randn(B, generator=g)
+        dy2 = torch.randn(B, generator=g)
+        with torch.no_grad():
+            E, _, _, _ = emb.lookup(rows)
+        S = E.view(B, F, D).sum(1).contiguous()
+        dEc, dy2c, dy1c = dE.to(cuda), dy2.to(cuda), dy1.to(cuda)
+        # oracle gradient (autograd through gather + FM second order), then the TF Adam rule
+        t = p64["emb"].clone().requires_grad_(True)
+        w = p64["w1"].clone().requires_grad_(True)
+        r = torch.from_numpy(rows_np)
+        Eo = t[r]
+        loss = ((w[r] * fm_mask).sum(1) * dy1.double()).sum()
+        if use_dE:
+            loss = loss + (Eo.reshape(B, -1) * dE.double()).sum()
+        if use_fm:
+            loss = loss + (om.fm_second_order(Eo).reshape(-1) * dy2.double()).sum()
+        loss.backward()
+        gw = w.grad
+        # first-order weights exist only for the masked fields: lazy rows = their lookups
+        # (the kernel never touches theta1 of a row whose field has no first-order term)
+        fsel = [f for f in range(F) if (mask >> f) & 1]
+        opt.step(p64, {"emb": t.grad, "w1": gw},
+                 lazy_rows={"emb": r.reshape(-1), "w1": r[:, fsel].reshape(-1)})
+        lr_t = st.next_lr_t()
+        sm = torch.cuda.current_stream().cuda_stream
+        assert lib.ctr_count_rows(P(rows), rows.numel(), D, P(emb.rec), emb.ld, sm) == 0
+        rc = lib.ctr_embed_bwd_adam(P(rows), P(dEc) if use_dE else None, P(S) if use_fm else None,
+                                    P(dy2c) if use_fm else None, P(dy1c), mask, offs, B, F, D,
+                                    P(emb.rec), emb.ld, lr_t, st.beta1, st.beta2, st.eps,
+                                    st.state_ptr, sm)
+        assert rc == 0, _lib.last_error()
+        st.advance()
+        torch.cuda.synchronize()
+        assert float(emb.dtable.abs().max()) == 0.0 and float(emb.dw1.abs().max()) == 0.0
+        assert int(emb.rec[:, 4 * D + 5].view(torch.int32).abs().max()) == 0      # cnt
+        assert float(emb.rec[:, 4 * D + 6].abs().max()) == 0.0                    # c
+    # w1 of unmasked fields: the oracle's lazy rule decays nothing there either (zero gradient,
+    # rows not listed) - compare everything
+    assert torch.allclose(emb.table.cpu().double(), p64["emb"], rtol=1e-5, atol=2e-6)
+    sel = torch.zeros(lay.total_rows, dtype=torch.bool)
+    for f in range(F):
+        if (mask >> f) & 1:
+            sel[lay.offsets[f]:lay.offsets[f + 1]] = True
+    assert torch.allclose(emb.w1.cpu().double()[sel], p64["w1"][sel], rtol=1e-5, atol=2e-6)
+
+
 def test_embed_rejects_bad_arguments(cuda):
     from recsys_b200 import _lib
     lib = _lib.load()
