@@ -406,6 +406,7 @@ def run_ours(args):
             "bwd": {"us": kern["bwd_us"], "GBps": ALG_BYTES_BWD * B / kern["bwd_us"] / 1e3,
                     "moved_GBps": kern["bwd_moved"] * B / kern["bwd_us"] / 1e3},
             "adam_rows_us": kern["adam_us"],
+            "scatter_plus_adam_us": kern.get("scatter_plus_adam_us"),
             "large_batch": kern.get("large"),
             # the same algorithmic bytes over the WHOLE step (tower, optimiser and launch gaps
             # included): what the step as a unit achieves against the HBM roofline
@@ -535,6 +536,41 @@ def time_hot_kernels(model, devb, K, W, stream):
             emb.dtable.zero_()
             if emb.dw1 is not None:
                 emb.dw1.zero_()
+            # scatter-add + row optimiser at this batch: the unfused pair (bwdL above + adam_rows)
+            # against the fused pass (ctr_count_rows + ctr_embed_bwd_adam, one visit per record)
+            if getattr(emb, "can_fuse", False):
+                def adamL(i):
+                    emb._tag += 1
+                    lib.ctr_adam_rows(p(rl[i % 4]), BL * F, D, p(emb.table), p(emb._m), p(emb._v),
+                                      p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
+                                      p(getattr(emb, "_v1", None)), p(emb.dw1), p(emb._claim),
+                                      emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, emb.ld, emb.ld1,
+                                      emb.ldc, st)
+
+                def pairL(i):
+                    bwdL(i)
+                    adamL(i)
+
+                def fusedL(i):
+                    lib.ctr_count_rows(p(rl[i % 4]), BL * F, D, p(emb.rec), emb.ld, st)
+                    lib.ctr_embed_bwd_adam(p(rl[i % 4]), p(dEL), p(SL), p(yl), p(yl), emb.w1_fields,
+                                           emb._offsets_host, BL, F, D, p(emb.rec), emb.ld, 1e-3, 0.9,
+                                           0.999, 1e-8, None, st)
+                tp_, tu_ = timeit(pairL, once=True), timeit(fusedL)
+                res["large"]["scatter_plus_adam_us"] = {"unfused_bwd_then_adam_rows": tp_,
+                                                        "fused_count_then_bwd_adam": tu_}
+                # the same comparison at the step's own batch
+                def pairS(i):
+                    bwd(i)
+                    adam(i)
+
+                def fusedS(i):
+                    lib.ctr_count_rows(p(rows[i % len(rows)]), B * F, D, p(emb.rec), emb.ld, st)
+                    lib.ctr_embed_bwd_adam(p(rows[i % len(rows)]), p(dE), p(Sb), p(dy), p(dy),
+                                           emb.w1_fields, emb._offsets_host, B, F, D, p(emb.rec),
+                                           emb.ld, 1e-3, 0.9, 0.999, 1e-8, None, st)
+                res["scatter_plus_adam_us"] = {"unfused_bwd_then_adam_rows": timeit(pairS, once=True),
+                                               "fused_count_then_bwd_adam": timeit(fusedS)}
         except Exception as e:  # pragma: no cover
             res["large"] = {"error": str(e)[:200]}
     return res

@@ -490,6 +490,69 @@ int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, i
                          float* dtable, float* dw1, int64_t g_stride, int64_t gw1_stride,
                          int64_t dtable_stride, int64_t dw1_stride, ctr_stream_t stream);
 
+/* ------------------------------------- row-sharded table, device-initiated exchange (NVLink P2P)
+ * The NCCL-free version of the exchange above (one process per GPU on one NVSwitch box): every
+ * rank owns a same-shaped ARENA in its HBM and maps every peer's arena (cudaIpc); the kernels of a
+ * step store straight into the consumer's arena and raise a sequence-numbered flag there.
+ *
+ *   arena := { int step; int err; ... | req_flag[2][G] req_cnt[2][G] resp_flag[G] grad_flag[G]
+ *              dense_flag[G] counts[G] done[1+G] | req_ids[2][G][capacity] (int32, owner side)
+ *              | resp[G][capacity][P] (fp32, requester side) | grad[G][capacity][P] (owner side)
+ *              | dense[G][n_dense] }        P = record_floats = D + 4: row | w1 | pad, and on the
+ *                                           way back gradient | dy1 dy2 pad
+ *   capacity >= the lookups of one rank per step (worst case: all for one owner) - no overflow.
+ * The layout (byte offsets below) is chosen by the caller and must be identical on every rank.
+ *
+ * ctr_p2p_alloc / _open / _close / _free: the ONLY entry points of this library that allocate:
+ * cudaMalloc'ed, zero-filled arena + its 64-byte cudaIpcMemHandle_t; map a peer's handle.
+ * Per step (all async on `stream`, graph-capturable; K1 first - it opens the step):
+ *   K1 ctr_p2p_bucket_send   rows[n] (global rows) -> owner = row % G; owner-local ids stored into
+ *                            the owner's req_ids[step parity][me][pos]; slot[i] = owner*capacity+pos
+ *   K2 ctr_p2p_gather_reply  owner: per requester, wait for its ids, gather row | w1 from the local
+ *                            row records into the requester's resp[me][pos]; count_lookups != 0
+ *                            also counts them per row (the `cnt` word of ctr_embed_bwd_adam)
+ *   K3 ctr_embed_fwd over resp (table = own arena + off_resp, row_stride = w1_stride = P, rows =
+ *                            slot), after ctr_p2p_wait(ctx, 0)
+ *   K4 ctr_p2p_grad_send     per slot: dE + dy2*S | dy1 dy2 stored into the owner's grad[me][pos]
+ *   K5 ctr_p2p_scatter_adam  owner: per requester, wait for its gradients; scatter-add + TF-Adam in
+ *                            one pass (the lookup that completes a row updates it)
+ *   K6 ctr_p2p_dense_push + ctr_p2p_adam_dense   replicated dense weights: gradients stored into
+ *                            every peer's dense[me]; Adam over their sum in rank order (bitwise
+ *                            identical on every rank); zeroes g_local; advance_state as ctr_adam_dense
+ * Every wait is bounded by spin_limit_ms (0 = 10 s): a peer that never arrives sets arena.err
+ * (ctr_p2p_status) instead of hanging the GPU. */
+#define CTR_P2P_MAX_RANKS 8
+typedef struct {
+  void* peer[CTR_P2P_MAX_RANKS]; /* arena base of every rank as mapped in THIS process */
+  int32_t me, G, capacity, record_floats;
+  int64_t off_req_flag, off_req_cnt, off_resp_flag, off_grad_flag, off_dense_flag;
+  int64_t off_req_ids, off_resp, off_grad, off_dense, off_counts, off_done;
+  int64_t n_dense;
+  int32_t spin_limit_ms, pad_;
+} ctr_p2p_ctx;
+int ctr_p2p_alloc(int64_t bytes, void** ptr, void* ipc_handle_out);
+int ctr_p2p_open(const void* ipc_handle, void** ptr);
+int ctr_p2p_close(void* ptr);
+int ctr_p2p_free(void* ptr);
+int ctr_p2p_bucket_send(const int32_t* rows, int64_t n, const ctr_p2p_ctx* ctx, int32_t* slot,
+                        ctr_stream_t stream);
+int ctr_p2p_gather_reply(float* rec, int64_t row_stride, int D, int with_w1, int count_lookups,
+                         const ctr_p2p_ctx* ctx, ctr_stream_t stream);
+/* what: 0 = every owner's reply, 1 = every requester's gradients, 2 = every rank's dense gradients */
+int ctr_p2p_wait(const ctr_p2p_ctx* ctx, int what, ctr_stream_t stream);
+int ctr_p2p_grad_send(const int32_t* slot, const float* dE, const float* S, const float* dy2,
+                      const float* dy1, uint64_t w1_fields, int B, int F, int D,
+                      const ctr_p2p_ctx* ctx, ctr_stream_t stream);
+int ctr_p2p_scatter_adam(float* rec, int64_t row_stride, int D, int with_w1, int has_c, float lr_t,
+                         float beta1, float beta2, float eps, const float* state_dev,
+                         const ctr_p2p_ctx* ctx, ctr_stream_t stream);
+int ctr_p2p_dense_push(const float* grad, int64_t n, const ctr_p2p_ctx* ctx, ctr_stream_t stream);
+int ctr_p2p_adam_dense(float* theta, float* m, float* v, float* g_local, int64_t n, float lr_t,
+                       float beta1, float beta2, float eps, float* state_dev, int advance_state,
+                       const ctr_p2p_ctx* ctx, ctr_stream_t stream);
+/* Synchronous: the arena's step counter and error word (bit 0: a bounded wait timed out). */
+int ctr_p2p_status(const ctr_p2p_ctx* ctx, int32_t* step_out, int32_t* err_out);
+
 #ifdef __cplusplus
 }
 #endif

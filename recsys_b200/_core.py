@@ -162,6 +162,7 @@ class _ModelBase:
 
     def spec(self, features, labels, mode) -> EstimatorSpec:
         training = mode == ModeKeys.TRAIN
+        self._training = training
         with torch.set_grad_enabled(training):
             logits, pred, loss = self.forward(features, None if mode == ModeKeys.PREDICT else labels,
                                               training)
@@ -198,11 +199,24 @@ class _ModelBase:
         # stream they were created on) alive, which breaks a later CUDA-graph capture
         self.last = {k: v.detach() for k, v in self.last.items()}
 
+    # Lookups per step from which the fused scatter + optimiser pass (ctr_embed_bwd_adam) pays off.
+    # Measured on B200 (profiles/r02_*): at batch 4096 x 39 fields the step is bound by dependent
+    # memory latency and the fused pass ties with the unfused pair (134.8 vs 132.0 us per step);
+    # from a few hundred thousand lookups on the records no longer stay in L2 between the two
+    # unfused passes and touching each record once wins.
+    FUSED_ROW_ADAM_MIN_LOOKUPS = 1 << 19
+
     def _arm_row_optimiser(self, lr_t):
-        """Tables that support it run their scatter-add and row Adam fused in the backward."""
+        """Tables that support it run their scatter-add and row Adam fused in the backward:
+        params['fused_row_adam'] = True / False / 'auto' (default: by the number of lookups).
+        The peer-memory sharded table always does (its owner-side pass is the fused one)."""
+        want = self.params.get("fused_row_adam", "auto")
         for emb in (getattr(self, "emb", None), getattr(self, "emb_dnn", None)):
-            if emb is not None and getattr(emb, "can_fuse", False) and self.rows is not None \
-                    and self.params.get("fused_row_adam", True):
+            if emb is None or not getattr(emb, "can_fuse", False) or self.rows is None:
+                continue
+            on = want if isinstance(want, bool) else \
+                self.rows.numel() >= self.FUSED_ROW_ADAM_MIN_LOOKUPS
+            if on or getattr(emb, "p2p", False):
                 emb.arm_fused(self.rows, lr_t, self.adam)
 
     def apply_gradients(self):
@@ -231,19 +245,32 @@ class _CriteoBase(_ModelBase):
         seed = int(params.get("seed", 0))
         self.world = 1
         if params.get("shard_embedding"):
-            # row-sharded table over the ranks of the default process group (sharded.py)
+            # row-sharded table over the ranks of the default process group: exchanged over NVLink
+            # peer memory by our own kernels (p2p.py; the default on CUDA), or through NCCL
+            # all-to-alls (sharded.py; also what the gloo CPU tests drive)
             import torch.distributed as dist
-            from . import sharded
             self.world = dist.get_world_size()
-            self.emb = sharded.ShardedFieldEmbedding(
-                self.lay, self.device, with_w1=self.want_w1, w1_fields=mask,
-                adam_mode=params.get("embedding_adam", "lazy"), seed=seed,
-                slack=float(params.get("shard_slack", 1.5)), shard_ops=params.get("shard_ops"))
+            exchange = params.get("shard_exchange") or \
+                ("p2p" if (self.device.type == "cuda" and params.get("shard_ops") is None) else "nccl")
+            if exchange == "p2p":
+                from . import p2p
+                if params.get("embedding_adam", "lazy") != "lazy":
+                    raise ValueError("shard_exchange='p2p' implements the lazy row optimiser only")
+                self.emb = p2p.P2PShardedEmbedding(self.lay, self.device, with_w1=self.want_w1,
+                                                   w1_fields=mask, seed=seed)
+            else:
+                from . import sharded
+                self.emb = sharded.ShardedFieldEmbedding(
+                    self.lay, self.device, with_w1=self.want_w1, w1_fields=mask,
+                    adam_mode=params.get("embedding_adam", "lazy"), seed=seed,
+                    slack=float(params.get("shard_slack", 1.5)), shard_ops=params.get("shard_ops"))
         else:
             self.emb = ops.FieldEmbedding(self.lay, self.device, with_w1=self.want_w1,
                                           w1_fields=mask,
                                           adam_mode=params.get("embedding_adam", "lazy"), seed=seed)
         self.ids = ops.IdPipeline(self.lay, self.device)
+        if hasattr(self.emb, "status"):
+            self.emb.status = self.ids.status       # slab overflow raises through the status word
         self.rows = None
         # fused tower + loss head kernels (tower.cu); False keeps the torch (cuBLAS) tower
         self.fused = bool(params.get("fused_tower", True))
@@ -274,6 +301,9 @@ class _CriteoBase(_ModelBase):
             zero_buf.zero_()
         r = self.ids(features, want_logx=want_logx)
         self.rows, logx = r if want_logx else (r, None)
+        if getattr(self.emb, "p2p", False):
+            self.emb.n_dense = self.dense.numel
+            kw["training"] = self._training
         return (logx,) + tuple(self.emb.lookup(self.rows, **kw))
 
     def _fused_head(self, zs, labels, training, shape):
@@ -314,11 +344,17 @@ class _CriteoBase(_ModelBase):
         if tw is not None:
             tw.join()
 
+    def _dense_step(self, lr_t):
+        if getattr(self.emb, "p2p", False):       # all-reduce + Adam over peer memory, no NCCL
+            self.emb.dense_step(self.dense, lr_t, self.adam)
+        else:
+            self._sync_dense_grads()
+            self.dense.adam_step(lr_t, self.adam)
+
     def _apply_gradients(self, lr_t):
         self.emb.adam_step(self.rows, lr_t, self.adam)     # overlaps the side-stream dW kernels
         self._join_tower()
-        self._sync_dense_grads()
-        self.dense.adam_step(lr_t, self.adam)
+        self._dense_step(lr_t)
 
 
 # ============================================================================ FM
@@ -371,7 +407,8 @@ class DeepFMModel(_CriteoBase):
     def forward(self, features, labels, training):
         if not self.fused:
             return super().forward(features, labels, training)
-        lo = self.tower.use_presplit and (self.world == 1 or getattr(self.emb.ops, "packed", False))
+        lo = self.tower.use_presplit and (self.world == 1 or getattr(self.emb, "p2p", False) or
+                                          getattr(getattr(self.emb, "ops", None), "packed", False))
         ws = self.tower.begin_step(self._batch_size(features), expect_lo=lo)
         _, E, y1s, y2, _ = self._lookup(features, zero_buf=ws, want_fm=True, want_y1=True,
                                         **({"want_lo": True} if lo else {}))
@@ -469,6 +506,9 @@ class XDeepFMModel(_CriteoBase):
         self.cin_layers = list(map(int, str(params["cross_layers"]).split(",")))
         self.cin_precision = params.get("cin_precision", "tf32x3")
         self.share = bool(params.get("share_embeddings", False))
+        if self.world > 1 and not self.share:
+            raise ValueError("xdeepfm with shard_embedding needs share_embeddings=True: the DNN "
+                             "branch's second set of tables (xdeepfm/xdeepfm.py:185) is not sharded")
         seed = int(params.get("seed", 0))
         self.emb_dnn = None if self.share else ops.FieldEmbedding(
             self.lay, self.device, with_w1=False, adam_mode=params.get("embedding_adam", "lazy"),
@@ -551,8 +591,7 @@ class XDeepFMModel(_CriteoBase):
         if self.emb_dnn is not None:
             self.emb_dnn.adam_step(self.rows, lr_t, self.adam)
         self._join_tower()
-        self._sync_dense_grads()
-        self.dense.adam_step(lr_t, self.adam)
+        self._dense_step(lr_t)
 
 
 # =========================================================================== DIN

@@ -66,6 +66,17 @@ class DinOpts(C.Structure):
                 ("unit", C.c_uint32), ("table_rows", C.c_int32), ("status", C.c_void_p)]
 
 
+class P2PCtx(C.Structure):
+    """ctr_p2p_ctx (include/ctr_b200.h)."""
+    _fields_ = [("peer", C.c_void_p * 8), ("me", C.c_int32), ("G", C.c_int32),
+                ("capacity", C.c_int32), ("record_floats", C.c_int32),
+                ("off_req_flag", C.c_int64), ("off_req_cnt", C.c_int64), ("off_resp_flag", C.c_int64),
+                ("off_grad_flag", C.c_int64), ("off_dense_flag", C.c_int64),
+                ("off_req_ids", C.c_int64), ("off_resp", C.c_int64), ("off_grad", C.c_int64),
+                ("off_dense", C.c_int64), ("off_counts", C.c_int64), ("off_done", C.c_int64),
+                ("n_dense", C.c_int64), ("spin_limit_ms", C.c_int32), ("pad_", C.c_int32)]
+
+
 class FieldDesc(C.Structure):
     """ctr_field_desc (include/ctr_b200.h)."""
     _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("n_rows", C.c_int32),
@@ -134,6 +145,20 @@ SIGNATURES = {
     "ctr_gather_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f]),
     "ctr_scatter_add_rows": (c_i, [c_f, c_f, c_f, c_i64, c_i, c_f, c_f, c_i64, c_i64, c_i64, c_i64,
                                    c_f]),
+    "ctr_p2p_alloc": (c_i, [c_i64, C.POINTER(C.c_void_p), c_f]),
+    "ctr_p2p_open": (c_i, [c_f, C.POINTER(C.c_void_p)]),
+    "ctr_p2p_close": (c_i, [c_f]),
+    "ctr_p2p_free": (c_i, [c_f]),
+    "ctr_p2p_bucket_send": (c_i, [c_f, c_i64, C.POINTER(P2PCtx), c_f, c_f]),
+    "ctr_p2p_gather_reply": (c_i, [c_f, c_i64, c_i, c_i, c_i, C.POINTER(P2PCtx), c_f]),
+    "ctr_p2p_wait": (c_i, [C.POINTER(P2PCtx), c_i, c_f]),
+    "ctr_p2p_grad_send": (c_i, [c_f, c_f, c_f, c_f, c_f, c_u64, c_i, c_i, c_i, C.POINTER(P2PCtx), c_f]),
+    "ctr_p2p_scatter_adam": (c_i, [c_f, c_i64, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_f,
+                                   C.POINTER(P2PCtx), c_f]),
+    "ctr_p2p_dense_push": (c_i, [c_f, c_i64, C.POINTER(P2PCtx), c_f]),
+    "ctr_p2p_adam_dense": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_f, c_i,
+                                 C.POINTER(P2PCtx), c_f]),
+    "ctr_p2p_status": (c_i, [C.POINTER(P2PCtx), c_f, c_f]),
     "ctr_transpose_fd": (c_i, [c_f, c_i, c_i, c_i, c_f, c_i, c_f]),
     "ctr_transpose_df_add": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
 }

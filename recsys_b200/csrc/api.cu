@@ -59,6 +59,24 @@ int ensure_arch() {
   return CTR_OK;
 }
 
+static cudaStream_t g_aux[64];
+static cudaEvent_t g_fork[64], g_join[64];
+
+bool aux_stream(cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t* join) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_aux[dev] == nullptr) {
+    if (cudaStreamCreateWithFlags(&g_aux[dev], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&g_fork[dev], cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&g_join[dev], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  *stream = g_aux[dev];
+  *fork = g_fork[dev];
+  *join = g_join[dev];
+  return true;
+}
+
 int sm_count() {
   int mj = 0, sm = 0;
   if (query_device(&mj, &sm) != CTR_OK) return 148;

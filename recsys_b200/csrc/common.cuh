@@ -17,6 +17,10 @@ int fail_arg(const char* fn, const char* what);
 int check_cuda(cudaError_t e, const char* fn);
 int ensure_arch();      // CTR_OK or CTR_ERR_ARCH (cached per device)
 int sm_count();         // multiprocessors of the current device (cached)
+// A library-owned non-blocking stream + two timing-less events per device, for entry points that
+// fork part of their work beside the caller's stream and join it back before returning (works
+// under CUDA-graph capture: the fork / join become graph dependencies).  false on CUDA error.
+bool aux_stream(cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t* join);
 
 #define CTR_REQUIRE(cond, fn, what) \
   do {                              \

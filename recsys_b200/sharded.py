@@ -190,6 +190,7 @@ class ShardedFieldEmbedding:
         self.recv_ids = None
         self.counts = None
         self.capacity = 0
+        self.status = None      # the model's sticky status word (int32[1]); overflow sets bit 2
 
     # state -----------------------------------------------------------------------
     def load(self, table=None, w1=None):
@@ -277,6 +278,8 @@ class _ShardedEmbedFn(torch.autograd.Function):
             E, S, y1, y2, xl = emb.ops.interact_fwd(vec_back, w1_back, slot2d, D, emb.w1_fields,
                                                     want_fm, want_y1, cross_w, cross_b)
         emb.recv_ids, emb.counts, emb.capacity = recv_ids, counts, cap
+        if emb.status is not None:       # sticky: bit 2 of the model's status word (see _core.py)
+            emb.status.bitwise_or_((counts.max() > cap).to(torch.int32).mul_(4))
         ctx.emb, ctx.slot2d, ctx.recv_ids, ctx.E, ctx.S, ctx.vec = emb, slot2d, recv_ids, E, S, vec_back
         ctx.cross_w, ctx.cross_b = cross_w, cross_b
         cross = cross_w is not None
@@ -325,6 +328,86 @@ class _ShardedEmbedFn(torch.autograd.Function):
         return None, None, None, None, None, dcw, dcb
 
 
+# ------------------------------------------------------------------- parity (N > 1)
+def parity_check(rank, world, dev, exchange, B=256, steps=2):
+    """Sharded-vs-oracle parity on the live process group, before anything is timed (the driver's
+    GPU test box has one GPU, so this is where the multi-rank path is checked on hardware): a
+    small DeepFM with known weights, ``steps`` train steps per rank on its own batch, against the
+    fp64 oracle - logits per step, then the full table / first-order weights / first dense layer
+    after the optimiser steps (oracle gradients summed over the ranks, tfsem.TFAdam, lazy rows).
+    The oracle is the checker here, nothing of it is timed or shipped."""
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "scripts")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import make_golden as mg
+    from oracle import criteo, models as om, tfsem
+    from . import _core
+    from . import criteo_schema as cs
+    from .deepfm import deepfm
+    from .estimator import VariableStore
+
+    spec = mg.small_spec()
+    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
+    hb = [spec.rows[spec.fields.index(k)] for k in criteo.CAT]
+    lin, emb = cs.build_columns(16, linear="indicator_all", hash_buckets=hb)
+    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
+              "learning_rate": 1e-2, "dropout": 0.0, "deep_layers": "32,16", "device": dev,
+              "variable_store": VariableStore(), "shard_embedding": True, "shard_slack": 8.0,
+              "shard_exchange": exchange}
+    m = params["variable_store"].get("deepfm", lambda: _core.DeepFMModel(params))
+    m.load_state(p64)
+    train = {k: v for k, v in p64.items() if not k.endswith((".bn.mean", ".bn.var"))}
+    opt = tfsem.TFAdam(train, lr=1e-2)
+    worst_logit = 0.0
+    for s in range(steps):
+        feats_all, batch_all = mg.model_batch("deepfm", B * world, 70 + s, spec)
+        sl = slice(rank * B, (rank + 1) * B)
+        feats = {k: torch.from_numpy(np.asarray(v)[sl]) for k, v in feats_all.items()}
+        labels = batch_all["labels"][sl]
+        sp = deepfm.model_fn(feats, labels, "train", params)
+        out64, g64 = om.loss_and_grads("deepfm", p64, {"rows": batch_all["rows"][sl], "labels": labels})
+        logits = m.last["logits"].detach().cpu().double()
+        rel = float(((logits - out64["logits"]).abs() / (out64["logits"].abs() + 0.1)).max())
+        worst_logit = max(worst_logit, rel)
+        sp.train_op()
+        # global gradient = mean over the replicas' losses: sum_r g_r / world
+        gsum = {}
+        for k in sorted(train):
+            t = (g64[k].to(dev) / world).contiguous()
+            dist.all_reduce(t)
+            gsum[k] = t.cpu()
+        rows_all = batch_all["rows"].reshape(-1)
+        opt.step(train, gsum, lazy_rows={"emb": rows_all, "w1": rows_all})
+        p64.update(train)
+    torch.cuda.synchronize()
+    tab = m.emb.full_table() if hasattr(m.emb, "full_table") else None
+    if tab is None:      # NCCL path: gather the shards the same way
+        rl = (m.emb.R + m.emb.G - 1) // m.emb.G
+        mine = torch.zeros(rl, m.emb.D, device=dev)
+        mine[:m.emb.R_local] = m.emb.table
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        tab = torch.zeros(m.emb.R, m.emb.D, device=dev)
+        for r in range(world):
+            tab[r::world] = parts[r][:(m.emb.R - r + world - 1) // world]
+    err_tab = float((tab.cpu().double() - p64["emb"]).abs().max())
+    err_w0 = float((m.dense["dnn.0.w"].detach().cpu().double() - p64["dnn.0.w"]).abs().max())
+    moved = float((tab.cpu().double() - om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16),
+                                                       seed=3)["emb"]).abs().max())
+    m.emb.check_overflow()
+    res = torch.tensor([worst_logit, err_tab, err_w0], dtype=torch.float64, device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    worst_logit, err_tab, err_w0 = (float(x) for x in res)
+    ok = worst_logit <= 1e-4 and err_tab <= 2e-4 and err_w0 <= 2e-4 and moved > 1e-3
+    return {"ok": bool(ok), "max_logit_rel_err": worst_logit, "table_abs_err_after_adam": err_tab,
+            "dense_abs_err_after_adam": err_w0, "table_moved": moved, "steps": steps,
+            "batch_per_rank": B, "world": world, "exchange": exchange,
+            "tolerance": "logits 1e-4 rel; parameters 2e-4 abs after %d Adam steps at lr 1e-2" % steps}
+
+
 # ------------------------------------------------------------------- bench (N > 1)
 def sharded_columns(total_rows: int, embedding_size: int, n_fields: int = 39):
     """Synthetic config 5: ``n_fields`` hashed fields sharing ``total_rows`` rows."""
@@ -363,7 +446,10 @@ def bench_main(args, rank, local, world):
               # exchange slabs sized 1.1x the mean per-(src,dst) load: uniform ids spread by < 1 %
               # (7 sigma = 0.05); check_overflow() below verifies that nothing was dropped
               "shard_slack": float(os.environ.get("CTR_SHARD_SLACK", "1.1")),
+              "shard_exchange": os.environ.get("CTR_SHARD_EXCHANGE", "p2p"),
               "seed": 0}
+    exchange = params["shard_exchange"]
+    parity = parity_check(rank, world, dev, exchange)
     lay = fc.layout(emb)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     rng = np.random.default_rng(1234 + rank)
@@ -447,6 +533,7 @@ def bench_main(args, rank, local, world):
         except Exception:
             clocks = None
     model.emb.check_overflow()
+    model.check_status()
     if os.environ.get("CTR_TRACE"):         # in-graph kernel timeline of a few steps (every rank
         from torch.profiler import ProfilerActivity, profile   # runs them; rank 0 prints)
         dist.barrier()
@@ -461,8 +548,15 @@ def bench_main(args, rank, local, world):
                     a = agg.setdefault(e.name[:64], [0.0, 0])
                     a[0] += e.device_time
                     a[1] += 1
-            for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-                sys.stderr.write("TRACE %8.2f us x %4.1f/step  %s\n" % (t / n, n / 6, k))
+            lines = ["%8.2f us x %4.1f/step  %s" % (t / n, n / 6, k)
+                     for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])]
+            for ln in lines:
+                sys.stderr.write("TRACE " + ln + "\n")
+            out = os.environ.get("CTR_TRACE")
+            if out not in ("1", ""):
+                with open(out, "w") as fh:
+                    fh.write("in-graph kernel times of the sharded DeepFM step, rank 0 of %d, %s exchange, "
+                             "%.3f ms/step\n" % (world, exchange, ms / K) + "\n".join(lines) + "\n")
         dist.barrier()
     if rank == 0:
         f, l = host[0]
@@ -477,8 +571,11 @@ def bench_main(args, rank, local, world):
                                    "fwd+bwd+Adam(lazy rows)" % (total_rows, world, B),
                        "fields": 39, "embedding_size": 16, "batch_per_gpu": B, "global_batch": B * world,
                        "table_rows": total_rows, "id_dist": "uniform",
-                       "exchange": "3 all-to-alls per step (ids; row|w1 slab; gradient slab), "
-                                   "slab slack %.2f" % params["shard_slack"],
+                       "exchange": ("device-initiated over NVLink peer memory (cudaIpc arenas, flag "
+                                    "words; no NCCL call in the step; worst-case slabs)"
+                                    if exchange == "p2p" else
+                                    "3 NCCL all-to-alls per step (ids; row|w1 slab; gradient slab), "
+                                    "slab slack %.2f" % params["shard_slack"]),
                        "l2": "%.1f GB table shard per GPU > L2; distinct id batch every step"
                              % (total_rows / world * 64 / 1e9),
                        "parallelism": "row-sharded table x%d + replicated dense weights (all-reduce)" % world},
@@ -490,9 +587,38 @@ def bench_main(args, rank, local, world):
                            "deepfm.model_fn(pinned PackedFeatures, labels, 'train', params).train_op()"},
             "clocks": clocks,
             "gpu_launches": per_step_launches * K * world, "gpu_launches_per_step": per_step_launches,
-            "nvlink_bytes_per_gpu_per_step": int((G - 1) / G * B * 39 * (4 + 64 + 64 + 8)),
             "launch_mode": mode,
+            "parity_ok": parity["ok"], "parity": parity,
         }
+        # NVLink roofline: bytes this GPU must send per step (ids + its share of rows it owns +
+        # gradients, each (G-1)/G remote; P = 20 floats per record; + the dense gradient to G-1
+        # peers) over the measured 770 GB/s per direction (B200_PROFILING.md)
+        rec_b = 80
+        n_dense = int(model.dense.numel)
+        nv = (G - 1) / G * B * 39 * (4 + rec_b + rec_b) + (G - 1) * n_dense * 4
+        line["nvlink_bytes_per_gpu_per_step"] = int(nv)
+        line["roofline"] = {"bound": "nvlink", "achieved": nv / (ms / K * 1e-3) / 1e9, "peak": 770.0,
+                            "unit": "GB/s", "frac": nv / (ms / K * 1e-3) / 1e9 / 770.0, "traffic": None,
+                            "peak_source": "measured peer copy, one direction per GPU "
+                                           "(B200_PROFILING.md; 900 nominal)",
+                            "kernel": "p2p_gather_reply + p2p_grad_send + p2p_dense_push (stores "
+                                      "into peer HBM)" if exchange == "p2p" else "NCCL all_to_all",
+                            "note": "the step is latency bound (small messages): the fraction says how "
+                                    "far the wire is from being the limit",
+                            "whole_step_hbm": {"achieved": 8276.0 * B / (ms / K * 1e-3) / 1e9,
+                                               "unit": "GB/s per GPU (algorithmic 8276 B/sample)"}}
+        if not getattr(args, "no_cpu_baseline", False):
+            try:
+                import bench as _bench
+                n_cpu, el, cores = _bench.time_oracle("deepfm", B, "ref", "uniform",
+                                                      max_seconds=min(args.cpu_seconds, 10.0))
+                line["cpu_baseline"] = {
+                    "value": n_cpu * B / el, "unit": "samples/s", "cores": cores, "kind": "port",
+                    "sample": "%d fwd+bwd steps of batch %d (%.1f s) of the oracle's torch-CPU fp32 "
+                              "deepfm on the reference-capped table (the 1e9-row table does not fit "
+                              "host memory twice); rank 0 only; no optimizer step" % (n_cpu, B, el)}
+            except Exception as e:        # the baseline is informative, never fatal
+                line["cpu_baseline"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     # Tearing NCCL down under live CUDA graphs that captured its collectives can hang at exit:
     # agree that everyone is done, then leave without running the destructors.

@@ -285,6 +285,7 @@ def test_fused_scatter_adam_matches_tf_adam_on_the_oracle_gradient(cuda, B, D, u
         assert float(emb.dtable.abs().max()) == 0.0 and float(emb.dw1.abs().max()) == 0.0
         assert int(emb.rec[:, 4 * D + 5].view(torch.int32).abs().max()) == 0      # cnt
         assert float(emb.rec[:, 4 * D + 6].abs().max()) == 0.0                    # c
+        assert int(emb.rec[:, 4 * D + 7].view(torch.int32).abs().max()) == 0      # arr
     # w1 of unmasked fields: the oracle's lazy rule decays nothing there either (zero gradient,
     # rows not listed) - compare everything
     assert torch.allclose(emb.table.cpu().double(), p64["emb"], rtol=1e-5, atol=2e-6)

@@ -178,14 +178,18 @@ def test_modes_and_estimator_spec_contract(cuda):
     assert params["variable_store"].global_step == 1
 
 
-@pytest.mark.parametrize("mode", ["exact_tf", "lazy"])
+@pytest.mark.parametrize("mode", ["exact_tf", "lazy", "lazy-fused"])
 def test_training_steps_follow_tf_adam(cuda, mode):
     """Three optimiser steps of DeepFM == oracle forward/backward + tfsem.TFAdam
-    (dense-decay semantics for exact_tf; touched rows only for lazy)."""
+    (dense-decay semantics for exact_tf; touched rows only for lazy; lazy-fused = scatter-add and
+    row Adam in one pass, ctr_embed_bwd_adam)."""
     from recsys_b200.deepfm import deepfm
     spec = mg.small_spec()
     p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
-    m, params = _build("deepfm", spec, cuda, embedding_adam=mode, learning_rate=1e-2)
+    fused = mode.endswith("-fused")
+    mode = mode.split("-")[0]
+    m, params = _build("deepfm", spec, cuda, embedding_adam=mode, learning_rate=1e-2,
+                       fused_row_adam=fused)
     m.load_state(p64)
     train = {k: v for k, v in p64.items() if not k.endswith((".bn.mean", ".bn.var"))}
     opt = tfsem.TFAdam(train, lr=1e-2)
