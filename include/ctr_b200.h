@@ -496,7 +496,8 @@ int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, i
  * step store straight into the consumer's arena and raise a sequence-numbered flag there.
  *
  *   arena := { int step; int err; ... | req_flag[2][G] req_cnt[2][G] resp_flag[G] grad_flag[G]
- *              dense_flag[G] counts[G] done[1+G] | req_ids[2][G][capacity] (int32, owner side)
+ *              dense_flag[G] counts[G] sent[G] done[1+G] | req_ids[2][G][capacity] (int32, owner side)
+ *              | inv[G][capacity] (int32, requester side: lookup index of every slab position)
  *              | resp[G][capacity][P] (fp32, requester side) | grad[G][capacity][P] (owner side)
  *              | dense[G][n_dense] }        P = record_floats = D + 4: row | w1 | pad, and on the
  *                                           way back gradient | dy1 dy2 pad
@@ -511,9 +512,10 @@ int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, i
  *   K2 ctr_p2p_gather_reply  owner: per requester, wait for its ids, gather row | w1 from the local
  *                            row records into the requester's resp[me][pos]; count_lookups != 0
  *                            also counts them per row (the `cnt` word of ctr_embed_bwd_adam)
- *   K3 ctr_embed_fwd over resp (table = own arena + off_resp, row_stride = w1_stride = P, rows =
- *                            slot), after ctr_p2p_wait(ctx, 0)
- *   K4 ctr_p2p_grad_send     per slot: dE + dy2*S | dy1 dy2 stored into the owner's grad[me][pos]
+ *   K3 ctr_embed_fwd_p2p     the fused lookup + interaction kernel over the reply slab (slots as
+ *                            row ids); waits for every owner's reply flag inside the kernel
+ *   K4 ctr_p2p_grad_send     in slab order (inv[]): dE + dy2*S | dy1 dy2 stored into the owner's
+ *                            grad[me][pos] as contiguous runs (`slot` is unused, kept for symmetry)
  *   K5 ctr_p2p_scatter_adam  owner: per requester, wait for its gradients; scatter-add + TF-Adam in
  *                            one pass (the lookup that completes a row updates it)
  *   K6 ctr_p2p_dense_push + ctr_p2p_adam_dense   replicated dense weights: gradients stored into
@@ -527,6 +529,7 @@ typedef struct {
   int32_t me, G, capacity, record_floats;
   int64_t off_req_flag, off_req_cnt, off_resp_flag, off_grad_flag, off_dense_flag;
   int64_t off_req_ids, off_resp, off_grad, off_dense, off_counts, off_done;
+  int64_t off_inv, off_sent; /* requester side: inv[G][capacity] int32 lookup index per slab position; sent[G] */
   int64_t n_dense;
   int32_t spin_limit_ms, pad_;
 } ctr_p2p_ctx;
@@ -538,6 +541,12 @@ int ctr_p2p_bucket_send(const int32_t* rows, int64_t n, const ctr_p2p_ctx* ctx, 
                         ctr_stream_t stream);
 int ctr_p2p_gather_reply(float* rec, int64_t row_stride, int D, int with_w1, int count_lookups,
                          const ctr_p2p_ctx* ctx, ctr_stream_t stream);
+/* K3: ctr_embed_fwd over this rank's reply slab (rows = slot [B,F], row | w1 records of
+ * record_floats), preceded IN THE SAME KERNEL by the wait for every owner's reply flag. */
+int ctr_embed_fwd_p2p(const int32_t* slot, int B, int F, int D, uint64_t w1_fields, int with_w1,
+                      float* E, float* S, float* y1, float* y2, const float* cross_w,
+                      const float* cross_b, int cross_layers, float* xl, float* E_lo,
+                      const ctr_p2p_ctx* ctx, ctr_stream_t stream);
 /* what: 0 = every owner's reply, 1 = every requester's gradients, 2 = every rank's dense gradients */
 int ctr_p2p_wait(const ctr_p2p_ctx* ctx, int what, ctr_stream_t stream);
 int ctr_p2p_grad_send(const int32_t* slot, const float* dE, const float* S, const float* dy2,

@@ -74,7 +74,7 @@ class P2PCtx(C.Structure):
                 ("off_grad_flag", C.c_int64), ("off_dense_flag", C.c_int64),
                 ("off_req_ids", C.c_int64), ("off_resp", C.c_int64), ("off_grad", C.c_int64),
                 ("off_dense", C.c_int64), ("off_counts", C.c_int64), ("off_done", C.c_int64),
-                ("n_dense", C.c_int64), ("spin_limit_ms", C.c_int32), ("pad_", C.c_int32)]
+                ("off_inv", C.c_int64), ("off_sent", C.c_int64), ("n_dense", C.c_int64), ("spin_limit_ms", C.c_int32), ("pad_", C.c_int32)]
 
 
 class FieldDesc(C.Structure):
@@ -151,6 +151,8 @@ SIGNATURES = {
     "ctr_p2p_free": (c_i, [c_f]),
     "ctr_p2p_bucket_send": (c_i, [c_f, c_i64, C.POINTER(P2PCtx), c_f, c_f]),
     "ctr_p2p_gather_reply": (c_i, [c_f, c_i64, c_i, c_i, c_i, C.POINTER(P2PCtx), c_f]),
+    "ctr_embed_fwd_p2p": (c_i, [c_f, c_i, c_i, c_i, c_u64, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f,
+                                c_f, C.POINTER(P2PCtx), c_f]),
     "ctr_p2p_wait": (c_i, [C.POINTER(P2PCtx), c_i, c_f]),
     "ctr_p2p_grad_send": (c_i, [c_f, c_f, c_f, c_f, c_f, c_u64, c_i, c_i, c_i, C.POINTER(P2PCtx), c_f]),
     "ctr_p2p_scatter_adam": (c_i, [c_f, c_i64, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_f,

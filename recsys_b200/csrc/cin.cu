@@ -3,6 +3,7 @@
 #include "cin_simt.cuh"
 #include "cin_tc.cuh"
 #include "cin_dw_tc.cuh"
+#include "cin_dw_fused.cuh"
 
 namespace ctr {
 

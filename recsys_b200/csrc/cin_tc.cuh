@@ -258,6 +258,8 @@ __global__ void cin_prep_a_kernel(const float* __restrict__ A, int lda, int K, f
 // ------------------------------------------------------------------- host side
 static bool cin_dw_tc_supported(int H);
 static int64_t cin_dw_tc_ws(int M, int m, int Hp, int H, int prec);
+static bool cin_dw_use_fused(int Hp, int H);
+static int64_t cin_dw_fused_ws(int M, int m, int Hp, int H, int prec);
 struct CinTcPlan {
   int Gp, FPT, NT, n_ntiles, m_pad, nkb, Kp, NA, S, n_pass;
   size_t smem;
@@ -369,7 +371,9 @@ static int64_t cin_tc_workspace_bytes(int B, int D, int m, int Hp, int H, int pr
   const int M = B * D;
   int64_t a = cin_tc_pass_ws(M, m, H, Hp, true, prec);   // fwd / dX0t: A = Xp, K = Hp, G = H
   int64_t b = cin_tc_pass_ws(M, m, Hp, H, true, prec);   // dXp: A = dpre, K = H, G = Hp
-  int64_t c = cin_dw_tc_supported(H) ? cin_dw_tc_ws(M, m, Hp, H, prec) : 0;   // dW: ZT + dpreT
+  int64_t c = 0;                                          // dW: XpT + X0T + dpreT (fused) or ZT + dpreT
+  if (cin_dw_use_fused(Hp, H)) c = cin_dw_fused_ws(M, m, Hp, H, prec);
+  else if (cin_dw_tc_supported(H)) c = cin_dw_tc_ws(M, m, Hp, H, prec);
   return std::max(std::max(a, b), c) + 1024;
 }
 
@@ -386,6 +390,17 @@ static int64_t cin_dw_tc_ws(int M, int m, int Hp, int H, int prec);
 static int cin_dw_tc(const float* X0t, int ld0, const float* Xp, int ldp, const float* dpre, int M,
                      int m, int Hp, int H, float* dW, int prec, void* ws, int64_t ws_bytes,
                      cudaStream_t st, const char* fn);
+// the same GEMM with the A operand built in shared memory (cin_dw_fused.cuh): no Z in global memory
+static bool cin_dw_fused_supported(int Hp, int H);
+static int64_t cin_dw_fused_ws(int M, int m, int Hp, int H, int prec);
+static int cin_dw_fused(const float* X0t, int ld0, const float* Xp, int ldp, const float* dpre, int M,
+                        int m, int Hp, int H, float* dW, int prec, void* ws, int64_t ws_bytes,
+                        cudaStream_t st, const char* fn);
+static bool cin_dw_use_fused(int Hp, int H) {
+  const char* e = ctr_knob("CTR_CIN_DW_FUSED");          // developer builds: 0 = the ZT path
+  if (e != nullptr && atoi(e) == 0) return false;
+  return cin_dw_fused_supported(Hp, H);
+}
 
 static int cin_tc_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp, const float* W,
                             const float* dpre, int B, int D, int m, int Hp, int H, float* dX0t,
@@ -408,7 +423,10 @@ static int cin_tc_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp,
     if (r != CTR_OK) return r;
   }
   // dW: split-K tcgen05 GEMM over the rows (cin_dw_tc.cuh); fp32 CUDA cores when H > 128
-  if (cin_dw_tc_supported(H)) {
+  if (cin_dw_use_fused(Hp, H)) {
+    r = cin_dw_fused(X0t, ld0, Xp, ldp, dpre, M, m, Hp, H, dW, prec, ws, ws_bytes, st, "ctr_cin_layer_bwd");
+    if (r != CTR_OK) return r;
+  } else if (cin_dw_tc_supported(H)) {
     r = cin_dw_tc(X0t, ld0, Xp, ldp, dpre, M, m, Hp, H, dW, prec, ws, ws_bytes, st, "ctr_cin_layer_bwd");
     if (r != CTR_OK) return r;
   } else {

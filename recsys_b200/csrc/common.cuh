@@ -117,6 +117,33 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// System-scope flag words (peer-memory exchange): release store / acquire load, wall clock.
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait until *flag >= seq (flags are monotonic step numbers).  Bounded: after limit_ns it sets
+// bit 0 of *err and returns, so a peer that never arrives cannot hang the GPU.
+__device__ __forceinline__ void wait_flag_bounded(const int* flag, int seq, long long limit_ns, int* err) {
+  if (ld_acquire_sys(flag) >= seq) return;
+  const unsigned long long t0 = gtime_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    __nanosleep(64);
+    if (gtime_ns() - t0 > static_cast<unsigned long long>(limit_ns)) {
+      atomicOr(err, 1);
+      return;
+    }
+  }
+}
 // lo part of the 3xTF32 split a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi.  tcgen05.mma.kind::tf32 reads
 // the top 19 bits of an fp32 word, so the raw value serves as "hi"; lo = x - trunc_tf32(x) (exact),
 // rounded to tf32 with integer ops (add half an ulp of the 10-bit mantissa; the tensor core drops

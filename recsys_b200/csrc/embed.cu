@@ -76,6 +76,13 @@ struct EmbedFwdParams {
   int cross_layers;
   int B;
   int F;
+  // peer-memory exchange (ctr_embed_fwd_p2p): flags to wait for before the first table read -
+  // every owner's reply flag must have reached the step number *wait_step
+  const int* wait_flags;
+  const int* wait_step;
+  int* wait_err;
+  long long wait_ns;
+  int wait_n;
 };
 
 constexpr int kFwdWarps = 8;
@@ -111,6 +118,9 @@ embed_fwd_kernel(const EmbedFwdParams p) {
     mbar_init(&s_bar[1], 1);
     mbar_fence_init();
   }
+  if (p.wait_flags != nullptr && tid < p.wait_n)
+    wait_flag_bounded(p.wait_flags + tid, *reinterpret_cast<const volatile int*>(p.wait_step),
+                      p.wait_ns, p.wait_err);
   if (RAW) {
     for (int i = tid; i < F; i += blockDim.x) s_fields[i] = p.fields[i];
     for (int i = tid; i < p.n_bnd; i += blockDim.x) s_bnd[i] = p.bnd[i];
@@ -896,6 +906,26 @@ int ctr_embed_fwd(const float* table, const float* w1, const int32_t* rows, int 
                   float* E_lo, int64_t row_stride, int64_t w1_stride, ctr_stream_t stream) {
   return embed_fwd_impl("ctr_embed_fwd", table, w1, rows, B, F, D, w1_fields, E, S, y1, y2, cross_w,
                         cross_b, cross_layers, xl, E_lo, row_stride, w1_stride, nullptr, stream);
+}
+
+int ctr_embed_fwd_p2p(const int32_t* slot, int B, int F, int D, uint64_t w1_fields, int with_w1,
+                      float* E, float* S, float* y1, float* y2, const float* cross_w,
+                      const float* cross_b, int cross_layers, float* xl, float* E_lo,
+                      const ctr_p2p_ctx* ctx, ctr_stream_t stream) {
+  CTR_REQUIRE(ctx && ctx->G >= 1 && ctx->G <= CTR_P2P_MAX_RANKS && ctx->me >= 0 && ctx->me < ctx->G &&
+                  ctx->peer[ctx->me] && ctx->record_floats == D + 4,
+              "ctr_embed_fwd_p2p", "bad exchange context");
+  char* base = static_cast<char*>(ctx->peer[ctx->me]);
+  const float* resp = reinterpret_cast<const float*>(base + ctx->off_resp);
+  EmbedFwdParams w{};
+  w.wait_flags = reinterpret_cast<const int*>(base + ctx->off_resp_flag);
+  w.wait_step = reinterpret_cast<const int*>(base);
+  w.wait_err = reinterpret_cast<int*>(base) + 1;
+  w.wait_n = ctx->G;
+  w.wait_ns = ctx->spin_limit_ms > 0 ? static_cast<long long>(ctx->spin_limit_ms) * 1000000LL : 10000000000LL;
+  return embed_fwd_impl("ctr_embed_fwd_p2p", resp, with_w1 ? resp + D : nullptr, slot, B, F, D,
+                        w1_fields, E, S, y1, y2, cross_w, cross_b, cross_layers, xl, E_lo,
+                        ctx->record_floats, ctx->record_floats, &w, stream);
 }
 
 int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, int n_cont,

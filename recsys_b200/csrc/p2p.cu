@@ -34,6 +34,7 @@ struct P2P {
   int me, G, cap, P;
   long long off_req_flag, off_req_cnt, off_resp_flag, off_grad_flag, off_dense_flag;
   long long off_req_ids, off_resp, off_grad, off_dense, off_counts, off_done;
+  long long off_inv, off_sent;      // requester side: inv[G][cap] lookup index per slab position, sent[G]
   long long n_dense;
   long long spin_limit_ns;
 };
@@ -46,30 +47,9 @@ __device__ __forceinline__ float* fptr(const P2P& c, int r, long long off) {
   return reinterpret_cast<float*>(c.peer[r] + off);
 }
 
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long gtime_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Wait until *flag >= seq (flags are monotonic).  Bounded: on timeout sets arena.err and returns.
+// Wait until *flag >= seq; on timeout sets arena.err and returns.
 __device__ __forceinline__ void wait_flag(const P2P& c, const int* flag, int seq) {
-  if (ld_acquire_sys(flag) >= seq) return;
-  const unsigned long long t0 = gtime_ns();
-  while (ld_acquire_sys(flag) < seq) {
-    __nanosleep(64);
-    if (gtime_ns() - t0 > static_cast<unsigned long long>(c.spin_limit_ns)) {
-      atomicOr(hdr(c, c.me) + 1, 1);
-      return;
-    }
-  }
+  wait_flag_bounded(flag, seq, c.spin_limit_ns, hdr(c, c.me) + 1);
 }
 
 // Last-block detection: every block calls this once after its last global store; returns true in
@@ -91,33 +71,53 @@ __device__ __forceinline__ bool last_block(int* counter, int nblocks) {
 }
 
 // ----------------------------------------------------------------------------- K1
-// One lookup per thread; lanes of a warp that target the same owner take consecutive positions
-// with one atomic.  slot[i] = owner * cap + pos (what K3 / K4 index the slabs with).
+// CTA = a contiguous run of kBktPerThread x 256 lookups.  Positions are handed out in two levels:
+// lanes of a warp that target the same owner take consecutive ranks with one shared-memory atomic,
+// the CTA reserves its range of every owner's slab with ONE global atomic per owner.  Besides the
+// owner-local id stored into the owner's arena, the requester keeps inv[owner][pos] = lookup index
+// (so that K4 can stream the gradients out in slab order) and slot[i] = owner * cap + pos (what K3
+// indexes the reply slab with).
+constexpr int kBktPerThread = 4;
 __global__ void __launch_bounds__(256)
 p2p_bucket_send_kernel(const int* __restrict__ rows, long long n, const P2P c, int* __restrict__ slot) {
+  __shared__ int s_cnt[CTR_P2P_MAX_RANKS], s_base[CTR_P2P_MAX_RANKS];
   const int seq = hdr(c, c.me)[0] + 1;
   const int par = seq & 1;
   int* counts = iptr(c, c.me, c.off_counts);
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long nr = (n + stride - 1) / stride;
-  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  int* inv = iptr(c, c.me, c.off_inv);
   const int lane = threadIdx.x & 31;
-  for (long long k = 0; k < nr; ++k, i += stride) {
-    const bool ok = i < n;
-    const int row = ok ? __ldg(rows + i) : -1;
-    const int owner = ok ? row % c.G : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, owner);
-    if (!ok) continue;
+  if (threadIdx.x < CTR_P2P_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long i0 = static_cast<long long>(blockIdx.x) * (256 * kBktPerThread) + threadIdx.x;
+  int row[kBktPerThread], owner[kBktPerThread], rank[kBktPerThread];
+#pragma unroll
+  for (int u = 0; u < kBktPerThread; ++u) {
+    const long long i = i0 + u * 256;
+    row[u] = i < n ? __ldg(rows + i) : -1;
+  }
+#pragma unroll
+  for (int u = 0; u < kBktPerThread; ++u) {
+    owner[u] = row[u] >= 0 ? row[u] % c.G : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, owner[u]);
     const int leader = __ffs(peers) - 1;
-    const int rank_in = __popc(peers & ((1u << lane) - 1u));
     int base = 0;
-    if (lane == leader) base = atomicAdd(counts + owner, __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const int pos = base + rank_in;          // < cap by construction (cap = n)
-    int* dst = iptr(c, owner, c.off_req_ids) +
+    if (lane == leader && owner[u] >= 0) base = atomicAdd(&s_cnt[owner[u]], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[u] = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  if (threadIdx.x < c.G) s_base[threadIdx.x] = atomicAdd(counts + threadIdx.x, s_cnt[threadIdx.x]);
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kBktPerThread; ++u) {
+    if (owner[u] < 0) continue;
+    const long long i = i0 + u * 256;
+    const int pos = s_base[owner[u]] + rank[u];          // < cap by construction (cap >= n)
+    int* dst = iptr(c, owner[u], c.off_req_ids) +
                (static_cast<long long>(par) * c.G + c.me) * c.cap + pos;
-    *dst = row / c.G;
-    slot[i] = owner * c.cap + pos;
+    *dst = row[u] / c.G;
+    inv[static_cast<long long>(owner[u]) * c.cap + pos] = static_cast<int>(i);
+    slot[i] = owner[u] * c.cap + pos;
   }
   if (last_block(iptr(c, c.me, c.off_done), gridDim.x)) {
     if (threadIdx.x < c.G) {
@@ -126,6 +126,7 @@ p2p_bucket_send_kernel(const int* __restrict__ rows, long long n, const P2P c, i
       *reinterpret_cast<volatile int*>(iptr(c, o, c.off_req_cnt) + par * c.G + c.me) = cnt;
       __threadfence_system();
       st_release_sys(iptr(c, o, c.off_req_flag) + par * c.G + c.me, seq);
+      iptr(c, c.me, c.off_sent)[o] = cnt;               // K4 of this step reads it
       counts[o] = 0;
     }
     __syncthreads();
@@ -181,39 +182,47 @@ __global__ void p2p_wait_kernel(const P2P c, long long off_flags) {
 }
 
 // ----------------------------------------------------------------------------- K4
-// Warp per sample (the forward's layout): lane l of iteration it holds float4 it*32+l of the
-// sample's concatenated gradient, i.e. quarter q = lane % LPR of field f = it*RPW + lane / LPR.
-template <int D, int NIT>
+// Slab order: CTA b serves owner o = b % G; five lanes per record (four gradient quarters + the
+// tail {dy1, dy2}), six records per warp instruction, so the remote stores of a warp are one
+// contiguous 480-byte run of the owner's grad[me] slab (NVLink likes long writes; the scattered
+// side - dE[b,f,:] through inv[] - is local).
+template <int D>
 __global__ void __launch_bounds__(256)
-p2p_grad_send_kernel(const int* __restrict__ slot, const float* __restrict__ dE,
-                     const float* __restrict__ S, const float* __restrict__ dy2,
-                     const float* __restrict__ dy1, unsigned long long w1_fields, int B, int F,
-                     const P2P c) {
+p2p_grad_send_kernel(const float* __restrict__ dE, const float* __restrict__ S,
+                     const float* __restrict__ dy2, const float* __restrict__ dy1,
+                     unsigned long long w1_fields, int F, const P2P c) {
   constexpr int LPR = D / 4;
-  constexpr int RPW = 32 / LPR;
+  constexpr int GL = LPR + 1;                 // lanes per record
+  constexpr int RPW = 32 / GL;                // records per warp instruction
   const int seq = hdr(c, c.me)[0];
-  const int lane = threadIdx.x & 31, r = lane / LPR, q = lane % LPR;
+  const int o = blockIdx.x % c.G;
+  const int share = blockIdx.x / c.G, nshare = gridDim.x / c.G;
+  const int lane = threadIdx.x & 31, r = lane / GL, q = lane % GL;
   const int wpb = blockDim.x >> 5;
-  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
-    const float cdy = dy2 != nullptr ? __ldg(dy2 + b) : 0.f;
-    const float wdy = dy1 != nullptr ? __ldg(dy1 + b) : 0.f;
-    const float4 sv = dy2 != nullptr ? ldg4(S + static_cast<size_t>(b) * D + q * 4) : f4_zero();
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int f = it * RPW + r;
-      if (f >= F) continue;
-      const int sl = __ldg(slot + static_cast<size_t>(b) * F + f);
-      if (sl < 0) continue;
-      float4 g = dE != nullptr ? ld4_stream(dE + static_cast<size_t>(b) * F * D + (it * 32 + lane) * 4)
-                               : f4_zero();
-      g.x = fmaf(cdy, sv.x, g.x); g.y = fmaf(cdy, sv.y, g.y);
-      g.z = fmaf(cdy, sv.z, g.z); g.w = fmaf(cdy, sv.w, g.w);
-      const int owner = sl / c.cap, pos = sl - owner * c.cap;
-      float* o = fptr(c, owner, c.off_grad) + (static_cast<long long>(c.me) * c.cap + pos) * c.P;
-      *reinterpret_cast<float4*>(o + q * 4) = g;
-      if (q == 0)
-        *reinterpret_cast<float4*>(o + D) =
-            make_float4(((w1_fields >> f) & 1ull) ? wdy : 0.f, cdy, 0.f, 0.f);
+  if (share < nshare) {
+    const int cnt = min(iptr(c, c.me, c.off_sent)[o], c.cap);
+    const int* inv = iptr(c, c.me, c.off_inv) + static_cast<long long>(o) * c.cap;
+    float* out = fptr(c, o, c.off_grad) + static_cast<long long>(c.me) * c.cap * c.P;
+    const int w = share * wpb + (threadIdx.x >> 5), nw = nshare * wpb;
+    for (int p0 = w * RPW; p0 < cnt; p0 += nw * RPW) {
+      const int pos = p0 + r;
+      if (r >= RPW || pos >= cnt) continue;
+      const int i = __ldg(inv + pos);
+      const int b = i / F, f = i - b * F;
+      float4 v;
+      if (q < LPR) {
+        v = dE != nullptr ? ld4_stream(dE + static_cast<size_t>(i) * D + q * 4) : f4_zero();
+        if (dy2 != nullptr) {
+          const float cdy = __ldg(dy2 + b);
+          const float4 sv = ldg4(S + static_cast<size_t>(b) * D + q * 4);
+          v.x = fmaf(cdy, sv.x, v.x); v.y = fmaf(cdy, sv.y, v.y);
+          v.z = fmaf(cdy, sv.z, v.z); v.w = fmaf(cdy, sv.w, v.w);
+        }
+      } else {
+        v = make_float4((dy1 != nullptr && ((w1_fields >> f) & 1ull)) ? __ldg(dy1 + b) : 0.f,
+                        dy2 != nullptr ? __ldg(dy2 + b) : 0.f, 0.f, 0.f);
+      }
+      *reinterpret_cast<float4*>(out + static_cast<long long>(pos) * c.P + q * 4) = v;
     }
   }
   if (last_block(iptr(c, c.me, c.off_done), gridDim.x)) {
@@ -357,6 +366,7 @@ static P2P make_ctx(const ctr_p2p_ctx* x) {
   c.off_grad_flag = x->off_grad_flag; c.off_dense_flag = x->off_dense_flag;
   c.off_req_ids = x->off_req_ids; c.off_resp = x->off_resp; c.off_grad = x->off_grad;
   c.off_dense = x->off_dense; c.off_counts = x->off_counts; c.off_done = x->off_done;
+  c.off_inv = x->off_inv; c.off_sent = x->off_sent;
   c.n_dense = x->n_dense;
   c.spin_limit_ns = x->spin_limit_ms > 0 ? static_cast<long long>(x->spin_limit_ms) * 1000000LL
                                          : 10000000000LL;
@@ -423,8 +433,8 @@ int ctr_p2p_bucket_send(const int32_t* rows, int64_t n, const ctr_p2p_ctx* ctx, 
   CTR_REQUIRE(rows && slot && n >= 0 && ctx_ok(ctx), "ctr_p2p_bucket_send", "bad argument");
   CTR_REQUIRE(n <= ctx->capacity, "ctr_p2p_bucket_send",
               "capacity must cover all lookups of a rank (worst case: one owner)");
-  const int grid = static_cast<int>(std::max<long long>(
-      1, std::min<long long>((n + 255) / 256, sm_count() * 4LL)));
+  const long long per_cta = 256LL * kBktPerThread;
+  const int grid = static_cast<int>(std::max<long long>(1, (n + per_cta - 1) / per_cta));
   p2p_bucket_send_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, n, make_ctx(ctx), slot);
   CTR_LAUNCH_CHECK("ctr_p2p_bucket_send");
 }
@@ -459,31 +469,22 @@ int ctr_p2p_grad_send(const int32_t* slot, const float* dE, const float* S, cons
                       const float* dy1, uint64_t w1_fields, int B, int F, int D,
                       const ctr_p2p_ctx* ctx, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
-  CTR_REQUIRE(slot && (dE || dy2) && B >= 0 && F > 0 && F <= CTR_MAX_FIELDS && ctx_ok(ctx),
+  (void)slot;       // the slab order comes from the arena's inv[] (written by ctr_p2p_bucket_send)
+  CTR_REQUIRE((dE || dy2) && B >= 0 && F > 0 && F <= CTR_MAX_FIELDS && ctx_ok(ctx),
               "ctr_p2p_grad_send", "bad argument");
   CTR_REQUIRE(!dy2 || S, "ctr_p2p_grad_send", "dy2 needs S");
   CTR_REQUIRE(aligned16(dE) && aligned16(S), "ctr_p2p_grad_send", "pointers must be 16-byte aligned");
   CTR_REQUIRE((D == 8 || D == 16 || D == 32) && ctx->record_floats == D + 4, "ctr_p2p_grad_send",
               "D in {8,16,32}, record_floats == D + 4");
-  const int rpw = 32 / (D / 4);
-  const int need = (F + rpw - 1) / rpw;
-  CTR_REQUIRE(need <= 10, "ctr_p2p_grad_send", "F*D too large (max 1280 floats per sample)");
-  if (B == 0) B = 0;
-  const int grid = std::max(1, std::min((B + 7) / 8, sm_count() * 4));
+  const int G = ctx->G;
+  const int grid = std::max(1, (sm_count() * 4) / G) * G;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const P2P c = make_ctx(ctx);
-#define CTR_GS(DD, NN) p2p_grad_send_kernel<DD, NN><<<grid, 256, 0, st>>>(slot, dE, S, dy2, dy1, w1_fields, B, F, c)
-#define CTR_GSD(DD)                                   \
-  if (need <= 2) CTR_GS(DD, 2);                       \
-  else if (need <= 5) CTR_GS(DD, 5);                  \
-  else CTR_GS(DD, 10);
   switch (D) {
-    case 8: CTR_GSD(8) break;
-    case 16: CTR_GSD(16) break;
-    default: CTR_GSD(32) break;
+    case 8: p2p_grad_send_kernel<8><<<grid, 256, 0, st>>>(dE, S, dy2, dy1, w1_fields, F, c); break;
+    case 16: p2p_grad_send_kernel<16><<<grid, 256, 0, st>>>(dE, S, dy2, dy1, w1_fields, F, c); break;
+    default: p2p_grad_send_kernel<32><<<grid, 256, 0, st>>>(dE, S, dy2, dy1, w1_fields, F, c); break;
   }
-#undef CTR_GSD
-#undef CTR_GS
   CTR_LAUNCH_CHECK("ctr_p2p_grad_send");
 }
 

@@ -44,10 +44,12 @@ class P2PArena:
         self.n_dense = _align(max(int(n_dense), 4), 4)
         off, o = {}, 256                                   # [0, 256): header {step, err}
         for name, n_int in (("req_flag", 2 * G), ("req_cnt", 2 * G), ("resp_flag", G),
-                            ("grad_flag", G), ("dense_flag", G), ("counts", G), ("done", 1 + G)):
+                            ("grad_flag", G), ("dense_flag", G), ("counts", G), ("sent", G),
+                            ("done", 1 + G)):
             off[name] = o
             o = _align(o + 4 * n_int)
         for name, nbytes in (("req_ids", 2 * G * self.capacity * 4),
+                             ("inv", G * self.capacity * 4),
                              ("resp", G * self.capacity * P * 4),
                              ("grad", G * self.capacity * P * 4),
                              ("dense", G * self.n_dense * 4)):
@@ -79,6 +81,7 @@ class P2PArena:
         c.off_resp_flag, c.off_grad_flag, c.off_dense_flag = off["resp_flag"], off["grad_flag"], off["dense_flag"]
         c.off_req_ids, c.off_resp, c.off_grad, c.off_dense = off["req_ids"], off["resp"], off["grad"], off["dense"]
         c.off_counts, c.off_done = off["counts"], off["done"]
+        c.off_inv, c.off_sent = off["inv"], off["sent"]
         c.n_dense, c.spin_limit_ms = self.n_dense, int(spin_limit_ms)
         self.ctx = c
         dist.barrier(group=group)          # every arena is mapped before anyone stores into one
@@ -242,9 +245,6 @@ class _P2PEmbedFn(torch.autograd.Function):
         _call("ctr_p2p_bucket_send", _p(rows), B * F, a.ref, _p(slot), _stream())             # K1
         _call("ctr_p2p_gather_reply", _p(emb.rec), emb.ld, D, 1 if want_y1 else 0,
               1 if emb._count else 0, a.ref, _stream())                                       # K2
-        _call("ctr_p2p_wait", a.ref, 0, _stream())
-        P = a.P
-        resp = a.ptr + a.off["resp"]
         E = torch.empty((B, F * D), dtype=torch.float32, device=dev)
         E_lo = torch.empty_like(E) if emb._want_lo else None
         S = torch.empty((B, D), dtype=torch.float32, device=dev) if want_fm else None
@@ -252,9 +252,9 @@ class _P2PEmbedFn(torch.autograd.Function):
         y1 = torch.empty(B, dtype=torch.float32, device=dev) if want_y1 else None
         cross = cross_w is not None
         xl = torch.empty((B, F * D), dtype=torch.float32, device=dev) if cross else None
-        _call("ctr_embed_fwd", resp, resp + 4 * D if want_y1 else None, _p(slot), B, F, D,
-              emb.w1_fields, _p(E), _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b),
-              cross_w.shape[0] if cross else 0, _p(xl), _p(E_lo), P, P, _stream())            # K3
+        _call("ctr_embed_fwd_p2p", _p(slot), B, F, D, emb.w1_fields, 1 if want_y1 else 0, _p(E),
+              _p(S), _p(y1), _p(y2), _p(cross_w), _p(cross_b), cross_w.shape[0] if cross else 0,
+              _p(xl), _p(E_lo), a.ref, _stream())                                             # K3
         emb.last_E_lo = E_lo
         ctx.emb, ctx.slot, ctx.E, ctx.S = emb, slot, E, S
         ctx.cross_w, ctx.cross_b = cross_w, cross_b

@@ -328,86 +328,6 @@ class _ShardedEmbedFn(torch.autograd.Function):
         return None, None, None, None, None, dcw, dcb
 
 
-# ------------------------------------------------------------------- parity (N > 1)
-def parity_check(rank, world, dev, exchange, B=256, steps=2):
-    """Sharded-vs-oracle parity on the live process group, before anything is timed (the driver's
-    GPU test box has one GPU, so this is where the multi-rank path is checked on hardware): a
-    small DeepFM with known weights, ``steps`` train steps per rank on its own batch, against the
-    fp64 oracle - logits per step, then the full table / first-order weights / first dense layer
-    after the optimiser steps (oracle gradients summed over the ranks, tfsem.TFAdam, lazy rows).
-    The oracle is the checker here, nothing of it is timed or shipped."""
-    import sys
-    import numpy as np
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for p in (root, os.path.join(root, "scripts")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    import make_golden as mg
-    from oracle import criteo, models as om, tfsem
-    from . import _core
-    from . import criteo_schema as cs
-    from .deepfm import deepfm
-    from .estimator import VariableStore
-
-    spec = mg.small_spec()
-    p64 = om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16), seed=3)
-    hb = [spec.rows[spec.fields.index(k)] for k in criteo.CAT]
-    lin, emb = cs.build_columns(16, linear="indicator_all", hash_buckets=hb)
-    params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
-              "learning_rate": 1e-2, "dropout": 0.0, "deep_layers": "32,16", "device": dev,
-              "variable_store": VariableStore(), "shard_embedding": True, "shard_slack": 8.0,
-              "shard_exchange": exchange}
-    m = params["variable_store"].get("deepfm", lambda: _core.DeepFMModel(params))
-    m.load_state(p64)
-    train = {k: v for k, v in p64.items() if not k.endswith((".bn.mean", ".bn.var"))}
-    opt = tfsem.TFAdam(train, lr=1e-2)
-    worst_logit = 0.0
-    for s in range(steps):
-        feats_all, batch_all = mg.model_batch("deepfm", B * world, 70 + s, spec)
-        sl = slice(rank * B, (rank + 1) * B)
-        feats = {k: torch.from_numpy(np.asarray(v)[sl]) for k, v in feats_all.items()}
-        labels = batch_all["labels"][sl]
-        sp = deepfm.model_fn(feats, labels, "train", params)
-        out64, g64 = om.loss_and_grads("deepfm", p64, {"rows": batch_all["rows"][sl], "labels": labels})
-        logits = m.last["logits"].detach().cpu().double()
-        rel = float(((logits - out64["logits"]).abs() / (out64["logits"].abs() + 0.1)).max())
-        worst_logit = max(worst_logit, rel)
-        sp.train_op()
-        # global gradient = mean over the replicas' losses: sum_r g_r / world
-        gsum = {}
-        for k in sorted(train):
-            t = (g64[k].to(dev) / world).contiguous()
-            dist.all_reduce(t)
-            gsum[k] = t.cpu()
-        rows_all = batch_all["rows"].reshape(-1)
-        opt.step(train, gsum, lazy_rows={"emb": rows_all, "w1": rows_all})
-        p64.update(train)
-    torch.cuda.synchronize()
-    tab = m.emb.full_table() if hasattr(m.emb, "full_table") else None
-    if tab is None:      # NCCL path: gather the shards the same way
-        rl = (m.emb.R + m.emb.G - 1) // m.emb.G
-        mine = torch.zeros(rl, m.emb.D, device=dev)
-        mine[:m.emb.R_local] = m.emb.table
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)
-        tab = torch.zeros(m.emb.R, m.emb.D, device=dev)
-        for r in range(world):
-            tab[r::world] = parts[r][:(m.emb.R - r + world - 1) // world]
-    err_tab = float((tab.cpu().double() - p64["emb"]).abs().max())
-    err_w0 = float((m.dense["dnn.0.w"].detach().cpu().double() - p64["dnn.0.w"]).abs().max())
-    moved = float((tab.cpu().double() - om.init_params("deepfm", spec.total_rows, deep_layers=(32, 16),
-                                                       seed=3)["emb"]).abs().max())
-    m.emb.check_overflow()
-    res = torch.tensor([worst_logit, err_tab, err_w0], dtype=torch.float64, device=dev)
-    dist.all_reduce(res, op=dist.ReduceOp.MAX)
-    worst_logit, err_tab, err_w0 = (float(x) for x in res)
-    ok = worst_logit <= 1e-4 and err_tab <= 2e-4 and err_w0 <= 2e-4 and moved > 1e-3
-    return {"ok": bool(ok), "max_logit_rel_err": worst_logit, "table_abs_err_after_adam": err_tab,
-            "dense_abs_err_after_adam": err_w0, "table_moved": moved, "steps": steps,
-            "batch_per_rank": B, "world": world, "exchange": exchange,
-            "tolerance": "logits 1e-4 rel; parameters 2e-4 abs after %d Adam steps at lr 1e-2" % steps}
-
-
 # ------------------------------------------------------------------- bench (N > 1)
 def sharded_columns(total_rows: int, embedding_size: int, n_fields: int = 39):
     """Synthetic config 5: ``n_fields`` hashed fields sharing ``total_rows`` rows."""
@@ -449,7 +369,11 @@ def bench_main(args, rank, local, world):
               "shard_exchange": os.environ.get("CTR_SHARD_EXCHANGE", "p2p"),
               "seed": 0}
     exchange = params["shard_exchange"]
-    parity = parity_check(rank, world, dev, exchange)
+    # sharded-vs-oracle parity on the live process group before anything is timed; the checker
+    # lives with the bench (the package never imports the oracle)
+    parity_fn = getattr(args, "parity_check", None)
+    parity = parity_fn(rank, world, dev, exchange) if parity_fn is not None else \
+        {"ok": None, "skipped": "no checker supplied"}
     lay = fc.layout(emb)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     rng = np.random.default_rng(1234 + rank)
@@ -607,11 +531,10 @@ def bench_main(args, rank, local, world):
                                     "far the wire is from being the limit",
                             "whole_step_hbm": {"achieved": 8276.0 * B / (ms / K * 1e-3) / 1e9,
                                                "unit": "GB/s per GPU (algorithmic 8276 B/sample)"}}
-        if not getattr(args, "no_cpu_baseline", False):
+        if not getattr(args, "no_cpu_baseline", False) and getattr(args, "time_oracle", None):
             try:
-                import bench as _bench
-                n_cpu, el, cores = _bench.time_oracle("deepfm", B, "ref", "uniform",
-                                                      max_seconds=min(args.cpu_seconds, 10.0))
+                n_cpu, el, cores = args.time_oracle("deepfm", B, "ref", "uniform",
+                                                    max_seconds=min(args.cpu_seconds, 10.0))
                 line["cpu_baseline"] = {
                     "value": n_cpu * B / el, "unit": "samples/s", "cores": cores, "kind": "port",
                     "sample": "%d fwd+bwd steps of batch %d (%.1f s) of the oracle's torch-CPU fp32 "

@@ -35,7 +35,8 @@ def main():
     lin, emb = cs.build_columns(16, linear="indicator_all", hash_buckets=hb)
     params = {"linear_feature_columns": lin, "embedding_feature_columns": emb, "embedding_size": 16,
               "learning_rate": 1e-3, "dropout": 0.0, "deep_layers": "32,16", "device": dev,
-              "variable_store": VariableStore(), "shard_embedding": True, "shard_slack": 4.0}
+              "variable_store": VariableStore(), "shard_embedding": True, "shard_slack": 4.0,
+              "shard_exchange": "nccl"}      # backward() alone, then the gathered gradient
     m = params["variable_store"].get("deepfm", lambda: _core.DeepFMModel(params))
     m.load_state(p64)
     sp = deepfm.model_fn(feats, labels, "train", params)

@@ -72,3 +72,20 @@ def test_sharded_deepfm_matches_oracle_over_nccl(cuda):
            os.path.join(ROOT, "tests", "sharded_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "SHARDED-PARITY-OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_sharded_train_steps_match_oracle_on_both_exchanges(cuda):
+    """>= 2 GPUs: three train steps of the row-sharded DeepFM through the peer-memory exchange
+    kernels (csrc/p2p.cu) and through the NCCL all-to-alls, each against the fp64 oracle +
+    TF-Adam on the gathered table (bench.sharded_parity_check)."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2); bench.py --gpus N runs the same check "
+                    "before timing and reports parity_ok")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 200),
+           os.path.join(ROOT, "tests", "p2p_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "SHARDED-EXCHANGE-PARITY-OK" in res.stdout, \
+        res.stdout[-3000:] + res.stderr[-3000:]
