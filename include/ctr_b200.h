@@ -282,6 +282,16 @@ int ctr_cin_layer_bwd(const float* X0t, int ld0, const float* Xp, int ldp, const
                       const float* dpre, int B, int D, int m, int Hp, int H, float* dX0t,
                       float* dXp, float* dW, float* dbias, int prec, void* workspace,
                       int64_t workspace_bytes, ctr_stream_t stream);
+/* The sum-pool over the embedding axis (xdeepfm/xdeepfm.py:180-181) on d-major rows and its
+ * backward folded with the ReLU of the layer it feeds back into:
+ *   pooled[b, h] = sum_d out[b*D+d, h]                                       (ld_pooled >= H)
+ *   dpre[b*D+d, h] = (dpool[b, h] + dacc[b*D+d, h]) * 1[out[b*D+d, h] > 0]   (dacc nullable: what the
+ *                    next layer's backward accumulated for this layer's output)
+ * H, ld_pooled, ld_dpool multiples of 4. */
+int ctr_cin_pool(const float* out, int B, int D, int H, float* pooled, int ld_pooled,
+                 ctr_stream_t stream);
+int ctr_cin_dpre(const float* dpool, int ld_dpool, const float* dacc, const float* out, int B, int D,
+                 int H, float* dpre, ctr_stream_t stream);
 /* [B, F, D] (E layout) <-> [B*D, ld] d-major rows (zero padded to ld). */
 int ctr_transpose_fd(const float* E, int B, int F, int D, float* Xt, int ld, ctr_stream_t stream);
 int ctr_transpose_df_add(const float* dXt, int ld, int B, int F, int D, float* dE,

@@ -199,24 +199,18 @@ class _ModelBase:
         # stream they were created on) alive, which breaks a later CUDA-graph capture
         self.last = {k: v.detach() for k, v in self.last.items()}
 
-    # Lookups per step from which the fused scatter + optimiser pass (ctr_embed_bwd_adam) pays off.
-    # Measured on B200 (profiles/r02_*): at batch 4096 x 39 fields the step is bound by dependent
-    # memory latency and the fused pass ties with the unfused pair (134.8 vs 132.0 us per step);
-    # from a few hundred thousand lookups on the records no longer stay in L2 between the two
-    # unfused passes and touching each record once wins.
-    FUSED_ROW_ADAM_MIN_LOOKUPS = 1 << 19
-
     def _arm_row_optimiser(self, lr_t):
-        """Tables that support it run their scatter-add and row Adam fused in the backward:
-        params['fused_row_adam'] = True / False / 'auto' (default: by the number of lookups).
-        The peer-memory sharded table always does (its owner-side pass is the fused one)."""
-        want = self.params.get("fused_row_adam", "auto")
+        """params['fused_row_adam'] = True runs a table's scatter-add and row Adam in one pass
+        inside the backward (ctr_count_rows + ctr_embed_bwd_adam).  Default False: measured on B200
+        (profiles/r02_*), on one GPU the extra counting pass costs more than the second visit it
+        saves - 51 vs 35 us at batch 4096 x 39 fields, 469 vs 352 us at batch 65 536 - so the
+        unfused pair stays the default.  The peer-memory sharded table always fuses: its owner
+        counts the lookups for free while it gathers the rows (K2), and applies them in K5."""
+        want = bool(self.params.get("fused_row_adam", False))
         for emb in (getattr(self, "emb", None), getattr(self, "emb_dnn", None)):
             if emb is None or not getattr(emb, "can_fuse", False) or self.rows is None:
                 continue
-            on = want if isinstance(want, bool) else \
-                self.rows.numel() >= self.FUSED_ROW_ADAM_MIN_LOOKUPS
-            if on or getattr(emb, "p2p", False):
+            if want or getattr(emb, "p2p", False):
                 emb.arm_fused(self.rows, lr_t, self.adam)
 
     def apply_gradients(self):

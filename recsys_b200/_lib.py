@@ -161,6 +161,8 @@ SIGNATURES = {
     "ctr_p2p_adam_dense": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_f, c_i,
                                  C.POINTER(P2PCtx), c_f]),
     "ctr_p2p_status": (c_i, [C.POINTER(P2PCtx), c_f, c_f]),
+    "ctr_cin_pool": (c_i, [c_f, c_i, c_i, c_i, c_f, c_i, c_f]),
+    "ctr_cin_dpre": (c_i, [c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f, c_f]),
     "ctr_transpose_fd": (c_i, [c_f, c_i, c_i, c_i, c_f, c_i, c_f]),
     "ctr_transpose_df_add": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
 }

@@ -44,11 +44,74 @@ transpose_df_add_kernel(const float* __restrict__ dXt, int ld, int B, int F, int
   }
 }
 
+// pooled[b, h] = sum_d out[(b*D+d), h]   (xdeepfm/xdeepfm.py:180-181): thread per (b, 4 columns).
+__global__ void __launch_bounds__(256)
+cin_pool_kernel(const float* __restrict__ out, int B, int D, int H, float* __restrict__ pooled,
+                int ldp) {
+  const int hq = H >> 2;
+  const long long n = static_cast<long long>(B) * hq;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += gridDim.x * 256LL) {
+    const int b = static_cast<int>(e / hq), q = static_cast<int>(e % hq);
+    float4 a = f4_zero();
+    for (int d = 0; d < D; ++d)
+      a = f4_add(a, ldg4(out + (static_cast<size_t>(b) * D + d) * H + q * 4));
+    *reinterpret_cast<float4*>(pooled + static_cast<size_t>(b) * ldp + q * 4) = a;
+  }
+}
+
+// dpre[(b*D+d), h] = (dpool[b, h] + dacc[(b*D+d), h]) * 1[out[(b*D+d), h] > 0]: the gradient of the
+// sum-pool broadcast over d, plus what the next layer sent back (dacc, nullable), through the ReLU.
+__global__ void __launch_bounds__(256)
+cin_dpre_kernel(const float* __restrict__ dpool, int ldp, const float* __restrict__ dacc,
+                const float* __restrict__ out, int B, int D, int H, float* __restrict__ dpre) {
+  const int hq = H >> 2;
+  const long long n = static_cast<long long>(B) * D * hq;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += gridDim.x * 256LL) {
+    const long long r = e / hq;
+    const int q = static_cast<int>(e % hq);
+    const int b = static_cast<int>(r / D);
+    float4 g = ldg4(dpool + static_cast<size_t>(b) * ldp + q * 4);
+    if (dacc != nullptr) g = f4_add(g, ldg4(dacc + static_cast<size_t>(r) * H + q * 4));
+    const float4 o = ldg4(out + static_cast<size_t>(r) * H + q * 4);
+    g.x = o.x > 0.f ? g.x : 0.f;
+    g.y = o.y > 0.f ? g.y : 0.f;
+    g.z = o.z > 0.f ? g.z : 0.f;
+    g.w = o.w > 0.f ? g.w : 0.f;
+    *reinterpret_cast<float4*>(dpre + static_cast<size_t>(r) * H + q * 4) = g;
+  }
+}
+
 }  // namespace ctr
 
 using namespace ctr;
 
 extern "C" {
+
+int ctr_cin_pool(const float* out, int B, int D, int H, float* pooled, int ld_pooled,
+                 ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(out && pooled && B >= 0 && D > 0 && H > 0 && (H & 3) == 0 && (ld_pooled & 3) == 0 &&
+                  ld_pooled >= H && aligned16(out) && aligned16(pooled),
+              "ctr_cin_pool", "bad argument (H and ld_pooled multiples of 4, 16-byte aligned)");
+  if (B == 0) return CTR_OK;
+  const long long n = static_cast<long long>(B) * (H / 4);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 8LL));
+  cin_pool_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, B, D, H, pooled, ld_pooled);
+  CTR_LAUNCH_CHECK("ctr_cin_pool");
+}
+
+int ctr_cin_dpre(const float* dpool, int ld_dpool, const float* dacc, const float* out, int B, int D,
+                 int H, float* dpre, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(dpool && out && dpre && B >= 0 && D > 0 && H > 0 && (H & 3) == 0 && (ld_dpool & 3) == 0 &&
+                  aligned16(dpool) && aligned16(dacc) && aligned16(out) && aligned16(dpre),
+              "ctr_cin_dpre", "bad argument (H and ld_dpool multiples of 4, 16-byte aligned)");
+  if (B == 0) return CTR_OK;
+  const long long n = static_cast<long long>(B) * D * (H / 4);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 16LL));
+  cin_dpre_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dpool, ld_dpool, dacc, out, B, D, H, dpre);
+  CTR_LAUNCH_CHECK("ctr_cin_dpre");
+}
 
 int ctr_transpose_fd(const float* E, int B, int F, int D, float* Xt, int ld, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();

@@ -628,7 +628,15 @@ class _CINFn(torch.autograd.Function):
                   m, Hp, H, _p(out), prec, _p(ws), ws.numel(), _stream())
             outs.append(out)
             Xp, ldp, Hp = out, H, H
-        pooled = torch.cat([o.view(B, D, -1).sum(1) for o in outs], 1)      # :180-181
+        Hs = [int(W.shape[1]) for W in Ws]
+        if all(h % 4 == 0 for h in Hs):       # sum over d straight into the concatenated tensor
+            pooled = torch.empty((B, sum(Hs)), dtype=torch.float32, device=dev)
+            off = 0
+            for o, h in zip(outs, Hs):
+                _call("ctr_cin_pool", _p(o), B, D, h, _p(pooled) + 4 * off, pooled.shape[1], _stream())
+                off += h
+        else:
+            pooled = torch.cat([o.view(B, D, -1).sum(1) for o in outs], 1)      # :180-181
         ctx.meta = (m, D, prec, ld0, B)
         ctx.saved = (X0t, outs, Ws, ws)
         return pooled
@@ -646,13 +654,25 @@ class _CINFn(torch.autograd.Function):
         dX0t = torch.zeros_like(X0t)
         dWs = [torch.zeros_like(W) for W in Ws]
         dbs = [torch.zeros(h, dtype=torch.float32, device=dev) for h in Hs]
-        # gradient arriving at each layer output from the sum-pool (broadcast over d)
-        douts = [dp[:, offs[k]:offs[k + 1]].unsqueeze(1).expand(B, D, Hs[k]).reshape(B * D, Hs[k])
-                 .contiguous() for k in range(n)]
+        fused = all(h % 4 == 0 for h in Hs) and dp.shape[1] % 4 == 0
+        dp = dp.contiguous()
+        if fused:
+            # dacc[k]: what layer k+1's backward accumulates for layer k's output (zero for the last)
+            dacc = [torch.zeros((B * D, Hs[k]), dtype=torch.float32, device=dev) if k < n - 1 else None
+                    for k in range(n)]
+        else:
+            # gradient arriving at each layer output from the sum-pool (broadcast over d)
+            douts = [dp[:, offs[k]:offs[k + 1]].unsqueeze(1).expand(B, D, Hs[k]).reshape(B * D, Hs[k])
+                     .contiguous() for k in range(n)]
         for k in range(n - 1, -1, -1):
-            dpre = (douts[k] * (outs[k] > 0)).contiguous()
+            if fused:   # (pool gradient broadcast over d + dacc) through the ReLU, one kernel
+                dpre = torch.empty((B * D, Hs[k]), dtype=torch.float32, device=dev)
+                _call("ctr_cin_dpre", _p(dp) + 4 * offs[k], dp.shape[1], _p(dacc[k]), _p(outs[k]), B, D,
+                      Hs[k], _p(dpre), _stream())
+            else:
+                dpre = (douts[k] * (outs[k] > 0)).contiguous()
             if k > 0:
-                Xp, ldp, Hp, dXp = outs[k - 1], Hs[k - 1], Hs[k - 1], douts[k - 1]
+                Xp, ldp, Hp, dXp = outs[k - 1], Hs[k - 1], Hs[k - 1], (dacc if fused else douts)[k - 1]
             else:
                 Xp, ldp, Hp, dXp = X0t, ld0, m, dX0t
             _call("ctr_cin_layer_bwd", _p(X0t), ld0, _p(Xp), ldp, _p(Ws[k].contiguous()), _p(dpre),

@@ -462,8 +462,8 @@ def bench_main(args, rank, local, world):
         from torch.profiler import ProfilerActivity, profile   # runs them; rank 0 prints)
         dist.barrier()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            for i in range(6):
-                step(host[i % len(host)])
+            for i in range(6):          # device-resident batches: least skew between the ranks
+                step(devb[i % len(devb)])
             torch.cuda.synchronize()
         if rank == 0:
             agg = {}
