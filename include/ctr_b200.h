@@ -40,6 +40,11 @@ int ctr_version(void);
 const char* ctr_last_error(void);
 /* 0 when the current CUDA device can run this library (cc 10.x). */
 int ctr_device_check(void);
+/* Process-wide tuning options (results never depend on them):
+ *   "bwd_aggregate" (default 1): ctr_embed_bwd sums the slots of one warp instruction that hit the
+ *   same row in registers (__match_any_sync) and issues one RED per distinct row - the
+ *   warp-aggregated scatter-add; 0 = one RED per slot (the A/B switch of bench.py --dist zipf). */
+int ctr_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------- id pipeline
  * Replaces the id-producing half of tf.feature_column.input_layer:

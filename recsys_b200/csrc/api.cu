@@ -77,6 +77,17 @@ bool aux_stream(cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t* join) {
   return true;
 }
 
+static std::string g_opt_names[16];
+static int g_opt_values[16];
+static int g_opt_n = 0;
+
+int option_get(const char* name, int dflt) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < g_opt_n; ++i)
+    if (g_opt_names[i] == name) return g_opt_values[i];
+  return dflt;
+}
+
 int sm_count() {
   int mj = 0, sm = 0;
   if (query_device(&mj, &sm) != CTR_OK) return 148;
@@ -92,5 +103,20 @@ int ctr_version(void) { return 100; }
 const char* ctr_last_error(void) { return ctr::g_last_error.c_str(); }
 
 int ctr_device_check(void) { return ctr::ensure_arch(); }
+
+int ctr_set_option(const char* name, int value) {
+  if (name == nullptr) return ctr::fail_arg("ctr_set_option", "null name");
+  const std::string n(name);
+  if (n != "bwd_aggregate") return ctr::fail_arg("ctr_set_option", "unknown option");
+  std::lock_guard<std::mutex> lk(ctr::g_mu);
+  for (int i = 0; i < ctr::g_opt_n; ++i)
+    if (ctr::g_opt_names[i] == n) {
+      ctr::g_opt_values[i] = value;
+      return CTR_OK;
+    }
+  ctr::g_opt_names[ctr::g_opt_n] = n;
+  ctr::g_opt_values[ctr::g_opt_n++] = value;
+  return CTR_OK;
+}
 
 }  // extern "C"

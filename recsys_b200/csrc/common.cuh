@@ -21,6 +21,8 @@ int sm_count();         // multiprocessors of the current device (cached)
 // fork part of their work beside the caller's stream and join it back before returning (works
 // under CUDA-graph capture: the fork / join become graph dependencies).  false on CUDA error.
 bool aux_stream(cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t* join);
+// Documented runtime options (ctr_set_option): value of `name`, or `dflt` when it was never set.
+int option_get(const char* name, int dflt);
 
 #define CTR_REQUIRE(cond, fn, what) \
   do {                              \

@@ -15,7 +15,7 @@
 // one of them puts every sample in one row) are accumulated one-hot in
 // registers and flushed with a handful of vector REDs; all other fields go
 // straight to red.global.add.v4.f32.
-#include "common.cuh"
+#include "row_commit.cuh"
 
 namespace ctr {
 
@@ -367,7 +367,7 @@ struct EmbedBwdParams {
 
 constexpr int kTinyRows = 32;
 
-template <int D>
+template <int D, bool AGG>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) {
   constexpr int LPR = D / 4;
   constexpr int RPW = 32 / LPR;
@@ -430,7 +430,14 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          if (rid[u] >= 0) {    // negative ids (sharded overflow slots) are skipped
+          bool leader = true;
+          if (AGG) {
+            // warp-aggregated scatter: slots of this instruction that hit the same row (hot rows
+            // under a skewed id distribution) are summed in registers, one RED goes out
+            float gc = 0.f;
+            merge_duplicates<LPR>(rid[u] >= 0 ? rid[u] : -1 - r, g[u], gw[u], gc, leader, lane, q);
+          }
+          if (rid[u] >= 0 && leader) {    // negative ids (sharded overflow slots) are skipped
             red_add_v4(p.dtable + static_cast<size_t>(rid[u]) * p.ld + q * 4, g[u]);
             if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(rid[u]) * p.ld1, gw[u]);
           }
@@ -982,12 +989,16 @@ int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const fl
   const long long ntask = static_cast<long long>(F) * p.nchunks;
   const int grid = static_cast<int>(std::min<long long>((ntask + 7) / 8, sm_count() * 8LL));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CTR_BWD(DD)                                                     \
+  if (option_get("bwd_aggregate", 1)) embed_bwd_kernel<DD, true><<<grid, 256, 0, st>>>(p); \
+  else embed_bwd_kernel<DD, false><<<grid, 256, 0, st>>>(p);
   switch (D) {
-    case 8: embed_bwd_kernel<8><<<grid, 256, 0, st>>>(p); break;
-    case 16: embed_bwd_kernel<16><<<grid, 256, 0, st>>>(p); break;
-    case 32: embed_bwd_kernel<32><<<grid, 256, 0, st>>>(p); break;
+    case 8: CTR_BWD(8) break;
+    case 16: CTR_BWD(16) break;
+    case 32: CTR_BWD(32) break;
     default: return fail_arg("ctr_embed_bwd", "D must be 8, 16 or 32");
   }
+#undef CTR_BWD
   CTR_LAUNCH_CHECK("ctr_embed_bwd");
 }
 

@@ -365,7 +365,10 @@ def bench_main(args, rank, local, world):
               "variable_store": VariableStore(), "embedding_adam": "lazy", "shard_embedding": True,
               # exchange slabs sized 1.1x the mean per-(src,dst) load: uniform ids spread by < 1 %
               # (7 sigma = 0.05); check_overflow() below verifies that nothing was dropped
-              "shard_slack": float(os.environ.get("CTR_SHARD_SLACK", "1.1")),
+              # (Zipf ids put most lookups of a field on one owner: worst-case slabs there; the
+              # peer-memory exchange always has worst-case slabs and ignores this)
+              "shard_slack": float(os.environ.get(
+                  "CTR_SHARD_SLACK", "1.1" if getattr(args, "dist", "uniform") == "uniform" else str(world))),
               "shard_exchange": os.environ.get("CTR_SHARD_EXCHANGE", "p2p"),
               "seed": 0}
     exchange = params["shard_exchange"]
@@ -380,7 +383,11 @@ def bench_main(args, rank, local, world):
     host, devb = [], []
     keys = [c.key for c in lay.columns]
     for _ in range(min(args.n_batches, 16)):
-        cat = torch.from_numpy(np.stack([rng.integers(0, n, size=B) for n in lay.rows], 1)).pin_memory()
+        if getattr(args, "dist", "uniform") == "zipf":     # hot rows: Zipf(1.05) clipped to the field
+            cols = [np.minimum(rng.zipf(1.05, size=B) - 1, n - 1) for n in lay.rows]
+        else:
+            cols = [rng.integers(0, n, size=B) for n in lay.rows]
+        cat = torch.from_numpy(np.stack(cols, 1).astype(np.int64)).pin_memory()
         cont = torch.zeros((B, 0), dtype=torch.float32).pin_memory()
         lab = torch.from_numpy((rng.random((B, 1)) < 0.22).astype(np.float32)).pin_memory()
         host.append((PackedFeatures(cont, cat, [], keys), lab))
@@ -494,7 +501,7 @@ def bench_main(args, rank, local, world):
                                    "GPUs, NCCL all-to-all of ids/vectors/grads, local batch %d, "
                                    "fwd+bwd+Adam(lazy rows)" % (total_rows, world, B),
                        "fields": 39, "embedding_size": 16, "batch_per_gpu": B, "global_batch": B * world,
-                       "table_rows": total_rows, "id_dist": "uniform",
+                       "table_rows": total_rows, "id_dist": getattr(args, "dist", "uniform"),
                        "exchange": ("device-initiated over NVLink peer memory (cudaIpc arenas, flag "
                                     "words; no NCCL call in the step; worst-case slabs)"
                                     if exchange == "p2p" else
