@@ -52,6 +52,9 @@ def parse(argv=None):
                     help="exact_tf = the reference's optimiser semantics: TF's sparse Adam apply "
                          "decays m, v of every table row every step (fm/fm.py:162-163)")
     ap.add_argument("--fused-tower", type=int, default=None, help="1/0: force the fused tower kernels")
+    ap.add_argument("--no-bwd-aggregate", action="store_true",
+                    help="A/B: one RED per slot in the scatter's general path instead of the "
+                         "warp-aggregated form (ctr_set_option('bwd_aggregate', 0))")
     return ap.parse_args(argv)
 
 
@@ -229,6 +232,8 @@ def workload_config(args):
     return {"workload": "%s Criteo 39-field emb16 batch=%d%s fwd+bwd+%s" % (args.model, args.batch, extra, adam),
             "fields": 39, "embedding_size": 16, "batch": args.batch, "deep_layers": "100,100",
             "table_rows": rows, "table": args.table, "id_dist": args.dist,
+            "scatter": "one RED per slot (A/B)" if getattr(args, "no_bwd_aggregate", False)
+                       else "warp-aggregated (match-any) + shared-memory tiles for <= 32-row fields",
             "l2": "table %.2f GB > 126 MB L2; a distinct id batch every step (no flush needed)"
                   % (rows * 64 / 1e9) if args.table == "full" else
                   "reference-capped table 53.8 MB is L2-resident; distinct id batch every step",
@@ -308,11 +313,14 @@ def sharded_parity_check(rank, world, dev, exchange, B=256, steps=2):
     res = torch.tensor([worst_logit, err_tab, err_w0], dtype=torch.float64, device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     worst_logit, err_tab, err_w0 = (float(x) for x in res)
-    ok = worst_logit <= 1e-4 and err_tab <= 2e-4 and err_w0 <= 2e-4 and moved > 1e-3
+    # parameters after Adam: the rule divides by sqrt(v), so fp32 summation-order noise on a
+    # near-zero gradient element is amplified to a few per cent of lr (1e-2 here) - 1e-3 abs
+    ok = worst_logit <= 1e-4 and err_tab <= 1e-3 and err_w0 <= 1e-3 and moved > 1e-2
     return {"ok": bool(ok), "max_logit_rel_err": worst_logit, "table_abs_err_after_adam": err_tab,
             "dense_abs_err_after_adam": err_w0, "table_moved": moved, "steps": steps,
             "batch_per_rank": B, "world": world, "exchange": exchange,
-            "tolerance": "logits 1e-4 rel; parameters 2e-4 abs after %d Adam steps at lr 1e-2" % steps}
+            "tolerance": "logits 1e-4 rel; parameters 1e-3 abs after %d Adam steps at lr 1e-2 "
+                         "(the table moves by %.3f)" % (steps, moved)}
 
 
 
@@ -357,6 +365,8 @@ def run_ours(args):
     from recsys_b200.data import SyntheticCriteo
     from recsys_b200.estimator import GraphedTrainStep
     _lib.load()
+    if args.no_bwd_aggregate:
+        _lib.check(_lib.load().ctr_set_option(b"bwd_aggregate", 0))
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     if args.model == "din":
         mod, params, host_batches = build_din(args, dev)

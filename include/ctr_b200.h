@@ -172,12 +172,13 @@ int ctr_dcn_cross_bwd(const float* x0, const float* w, const float* b, int L, in
  * tf.train.AdamOptimizer semantics (fm/fm.py:162): eps outside the sqrt,
  *   lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t).
  * The schedule can live on the device so that a captured CUDA graph advances it on replay:
- * state_dev = float[4] {t = optimiser steps completed, lr_t of the step in progress (step t+1),
- * lr, block counter}.  When state_dev is non-null the kernels of a step read lr_t (and the claim
+ * state_dev = float[4] {t = optimiser steps completed (a uint32 BIT PATTERN in the first word: a
+ * float counter would saturate at 2^24 steps), lr_t of the step in progress (step t+1), lr, block
+ * counter}.  When state_dev is non-null the kernels of a step read lr_t (and the claim
  * tag = t+1) from it and ignore the by-value arguments; the step's LAST optimiser launch -
  * ctr_adam_dense with advance_state != 0 - moves the schedule on (its last block to finish does
  * t += 1 and recomputes lr_t), so advancing costs no launch.  ctr_adam_tick(state, lr, ...) sets lr
- * and advances once: from {-1,0,0,0} it initialises the schedule at t = 0; it is also the way to
+ * and advances once: from t = 0xFFFFFFFF (and zeros) it initialises the schedule at t = 0; it is also the way to
  * advance for a caller whose step does not end with ctr_adam_dense.
  * ctr_adam_dense: every element (TF's sparse apply decays m, v of every row [TF-sem]).
  * g is zeroed afterwards when zero_g != 0. */
@@ -525,14 +526,17 @@ int ctr_scatter_add_rows(const int32_t* ids, const float* g, const float* gw1, i
  *   K1 ctr_p2p_bucket_send   rows[n] (global rows) -> owner = row % G; owner-local ids stored into
  *                            the owner's req_ids[step parity][me][pos]; slot[i] = owner*capacity+pos
  *   K2 ctr_p2p_gather_reply  owner: per requester, wait for its ids, gather row | w1 from the local
- *                            row records into the requester's resp[me][pos]; count_lookups != 0
- *                            also counts them per row (the `cnt` word of ctr_embed_bwd_adam)
+ *                            row records into the requester's resp[me][pos] (count_lookups is
+ *                            reserved and ignored)
  *   K3 ctr_embed_fwd_p2p     the fused lookup + interaction kernel over the reply slab (slots as
  *                            row ids); waits for every owner's reply flag inside the kernel
  *   K4 ctr_p2p_grad_send     in slab order (inv[]): dE + dy2*S | dy1 dy2 stored into the owner's
  *                            grad[me][pos] as contiguous runs (`slot` is unused, kept for symmetry)
- *   K5 ctr_p2p_scatter_adam  owner: per requester, wait for its gradients; scatter-add + TF-Adam in
- *                            one pass (the lookup that completes a row updates it)
+ *   K5 ctr_p2p_scatter_adam  owner, two launches: (a) per requester, wait for its gradients and
+ *                            RED them into the records' accumulators (g, g1, c = sum dy2; duplicates
+ *                            of a warp instruction summed in registers); (b) one TF-Adam update per
+ *                            distinct row (claim word tagged with the step number), gradient
+ *                            g - c*theta, accumulators cleared
  *   K6 ctr_p2p_dense_push + ctr_p2p_adam_dense   replicated dense weights: gradients stored into
  *                            every peer's dense[me]; Adam over their sum in rank order (bitwise
  *                            identical on every rank); zeroes g_local; advance_state as ctr_adam_dense

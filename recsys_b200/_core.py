@@ -340,14 +340,15 @@ class _CriteoBase(_ModelBase):
 
     def _dense_step(self, lr_t):
         if getattr(self.emb, "p2p", False):       # all-reduce + Adam over peer memory, no NCCL
-            self.emb.dense_step(self.dense, lr_t, self.adam)
+            self.emb.dense_step(self.dense, lr_t, self.adam, getattr(self, "tower", None))
         else:
             self._sync_dense_grads()
             self.dense.adam_step(lr_t, self.adam)
 
     def _apply_gradients(self, lr_t):
         self.emb.adam_step(self.rows, lr_t, self.adam)     # overlaps the side-stream dW kernels
-        self._join_tower()
+        if not getattr(self.emb, "p2p", False):
+            self._join_tower()                             # (the peer path joins on its side stream)
         self._dense_step(lr_t)
 
 

@@ -119,6 +119,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// Device Adam schedule {t, lr_t, lr, block counter}: t = optimiser steps completed, kept as a
+// uint32 BIT PATTERN in state[0] (a float counter would stop counting at 2^24 steps).
+__device__ __forceinline__ unsigned adam_step_of(const float* state) { return __float_as_uint(state[0]); }
 // System-scope flag words (peer-memory exchange): release store / acquire load, wall clock.
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) din_att_fwd_kernel(const DinParams p) {
   din_load_weights<E>(s, p);
   __syncthreads();
   const float b3 = p.b3[0];
-  const unsigned step = (DROP && p.dstate != nullptr) ? static_cast<unsigned>(p.dstate[0]) : 0u;
+  const unsigned step = (DROP && p.dstate != nullptr) ? adam_step_of(p.dstate) : 0u;
 
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
     float q[E];
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) din_att_bwd_kernel(const DinParams p) {
 #pragma unroll
   for (int j = 0; j < kH2; ++j) dW3acc[j] = 0.f;
   float db3acc = 0.f;
-  const unsigned step = (DROP && p.dstate != nullptr) ? static_cast<unsigned>(p.dstate[0]) : 0u;
+  const unsigned step = (DROP && p.dstate != nullptr) ? adam_step_of(p.dstate) : 0u;
 
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
     float q[E], g[E], dq[E];
@@ -585,7 +585,7 @@ static int din_bwd_launch(const DinParams& p, cudaStream_t st) {
 // inject the kernel's masks into the oracle.
 __global__ void din_dropout_mask_kernel(const DinParams p, unsigned layer, long long n_rows, int H,
                                         float* __restrict__ out) {
-  const unsigned step = p.dstate != nullptr ? static_cast<unsigned>(p.dstate[0]) : 0u;
+  const unsigned step = p.dstate != nullptr ? adam_step_of(p.dstate) : 0u;
   const int nb = (H + 7) / 8;
   const long long n = n_rows * nb;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;

@@ -666,9 +666,9 @@ __global__ void criteo_rows_kernel(const float* __restrict__ xcont, int n_cont,
 // The kernels of step t+1 read tag = t+1 and lr_t = [1]; the LAST optimiser kernel of the step
 // (ctr_adam_dense with advance_state) moves the schedule on, so no launch is spent on it.
 __device__ __forceinline__ void adam_advance(float* __restrict__ state, float b1, float b2) {
-  const float t = state[0] + 1.f;
-  const float tn = t + 1.f;
-  state[0] = t;
+  const unsigned t = adam_step_of(state) + 1u;     // integer step counter (bit pattern of state[0])
+  const float tn = static_cast<float>(t) + 1.f;
+  state[0] = __uint_as_float(t);
   state[1] = state[2] * sqrtf(1.f - powf(b2, tn)) / (1.f - powf(b1, tn));
 }
 // ctr_adam_tick: set lr and advance once (from t = -1 this initialises the schedule at t = 0).
@@ -739,7 +739,7 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
                  float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
                  float b2, float eps, const float* __restrict__ state, long long ld, long long ld1, long long ldc) {
   if (state != nullptr) {
-    tag = static_cast<int>(state[0]) + 1;      // the step in progress
+    tag = static_cast<int>(adam_step_of(state)) + 1;      // the step in progress
     lr_t = state[1];
   }
   constexpr int LPR = D >= 4 ? D / 4 : 1;

@@ -148,7 +148,7 @@ tower_layer_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop
   unsigned step = 0;
   if (PRO) {
     fill_pro_tables(sm, pro, K);
-    if (pro.state != nullptr) step = static_cast<unsigned>(pro.state[0]);
+    if (pro.state != nullptr) step = adam_step_of(pro.state);
     __syncthreads();
   }
   float acc[MT][2][4];
@@ -240,7 +240,7 @@ tower_out_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop p
     }
     __syncthreads();
   }
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const unsigned step = pro.state != nullptr ? adam_step_of(pro.state) : 0u;
   for (int r = blockIdx.x * 8 + warp; r < B; r += gridDim.x * 8) {
     float acc = 0.f;
     for (int k = lane; k < K; k += 32) {
@@ -264,7 +264,7 @@ tower_out_fwd_kernel(const float* __restrict__ X, int ldx, int K, const BnDrop p
 __global__ void __launch_bounds__(256)
 bn_drop_apply_kernel(const float* __restrict__ A, int K, const BnDrop pro, float* __restrict__ out,
                      int B) {
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const unsigned step = pro.state != nullptr ? adam_step_of(pro.state) : 0u;
   const long long n = static_cast<long long>(B) * K;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += gridDim.x * 256LL) {
     const int r = static_cast<int>(e / K), k = static_cast<int>(e % K);
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256)
 bn_drop_apply_bwd_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ A, int K,
                          const BnDrop pro, float* __restrict__ dn, float* __restrict__ dbeta,
                          float* __restrict__ dgamma, int B) {
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const unsigned step = pro.state != nullptr ? adam_step_of(pro.state) : 0u;
   const int r0 = blockIdx.x * 32, r1 = min(B, r0 + 32);
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float mu, rstd;
@@ -399,7 +399,7 @@ tower_layer_bwd_data_kernel(const GradSrc gs, int N, const float* __restrict__ W
   constexpr int BM = MT * 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int r0 = blockIdx.x * BM, k0 = blockIdx.y * kTwBN;
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const unsigned step = pro.state != nullptr ? adam_step_of(pro.state) : 0u;
   fill_gs_tables(sm, gs, N);
   if (pro.enabled) fill_pro_tables(sm, pro, K);
   __syncthreads();
@@ -592,7 +592,7 @@ tower_out_bwd_kernel(const GradSrc gs, const float* __restrict__ X, int ldx,
                      float* __restrict__ dbeta_prev, float* __restrict__ dgamma_prev, int B) {
   __shared__ float s_dp[kOutRows];
   const int r0 = blockIdx.x * kOutRows;
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const unsigned step = pro.state != nullptr ? adam_step_of(pro.state) : 0u;
   if (threadIdx.x < kOutRows) {
     const int r = r0 + threadIdx.x;
     float v = 0.f;
@@ -665,7 +665,7 @@ tower_layer_bwd_weights_kernel(const float* __restrict__ X, int ldx, int K, cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int k0 = blockIdx.x * kTwBM, n0 = blockIdx.y * kTwBN;
   const int rbeg = blockIdx.z * rows_per_split, rend = min(B, rbeg + rows_per_split);
-  const unsigned step = pro.state != nullptr ? static_cast<unsigned>(pro.state[0]) : 0u;
+  const unsigned step = pro.state != nullptr ? adam_step_of(pro.state) : 0u;
   fill_gs_tables(sm, gs, N);
   if (pro.enabled) fill_pro_tables(sm, pro, K);
   __syncthreads();

@@ -283,7 +283,7 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   c.p = A.training ? A.p_drop : 0.f;
   c.inv_keep = c.p > 0.f ? 1.f / (1.f - c.p) : 1.f;
   c.seed = A.seed;
-  c.step = A.state != nullptr ? static_cast<unsigned>(A.state[0]) : 0u;
+  c.step = A.state != nullptr ? adam_step_of(A.state) : 0u;
   int ws_layer = -1;
   const int k4 = 4 * lane;                      // this lane's columns in the element-wise passes
   // One tile per CTA (the usual case: B / 32 <= #SMs): everything a phase needs from an earlier

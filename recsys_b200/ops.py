@@ -230,7 +230,8 @@ class TFAdamState:
         """Back to t = 0 (tests; re-initialises the device schedule)."""
         self.t = 0
         if self.state is not None:
-            self.state.copy_(torch.tensor([-1.0, 0.0, 0.0, 0.0]))
+            self.state.zero_()
+            self.state.view(torch.int32)[0] = -1       # t is a uint32 bit pattern: -1 + 1 = step 0
             self.advance()
 
     def advance(self):

@@ -159,6 +159,8 @@ class P2PShardedEmbedding:
         self.can_fuse = True
         self._want_lo = False
         self._count = False
+        self._side = None
+        self._pre_scatter = None      # main-stream event: every dense gradient is complete
 
     # state -----------------------------------------------------------------------
     def load(self, table=None, w1=None):
@@ -194,6 +196,8 @@ class P2PShardedEmbedding:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(group=self.group)
                 self.arena.close()
+                # the new arena counts its steps from zero again: forget the old step tags
+                self.rec[:, 4 * self.D + 4].zero_()
             self.arena = P2PArena(self.device, lookups, self.D, self.n_dense, self.group,
                                   self.spin_limit_ms)
         return self.arena
@@ -224,13 +228,37 @@ class P2PShardedEmbedding:
                            "apply_gradients() is not supported on this path")
 
     # replicated dense weights ------------------------------------------------------
-    def dense_step(self, dense, lr_t, st):
+    def dense_step(self, dense, lr_t, st, tower=None):
         """All-reduce + Adam of the replicated dense parameters without NCCL: push this rank's
-        gradient into every arena, then Adam over the sum of the G copies (ends the step)."""
+        gradient into every arena, then Adam over the sum of the G copies.  It runs on a side
+        stream, BESIDE the gradient exchange and the owner-side optimiser of the table (K4, K5):
+        it only depends on the dense gradients, which are complete before K4 starts (event
+        ``_pre_scatter``) and once the tower's weight-gradient kernels are done.  The Adam schedule
+        is advanced on the main stream after both have finished (K5 reads lr_t from it)."""
         a = self.arena
-        _call("ctr_p2p_dense_push", _p(dense.grad), dense.numel, a.ref, _stream())
-        _call("ctr_p2p_adam_dense", _p(dense.flat), _p(dense.m), _p(dense.v), _p(dense.grad),
-              dense.numel, lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, 1, a.ref, _stream())
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = tower.side if tower is not None else self._side
+        if self._pre_scatter is not None:
+            side.wait_event(self._pre_scatter)
+            self._pre_scatter = None
+        else:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+        if tower is not None and tower._pending is not None:
+            side.wait_event(tower._pending)
+            tower._pending = None
+        with torch.cuda.stream(side):
+            _call("ctr_p2p_dense_push", _p(dense.grad), dense.numel, a.ref, side.cuda_stream)
+            _call("ctr_p2p_adam_dense", _p(dense.flat), _p(dense.m), _p(dense.v), _p(dense.grad),
+                  dense.numel, lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, 0, a.ref,
+                  side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
+        st.advance()                      # t += 1, lr_t of the next step (ctr_adam_tick)
 
 
 class _P2PEmbedFn(torch.autograd.Function):
@@ -290,6 +318,8 @@ class _P2PEmbedFn(torch.autograd.Function):
         if dE is None and dy2 is None:
             dE = torch.zeros_like(ctx.E)
         lr_t, st = fused
+        emb._pre_scatter = torch.cuda.Event()
+        emb._pre_scatter.record(torch.cuda.current_stream())
         _call("ctr_p2p_grad_send", _p(ctx.slot), _p(dE), _p(ctx.S) if dy2 is not None else None,
               _p(dy2), _p(dy1), emb.w1_fields, B, F, D, a.ref, _stream())                     # K4
         _call("ctr_p2p_scatter_adam", _p(emb.rec), emb.ld, D, 1 if emb.with_w1 else 0,

@@ -487,7 +487,10 @@ def bench_main(args, rank, local, world):
             if out not in ("1", ""):
                 with open(out, "w") as fh:
                     fh.write("in-graph kernel times of the sharded DeepFM step, rank 0 of %d, %s exchange, "
-                             "%.3f ms/step\n" % (world, exchange, ms / K) + "\n".join(lines) + "\n")
+                             "%.3f ms/step (CUPTI over 6 graph replays; a kernel that waits on a peer's "
+                             "flag - p2p_gather_reply, p2p_scatter, p2p_adam_dense, the lookup - includes "
+                             "the wait, and the first replay absorbs the ranks' start-up skew)\n"
+                             % (world, exchange, ms / K) + "\n".join(lines) + "\n")
         dist.barrier()
     if rank == 0:
         f, l = host[0]

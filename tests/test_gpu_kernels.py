@@ -382,6 +382,33 @@ def test_adam_rows_and_dense_match_tf_rule(cuda):
         assert torch.allclose(emb.w1.cpu().double(), p["w1"], rtol=1e-5, atol=1e-6)
 
 
+def test_adam_schedule_counts_past_2_to_the_24(cuda):
+    """the device step counter must not saturate (a float32 counter stops at 2^24,
+    after which the lazy optimiser's claim tag repeats and rows stop updating).  It is a uint32
+    bit pattern: two steps from t = 2^24 still update the touched rows and end at 2^24 + 2."""
+    ops = _ops()
+    from recsys_b200 import feature_column as fc
+    D = 16
+    lay = fc.layout([fc.embedding_column(fc.categorical_column_with_hash_bucket("a", 100), D)])
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=False, adam_mode="lazy", seed=1)
+    st = ops.TFAdamState(lr=1e-2, device=cuda)
+    st.state.view(torch.int32)[0] = 2 ** 24 - 1
+    st.advance()
+    assert int(st.state.view(torch.int32)[0]) == 2 ** 24
+    rows = torch.arange(10, device=cuda, dtype=torch.int32).reshape(-1, 1)
+    prev = emb.table.clone()
+    for step in range(2):
+        emb.dtable[:10] = 1.0
+        emb.adam_step(rows, st.next_lr_t(), st)
+        st.advance()
+        torch.cuda.synchronize()
+        moved = (emb.table[:10] - prev[:10]).abs().min()
+        assert float(moved) > 1e-4, "step %d: the rows did not move" % step
+        assert float(emb.dtable.abs().max()) == 0.0
+        prev = emb.table.clone()
+    assert int(st.state.view(torch.int32)[0]) == 2 ** 24 + 2
+
+
 # -------------------------------------------------------------------------- CIN
 def _cin_oracle(E, Ws, bs, m, D):
     p = {}
