@@ -491,7 +491,7 @@ def run_ours(args):
             "traffic": ncu_traffic(B), "peak_source": peak_src,
             "traffic_note": "ncu --set full, caches flushed before each kernel (dE / E / S of the "
                             "backward are L2 hits inside a real step); per launch pair, bytes",
-            "kernel": "embed_fwd_kernel<16,5,false> + embed_bwd_kernel<16> (one pair per step), "
+            "kernel": "embed_fwd_kernel<16,5,false> + embed_bwd_kernel<16,AGG> (one pair per step), "
                       "each timed alone as 32 launches on distinct id batches inside a CUDA graph",
             "algorithmic_bytes_per_launch_pair": ALG_BYTES * B,
             "fwd": {"us": kern["fwd_us"], "GBps": ALG_BYTES_FWD * B / kern["fwd_us"] / 1e3,

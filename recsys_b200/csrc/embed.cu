@@ -344,166 +344,7 @@ static int dispatch_fwd(const EmbedFwdParams& p, int D, cudaStream_t st) {
   }
 }
 
-// ----------------------------------------------------------------- backward
-struct EmbedBwdParams {
-  const int* rows;
-  const float* dE;
-  const float* E;
-  const float* table;
-  const float* S;
-  const float* dy2;
-  const float* dy1;
-  float* dtable;
-  float* dw1;
-  unsigned long long w1_fields;
-  long long ld;     // row stride of table / dtable (floats)
-  long long ld1;    // stride of dw1 (floats)
-  int B;
-  int F;
-  int chunk;
-  int nchunks;
-  int off[CTR_MAX_FIELDS + 1];
-};
-
-constexpr int kTinyRows = 32;
-
-template <int D, bool AGG>
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) {
-  constexpr int LPR = D / 4;
-  constexpr int RPW = 32 / LPR;
-  constexpr int J = kTinyRows / RPW;  // rows per lane group in the tiny-field flush
-  constexpr int PT = D + 4;           // pitch of the tiny-field tile (floats): conflict-free float4 rows
-  __shared__ __align__(16) float s_tiny[8 * kTinyRows * PT];
-  __shared__ float s_tinyw[8 * kTinyRows];
-  const int lane = threadIdx.x & 31;
-  const int r = lane / LPR;
-  const int q = lane % LPR;
-  const int F = p.F;
-  const int wpb = blockDim.x >> 5;
-  const int ntask = F * p.nchunks;
-
-  for (int task = blockIdx.x * wpb + (threadIdx.x >> 5); task < ntask; task += gridDim.x * wpb) {
-    const int f = task % F;
-    const int c = task / F;
-    const int b_begin = c * p.chunk;
-    const int b_end = min(p.B, b_begin + p.chunk);
-    const int off = p.off[f];
-    const int nrow = p.off[f + 1] - off;
-    const bool tiny = nrow <= kTinyRows;
-    const bool has_w1 = p.dw1 != nullptr && p.dy1 != nullptr && ((p.w1_fields >> f) & 1ull);
-
-    // gradient of one (sample, field) slot: g = dE + dy2 * (S - E)   (fm/fm.py:123-129)
-    auto slot_grad = [&](int b, int rid, float4& g, float& gw) {
-      const size_t eo = (static_cast<size_t>(b) * F + f) * D + q * 4;
-      g = p.dE != nullptr ? ld4_stream(p.dE + eo) : f4_zero();
-      if (p.dy2 != nullptr) {
-        const float4 e = p.E != nullptr ? ldg4(p.E + eo)
-                                        : ldg4(p.table + static_cast<size_t>(rid) * p.ld + q * 4);
-        const float4 sv = ldg4(p.S + static_cast<size_t>(b) * D + q * 4);
-        const float cdy = __ldg(p.dy2 + b);
-        g.x = fmaf(cdy, sv.x - e.x, g.x);
-        g.y = fmaf(cdy, sv.y - e.y, g.y);
-        g.z = fmaf(cdy, sv.z - e.z, g.z);
-        g.w = fmaf(cdy, sv.w - e.w, g.w);
-      }
-      gw = has_w1 ? __ldg(p.dy1 + b) : 0.f;
-    };
-
-    if (!tiny) {
-      // UNR slots per lane in flight: all row ids first, then all operand loads, then the REDs
-      // (the RED asm is a memory barrier for the compiler, so the batching is done by hand).
-      constexpr int UNR = 4;
-      for (int bb = b_begin; bb < b_end; bb += RPW * UNR) {
-        int rid[UNR];
-        float4 g[UNR];
-        float gw[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int b = bb + u * RPW + r;
-          rid[u] = b < b_end ? __ldg(p.rows + static_cast<size_t>(b) * F + f) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          g[u] = f4_zero();
-          gw[u] = 0.f;
-          if (rid[u] >= 0) slot_grad(bb + u * RPW + r, rid[u], g[u], gw[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          bool leader = true;
-          if (AGG) {
-            // warp-aggregated scatter: slots of this instruction that hit the same row (hot rows
-            // under a skewed id distribution) are summed in registers, one RED goes out
-            float gc = 0.f;
-            merge_duplicates<LPR>(rid[u] >= 0 ? rid[u] : -1 - r, g[u], gw[u], gc, leader, lane, q);
-          }
-          if (rid[u] >= 0 && leader) {    // negative ids (sharded overflow slots) are skipped
-            red_add_v4(p.dtable + static_cast<size_t>(rid[u]) * p.ld + q * 4, g[u]);
-            if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(rid[u]) * p.ld1, gw[u]);
-          }
-        }
-      }
-      continue;
-    }
-
-    // Tiny field (<= 32 rows: the 13 bucketised numerics, the small hashed fields): the chunk's
-    // gradients are summed per row in a warp-private shared-memory tile and flushed with <= 32
-    // vector REDs.  A slot adds its float4 with a plain read-modify-write; slots of one warp
-    // instruction that hit the same row take turns (rank within their __match_any group), so a
-    // field that puts every sample in one row (_c5) costs 8 rounds and an all-distinct
-    // one a single round.  (The earlier register one-hot form broadcast every slot to every lane:
-    // 30 instructions per slot, 44 % of the kernel's issue slots.)
-    float* sacc = &s_tiny[(threadIdx.x >> 5) * kTinyRows * PT];
-    float* saccw = &s_tinyw[(threadIdx.x >> 5) * kTinyRows];
-    for (int i = lane; i < kTinyRows * PT / 4; i += 32) reinterpret_cast<float4*>(sacc)[i] = f4_zero();
-    saccw[lane] = 0.f;
-    __syncwarp();
-    constexpr int TU = 4;
-    for (int bb = b_begin; bb < b_end; bb += RPW * TU) {
-      int lid[TU];
-      float4 g[TU];
-      float gw[TU];
-#pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        const int b = bb + u * RPW + r;
-        lid[u] = b < b_end ? __ldg(p.rows + static_cast<size_t>(b) * F + f) : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        g[u] = f4_zero();
-        gw[u] = 0.f;
-        if (lid[u] >= 0) slot_grad(bb + u * RPW + r, lid[u], g[u], gw[u]);
-        lid[u] = lid[u] >= 0 ? lid[u] - off : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        const bool live = lid[u] >= 0 && lid[u] < kTinyRows;
-        const unsigned peers = __match_any_sync(0xffffffffu, live ? lid[u] : -1 - r);
-        // slots with the same row before mine (each slot is LPR lanes)
-        const int rank = live ? __popc(peers & ((1u << (lane - q)) - 1u)) / LPR : 0;
-        const int rounds = __reduce_max_sync(0xffffffffu, rank) + 1;
-        for (int k = 0; k < rounds; ++k) {
-          if (live && rank == k) {
-            float4* dst = reinterpret_cast<float4*>(&sacc[lid[u] * PT + q * 4]);
-            *dst = f4_add(*dst, g[u]);
-            if (q == 0) saccw[lid[u]] += gw[u];
-          }
-          __syncwarp();
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int lr = r + RPW * j;
-      if (lr < nrow) {
-        red_add_v4(p.dtable + static_cast<size_t>(off + lr) * p.ld + q * 4,
-                   *reinterpret_cast<const float4*>(&sacc[lr * PT + q * 4]));
-        if (has_w1 && q == 0) red_add_f32(p.dw1 + static_cast<size_t>(off + lr) * p.ld1, saccw[lr]);
-      }
-    }
-    __syncwarp();
-  }
-}
+// (the scatter-add backward lives in embed_adam.cu)
 
 // ------------------------------------------------------------ stand-alone cross
 // xl forward on an existing x0[B,W] (used when E comes from somewhere else, and
@@ -956,50 +797,6 @@ int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, i
   raw.zero_buf = zero_n > 0 ? zero_buf : nullptr; raw.zero_n4 = zero_n >> 2;
   return embed_fwd_impl("ctr_embed_fwd_raw", table, w1, nullptr, B, F, D, w1_fields, E, S, y1, y2,
                         cross_w, cross_b, cross_layers, xl, E_lo, row_stride, w1_stride, &raw, stream);
-}
-
-int ctr_embed_bwd(const int32_t* rows, const float* dE, const float* E, const float* table,
-                  const float* S, const float* dy2, const float* dy1, uint64_t w1_fields,
-                  const int64_t* row_offsets_host, int B, int F, int D, float* dtable, float* dw1,
-                  int64_t row_stride, int64_t w1_stride, ctr_stream_t stream) {
-  CTR_ARCH_OR_RETURN();
-  CTR_REQUIRE(rows && dtable && row_offsets_host, "ctr_embed_bwd", "null rows/dtable/row_offsets");
-  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_embed_bwd", "need 0 < F <= 64");
-  CTR_REQUIRE(dE || dy2, "ctr_embed_bwd", "nothing to scatter: dE and dy2 both null");
-  CTR_REQUIRE(!dy2 || (S && (E || table)), "ctr_embed_bwd", "dy2 needs S and E (or table)");
-  CTR_REQUIRE(aligned16(dE) && aligned16(E) && aligned16(table) && aligned16(S) && aligned16(dtable),
-              "ctr_embed_bwd", "pointers must be 16-byte aligned");
-  CTR_REQUIRE(row_offsets_host[F] < (1LL << 31), "ctr_embed_bwd", "table too large for int32 rows");
-  if (row_stride <= 0) row_stride = D;
-  if (w1_stride <= 0) w1_stride = 1;
-  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, "ctr_embed_bwd",
-              "row_stride must be >= D and a multiple of 4 floats");
-  if (B == 0) return CTR_OK;
-  EmbedBwdParams p;
-  p.rows = rows; p.dE = dE; p.E = E; p.table = table; p.S = S; p.dy2 = dy2; p.dy1 = dy1;
-  p.dtable = dtable; p.dw1 = dw1; p.w1_fields = w1_fields; p.B = B; p.F = F;
-  p.ld = row_stride; p.ld1 = w1_stride;
-  for (int f = 0; f <= F; ++f) p.off[f] = static_cast<int>(row_offsets_host[f]);
-  // chunk: enough warp-tasks to fill the machine, few enough tiny-field flushes.
-  int chunk = 64;
-  while (chunk < 1024 && static_cast<long long>(F) * ((B + chunk - 1) / chunk) > sm_count() * 64LL)
-    chunk <<= 1;
-  p.chunk = chunk;
-  p.nchunks = (B + chunk - 1) / chunk;
-  const long long ntask = static_cast<long long>(F) * p.nchunks;
-  const int grid = static_cast<int>(std::min<long long>((ntask + 7) / 8, sm_count() * 8LL));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CTR_BWD(DD)                                                     \
-  if (option_get("bwd_aggregate", 1)) embed_bwd_kernel<DD, true><<<grid, 256, 0, st>>>(p); \
-  else embed_bwd_kernel<DD, false><<<grid, 256, 0, st>>>(p);
-  switch (D) {
-    case 8: CTR_BWD(8) break;
-    case 16: CTR_BWD(16) break;
-    case 32: CTR_BWD(32) break;
-    default: return fail_arg("ctr_embed_bwd", "D must be 8, 16 or 32");
-  }
-#undef CTR_BWD
-  CTR_LAUNCH_CHECK("ctr_embed_bwd");
 }
 
 int ctr_dcn_cross_fwd(const float* x0, const float* w, const float* b, int L, int B, int W,

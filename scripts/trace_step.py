@@ -29,11 +29,17 @@ def main():
     from recsys_b200 import feature_column as fc
     from recsys_b200.data import SyntheticCriteo
     from recsys_b200.estimator import GraphedTrainStep
-    mod, params = bench.build_model(args, dev)
-    lay = fc.layout(params["embedding_feature_columns"])
-    host = SyntheticCriteo(lay, args.batch, 8, dist="uniform", seed=0, device=None).batches
-    sp = mod.model_fn(ops.PackedFeatures(host[0][0].cont.to(dev), host[0][0].cat.to(dev), host[0][0].cont_keys,
-                                         host[0][0].cat_keys), host[0][1].to(dev), "train", params)
+    if args.model == "din":
+        args.n_batches = 8
+        mod, params, host = bench.build_din(args, dev)
+        sp = mod.model_fn({k: v.to(dev) for k, v in host[0][0].items()}, host[0][1].to(dev), "train", params)
+    else:
+        mod, params = bench.build_model(args, dev)
+        lay = fc.layout(params["embedding_feature_columns"])
+        host = SyntheticCriteo(lay, args.batch, 8, dist="uniform", seed=0, device=None).batches
+        sp = mod.model_fn(ops.PackedFeatures(host[0][0].cont.to(dev), host[0][0].cat.to(dev),
+                                             host[0][0].cont_keys, host[0][0].cat_keys),
+                          host[0][1].to(dev), "train", params)
     sp.train_op()
     step = GraphedTrainStep(mod.model_fn, params, host[0][0], host[0][1], warmup=3)
     for i in range(5):
