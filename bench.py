@@ -99,9 +99,9 @@ class ClockSampler:
 
 def ncu_traffic(batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the lookup forward + scatter
-    backward pair, from the committed `ncu --set full` capture (profiles/r01_ncu_traffic.json,
-    written by scripts/summarise_ncu.py).  None when the capture is for another batch size."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    backward pair, from the committed `ncu --set full` capture (profiles/r02/ncu_traffic.json,
+    written by scripts/summarise_ncu.py --traffic).  None when the capture is for another batch."""
+    p = os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")
     try:
         d = json.load(open(p))
         if int(d.get("batch", -1)) != int(batch):
