@@ -43,7 +43,18 @@ int ctr_device_check(void);
 /* Process-wide tuning options (results never depend on them):
  *   "bwd_aggregate" (default 1): ctr_embed_bwd sums the slots of one warp instruction that hit the
  *   same row in registers (__match_any_sync) and issues one RED per distinct row - the
- *   warp-aggregated scatter-add; 0 = one RED per slot (the A/B switch of bench.py --dist zipf). */
+ *   warp-aggregated scatter-add; 0 = one RED per slot (the A/B switch of bench.py --dist zipf).
+ *   "adam_rows_bf" (reserved, default 1).
+ *   "fwd_prefetch_record" (default 0): ctr_embed_fwd_raw over a row-record table also prefetches
+ *   the rest of every looked-up record (moments, gradient accumulator) into L2, for the
+ *   scatter-add and the row optimiser that follow in the same step (measured: no gain, the
+ *   scatter and the optimiser are not DRAM bound at batch 4096).
+ *   "mid_coop" (default 1): ctr_tower_mid training launches are cooperative; 0 = plain launch
+ *   (equally safe while nothing resident on the device waits on that kernel).
+ *   "tcg_dw_stages" (default 2), "tcg_dw_splits" (default 0 = automatic): TMA ring depth and
+ *   split-K factor of the first tower layer's weight-gradient GEMM (it runs beside the scatter).
+ *   "adam_rows_inflight" (default 1): records in flight per lane group in ctr_adam_rows_bf
+ *   (1 or 2). */
 int ctr_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------- id pipeline
@@ -149,6 +160,29 @@ int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, i
                       int cross_layers, float* xl, float* E_lo, int64_t row_stride,
                       int64_t w1_stride, float* zero_buf, int64_t zero_n, ctr_stream_t stream);
 
+/* ctr_embed_fwd_raw and the first dense layer of the tower in ONE launch (D = 16, F <= 40,
+ * 16 <= N <= 128): act0[B, N] = relu(E . W0 + b0) (deepfm/deepfm.py:101) is formed from the
+ * gathered rows while they sit in shared memory - a cluster of 4 CTAs per 128 samples, each CTA
+ * gathers a quarter of the fields straight into the swizzled A tiles of a tcgen05 3xTF32 GEMM
+ * against TMA-fed k-blocks of W0 / W0_lo (the ctr_split_lo pair), and the four partial products
+ * and FM partial sums are added over distributed shared memory.  E / E_lo are still written (the
+ * weight-gradient GEMM of the backward reads them), S / y1 / y2 as by ctr_embed_fwd.
+ * stats_part (nullable): [ceil(B/128)][2][N] column sums of act0 and act0^2 per cluster, for
+ * ctr_tower_mid_args.stats0_part.  zero_buf as in ctr_embed_fwd_raw. */
+int ctr_embed_tower_fwd(const float* table, const float* w1, const float* xcont, int n_cont,
+                        const int64_t* xcat, int n_cat, const ctr_field_desc* fields_dev,
+                        const float* boundaries_dev, int n_boundaries, int32_t* rows_out,
+                        int32_t* status, int B,
+                        int F, int D, uint64_t w1_fields, float* E, float* E_lo, float* S, float* y1,
+                        float* y2, int64_t row_stride, int64_t w1_stride, const float* W0,
+                        const float* W0_lo, const float* b0, int N, float* act0, float* stats_part,
+                        float* zero_buf, int64_t zero_n, ctr_stream_t stream);
+
+/* Profiling aid: later ctr_embed_tower_fwd launches stamp %globaltimer (ns) of CTA (0,0) into
+ * timing_dev[0..7] at the phase boundaries (start | ids staged | loads issued | A tiles written |
+ * MMAs retired | partials visible to the cluster | act0 written | end); NULL switches it off. */
+int ctr_embed_tower_timing(uint64_t* timing_dev);
+
 /* Backward: scatter-add of the row gradients into dtable / dw1 (the IndexedSlices
  * gradient of the gathers, fm/fm.py:162-163), field-major, contention-free for
  * fields with <= 32 rows.
@@ -205,6 +239,16 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
                   int32_t tag, float lr_t, float beta1, float beta2, float eps,
                   const float* state_dev, int64_t row_stride, int64_t w1_stride,
                   int64_t claim_stride, ctr_stream_t stream);
+/* The same update for the id matrix rows[B, F] of one batch (what ctr_embed_fwd consumed), one
+ * wave deep: a warp takes 32 consecutive samples of ONE field, so the lookups of a hot row meet
+ * in one warp and are de-duplicated in registers (__match_any_sync) before the claim exchange,
+ * and only the records of the claim winners are fetched.  Same arguments and results as
+ * ctr_adam_rows(rows, B*F, ...); D in {8, 16, 32}. */
+int ctr_adam_rows_bf(const int32_t* rows, int B, int F, int D, float* theta, float* m, float* v,
+                     float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
+                     int32_t tag, float lr_t, float beta1, float beta2, float eps,
+                     const float* state_dev, int64_t row_stride, int64_t w1_stride,
+                     int64_t claim_stride, ctr_stream_t stream);
 
 /* Scatter-add and row optimiser in ONE pass (row-record layout only; rec = the record array,
  * row_stride >= 4D+8).  The unfused pair ctr_embed_bwd + ctr_adam_rows visits every touched record
@@ -480,6 +524,11 @@ typedef struct {
   uint32_t* barrier;
   unsigned long long* timing;                    /* nullable: 8 words, %globaltimer (ns) of block 0 at
                                                     the phase boundaries (profiling aid) */
+  const float* stats0_part;                      /* nullable: [n_stats0_part][2][H[0]] partial column sums
+                                                    of act[0] / act[0]^2 (ctr_embed_tower_fwd); they
+                                                    replace stats[0], which is then not read */
+  int32_t n_stats0_part;
+  int32_t pad_;
 } ctr_tower_mid_args;
 int ctr_tower_mid(const ctr_tower_mid_args* args, int B, ctr_stream_t stream);
 

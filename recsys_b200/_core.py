@@ -404,9 +404,13 @@ class DeepFMModel(_CriteoBase):
             return super().forward(features, labels, training)
         lo = self.tower.use_presplit and (self.world == 1 or getattr(self.emb, "p2p", False) or
                                           getattr(getattr(self.emb, "ops", None), "packed", False))
-        ws = self.tower.begin_step(self._batch_size(features), expect_lo=lo)
+        # one GPU, unsharded table: ids + lookup + FM terms + the first tower layer in ONE launch
+        fuse = bool(lo) and self.world == 1 and isinstance(self.emb, ops.FieldEmbedding) and \
+            self.tower.can_fuse_l0(self.F, self.D) and self._batch_size(features) >= 256
+        ws = self.tower.begin_step(self._batch_size(features), expect_lo=lo, fused_l0=fuse)
         _, E, y1s, y2, _ = self._lookup(features, zero_buf=ws, want_fm=True, want_y1=True,
-                                        **({"want_lo": True} if lo else {}))
+                                        **({"want_lo": True} if lo else {}),
+                                        **({"tower0": self.tower} if fuse else {}))
         return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),
                                 X_lo=self.emb.last_E_lo if lo else None)      # :91,100-129
 

@@ -57,7 +57,8 @@ class TowerMidArgs(C.Structure):
                 ("dz", C.c_void_p * 3), ("dhw", C.c_void_p), ("dhb", C.c_void_p),
                 ("db1", C.c_void_p), ("dw_out", C.c_void_p), ("db_out", C.c_void_p),
                 ("dgamma", _P4), ("dbeta", _P4), ("dbias", _P4), ("dn", _P4), ("dpre", _P4),
-                ("dpre0_lo", C.c_void_p), ("pre0", C.c_void_p), ("barrier", C.c_void_p), ("timing", C.c_void_p)]
+                ("dpre0_lo", C.c_void_p), ("pre0", C.c_void_p), ("barrier", C.c_void_p), ("timing", C.c_void_p),
+                ("stats0_part", C.c_void_p), ("n_stats0_part", C.c_int32), ("pad_", C.c_int32)]
 
 
 class DinOpts(C.Structure):
@@ -103,6 +104,10 @@ SIGNATURES = {
     "ctr_embed_fwd_raw": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i,
                                 c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i64, c_i64, c_f, c_i64,
                                 c_f]),
+    "ctr_embed_tower_fwd": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_u64,
+                                  c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f, c_i, c_f, c_f,
+                                  c_f, c_i64, c_f]),
+    "ctr_embed_tower_timing": (c_i, [c_f]),
     "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
                             c_i, c_i, c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_count_rows": (c_i, [c_f, c_i64, c_i, c_f, c_i64, c_f]),
@@ -114,6 +119,8 @@ SIGNATURES = {
     "ctr_adam_dense": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_i, c_f, c_i, c_f]),
     "ctr_adam_rows": (c_i, [c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                             C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_f]),
+    "ctr_adam_rows_bf": (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                               C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_f]),
     "ctr_din_att_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,
                               c_f, c_f, C.POINTER(DinOpts), c_f]),
     "ctr_din_dropout_mask": (c_i, [C.POINTER(DinOpts), c_i, c_i64, c_i, c_f, c_f]),
@@ -184,6 +191,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # tuning options from the environment: CTR_OPTIONS="name=value,name=value" (ctr_set_option)
+    for kv in filter(None, os.environ.get("CTR_OPTIONS", "").split(",")):
+        name, _, val = kv.partition("=")
+        if lib.ctr_set_option(name.strip().encode(), int(val)) != 0:
+            raise RuntimeError("CTR_OPTIONS: " + lib.ctr_last_error().decode())
     return lib
 
 

@@ -77,8 +77,8 @@ bool aux_stream(cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t* join) {
   return true;
 }
 
-static std::string g_opt_names[16];
-static int g_opt_values[16];
+static std::string g_opt_names[32];
+static int g_opt_values[32];
 static int g_opt_n = 0;
 
 int option_get(const char* name, int dflt) {
@@ -107,7 +107,12 @@ int ctr_device_check(void) { return ctr::ensure_arch(); }
 int ctr_set_option(const char* name, int value) {
   if (name == nullptr) return ctr::fail_arg("ctr_set_option", "null name");
   const std::string n(name);
-  if (n != "bwd_aggregate") return ctr::fail_arg("ctr_set_option", "unknown option");
+  static const char* const known[] = {"bwd_aggregate", "adam_rows_inflight", "adam_rows_bf",
+                                      "tcg_dw_stages", "tcg_dw_splits", "fwd_prefetch_record",
+                                      "mid_coop"};
+  bool ok = false;
+  for (const char* k : known) ok = ok || n == k;
+  if (!ok) return ctr::fail_arg("ctr_set_option", "unknown option");
   std::lock_guard<std::mutex> lk(ctr::g_mu);
   for (int i = 0; i < ctr::g_opt_n; ++i)
     if (ctr::g_opt_names[i] == n) {

@@ -15,36 +15,10 @@
 // one of them puts every sample in one row) are accumulated one-hot in
 // registers and flushed with a handful of vector REDs; all other fields go
 // straight to red.global.add.v4.f32.
+#include "criteo_ids.cuh"
 #include "row_commit.cuh"
 
 namespace ctr {
-
-// One row id of the Criteo id pipeline (fm/fm.py:76-80,89): numeric fields log -> Bucketize
-// (upper_bound), categorical fields offset + range check.  Shared by criteo_rows_kernel and the
-// lookup kernel's fused id stage, so both produce bit-identical ids.
-__device__ __forceinline__ int criteo_row_id(const ctr_field_desc& fd, const float* __restrict__ bnd,
-                                             const float* __restrict__ xcont, int n_cont,
-                                             const long long* __restrict__ xcat, int n_cat, int b,
-                                             float* __restrict__ logx, int* __restrict__ status) {
-  int id;
-  if (fd.kind == 0) {
-    // fm/fm.py:76-79: tf.log(x + off) in fp32, then Bucketize == upper_bound.
-    const float v = logf(xcont[static_cast<size_t>(b) * n_cont + fd.src] + fd.log_offset);
-    if (logx != nullptr) logx[static_cast<size_t>(b) * n_cont + fd.src] = v;
-    id = 0;
-    for (int k = 0; k < fd.bnd_count; ++k) id += (bnd[fd.bnd_begin + k] <= v) ? 1 : 0;
-    if (v != v) id = fd.bnd_count;
-  } else {
-    long long raw = xcat[static_cast<size_t>(b) * n_cat + fd.src];
-    if (raw < 0 || raw >= fd.n_rows) {
-      if (status != nullptr) atomicOr(status, 1);
-      raw %= fd.n_rows;
-      if (raw < 0) raw += fd.n_rows;
-    }
-    id = static_cast<int>(raw);
-  }
-  return fd.row_offset + id;
-}
 
 // ------------------------------------------------------------------ forward
 struct EmbedFwdParams {
@@ -83,6 +57,10 @@ struct EmbedFwdParams {
   int* wait_err;
   long long wait_ns;
   int wait_n;
+  // row records: bytes of the record behind the embedding row (m | v | g | first-order group) to
+  // pull into L2 while the tower runs - the scatter-add and the row optimiser of the same step
+  // then find their records in L2 instead of paying a DRAM page each (0 = off)
+  int prefetch_bytes;
 };
 
 constexpr int kFwdWarps = 8;
@@ -204,6 +182,17 @@ embed_fwd_kernel(const EmbedFwdParams p) {
                        ? ldg4(p.table + static_cast<size_t>(rid[s][it]) * p.ld + q * 4)
                        : f4_zero();
       }
+    }
+    if (p.prefetch_bytes > 0) {
+      // 64 B per lane (the default L2 fetch granularity), LPR lanes per row
+#pragma unroll
+      for (int s = 0; s < SPW; ++s)
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+          if (rid[s][it] >= 0)
+            for (int o = D * 4 + q * 64; o < D * 4 + p.prefetch_bytes; o += LPR * 64)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                  reinterpret_cast<const char*>(p.table + static_cast<size_t>(rid[s][it]) * p.ld) + o));
     }
     float y1p[SPW];
 #pragma unroll
@@ -675,6 +664,107 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
 }
 #undef CTR_ADAM1
 
+// The same update for a [B, F] id matrix, ONE WAVE deep.  adam_rows_kernel carries the whole
+// record of every lookup in registers (78 registers, 3 CTAs per SM), so the 159 744 lookups of a
+// 4096 x 39 batch take ~2.7 waves and every wave pays the full dependent chain id -> claim / record
+// -> exchange -> store.  Here the election costs one lane and a handful of registers per lookup:
+//   * warp = (field f, 32 consecutive samples): the ids of one field side by side, so lookups of a
+//     hot row (the <= 32-row fields put hundreds of samples on one row) meet in the same warp and
+//     __match_any_sync leaves one candidate per distinct row - a row that every sample hits costs
+//     B/32 exchanges instead of B;
+//   * candidates read the claim word (plain load: rows already claimed by another warp drop out
+//     without an atomic) and race with atomicExch; exactly one lookup per row wins;
+//   * the warp's winners are compacted through shared memory and only THEIR records are fetched,
+//     LPR lanes per record and U records in flight per lane group.
+// Every lookup of the batch is resident at once (5 CTAs x 8 warps per SM >= F * B / 32 warps at
+// the benchmark shape), so the kernel is one dependent chain long, not one per wave.
+template <int D, int U>
+__global__ void __launch_bounds__(256, U == 1 ? 5 : 4)
+adam_rows_bf_kernel(const int* __restrict__ rows, int B, int F, float* __restrict__ th,
+                    float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
+                    float* __restrict__ th1, float* __restrict__ m1, float* __restrict__ v1,
+                    float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
+                    float b2, float eps, const float* __restrict__ state, long long ld,
+                    long long ld1, long long ldc) {
+  if (state != nullptr) {
+    tag = static_cast<int>(adam_step_of(state)) + 1;      // the step in progress
+    lr_t = state[1];
+  }
+  constexpr int LPR = D / 4;
+  constexpr int GPW = 32 / LPR;          // records per warp instruction
+  __shared__ int s_win[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane % LPR, grp = lane / LPR;
+  const int wpf = (B + 31) >> 5;
+  const long long nwarps = static_cast<long long>(F) * wpf;
+  for (long long w = blockIdx.x * 8LL + warp; w < nwarps; w += gridDim.x * 8LL) {
+    const int f = static_cast<int>(w / wpf);
+    const int b = static_cast<int>(w - static_cast<long long>(f) * wpf) * 32 + lane;
+    const int rid = b < B ? __ldg(rows + static_cast<size_t>(b) * F + f) : -1;   // < 0: padding
+    const unsigned peers = __match_any_sync(0xffffffffu, rid);
+    bool won = rid >= 0 && (__ffs(peers) - 1) == lane;
+    if (won) won = __ldcg(claim + static_cast<size_t>(rid) * ldc) != tag;
+    if (won) won = atomicExch(claim + static_cast<size_t>(rid) * ldc, tag) != tag;
+    const unsigned wm = __ballot_sync(0xffffffffu, won);
+    const int nw = __popc(wm);
+    if (nw == 0) continue;                 // warp-uniform
+    if (won) s_win[warp][__popc(wm & ((1u << lane) - 1u))] = rid;
+    __syncwarp();
+    for (int k0 = 0; k0 < nw; k0 += GPW * U) {
+      int r[U];
+      float4 G[U], M[U], V[U], T[U];
+      float G1[U], M1[U], V1[U], T1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * GPW + grp;
+        r[u] = k < nw ? s_win[warp][k] : -1;
+        if (r[u] >= 0) {
+          // only the claim winner ever touches this row in this launch, and what it loads was
+          // written by earlier kernels
+          const size_t o = static_cast<size_t>(r[u]) * ld + q * 4;
+          G[u] = ld4_plain(g + o);
+          M[u] = ld4_plain(m + o);
+          V[u] = ld4_plain(v + o);
+          T[u] = ld4_plain(th + o);
+          if (th1 != nullptr && q == 0) {
+            const size_t o1 = static_cast<size_t>(r[u]) * ld1;
+            G1[u] = ld1_plain(g1 + o1);
+            M1[u] = ld1_plain(m1 + o1);
+            V1[u] = ld1_plain(v1 + o1);
+            T1[u] = ld1_plain(th1 + o1);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r[u] < 0) continue;
+        const size_t o = static_cast<size_t>(r[u]) * ld + q * 4;
+        float4 Gu = G[u], Mu = M[u], Vu = V[u], Tu = T[u];
+#define CTR_ADAM4(c)                                  \
+  Mu.c = b1 * Mu.c + (1.f - b1) * Gu.c;               \
+  Vu.c = b2 * Vu.c + (1.f - b2) * Gu.c * Gu.c;        \
+  Tu.c -= lr_t * Mu.c / (sqrtf(Vu.c) + eps);
+        CTR_ADAM4(x) CTR_ADAM4(y) CTR_ADAM4(z) CTR_ADAM4(w)
+#undef CTR_ADAM4
+        *reinterpret_cast<float4*>(m + o) = Mu;
+        *reinterpret_cast<float4*>(v + o) = Vu;
+        *reinterpret_cast<float4*>(th + o) = Tu;
+        *reinterpret_cast<float4*>(g + o) = f4_zero();
+        if (th1 != nullptr && q == 0) {   // the row's first-order weight rides on the same claim
+          const float Mn = b1 * M1[u] + (1.f - b1) * G1[u];
+          const float Vn = b2 * V1[u] + (1.f - b2) * G1[u] * G1[u];
+          const size_t o1 = static_cast<size_t>(r[u]) * ld1;
+          m1[o1] = Mn;
+          v1[o1] = Vn;
+          th1[o1] = T1[u] - lr_t * Mn / (sqrtf(Vn) + eps);
+          g1[o1] = 0.f;
+        }
+      }
+    }
+    __syncwarp();                          // s_win[warp] is rewritten by the next task
+  }
+}
+
 }  // namespace ctr
 
 // =========================================================================== C ABI
@@ -742,6 +832,11 @@ static int embed_fwd_impl(const char* fn, const float* table, const float* w1, c
   p.table = table; p.w1 = w1; p.rows = rows; p.E = E; p.E_lo = E_lo; p.S = S; p.y1 = y1; p.y2 = y2;
   p.cross_w = cross_w; p.cross_b = cross_b; p.xl = xl; p.w1_fields = w1_fields;
   p.cross_layers = cross_layers; p.B = B; p.F = F; p.ld = row_stride; p.ld1 = w1_stride;
+  // row-record layout (stride 4D+8 floats, include/ctr_b200.h "Row strides") in a training step
+  // (the RAW entry point with rows_out): prefetch the rest of each record
+  if (raw != nullptr && raw->rows_out != nullptr && row_stride == 4 * D + 8 &&
+      option_get("fwd_prefetch_record", 0) != 0)
+    p.prefetch_bytes = static_cast<int>(row_stride - D) * 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int r = cross ? dispatch_fwd<true>(p, D, st) : dispatch_fwd<false>(p, D, st);
   if (r != CTR_OK) return r;
@@ -891,6 +986,42 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
   }
 #undef CTR_AR
   CTR_LAUNCH_CHECK("ctr_adam_rows");
+}
+
+int ctr_adam_rows_bf(const int32_t* rows, int B, int F, int D, float* theta, float* m, float* v,
+                     float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
+                     int32_t tag, float lr_t, float beta1, float beta2, float eps,
+                     const float* state_dev, int64_t row_stride, int64_t w1_stride,
+                     int64_t claim_stride, ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(rows && theta && m && v && g && claim && B >= 0 && F >= 0, "ctr_adam_rows_bf",
+              "null pointer");
+  CTR_REQUIRE(D == 8 || D == 16 || D == 32, "ctr_adam_rows_bf", "D must be 8, 16 or 32");
+  CTR_REQUIRE(theta1 == nullptr || (m1 && v1 && g1), "ctr_adam_rows_bf",
+              "first-order vector needs m1/v1/g1");
+  CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_rows_bf",
+              "pointers must be 16-byte aligned");
+  if (row_stride <= 0) row_stride = D;
+  if (w1_stride <= 0) w1_stride = 1;
+  if (claim_stride <= 0) claim_stride = 1;
+  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, "ctr_adam_rows_bf",
+              "row_stride must be >= D and a multiple of 4 floats");
+  if (B == 0 || F == 0) return CTR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nwarps = static_cast<long long>(F) * ((B + 31) / 32);
+  const int U = option_get("adam_rows_inflight", 1) >= 2 ? 2 : 1;
+  const int grid = static_cast<int>(std::min<long long>((nwarps + 7) / 8, sm_count() * (U == 1 ? 5LL : 4LL)));
+#define CTR_ARB(DD, UU) adam_rows_bf_kernel<DD, UU><<<grid, 256, 0, st>>>(rows, B, F, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev, row_stride, w1_stride, claim_stride)
+#define CTR_ARB_D(DD) \
+  if (U == 2) CTR_ARB(DD, 2); else CTR_ARB(DD, 1)
+  switch (D) {
+    case 8: CTR_ARB_D(8); break;
+    case 16: CTR_ARB_D(16); break;
+    default: CTR_ARB_D(32); break;
+  }
+#undef CTR_ARB_D
+#undef CTR_ARB
+  CTR_LAUNCH_CHECK("ctr_adam_rows_bf");
 }
 
 }  // extern "C"

@@ -332,7 +332,8 @@ template <int EPI>
 static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn,
                           int M, int N, int K, int NT, int splits, float* out, int ldo,
                           const float* bias, float* stats, int relu, cudaStream_t st,
-                          const char* fn, const float* A_lo = nullptr, const float* B_lo = nullptr) {
+                          const char* fn, const float* A_lo = nullptr, const float* B_lo = nullptr,
+                          int max_stages = 8) {
   CTR_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && aligned16(A) && aligned16(Bm), fn,
               "tensor-core path needs 16-byte aligned operands");
   CTR_REQUIRE(NT % 16 == 0 && NT >= 16 && NT <= 256, fn, "bad NT");
@@ -368,6 +369,9 @@ static int tc_gemm_launch(const float* A, int lda, bool a_mn, const float* Bm, i
     p.lo_slots = 0;
   }
   p.stages = std::max(2, std::min(8, static_cast<int>((200u * 1024u) / p.stage_bytes) - p.lo_slots));
+  // a CTA never has more loads in flight than k-blocks; off-critical-path callers cap the ring
+  // further so that the kernels they run beside keep their shared memory (max_stages)
+  p.stages = std::max(2, std::min(p.stages, std::min(max_stages, p.kb_per_split)));
   if (const char* e = ctr_knob("CTR_TCG_STAGES")) p.stages = std::max(1, std::min(p.stages, atoi(e)));
   p.acc_stride = (NT + 31) / 32 * 32;
   // measured: one accumulator is as fast as many (the MMAs are operand-fetch bound, ~160 cycles

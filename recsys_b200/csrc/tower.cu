@@ -961,9 +961,13 @@ int ctr_tower_gemm_presplit(int kind, const float* A, const float* A_lo, const f
   CTR_REQUIRE(N <= 256 && aligned16(out), fn, "weights GEMM needs N <= 256 and an aligned output");
   const int mtiles = (K + kTcBM - 1) / kTcBM;
   int splits = std::max(1, std::min(sm_count() / mtiles, (B / kTcKB) / 4));
+  if (const int o = option_get("tcg_dw_splits", 0)) splits = std::max(1, o);
   if (const char* e = ctr_knob("CTR_TCG_SPLITS")) splits = std::max(1, atoi(e));
+  // runs on a side stream beside the embedding scatter: a 2-stage ring (128 KB) leaves the SM's
+  // shared memory to the scatter kernel's CTAs ("tcg_dw_stages")
   return tc_gemm_launch<TCG_EPI_RED>(A, K, true, Bm, N, true, K, N, B, round16(N), splits, out, N,
-                                     nullptr, nullptr, 0, st, fn, A_lo, B_lo);
+                                     nullptr, nullptr, 0, st, fn, A_lo, B_lo,
+                                     std::max(2, option_get("tcg_dw_stages", 2)));
 }
 
 int ctr_bn_drop_apply(const float* A, int K, const ctr_bn_drop* pro, float* out, int B,

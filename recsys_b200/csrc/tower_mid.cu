@@ -47,6 +47,7 @@ struct MidSmem {
   float To[kMidBM * kMidPA];
   float mu[kMidMaxH], rs[kMidMaxH], sc[kMidMaxH], sh[kMidMaxH];   // BN of the input-side layer
   float gmu[kMidMaxH], grs[kMidMaxH], gc1[kMidMaxH], gc2[kMidMaxH], gsc[kMidMaxH];  // grad source
+  float s0[2 * kMidMaxH];                    // layer-0 column sums assembled from stats0_part
   float vec[kMidMaxH];                       // bias of the layer / w_out
   float red[3][kMidWarps][kMidMaxH];         // per-warp column partials
   float scal[kMidWarps][8];
@@ -125,12 +126,14 @@ struct MidCtx {
   int training, B;
 };
 
-__device__ __forceinline__ void mid_bn_consts(const ctr_tower_mid_args& A, const MidCtx& c, int l,
-                                              int k, float* mu, float* rstd) {
+__device__ __forceinline__ void mid_bn_consts(const MidSmem& sm, const ctr_tower_mid_args& A,
+                                              const MidCtx& c, int l, int k, float* mu, float* rstd) {
   const int H = A.H[l];
   if (c.training) {
-    const float m = ldcg1(A.stats[l] + k) * c.inv_B;
-    const float v = fmaxf(ldcg1(A.stats[l] + H + k) * c.inv_B - m * m, 0.f);  // biased variance
+    const bool parts = l == 0 && A.stats0_part != nullptr;
+    const float m = (parts ? sm.s0[k] : ldcg1(A.stats[l] + k)) * c.inv_B;
+    const float v = fmaxf((parts ? sm.s0[H + k] : ldcg1(A.stats[l] + H + k)) * c.inv_B - m * m,
+                          0.f);  // biased variance
     *mu = m;
     *rstd = rsqrtf(v + A.eps);
   } else {
@@ -142,7 +145,7 @@ __device__ __forceinline__ void mid_fill_bn(MidSmem& sm, const ctr_tower_mid_arg
                                             const MidCtx& c, int l) {
   for (int k = threadIdx.x; k < A.H[l]; k += kMidThreads) {
     float mu, rstd;
-    mid_bn_consts(A, c, l, k, &mu, &rstd);
+    mid_bn_consts(sm, A, c, l, k, &mu, &rstd);
     sm.mu[k] = mu;
     sm.rs[k] = rstd;
     sm.sc[k] = rstd * A.gamma[l][k];
@@ -154,7 +157,7 @@ __device__ __forceinline__ void mid_fill_grad(MidSmem& sm, const ctr_tower_mid_a
   // threads from the top of the block, so that it overlaps mid_fill_bn (threads from the bottom)
   for (int k = kMidThreads - 1 - threadIdx.x; k < A.H[l]; k += kMidThreads) {
     float mu, rstd;
-    mid_bn_consts(A, c, l, k, &mu, &rstd);
+    mid_bn_consts(sm, A, c, l, k, &mu, &rstd);
     sm.gmu[k] = mu;
     sm.grs[k] = rstd;
     sm.gc1[k] = ldcg1(A.dbeta[l] + k) * c.inv_B;
@@ -294,6 +297,19 @@ tower_mid_kernel(const __grid_constant__ ctr_tower_mid_args A, const int B) {
   float4 a_c[2] = {f4_zero(), f4_zero()}, dn_c[2] = {f4_zero(), f4_zero()};
   float4 ap[2] = {f4_zero(), f4_zero()};
   mid_stamp(A, 0);
+  if (c.training && A.stats0_part != nullptr) {
+    // layer 0 came with its column sums as one block per producer cluster (ctr_embed_tower_fwd):
+    // add them up in a fixed order (no atomics upstream, no barrier here)
+    const int H0 = A.H[0];
+    for (int k = tid; k < 2 * H0; k += kMidThreads) {
+      float s = 0.f;
+      for (int q = 0; q < A.n_stats0_part; ++q) s += ldcg1(A.stats0_part + static_cast<size_t>(q) * 2 * H0 + k);
+      sm.s0[k] = s;
+      // the totals also go where the per-layer kernels of the backward expect them
+      if (blockIdx.x == 0 && A.stats[0] != nullptr) A.stats[0][k] = s;
+    }
+    __syncthreads();
+  }
   if (A.pre0 != nullptr) {
     // ---------------------------------------------- layer 0 epilogue (split-K GEMM partial sums)
     const int N = A.H[0];
@@ -659,7 +675,7 @@ int ctr_tower_mid(const ctr_tower_mid_args* a, int B, ctr_stream_t stream) {
     CTR_REQUIRE(l != 0 || a->pre0 == nullptr || (a->b[0] && aligned16(a->b[0]) && aligned16(a->pre0)),
                 "ctr_tower_mid", "pre0 needs an aligned b[0]");
     if (a->training) {
-      CTR_REQUIRE(a->stats[l] && a->dn[l] && a->dpre[l] && a->dbeta[l] && a->dgamma[l] && a->dbias[l],
+      CTR_REQUIRE((a->stats[l] || (l == 0 && a->stats0_part)) && a->dn[l] && a->dpre[l] && a->dbeta[l] && a->dgamma[l] && a->dbias[l],
                   "ctr_tower_mid", "training needs stats/dn/dpre/dbeta/dgamma/dbias per layer");
       CTR_REQUIRE(aligned16(a->dn[l]) && aligned16(a->dpre[l]), "ctr_tower_mid",
                   "dn/dpre must be 16-byte aligned");
@@ -676,6 +692,8 @@ int ctr_tower_mid(const ctr_tower_mid_args* a, int B, ctr_stream_t stream) {
     CTR_REQUIRE(a->barrier && a->dhw && a->dhb && a->dw_out && a->db_out &&
                     (!a->relu0 || a->C == 1 || a->db1),
                 "ctr_tower_mid", "training needs barrier and head/out gradient buffers");
+  CTR_REQUIRE(a->stats0_part == nullptr || (a->pre0 == nullptr && a->n_stats0_part >= 1), "ctr_tower_mid",
+              "stats0_part excludes pre0 and needs n_stats0_part >= 1");
   if (B == 0) return CTR_OK;
   static bool optin = false;
   const int smem = static_cast<int>(sizeof(MidSmem));
@@ -693,10 +711,7 @@ int ctr_tower_mid(const ctr_tower_mid_args* a, int B, ctr_stream_t stream) {
   // plain launch instead, which is equally safe here (grid <= #SMs at 1 CTA/SM, and nothing that
   // could occupy an SM ever waits on this kernel), for drivers that cannot capture cooperative
   // launches into a CUDA graph.
-  static const bool coop = [] {
-    const char* v = ctr_knob("CTR_MID_COOP");
-    return v == nullptr || atoi(v) != 0;
-  }();
+  const bool coop = option_get("mid_coop", 1) != 0;
   if (a->training && coop) {
     e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(tower_mid_kernel), dim3(grid),
                                     dim3(kMidThreads), kargs, smem, static_cast<cudaStream_t>(stream));

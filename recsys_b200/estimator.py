@@ -11,6 +11,7 @@ reference's checkpointing / summaries / distribution strategy are out of scope.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Optional
 
@@ -178,17 +179,19 @@ class Estimator:
 # ------------------------------------------------------------------ graphed step
 class GraphedTrainStep:
     """One whole train step - ``spec = model_fn(features, labels, TRAIN, params);
-    spec.train_op()`` - captured once into a CUDA graph over static device input
-    buffers and replayed per batch.
+    spec.train_op()`` - captured into CUDA graphs over static device input buffers and
+    replayed per batch.
 
-    ``__call__(features, labels)`` with HOST tensors (pinned for real overlap) copies the batch
-    to a device staging blob on a copy stream - which runs while the previous step's graph is
-    still executing - then, on the step stream, moves it into the static buffers with ONE
-    device-to-device copy and replays the graph; device tensors are copied straight into the
-    static buffers.  It returns the device loss tensor without synchronising; ``loss_to_host``
-    reads it back on a third stream so that the read does not sit between two replays."""
+    The step is captured TWICE, over two static input blobs, and the replays alternate: while
+    graph k runs on the step stream, the next batch is copied straight into the other blob on a
+    copy stream (pinned host tensors: H2D; batches already in HBM: one D2D), so no copy and no
+    copy-to-graph dependency sits between two replays.  ``__call__(features, labels)`` returns
+    the device loss tensor without synchronising; ``loss_to_host`` reads it back on a third
+    stream so that the read does not sit between two replays.  The loss is copied out of the
+    step's workspace on an auxiliary stream right after the forward (beside the backward)."""
 
-    def __init__(self, model_fn, params, example_features, example_labels, warmup: int = 3):
+    def __init__(self, model_fn, params, example_features, example_labels, warmup: int = 3,
+                 double_buffer: Optional[bool] = None):
         from .ops import PackedFeatures
         dev = params.get("device") or torch.device("cuda", torch.cuda.current_device())
         self.model_fn, self.params = model_fn, params
@@ -199,38 +202,74 @@ class GraphedTrainStep:
             torch.cuda.Stream(device=dev, priority=-1)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.d2h_stream = torch.cuda.Stream(device=dev)
+        self.aux_stream = torch.cuda.Stream(device=dev)
+        if double_buffer is None:
+            double_buffer = os.environ.get("CTR_GRAPH_DOUBLE", "1") != "0"
+        self.nbuf = 2 if double_buffer else 1
         f = example_features
         self._packed = isinstance(f, PackedFeatures)
         ex = {"cont": f.cont, "cat": f.cat} if self._packed else \
             {k: torch.as_tensor(v) for k, v in f.items()}
         ex["__labels__"] = example_labels
-        # static inputs (what the graph reads) and the staging copy, each ONE blob with views
-        self._blob, self._static = self._make_blob(ex, dev)
-        self._stage_blob, self._stage = self._make_blob(ex, dev)
-        self.labels = self._static.pop("__labels__")
-        if self._packed:
-            self.features = PackedFeatures(self._static["cont"], self._static["cat"], f.cont_keys,
-                                           f.cat_keys)
-        else:       # plain dict of tensors (e.g. the DIN features)
-            self.features = dict(self._static)
+        # static inputs (what graph k reads): ONE blob with views per buffer
+        self._blobs, self._statics, self._labels, self._features = [], [], [], []
+        for _ in range(self.nbuf):
+            blob, static = self._make_blob(ex, dev)
+            self._blobs.append(blob)
+            self._labels.append(static.pop("__labels__"))
+            self._statics.append(static)
+            if self._packed:
+                self._features.append(PackedFeatures(static["cont"], static["cat"], f.cont_keys,
+                                                     f.cat_keys))
+            else:       # plain dict of tensors (e.g. the DIN features)
+                self._features.append(dict(static))
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self._h2d_done = torch.cuda.Event()
-        self._stage_free = torch.cuda.Event()
+        self._ready = [torch.cuda.Event() for _ in range(self.nbuf)]     # batch landed in blob k
+        self._free = [torch.cuda.Event() for _ in range(self.nbuf)]      # graph k done with blob k
         self._loss_ready = torch.cuda.Event()
         self._loss_read = torch.cuda.Event()
-        self._stage_free.record(self.stream)
+        for e in self._free:
+            e.record(self.stream)
         self._loss_read.record(self.stream)
-        self._load(example_features, example_labels)
+        self._slot = 0          # the buffer the next batch goes to
+        self._last = 0          # the buffer of the latest batch
+        for k in range(self.nbuf):
+            self._slot = k
+            self._load(example_features, example_labels)
+        self._slot = 0
+        self.stream.wait_stream(self.copy_stream)
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):                 # allocator + lazy-init warm-up, eager
-                self._eager()
+                self._eager(0)
         self.stream.synchronize()
         import gc
         gc.collect()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=self.stream):
-            self._eager()
-        self.stream.synchronize()
+        self.graphs = []
+        for k in range(self.nbuf):
+            g = torch.cuda.CUDAGraph()
+            kw = {"pool": self.graphs[0].pool()} if self.graphs else {}
+            with torch.cuda.graph(g, stream=self.stream, **kw):
+                self._eager(k)
+            self.graphs.append(g)
+            self.stream.synchronize()
+        self.graph = self.graphs[0]
+
+    # buffer 0's views under the old names (tests, callers that fill the static inputs themselves)
+    @property
+    def features(self):
+        return self._features[0]
+
+    @property
+    def labels(self):
+        return self._labels[0]
+
+    @property
+    def _blob(self):
+        return self._blobs[0]
+
+    @property
+    def _static(self):
+        return self._statics[0]
 
     @staticmethod
     def _make_blob(example: dict, dev):
@@ -243,66 +282,76 @@ class GraphedTrainStep:
                  for k, t in example.items()}
         return blob, views
 
-    def _eager(self):
-        spec = self.model_fn(self.features, self.labels, ModeKeys.TRAIN, self.params)
+    def _eager(self, k: int = 0):
+        spec = self.model_fn(self._features[k], self._labels[k], ModeKeys.TRAIN, self.params)
+        # the loss leaves the step's workspace on the auxiliary stream, beside the backward
+        main, aux = torch.cuda.current_stream(), self.aux_stream
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            self.loss.copy_(spec.loss)
         spec.train_op()
-        self.loss.copy_(spec.loss)
+        main.wait_stream(aux)
 
     def _sources(self, features, labels):
         src = {"cont": features.cont, "cat": features.cat} if self._packed else \
-            {k: torch.as_tensor(features[k]) for k in self._static}
+            {k: torch.as_tensor(features[k]) for k in self._statics[0]}
         src["__labels__"] = labels
         return src
 
     def _load(self, features, labels):
+        """Copy a batch into the next buffer on the copy stream (beside the running replay)."""
+        k = self._slot
         src = self._sources(features, labels)
-        dst = dict(self._static)
-        dst["__labels__"] = self.labels
-        if all(t.is_cuda for t in src.values()):
-            with torch.cuda.stream(self.stream):     # already in HBM: straight into the static views
-                for k, t in src.items():
-                    dst[k].copy_(t, non_blocking=True)
-            return
+        dst = dict(self._statics[k])
+        dst["__labels__"] = self._labels[k]
         cs = self.copy_stream
-        cs.wait_event(self._stage_free)              # the previous batch has left the staging blob
+        cs.wait_event(self._free[k])                 # graph k's last replay has consumed blob k
         with torch.cuda.stream(cs):
-            for k, t in src.items():
-                self._stage[k].copy_(t, non_blocking=True)
-            self._h2d_done.record(cs)
-        self.stream.wait_event(self._h2d_done)
-        with torch.cuda.stream(self.stream):
-            self._blob.copy_(self._stage_blob, non_blocking=True)
-            self._stage_free.record(self.stream)
+            for key, t in src.items():
+                dst[key].copy_(t, non_blocking=True)
+            self._ready[k].record(cs)
+        return k
 
-    def __call__(self, features, labels):
-        self._load(features, labels)
-        self.stream.wait_event(self._loss_read)      # the previous loss has been read back
+    def _replay(self, k):
+        self.stream.wait_event(self._ready[k])
         with torch.cuda.stream(self.stream):
-            self.graph.replay()
+            self.graphs[k].replay()
+            self._free[k].record(self.stream)
+        self._last = k
+        self._slot = (k + 1) % self.nbuf
         return self.loss
 
+    def __call__(self, features, labels):
+        k = self._load(features, labels)
+        self.stream.wait_event(self._loss_read)      # the previous loss has been read back
+        return self._replay(k)
+
     def to_device_batch(self, features, labels) -> torch.Tensor:
-        """Lay a batch out on the device exactly like the static input blob (for batches that are
+        """Lay a batch out on the device exactly like a static input blob (for batches that are
         kept resident in HBM); ``run_device_batch`` then needs one D2D copy per step."""
         src = self._sources(features, labels)
-        ex = dict(self._static)
-        ex["__labels__"] = self.labels
-        blob, views = self._make_blob(ex, self._blob.device)
+        ex = dict(self._statics[0])
+        ex["__labels__"] = self._labels[0]
+        blob, views = self._make_blob(ex, self._blobs[0].device)
         with torch.cuda.stream(self.stream):
             for k, t in src.items():
                 views[k].copy_(t, non_blocking=True)
+        self.stream.synchronize()
         return blob
 
     def run_device_batch(self, blob: torch.Tensor):
-        with torch.cuda.stream(self.stream):
-            self._blob.copy_(blob, non_blocking=True)
-            self.graph.replay()
-        return self.loss
+        k = self._slot
+        cs = self.copy_stream
+        cs.wait_event(self._free[k])
+        with torch.cuda.stream(cs):
+            self._blobs[k].copy_(blob, non_blocking=True)
+            self._ready[k].record(cs)
+        return self._replay(k)
 
     def replay_resident(self):
-        """Replay on whatever is in the static buffers (inputs already in HBM)."""
+        """Replay on whatever is in the latest static buffer (inputs already in HBM)."""
         with torch.cuda.stream(self.stream):
-            self.graph.replay()
+            self.graphs[self._last].replay()
         return self.loss
 
     def loss_to_host(self, pinned_slot: torch.Tensor):

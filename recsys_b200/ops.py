@@ -408,7 +408,7 @@ class FieldEmbedding:
                               cross_w, cross_b)
 
     def lookup_features(self, idp: "IdPipeline", features, want_logx: bool = False,
-                        zero_buf: Optional[torch.Tensor] = None, **kw):
+                        zero_buf: Optional[torch.Tensor] = None, tower0=None, **kw):
         """``lookup(idp(features))`` in ONE launch (ctr_embed_fwd_raw): the id pipeline runs as the
         first stage of the lookup kernel, which also clears ``zero_buf`` (the tower's per-step
         accumulators) on the side.  -> (rows, logx or None, lookup outputs...)."""
@@ -424,10 +424,14 @@ class FieldEmbedding:
         logx = torch.empty((B, len(idp.cont_keys)), dtype=torch.float32, device=self.device) \
             if want_logx else None
         self._raw = (idp, cont, cat, logx, zero_buf)
+        # tower0 = FusedTower: its first layer is computed by the lookup kernel itself
+        # (ctr_embed_tower_fwd); the result is left in ``tower0.l0`` for ``tower_head``
+        self._tower0 = tower0 if (tower0 is not None and not want_logx) else None
         try:
             outs = self.lookup(rows, **kw)
         finally:
             self._raw = None
+            self._tower0 = None
         return (rows, logx) + tuple(outs)
 
     def zero_grad(self):
@@ -478,6 +482,15 @@ class FieldEmbedding:
         self._tag += 1
         n = rows.numel()
         w = self.with_w1
+        if rows.dim() == 2 and rows.shape[1] == self.F and rows.is_contiguous() and \
+                os.environ.get("CTR_ADAM_ROWS_BF", "0") != "0":
+            # the batch's [B, F] id matrix: the one-wave kernel (field-major warps, in-warp dedup)
+            _call("ctr_adam_rows_bf", _p(rows), rows.shape[0], self.F, self.D, _p(self.table),
+                  _p(self._m), _p(self._v), _p(self.dtable), _p(self.w1) if w else None,
+                  _p(self._m1) if w else None, _p(self._v1) if w else None,
+                  _p(self.dw1) if w else None, _p(self._claim), self._tag, lr_t, st.beta1, st.beta2,
+                  st.eps, st.state_ptr, self.ld, self.ld1, self.ldc, _stream())
+            return
         _call("ctr_adam_rows", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
               _p(self.dtable), _p(self.w1) if w else None, _p(self._m1) if w else None,
               _p(self._v1) if w else None, _p(self.dw1) if w else None, _p(self._claim), self._tag,
@@ -503,7 +516,22 @@ class _EmbedFn(torch.autograd.Function):
         E_lo = torch.empty_like(E) if getattr(emb, "_want_lo", False) else None
         emb.last_E_lo = E_lo
         raw = getattr(emb, "_raw", None)
-        if raw is not None:       # id pipeline fused in front: fills ``rows`` (and logx) as well
+        tw0 = getattr(emb, "_tower0", None) if raw is not None else None
+        if tw0 is not None and not cross and E_lo is not None:
+            # ids + gather + FM terms + first tower layer in one launch
+            idp, cont, cat, logx, zbuf = raw
+            N = tw0.sizes[1]
+            act0 = torch.empty((B, N), dtype=torch.float32, device=dev)
+            nparts = (B + 127) // 128
+            parts = torch.empty((nparts, 2, N), dtype=torch.float32, device=dev)
+            tw0.wait_w0_lo()
+            _call("ctr_embed_tower_fwd", _p(emb.table), _p(emb.w1), _p(cont), len(idp.cont_keys),
+                  _p(cat), len(idp.cat_keys), _p(idp.fields_dev), _p(idp.bnd_dev), idp.n_bnd, _p(rows),
+                  _p(idp.status), B, F, D, emb.w1_fields, _p(E), _p(E_lo), _p(S), _p(y1), _p(y2),
+                  emb.ld, emb.ld1, _p(tw0.P("0.w")), _p(tw0.w0_lo), _p(tw0.P("0.b")), N, _p(act0),
+                  _p(parts), _p(zbuf), zbuf.numel() if zbuf is not None else 0, _stream())
+            tw0.l0 = (act0, parts)
+        elif raw is not None:       # id pipeline fused in front: fills ``rows`` (and logx) as well
             idp, cont, cat, logx, zbuf = raw
             _call("ctr_embed_fwd_raw", _p(emb.table), _p(emb.w1), _p(cont), len(idp.cont_keys),
                   _p(cat), len(idp.cat_keys), _p(idp.fields_dev), _p(idp.bnd_dev), idp.n_bnd,
@@ -806,6 +834,19 @@ class FusedTower:
                                  device=dense.flat.device)
         self._w0_ready = None
         self._ws = None
+        self.l0 = None          # (act0, stats_part) left by the fused lookup + first layer kernel
+
+    def can_fuse_l0(self, F: int, D: int) -> bool:
+        """The first layer can be computed inside the lookup kernel (ctr_embed_tower_fwd)."""
+        return (self.use_presplit and D == 16 and 8 < F <= 40 and self.sizes[0] == F * D
+                and 16 <= self.sizes[1] <= 128 and os.environ.get("CTR_FUSED_L0", "1") != "0")
+
+    def wait_w0_lo(self):
+        """The current stream waits for the hi/lo split of the first layer's weights."""
+        if self._w0_ready is None:
+            self._begin_split()
+        torch.cuda.current_stream().wait_event(self._w0_ready)
+        self._w0_ready = None
 
     @property
     def use_mid(self):
@@ -825,16 +866,17 @@ class FusedTower:
         return bool(have_lo) and self.use_presplit and B >= 256 and \
             os.environ.get("CTR_TOWER_SPLITK", "1") != "0"
 
-    def begin_step(self, B=None, expect_lo=False):
+    def begin_step(self, B=None, expect_lo=False, fused_l0=False):
         """Start-of-step hook.  (1) Split the first layer's weights into hi/lo on the side stream
         (they only change in the optimiser), off the critical path of the id/lookup kernels.
         (2) With ``B``: allocate the step's workspace and return it, so that the caller can have
         the lookup kernel clear it (``FieldEmbedding.lookup_features(zero_buf=...)``); the tower
         then takes it as already zeroed."""
         self._ws = None
+        self.l0 = None
         ws = None
         if B is not None and self.use_mid:
-            splitk = self.splitk_for(B, expect_lo)
+            splitk = self.splitk_for(B, expect_lo) and not fused_l0
             ws = torch.empty(self.ws_numel(B, splitk), dtype=torch.float32,
                              device=self.dense.flat.device)
             self._ws = (ws, B, splitk)
@@ -1040,7 +1082,10 @@ class _TowerHeadFn(torch.autograd.Function):
             offs.append(n)
             n += 2 * H
         presplit = X_lo is not None and tw.use_presplit and B >= 256
-        splitk = tw.splitk_for(B, X_lo is not None)
+        l0, tw.l0 = tw.l0, None
+        if l0 is not None and (l0[0].shape[0] != B or not presplit):
+            l0 = None
+        splitk = tw.splitk_for(B, X_lo is not None) and l0 is None
         # (+ with the split-K first GEMM: its zero-initialised accumulation target).  Taken from
         # begin_step() when the lookup kernel has already cleared it, else one fill launch here.
         pre, tw._ws = tw._ws, None
@@ -1053,7 +1098,9 @@ class _TowerHeadFn(torch.autograd.Function):
         pre0 = ws[n + 4:].view(B, Hs[0]) if splitk else None
         acts = [torch.empty((B, H), **f32) for H in Hs]
         logits, prob, y = (torch.empty(B, **f32) for _ in range(3))
-        if presplit:
+        if l0 is not None:          # the lookup kernel has already produced act0 and its column sums
+            acts[0] = l0[0]
+        elif presplit:
             if tw._w0_ready is None:
                 tw.begin_step()
             torch.cuda.current_stream().wait_event(tw._w0_ready)
@@ -1087,6 +1134,8 @@ class _TowerHeadFn(torch.autograd.Function):
                 a.W[l], a.b[l] = _p(tw.P("%d.w" % l)), _p(tw.P("%d.b" % l))
             elif splitk:
                 a.b[0], a.pre0 = _p(tw.P("0.b")), _p(pre0)
+            if l == 0 and l0 is not None and training:
+                a.stats0_part, a.n_stats0_part = _p(l0[1]), l0[1].shape[0]
             a.gamma[l], a.beta[l] = _p(tw.P("%d.bn.gamma" % l)), _p(tw.P("%d.bn.beta" % l))
             a.mean[l], a.var[l] = _p(tw.P("%d.bn.mean" % l)), _p(tw.P("%d.bn.var" % l))
             a.act[l] = _p(acts[l])
@@ -1116,6 +1165,7 @@ class _TowerHeadFn(torch.autograd.Function):
         tw.last_acts = acts          # post-ReLU hidden activations of the latest call (tests)
         tw.last_y = y                # and the tower's output relu(h . w_out + b_out)
         ctx.saved = (X, acts, stats, dpre, dzs, dn, zs, labels, ws, X_lo, dpre0_lo)
+        ctx.l0 = l0
         ctx.mark_non_differentiable(logits, prob)
         return loss, logits, prob
 

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--model", default="deepfm")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--timeline", action="store_true",
+                    help="also print the last step's records with start offsets and streams")
     a = ap.parse_args()
     args = bench.parse(["--model", a.model] + (["--batch", str(a.batch)] if a.batch else []))
     if args.batch is None:
@@ -80,6 +82,17 @@ def main():
     for name in order:
         tot, cnt = per[name]
         print("  %7.2f us x %4.1f/step  %s" % (tot / cnt, cnt / n, name))
+    if a.timeline:
+        # the last step = records from the last blob copy (Memcpy DtoD) on
+        first = ev[0]["name"] if "Memcpy" not in ev[0]["name"] else next(
+            (e["name"] for e in ev if "Memcpy" not in e["name"] and "split_lo" not in e["name"]), ev[0]["name"])
+        starts = [i for i, e in enumerate(ev) if e["name"] == first]
+        i0 = max(0, (starts[-1] if starts else len(ev) - len(ev) // n) - 4)
+        t0 = ev[i0]["ts"]
+        print("timeline of the last step (start us, duration us, stream, name):")
+        for e in ev[i0:]:
+            print("  %8.2f %7.2f  s%-4s %s" % (e["ts"] - t0, e["dur"], e.get("args", {}).get("stream", "?"),
+                                            e["name"][:60]))
 
 
 if __name__ == "__main__":

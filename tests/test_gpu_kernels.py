@@ -161,6 +161,75 @@ def test_embed_fwd_matches_oracle(cuda, B, F, D, record):
     assert torch.allclose(y2.cpu().double(), y2o, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("B,N,fields", [(4096, 100, "criteo"), (300, 100, "criteo"), (256, 128, "criteo"),
+                                        (1000, 16, "criteo"), (515, 64, 12), (2048, 100, 40)])
+def test_embed_tower_fwd_matches_unfused(cuda, B, N, fields):
+    """ctr_embed_tower_fwd (ids + gather + FM terms + first tower layer on tcgen05, one launch)
+    against ctr_embed_fwd_raw + float64 relu(E . W0 + b0): ids, E and E_lo bit-identical; S / y1 /
+    y2 to summation-order tolerance; act0 to 3xTF32 tolerance (2e-5 of the row scale); the
+    per-cluster column sums add up to the column sums of act0."""
+    ops = _ops()
+    from recsys_b200 import _lib
+    from recsys_b200 import feature_column as fc
+    lib = _lib.load()
+    if fields == "criteo":
+        lay, _ = _criteo_layout()
+        spec = criteo.CriteoSpec()
+        feats, _ = criteo.synthetic_features(B, seed=B + N, spec=spec, dist="zipf")
+        tf = _to_torch_features(feats)
+    else:
+        rng = np.random.default_rng(fields)
+        nrows = [int(n) for n in rng.integers(2, 5000, size=fields)]
+        cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("k%02d" % i, n), 16)
+                for i, n in enumerate(nrows)]
+        lay = fc.layout(cols)
+        tf = {"k%02d" % i: torch.from_numpy(rng.integers(0, n, size=B)) for i, n in enumerate(nrows)}
+    F, D = lay.F, 16
+    pipe = ops.IdPipeline(lay, cuda)
+    emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=(1 << F) - 1 - 4, seed=3)
+    g = torch.Generator(device="cpu").manual_seed(N)
+    W0 = (torch.randn(F * D, N, generator=g) * (2.0 / (F * D)) ** 0.5).to(cuda)
+    b0 = (torch.randn(N, generator=g) * 0.1).to(cuda)
+    W0_lo = ops.split_lo(W0)
+    with torch.no_grad():
+        rows_a, _, Ea, y1a, y2a, _ = emb.lookup_features(pipe, tf, want_lo=True)
+        Elo_a = emb.last_E_lo.clone()
+        Sa = Ea.view(B, F, D).double().sum(1)
+    cont, cat = pipe.pack(tf)
+    p = ops._p
+    rows = torch.full((B, F), -7, dtype=torch.int32, device=cuda)
+    E = torch.full((B, F * D), float("nan"), device=cuda)
+    E_lo = torch.full_like(E, float("nan"))
+    S = torch.empty(B, D, device=cuda)
+    y1 = torch.empty(B, device=cuda)
+    y2 = torch.empty(B, device=cuda)
+    act0 = torch.full((B, N), float("nan"), device=cuda)
+    nparts = (B + 127) // 128
+    parts = torch.full((nparts, 2, N), float("nan"), device=cuda)
+    zbuf = torch.ones(64, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.ctr_embed_tower_fwd(p(emb.table), p(emb.w1), p(cont), len(pipe.cont_keys), p(cat),
+                                 len(pipe.cat_keys), p(pipe.fields_dev), p(pipe.bnd_dev), pipe.n_bnd, p(rows),
+                                 p(pipe.status), B, F, D, emb.w1_fields, p(E), p(E_lo), p(S), p(y1), p(y2),
+                                 emb.ld, emb.ld1, p(W0), p(W0_lo), p(b0), N, p(act0), p(parts), p(zbuf),
+                                 zbuf.numel(), st)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(rows, rows_a)
+    assert torch.equal(E, Ea) and torch.equal(E_lo, Elo_a)
+    assert float(zbuf.abs().max()) == 0.0
+    assert torch.allclose(S.double().cpu(), Sa.cpu(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(y1, y1a, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(y2, y2a, rtol=1e-4, atol=1e-4)
+    want = torch.relu(Ea.double() @ W0.double() + b0.double())
+    scale = float(want.abs().max())
+    err = float((act0.double() - want).abs().max())
+    assert err <= 2e-5 * scale + 1e-6, "act0 differs: %g (scale %g)" % (err, scale)
+    cs = torch.stack([act0.double().sum(0), (act0.double() ** 2).sum(0)])
+    got = parts.double().sum(0)
+    assert torch.allclose(got, cs, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("B,D,use_dE,use_fm,regather", [
     (1, 16, True, True, False), (77, 16, True, True, False), (4096, 16, True, True, False),
     (300, 16, False, True, True), (300, 16, True, False, False), (515, 32, True, True, False),
@@ -380,6 +449,50 @@ def test_adam_rows_and_dense_match_tf_rule(cuda):
             assert float(emb.dtable.abs().max()) == 0.0 and float(emb.dw1.abs().max()) == 0.0
         assert torch.allclose(emb.table.cpu().double(), p["emb"], rtol=1e-5, atol=1e-6)
         assert torch.allclose(emb.w1.cpu().double(), p["w1"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("D", [8, 16, 32])
+def test_adam_rows_bf_equals_flat_kernel(cuda, D, monkeypatch):
+    """ctr_adam_rows_bf (field-major warps, in-warp de-duplication, winners only) against
+    ctr_adam_rows on the same [B, F] ids, both in-flight depths: bit-identical tables, moments and
+    cleared gradients; ragged B, a one-row field, negative (padding) ids."""
+    ops = _ops()
+    from recsys_b200 import _lib
+    from recsys_b200 import feature_column as fc
+    lib = _lib.load()
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("a", 1), D),
+            fc.embedding_column(fc.categorical_column_with_hash_bucket("b", 7), D),
+            fc.embedding_column(fc.categorical_column_with_hash_bucket("c", 3000), D),
+            fc.embedding_column(fc.categorical_column_with_hash_bucket("d", 100000), D)]
+    lay = fc.layout(cols)
+    B = 1000 + 13
+    rows_np = _rand_rows(B, lay.offsets, seed=5)
+    rows_np[::17, 2] = -1
+    rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
+    g = torch.randn(lay.total_rows, D, device=cuda)
+    g1 = torch.randn(lay.total_rows, device=cuda)
+    results = []
+    for variant in ("flat", "n1", "n2"):
+        monkeypatch.setenv("CTR_ADAM_ROWS_BF", "0" if variant == "flat" else "1")
+        assert lib.ctr_set_option(b"adam_rows_inflight", int(variant[1]) if variant != "flat" else 1) == 0
+        emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=0b1111, adam_mode="lazy", seed=1)
+        st = ops.TFAdamState(lr=1e-2, device=cuda)
+        for step in range(2):
+            emb.dtable.copy_(g * (step + 1))
+            emb.dw1.copy_(g1)
+            emb.adam_step(rows, st.next_lr_t(), st)
+            st.advance()
+        torch.cuda.synchronize()
+        results.append(emb.rec.clone())
+    assert lib.ctr_set_option(b"adam_rows_inflight", 1) == 0
+    valid = torch.from_numpy(rows_np[rows_np >= 0].reshape(-1)).long()
+    touched = torch.zeros(lay.total_rows, dtype=torch.bool)
+    touched[valid] = True
+    ref = results[0].cpu()
+    assert float(ref[touched][:, 3 * D:4 * D].abs().max()) == 0.0          # g cleared where touched
+    assert float((ref[~touched][:, 3 * D:4 * D] - (2 * g).cpu()[~touched]).abs().max()) == 0.0
+    for r in results[1:]:
+        assert torch.equal(r.cpu(), ref)
 
 
 def test_adam_schedule_counts_past_2_to_the_24(cuda):
