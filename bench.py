@@ -561,11 +561,11 @@ def time_hot_kernels(model, devb, K, W, stream):
 
         def adam(i):
             emb._tag += 1
-            lib.ctr_adam_rows_bf(p(rows[i % len(rows)]), B, F, D, p(emb.table), p(emb._m),
-                                 p(emb._v), p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
-                                 p(getattr(emb, "_v1", None)), p(emb.dw1),
-                                 p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, emb.ld,
-                                 emb.ld1, emb.ldc, st)
+            lib.ctr_adam_rows(p(rows[i % len(rows)]), B * F, D, p(emb.table), p(emb._m), p(emb._v),
+                              p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
+                              p(getattr(emb, "_v1", None)), p(emb.dw1),
+                              p(emb._claim), emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, emb.ld, emb.ld1,
+                              emb.ldc, st)
 
         def timeit(fn, once=False):
             """Per-launch device time: the launches (one per distinct id batch) are captured into a
@@ -634,11 +634,11 @@ def time_hot_kernels(model, devb, K, W, stream):
             if getattr(emb, "can_fuse", False):
                 def adamL(i):
                     emb._tag += 1
-                    lib.ctr_adam_rows_bf(p(rl[i % 4]), BL, F, D, p(emb.table), p(emb._m), p(emb._v),
-                                         p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
-                                         p(getattr(emb, "_v1", None)), p(emb.dw1), p(emb._claim),
-                                         emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, emb.ld, emb.ld1,
-                                         emb.ldc, st)
+                    lib.ctr_adam_rows(p(rl[i % 4]), BL * F, D, p(emb.table), p(emb._m), p(emb._v),
+                                      p(emb.dtable), p(emb.w1), p(getattr(emb, "_m1", None)),
+                                      p(getattr(emb, "_v1", None)), p(emb.dw1), p(emb._claim),
+                                      emb._tag, 1e-3, 0.9, 0.999, 1e-8, None, emb.ld, emb.ld1,
+                                      emb.ldc, st)
 
                 def pairL(i):
                     bwdL(i)

@@ -168,15 +168,29 @@ int ctr_embed_fwd_raw(const float* table, const float* w1, const float* xcont, i
  * and FM partial sums are added over distributed shared memory.  E / E_lo are still written (the
  * weight-gradient GEMM of the backward reads them), S / y1 / y2 as by ctr_embed_fwd.
  * stats_part (nullable): [ceil(B/128)][2][N] column sums of act0 and act0^2 per cluster, for
- * ctr_tower_mid_args.stats0_part.  zero_buf as in ctr_embed_fwd_raw. */
+ * ctr_tower_mid_args.stats0_part.  zero_buf as in ctr_embed_fwd_raw.
+ * rows_in (nullable): the [B, F] ids when they were computed ahead of the step (ctr_criteo_rows on a
+ * copy stream, beside the previous step); the id stage and rows_out are then skipped. */
 int ctr_embed_tower_fwd(const float* table, const float* w1, const float* xcont, int n_cont,
                         const int64_t* xcat, int n_cat, const ctr_field_desc* fields_dev,
-                        const float* boundaries_dev, int n_boundaries, int32_t* rows_out,
-                        int32_t* status, int B,
+                        const float* boundaries_dev, int n_boundaries, const int32_t* rows_in,
+                        int32_t* rows_out, int32_t* status, int B,
                         int F, int D, uint64_t w1_fields, float* E, float* E_lo, float* S, float* y1,
                         float* y2, int64_t row_stride, int64_t w1_stride, const float* W0,
                         const float* W0_lo, const float* b0, int N, float* act0, float* stats_part,
                         float* zero_buf, int64_t zero_n, ctr_stream_t stream);
+
+/* The backward counterpart: the first layer's data gradient dE = dpre0 . W0^T (deepfm/deepfm.py:101,
+ * backward) and ctr_embed_bwd in ONE launch.  Each CTA forms dE for 128 samples x 10 fields in TMEM
+ * (tcgen05 3xTF32 from the ctr_split_lo pairs dpre0 / dpre0_lo [B, N] and W0 / W0_lo [F*D, N]) and
+ * scatters it from there: g[b,f,:] = dE[b,f,:] + dy2[b] * (S[b,:] - E[b,f,:]), warp-aggregated
+ * vector REDs into dtable / dw1 exactly as ctr_embed_bwd (fields with <= 32 rows are summed per row
+ * in shared memory first).  dE never touches global memory.  D = 16, 16 <= N <= 128. */
+int ctr_tower_embed_bwd(const float* dpre0, const float* dpre0_lo, const float* W0, const float* W0_lo,
+                        int N, const int32_t* rows, const float* E, const float* S, const float* dy2,
+                        const float* dy1, uint64_t w1_fields, const int64_t* row_offsets_host, int B,
+                        int F, int D, float* dtable, float* dw1, int64_t row_stride, int64_t w1_stride,
+                        ctr_stream_t stream);
 
 /* Profiling aid: later ctr_embed_tower_fwd launches stamp %globaltimer (ns) of CTA (0,0) into
  * timing_dev[0..7] at the phase boundaries (start | ids staged | loads issued | A tiles written |
@@ -220,6 +234,17 @@ int ctr_adam_tick(float* state_dev, float lr, float beta1, float beta2, ctr_stre
 int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
                    float beta2, float eps, int zero_g, float* state_dev, int advance_state,
                    ctr_stream_t stream);
+/* The step's closing optimiser kernels may run CONCURRENTLY (the dense weights on one stream, the
+ * touched rows on another): each takes advance_parties = the number of kernels that end the step
+ * together (0 = takes no part, 1 = alone, as ctr_adam_dense's advance_state), and the last block
+ * of the last one to finish moves the schedule on.  state_dev then has 8 words:
+ * {t, lr_t, lr, dense block counter, parties finished, row block counter, 0, 0}.
+ * ctr_adam_dense_ex also writes the 3xTF32 lo half (ctr_split_lo rule) of the updated slice
+ * theta[lo_begin, lo_begin + lo_n) to lo_dst (nullable) - the pre-split operand of the first
+ * tower layer for the NEXT step, which then needs no split launch. */
+int ctr_adam_dense_ex(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
+                      float beta2, float eps, int zero_g, float* state_dev, int advance_parties,
+                      float* lo_dst, int64_t lo_begin, int64_t lo_n, ctr_stream_t stream);
 /* Lazy variant: exactly one update per distinct row in rows[n] (claim[R] int32
  * scratch, tag must differ from the previous call's), then zeroes the row of g.  Negative
  * row ids are skipped.  theta1/m1/v1/g1 (nullable): a per-row scalar parameter indexed by the
@@ -239,16 +264,21 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
                   int32_t tag, float lr_t, float beta1, float beta2, float eps,
                   const float* state_dev, int64_t row_stride, int64_t w1_stride,
                   int64_t claim_stride, ctr_stream_t stream);
+int ctr_adam_rows_ex(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
+                     float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
+                     int32_t tag, float lr_t, float beta1, float beta2, float eps, float* state_dev,
+                     int64_t row_stride, int64_t w1_stride, int64_t claim_stride,
+                     int advance_parties, ctr_stream_t stream);
 /* The same update for the id matrix rows[B, F] of one batch (what ctr_embed_fwd consumed), one
  * wave deep: a warp takes 32 consecutive samples of ONE field, so the lookups of a hot row meet
  * in one warp and are de-duplicated in registers (__match_any_sync) before the claim exchange,
  * and only the records of the claim winners are fetched.  Same arguments and results as
- * ctr_adam_rows(rows, B*F, ...); D in {8, 16, 32}. */
+ * ctr_adam_rows_ex(rows, B*F, ...); D in {8, 16, 32}. */
 int ctr_adam_rows_bf(const int32_t* rows, int B, int F, int D, float* theta, float* m, float* v,
                      float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
                      int32_t tag, float lr_t, float beta1, float beta2, float eps,
-                     const float* state_dev, int64_t row_stride, int64_t w1_stride,
-                     int64_t claim_stride, ctr_stream_t stream);
+                     float* state_dev, int64_t row_stride, int64_t w1_stride,
+                     int64_t claim_stride, int advance_parties, ctr_stream_t stream);
 
 /* Scatter-add and row optimiser in ONE pass (row-record layout only; rec = the record array,
  * row_stride >= 4D+8).  The unfused pair ctr_embed_bwd + ctr_adam_rows visits every touched record

@@ -9,6 +9,8 @@ convention with the oracle so tests can load identical weights).
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional
 
@@ -274,6 +276,17 @@ class _CriteoBase(_ModelBase):
         super().load_state(state)
         self.emb.load(state.get("emb"), state.get("w1"))
 
+    def prefetch_ids(self, features) -> bool:
+        """Compute the batch's row ids into ``features.rows`` on the CURRENT stream - what
+        estimator.GraphedTrainStep runs on its copy stream right after the batch has landed, so the
+        id pipeline of step s+1 overlaps the compute of step s.  False when this model's step needs
+        more than the ids from the id stage (the log-normalised numerics of xDeepFM)."""
+        if getattr(self, "needs_logx", False) or self.world != 1 or \
+                getattr(features, "rows", None) is None or not hasattr(self.emb, "lookup_features"):
+            return False
+        self.ids(features, out=features.rows)
+        return True
+
     @staticmethod
     def _batch_size(features):
         if isinstance(features, ops.PackedFeatures):
@@ -414,6 +427,29 @@ class DeepFMModel(_CriteoBase):
         return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),
                                 X_lo=self.emb.last_E_lo if lo else None)      # :91,100-129
 
+    def _apply_gradients(self, lr_t):
+        """The step's two closing optimiser kernels side by side: the touched rows on the main
+        stream, the dense weights on the tower's side stream right behind the weight-gradient
+        kernels that feed them (every other dense gradient of this model is written by
+        ctr_tower_mid, before the fork).  The last of the two to finish advances the device
+        schedule; the dense launch also leaves the lo half of the first layer's weights for the
+        next step's lookup kernel."""
+        tw, emb = self.tower, self.emb
+        if (self.world != 1 or not self.fused or not isinstance(emb, ops.FieldEmbedding)
+                or emb.adam_mode != "lazy" or tw._pending is None or self.adam.state is None
+                or getattr(emb, "_fused_done", False) or getattr(emb, "_fused", None) is not None
+                or os.environ.get("CTR_DENSE_ON_SIDE", "1") == "0"):
+            return super()._apply_gradients(lr_t)
+        main = torch.cuda.current_stream()
+        emb.adam_step(self.rows, lr_t, self.adam, parties=2)
+        with torch.cuda.stream(tw.side):
+            self.dense.adam_step(lr_t, self.adam, parties=2,
+                                 lo=("dnn.0.w", tw.w0_lo) if tw.use_presplit else None)
+            done = torch.cuda.Event()
+            done.record(tw.side)
+        tw._pending = None
+        main.wait_event(done)
+
     def logits(self, features, training):
         P = self.dense
         self.rows = self.ids(features)
@@ -498,6 +534,7 @@ class XDeepFMModel(_CriteoBase):
     because the reference calls input_layer a second time (:185) [TF-sem]; pass
     params['share_embeddings']=True to use one set."""
     name = "xdeepfm"
+    needs_logx = True       # the id stage also yields the log-normalised numerics (:82)
 
     def __init__(self, params):
         super().__init__(params)

@@ -104,10 +104,12 @@ SIGNATURES = {
     "ctr_embed_fwd_raw": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i,
                                 c_u64, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i64, c_i64, c_f, c_i64,
                                 c_f]),
-    "ctr_embed_tower_fwd": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_u64,
+    "ctr_embed_tower_fwd": (c_i, [c_f, c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_u64,
                                   c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f, c_i, c_f, c_f,
                                   c_f, c_i64, c_f]),
     "ctr_embed_tower_timing": (c_i, [c_f]),
+    "ctr_tower_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_u64,
+                                  C.POINTER(C.c_int64), c_i, c_i, c_i, c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_u64, C.POINTER(C.c_int64), c_i,
                             c_i, c_i, c_f, c_f, c_i64, c_i64, c_f]),
     "ctr_count_rows": (c_i, [c_f, c_i64, c_i, c_f, c_i64, c_f]),
@@ -120,7 +122,11 @@ SIGNATURES = {
     "ctr_adam_rows": (c_i, [c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                             C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_f]),
     "ctr_adam_rows_bf": (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
-                               C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_f]),
+                               C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_i, c_f]),
+    "ctr_adam_rows_ex": (c_i, [c_f, c_i64, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                               C.c_int32, c_fl, c_fl, c_fl, c_fl, c_f, c_i64, c_i64, c_i64, c_i, c_f]),
+    "ctr_adam_dense_ex": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_i, c_f, c_i,
+                                c_f, c_i64, c_i64, c_f]),
     "ctr_din_att_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f, c_f, c_i, c_f, c_f,
                               c_f, c_f, C.POINTER(DinOpts), c_f]),
     "ctr_din_dropout_mask": (c_i, [C.POINTER(DinOpts), c_i, c_i64, c_i, c_f, c_f]),

@@ -501,6 +501,25 @@ __device__ __forceinline__ void adam_advance(float* __restrict__ state, float b1
   state[0] = __uint_as_float(t);
   state[1] = state[2] * sqrtf(1.f - powf(b2, tn)) / (1.f - powf(b1, tn));
 }
+// End of a step with several concurrent optimiser kernels: the state block continues with
+// [4] = parties that have finished, [5] = block counter of the row kernel ([3] is the dense
+// kernel's).  One thread per block calls this after the block's work; the last block of the last
+// party moves the schedule on (every block of every party read t / lr_t when it started).
+__device__ __forceinline__ void adam_party_done(float* __restrict__ state, int counter_word,
+                                                int parties, float b1, float b2) {
+  unsigned* cnt = reinterpret_cast<unsigned*>(state + counter_word);
+  __threadfence();
+  if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+    *cnt = 0u;
+    unsigned* pc = reinterpret_cast<unsigned*>(state + 4);
+    if (parties <= 1) {
+      adam_advance(state, b1, b2);
+    } else if (atomicAdd(pc, 1u) == static_cast<unsigned>(parties) - 1u) {
+      *pc = 0u;
+      adam_advance(state, b1, b2);
+    }
+  }
+}
 // ctr_adam_tick: set lr and advance once (from t = -1 this initialises the schedule at t = 0).
 __global__ void adam_tick_kernel(float* __restrict__ state, float lr, float b1, float b2) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -512,7 +531,8 @@ __global__ void adam_tick_kernel(float* __restrict__ state, float lr, float b1, 
 __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
                                   float* __restrict__ v, float* __restrict__ g, long long n,
                                   float lr_t, float b1, float b2, float eps, int zero_g,
-                                  float* __restrict__ state, int advance) {
+                                  float* __restrict__ state, int advance,
+                                  float* __restrict__ lo_dst, long long lo_beg, long long lo_n) {
   if (state != nullptr) lr_t = state[1];
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -531,6 +551,17 @@ __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
     reinterpret_cast<float4*>(v)[i] = V;
     reinterpret_cast<float4*>(th)[i] = T;
     if (zero_g) reinterpret_cast<float4*>(g)[i] = f4_zero();
+    if (lo_dst != nullptr) {      // the 3xTF32 lo half of a slice (the first tower layer's weights)
+      const long long e = (i << 2) - lo_beg;
+      if (e >= 0 && e + 3 < lo_n) {
+        *reinterpret_cast<float4*>(lo_dst + e) = tcg_lo4(T);
+      } else if (e > -4 && e < lo_n) {
+        const float t4[4] = {T.x, T.y, T.z, T.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (e + u >= 0 && e + u < lo_n) lo_dst[e + u] = tcg_lo(t4[u]);
+      }
+    }
   }
   for (long long i = (n4 << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
        i < n; i += stride) {
@@ -539,20 +570,16 @@ __global__ void adam_dense_kernel(float* __restrict__ th, float* __restrict__ m,
     const float V = b2 * v[i] + (1.f - b2) * G * G;
     m[i] = M;
     v[i] = V;
-    th[i] -= lr_t * M / (sqrtf(V) + eps);
+    const float Tn = th[i] - lr_t * M / (sqrtf(V) + eps);
+    th[i] = Tn;
     if (zero_g) g[i] = 0.f;
+    if (lo_dst != nullptr && i >= lo_beg && i - lo_beg < lo_n) lo_dst[i - lo_beg] = tcg_lo(Tn);
   }
   if (advance && state != nullptr) {
     // every block read lr_t when it started; the last one to finish moves the schedule on
+    // (advance = number of optimiser kernels that end the step together)
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned* cnt = reinterpret_cast<unsigned*>(state + 3);
-      __threadfence();
-      if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
-        *cnt = 0u;
-        adam_advance(state, b1, b2);
-      }
-    }
+    if (threadIdx.x == 0) adam_party_done(state, 3, advance, b1, b2);
   }
 }
 
@@ -567,7 +594,8 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
                  float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
                  float* __restrict__ th1, float* __restrict__ m1, float* __restrict__ v1,
                  float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
-                 float b2, float eps, const float* __restrict__ state, long long ld, long long ld1, long long ldc) {
+                 float b2, float eps, float* __restrict__ state, long long ld, long long ld1, long long ldc,
+                 int parties) {
   if (state != nullptr) {
     tag = static_cast<int>(adam_step_of(state)) + 1;      // the step in progress
     lr_t = state[1];
@@ -661,6 +689,10 @@ adam_rows_kernel(const int* __restrict__ rows, long long n, float* __restrict__ 
       }
     }
   }
+  if (parties > 0 && state != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) adam_party_done(state, 5, parties, b1, b2);
+  }
 }
 #undef CTR_ADAM1
 
@@ -684,8 +716,8 @@ adam_rows_bf_kernel(const int* __restrict__ rows, int B, int F, float* __restric
                     float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
                     float* __restrict__ th1, float* __restrict__ m1, float* __restrict__ v1,
                     float* __restrict__ g1, int* __restrict__ claim, int tag, float lr_t, float b1,
-                    float b2, float eps, const float* __restrict__ state, long long ld,
-                    long long ld1, long long ldc) {
+                    float b2, float eps, float* __restrict__ state, long long ld,
+                    long long ld1, long long ldc, int parties) {
   if (state != nullptr) {
     tag = static_cast<int>(adam_step_of(state)) + 1;      // the step in progress
     lr_t = state[1];
@@ -762,6 +794,10 @@ adam_rows_bf_kernel(const int* __restrict__ rows, int B, int F, float* __restric
       }
     }
     __syncwarp();                          // s_win[warp] is rewritten by the next task
+  }
+  if (parties > 0 && state != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) adam_party_done(state, 5, parties, b1, b2);
   }
 }
 
@@ -939,18 +975,29 @@ int ctr_adam_tick(float* state_dev, float lr, float beta1, float beta2, ctr_stre
   CTR_LAUNCH_CHECK("ctr_adam_tick");
 }
 
-int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
-                   float beta2, float eps, int zero_g, float* state_dev, int advance_state,
-                   ctr_stream_t stream) {
+int ctr_adam_dense_ex(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
+                      float beta2, float eps, int zero_g, float* state_dev, int advance_parties,
+                      float* lo_dst, int64_t lo_begin, int64_t lo_n, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(theta && m && v && g && n >= 0, "ctr_adam_dense", "null pointer / negative n");
   CTR_REQUIRE(aligned16(theta) && aligned16(m) && aligned16(v) && aligned16(g), "ctr_adam_dense",
               "pointers must be 16-byte aligned");
+  CTR_REQUIRE(lo_dst == nullptr || (lo_begin >= 0 && lo_n >= 0 && lo_begin + lo_n <= n &&
+                                    (lo_begin & 3) == 0 && aligned16(lo_dst)),
+              "ctr_adam_dense", "lo slice must lie inside theta, start at a multiple of 4, dst aligned");
   if (n == 0) return CTR_OK;
   const int grid = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, sm_count() * 8LL));
   adam_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g, state_dev, advance_state);
+      theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g, state_dev, advance_parties, lo_dst, lo_begin,
+      lo_n);
   CTR_LAUNCH_CHECK("ctr_adam_dense");
+}
+
+int ctr_adam_dense(float* theta, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, int zero_g, float* state_dev, int advance_state,
+                   ctr_stream_t stream) {
+  return ctr_adam_dense_ex(theta, m, v, g, n, lr_t, beta1, beta2, eps, zero_g, state_dev,
+                           advance_state != 0 ? 1 : 0, nullptr, 0, 0, stream);
 }
 
 int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
@@ -958,6 +1005,16 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
                   int32_t tag, float lr_t, float beta1, float beta2, float eps,
                   const float* state_dev, int64_t row_stride, int64_t w1_stride, int64_t claim_stride,
                   ctr_stream_t stream) {
+  return ctr_adam_rows_ex(rows, n, D, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2,
+                          eps, const_cast<float*>(state_dev), row_stride, w1_stride, claim_stride, 0,
+                          stream);
+}
+
+int ctr_adam_rows_ex(const int32_t* rows, int64_t n, int D, float* theta, float* m, float* v,
+                     float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
+                     int32_t tag, float lr_t, float beta1, float beta2, float eps, float* state_dev,
+                     int64_t row_stride, int64_t w1_stride, int64_t claim_stride,
+                     int advance_parties, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(rows && theta && m && v && g && claim && n >= 0, "ctr_adam_rows", "null pointer");
   CTR_REQUIRE(theta1 == nullptr || (m1 && v1 && g1 && D >= 4), "ctr_adam_rows",
@@ -976,7 +1033,7 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
   constexpr int U = 2;                      // lookups in flight per lane group
   const long long per_block = gpb * U;
   const int grid = static_cast<int>(std::min<long long>((n + per_block - 1) / per_block, sm_count() * 8LL));
-#define CTR_AR(DD) adam_rows_kernel<DD, U><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev, row_stride, w1_stride, claim_stride)
+#define CTR_AR(DD) adam_rows_kernel<DD, U><<<grid, 256, 0, st>>>(rows, n, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev, row_stride, w1_stride, claim_stride, advance_parties)
   switch (D) {
     case 1: CTR_AR(1); break;
     case 8: CTR_AR(8); break;
@@ -991,8 +1048,8 @@ int ctr_adam_rows(const int32_t* rows, int64_t n, int D, float* theta, float* m,
 int ctr_adam_rows_bf(const int32_t* rows, int B, int F, int D, float* theta, float* m, float* v,
                      float* g, float* theta1, float* m1, float* v1, float* g1, int32_t* claim,
                      int32_t tag, float lr_t, float beta1, float beta2, float eps,
-                     const float* state_dev, int64_t row_stride, int64_t w1_stride,
-                     int64_t claim_stride, ctr_stream_t stream) {
+                     float* state_dev, int64_t row_stride, int64_t w1_stride,
+                     int64_t claim_stride, int advance_parties, ctr_stream_t stream) {
   CTR_ARCH_OR_RETURN();
   CTR_REQUIRE(rows && theta && m && v && g && claim && B >= 0 && F >= 0, "ctr_adam_rows_bf",
               "null pointer");
@@ -1011,7 +1068,7 @@ int ctr_adam_rows_bf(const int32_t* rows, int B, int F, int D, float* theta, flo
   const long long nwarps = static_cast<long long>(F) * ((B + 31) / 32);
   const int U = option_get("adam_rows_inflight", 1) >= 2 ? 2 : 1;
   const int grid = static_cast<int>(std::min<long long>((nwarps + 7) / 8, sm_count() * (U == 1 ? 5LL : 4LL)));
-#define CTR_ARB(DD, UU) adam_rows_bf_kernel<DD, UU><<<grid, 256, 0, st>>>(rows, B, F, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev, row_stride, w1_stride, claim_stride)
+#define CTR_ARB(DD, UU) adam_rows_bf_kernel<DD, UU><<<grid, 256, 0, st>>>(rows, B, F, theta, m, v, g, theta1, m1, v1, g1, claim, tag, lr_t, beta1, beta2, eps, state_dev, row_stride, w1_stride, claim_stride, advance_parties)
 #define CTR_ARB_D(DD) \
   if (U == 2) CTR_ARB(DD, 2); else CTR_ARB(DD, 1)
   switch (D) {

@@ -47,6 +47,7 @@ struct EtParams {
   const ctr_field_desc* fields;
   const float* bnd;
   int n_cont, n_cat, n_bnd;
+  const int* rows_in;     // nullable: ids computed earlier (ctr_criteo_rows), the id stage is skipped
   int* rows_out;
   int* status;
   float* E;
@@ -167,6 +168,15 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
       for (long long i = tid; i < p.zero_n4; i += kEtGather)
         reinterpret_cast<float4*>(p.zero_buf)[i] = f4_zero();
     const int f0 = kg * p.fpc;
+    int rid[2 * kEtMaxFPC];
+    if (p.rows_in != nullptr) {
+      // the ids were computed ahead of the step (on the copy stream, beside the previous step)
+#pragma unroll
+      for (int i = 0; i < 2 * kEtMaxFPC; ++i) {
+        const int j = i >> 1, bb = m0 + 16 * warp + 8 * (i & 1) + r8, f = f0 + j;
+        rid[i] = (j < p.fpc && bb < B && f < F) ? __ldg(p.rows_in + static_cast<size_t>(bb) * F + f) : -1;
+      }
+    } else {
     // ids of the CTA's 128 x fpc (sample, field) pairs: every thread computes its share with
     // independent loads (no shuffle between them), staged in the not yet used tail of the A
     // ring, then each lane picks up the ids of its rows
@@ -214,13 +224,13 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     et_stamp(p, 1);
-    int rid[2 * kEtMaxFPC];
 #pragma unroll
     for (int i = 0; i < 2 * kEtMaxFPC; ++i) {
       const int j = i >> 1, row = 16 * warp + 8 * (i & 1) + r8;
       rid[i] = j < p.fpc ? ids_s[row * p.fpc + j] : -1;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");     // the staging area becomes an A tile again
+    }
     float4 v[2 * kEtMaxFPC];
 #pragma unroll
     for (int i = 0; i < 2 * kEtMaxFPC; ++i)
@@ -451,6 +461,290 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
   }
 }
 
+
+// ======================================================================== backward
+// Fused first-layer data gradient + embedding scatter-add:  dE = dpre0 . W0^T is formed per
+// (128 samples, 10 fields) tile in TMEM and consumed from there - row gradient dE + dy2 * (S - E)
+// (fm/fm.py:123-129), warp-aggregated vector REDs into the table's gradient accumulator, first-order
+// gradient - so dE never exists in global memory and the GEMM -> scatter kernel boundary is gone
+// (unfused: 11.7 us GEMM + 18.3 us scatter at B = 4096).  One CTA per (M tile, field group), no
+// cross-CTA reduction:
+//   TMA         dpre0 / dpre0_lo k-blocks (all resident) and the W0 / W0_lo rows of the CTA's
+//               fields (K-major, 2-stage ring)
+//   MMA         tcgen05.mma, 3xTF32; the last k-block only issues the k-steps that hold data
+//   epilogue    8 warps, two per TMEM lane quarter, lane = sample: per field 16 accumulator
+//               columns -> registers; fields with more than 32 rows: duplicates inside the warp are
+//               summed into one lane (__match_any_sync), 4 vector REDs per distinct row; fields with
+//               <= 32 rows (every sample of the warp hits a handful of rows): the 32 slots are summed
+//               per row in a warp-private shared-memory tile first, one RED group per row that was hit
+constexpr int kEbThreads = 256;
+constexpr int kEbFPC = 10;                       // fields per CTA
+constexpr int kEbNT = kEbFPC * kEtD;             // 160 accumulator columns
+constexpr int kEbBStage = 2 * kEbNT * kTcKB * 4; // W0 hi | lo k-block: 2 x 20 KB
+constexpr int kEbMaxKB = 4;                      // H0 <= 128
+constexpr int kEbFPW = kEbFPC / 2;               // fields per epilogue warp
+
+struct EbParams {
+  const int* rows;
+  const float* E;
+  const float* S;
+  const float* dy2;
+  const float* dy1;
+  float* dtable;
+  float* dw1;
+  long long ld_g, ld_w;
+  unsigned long long w1_fields;
+  unsigned long long tiny_fields;     // bit f: field f has <= 32 rows
+  int off[CTR_MAX_FIELDS + 1];
+  int B, F, H, nkb, last_ksteps;
+  uint32_t idesc;
+  uint64_t desc_k;
+  unsigned long long* timing;
+};
+
+// All 8 warps are epilogue warps (two per TMEM lane quarter, lane = sample); lane 0 of warp 0
+// first issues every TMA load, lane 0 of warp 1 issues the MMAs.  Everything the epilogue needs
+// that does not depend on the GEMM - row ids, S, dy, the E rows of the FM term - is requested
+// before the roles split, so it is in registers when the accumulator is ready.
+__global__ void __launch_bounds__(kEbThreads, 1)
+tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                       const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
+                       const EbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  // [A: nkb x (hi | lo)] [B ring: 2 x (hi | lo)] [barriers]; the epilogue's tiles reuse A
+  uint8_t* a_all = smem;
+  uint8_t* b_ring = smem + static_cast<size_t>(kEbMaxKB) * 2 * kTcABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + 2 * kEbBStage);
+  uint64_t* a_full = bars;            // [kEbMaxKB]
+  uint64_t* b_full = bars + 4;        // [2]
+  uint64_t* b_empty = bars + 6;       // [2]
+  uint64_t* t_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * kTcBM;
+  const int kg = blockIdx.y;
+  const int f0 = kg * kEbFPC;
+  const bool stamp = p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 64;
+  if (stamp) p.timing[0] = gtime_ns();
+
+  if (tid == 0) {
+    for (int s = 0; s < kEbMaxKB; ++s) mbar_init(&a_full[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    // every A k-block and the first two B stages: in flight before anything else
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      mbar_expect_tx(&a_full[kb], 2 * kTcABytes);
+      uint8_t* sa = a_all + static_cast<size_t>(kb) * 2 * kTcABytes;
+      tma_load_2d(sa, &tmA, kb * kTcKB, m0, &a_full[kb]);
+      tma_load_2d(sa + kTcABytes, &tmAlo, kb * kTcKB, m0, &a_full[kb]);
+    }
+    for (int kb = 0; kb < min(2, p.nkb); ++kb) {
+      mbar_expect_tx(&b_full[kb], kEbBStage);
+      uint8_t* sb = b_ring + static_cast<size_t>(kb) * kEbBStage;
+      tma_load_2d(sb, &tmW, kb * kTcKB, f0 * kEtD, &b_full[kb]);
+      tma_load_2d(sb + kEbBStage / 2, &tmWlo, kb * kTcKB, f0 * kEtD, &b_full[kb]);
+    }
+  }
+  __syncwarp();
+
+  // ---------------------------------------------- epilogue operands that do not need the GEMM
+  const int quarter = warp & 3, sub = warp >> 2;             // two warps per lane quarter
+  const int b = m0 + quarter * 32 + lane;
+  const bool live = b < p.B;
+  const bool fm = p.dy2 != nullptr;
+  int rid[kEbFPW];
+  float4 Ev[kEbFPW][4];
+#pragma unroll
+  for (int t = 0; t < kEbFPW; ++t) {
+    const int f = f0 + sub + 2 * t;
+    rid[t] = (live && f < p.F) ? __ldg(p.rows + static_cast<size_t>(b) * p.F + f) : -1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      Ev[t][c] = (fm && live && f < p.F)
+                     ? ldg4(p.E + (static_cast<size_t>(b) * p.F + f) * kEtD + 4 * c) : f4_zero();
+  }
+  float4 Sv[4];
+  float d2 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) Sv[c] = (fm && live) ? ldg4(p.S + static_cast<size_t>(b) * kEtD + 4 * c) : f4_zero();
+  if (live) {
+    if (fm) d2 = __ldg(p.dy2 + b);
+    if (p.dy1 != nullptr) d1 = __ldg(p.dy1 + b);
+  }
+
+  if (tid == 0) {
+    // ------------------------------------------------ TMA producer: the remaining B stages
+    for (int kb = 2; kb < p.nkb; ++kb) {
+      const uint32_t st = kb & 1, ph = (kb >> 1) & 1;
+      mbar_wait(&b_empty[st], ph ^ 1);
+      mbar_expect_tx(&b_full[st], kEbBStage);
+      uint8_t* sb = b_ring + static_cast<size_t>(st) * kEbBStage;
+      tma_load_2d(sb, &tmW, kb * kTcKB, f0 * kEtD, &b_full[st]);
+      tma_load_2d(sb + kEbBStage / 2, &tmWlo, kb * kTcKB, f0 * kEtD, &b_full[st]);
+    }
+  } else if (tid == 32) {
+    // -------------------------------------------------------------------- MMA issuer
+    uint32_t accum = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const uint32_t st = kb & 1, ph = (kb >> 1) & 1;
+      mbar_wait(&a_full[kb], 0);
+      mbar_wait(&b_full[st], ph);
+      tc_fence_after();
+      const uint32_t ah = smem_u32(a_all + static_cast<size_t>(kb) * 2 * kTcABytes);
+      const uint32_t al = ah + kTcABytes;
+      const uint32_t bh = smem_u32(b_ring + static_cast<size_t>(st) * kEbBStage);
+      const uint32_t bl = bh + kEbBStage / 2;
+      const int ks = kb == p.nkb - 1 ? p.last_ksteps : 4;
+      for (int k = 0; k < ks; ++k) {
+        tc_mma_tf32(tmem_base, p.desc_k | (((ah + k * 32) >> 4) & 0x3FFF),
+                    p.desc_k | (((bh + k * 32) >> 4) & 0x3FFF), p.idesc, accum);
+        accum = 1;
+      }
+      for (int k = 0; k < ks; ++k)   // (lo, hi)
+        tc_mma_tf32(tmem_base, p.desc_k | (((al + k * 32) >> 4) & 0x3FFF),
+                    p.desc_k | (((bh + k * 32) >> 4) & 0x3FFF), p.idesc, 1);
+      for (int k = 0; k < ks; ++k)   // (hi, lo)
+        tc_mma_tf32(tmem_base, p.desc_k | (((ah + k * 32) >> 4) & 0x3FFF),
+                    p.desc_k | (((bl + k * 32) >> 4) & 0x3FFF), p.idesc, 1);
+      tc_commit(&b_empty[st]);
+    }
+    tc_commit(t_full);
+  }
+  __syncwarp();
+
+  // ----------------------------------------------------------------------- epilogue
+  if (stamp) p.timing[1] = gtime_ns();
+  mbar_wait(t_full, 0);
+  tc_fence_after();
+  if (stamp) p.timing[2] = gtime_ns();
+  // warp-private tile for the <= 32-row fields: [32 rows][16 + 4] floats, in the retired A region
+  float* tileb = reinterpret_cast<float*>(a_all) + warp * (32 * 20 + 64);
+  float* tw1 = tileb + 32 * 20;
+  int* tcnt = reinterpret_cast<int*>(tw1 + 32);
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+  for (int t = 0; t < kEbFPW; ++t) {
+    const int j = sub + 2 * t, f = f0 + j;
+    if (f < p.F) {                                             // warp-uniform
+      float x[16];
+      tc_ld<16>(taddr + j * kEtD, x);
+      float4 g[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        g[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+        const float4 ev = Ev[t][c];
+        g[c].x = fmaf(d2, Sv[c].x - ev.x, g[c].x);
+        g[c].y = fmaf(d2, Sv[c].y - ev.y, g[c].y);
+        g[c].z = fmaf(d2, Sv[c].z - ev.z, g[c].z);
+        g[c].w = fmaf(d2, Sv[c].w - ev.w, g[c].w);
+      }
+      const bool has_w1 = p.dw1 != nullptr && p.dy1 != nullptr && ((p.w1_fields >> f) & 1ull);
+      const int r = rid[t];
+      float gw = has_w1 ? d1 : 0.f;
+      if ((p.tiny_fields >> f) & 1ull) {
+        // every row of the field fits the tile: sum the warp's 32 slots per row, lanes that hit the
+        // same row take turns (rank inside their __match_any_sync group)
+        const int lid = r >= 0 ? r - p.off[f] : -1;
+        for (int i = lane; i < 32 * 20 / 4; i += 32) reinterpret_cast<float4*>(tileb)[i] = f4_zero();
+        tw1[lane] = 0.f;
+        tcnt[lane] = 0;
+        __syncwarp();
+        const unsigned peers = __match_any_sync(0xffffffffu, lid >= 0 ? lid : -1 - lane);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int rounds = __reduce_max_sync(0xffffffffu, lid >= 0 ? rank : 0) + 1;
+        for (int k = 0; k < rounds; ++k) {
+          if (lid >= 0 && rank == k) {
+            float4* dst = reinterpret_cast<float4*>(tileb + lid * 20);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = f4_add(dst[c], g[c]);
+            tw1[lid] += gw;
+            tcnt[lid] += 1;
+          }
+          __syncwarp();
+        }
+        // flush: 4 lanes per row (one 64-byte RED group per row and instruction)
+        const int nrow = p.off[f + 1] - p.off[f];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int lr = 8 * k + (lane >> 2), cc = lane & 3;
+          if (lr < nrow && tcnt[lr] > 0) {
+            red_add_v4(p.dtable + static_cast<size_t>(p.off[f] + lr) * p.ld_g + 4 * cc,
+                       *reinterpret_cast<const float4*>(tileb + lr * 20 + 4 * cc));
+            if (has_w1 && cc == 0) red_add_f32(p.dw1 + static_cast<size_t>(p.off[f] + lr) * p.ld_w, tw1[lr]);
+          }
+        }
+        __syncwarp();
+      } else {
+        // large field: duplicates inside the warp are rare - sum them into the first lane of the group
+        const unsigned peers = __match_any_sync(0xffffffffu, r >= 0 ? r : -1 - lane);
+        const bool leader = (peers & ((1u << lane) - 1u)) == 0u;
+        if (__reduce_max_sync(0xffffffffu, __popc(peers)) > 1) {
+          unsigned rest = peers & ~(1u << lane);
+          while (__ballot_sync(0xffffffffu, rest != 0u) != 0u) {
+            const int src = rest != 0u ? __ffs(rest) - 1 : lane;
+            const bool ok = rest != 0u && leader;
+            rest &= rest - 1u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 o = f4_shfl(g[c], src);
+              if (ok) g[c] = f4_add(g[c], o);
+            }
+            const float ow = __shfl_sync(0xffffffffu, gw, src);
+            if (ok) gw += ow;
+          }
+        }
+        // through the warp's tile, so that 4 lanes RED one row's 64 bytes in ONE instruction (one
+        // L2 transaction per row instead of four half-sector ones)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(tileb + lane * 20 + 4 * c) = g[c];
+        __syncwarp();
+        const int r_eff = (r >= 0 && leader) ? r : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int src = 8 * k + (lane >> 2), cc = lane & 3;
+          const int rk = __shfl_sync(0xffffffffu, r_eff, src);
+          const float gwk = __shfl_sync(0xffffffffu, gw, src);
+          if (rk >= 0) {
+            red_add_v4(p.dtable + static_cast<size_t>(rk) * p.ld_g + 4 * cc,
+                       *reinterpret_cast<const float4*>(tileb + src * 20 + 4 * cc));
+            if (has_w1 && cc == 0) red_add_f32(p.dw1 + static_cast<size_t>(rk) * p.ld_w, gwk);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (stamp) p.timing[3] = gtime_ns();
+  tc_fence_before();
+  __syncthreads();
+  if (stamp) p.timing[4] = gtime_ns();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
+                 : "memory");
+  }
+}
+
 }  // namespace ctr
 
 using namespace ctr;
@@ -466,20 +760,21 @@ int ctr_embed_tower_timing(uint64_t* timing_dev) {
 
 int ctr_embed_tower_fwd(const float* table, const float* w1, const float* xcont, int n_cont,
                         const int64_t* xcat, int n_cat, const ctr_field_desc* fields_dev,
-                        const float* boundaries_dev, int n_boundaries, int32_t* rows_out,
-                        int32_t* status, int B,
+                        const float* boundaries_dev, int n_boundaries, const int32_t* rows_in,
+                        int32_t* rows_out, int32_t* status, int B,
                         int F, int D, uint64_t w1_fields, float* E, float* E_lo, float* S, float* y1,
                         float* y2, int64_t row_stride, int64_t w1_stride, const float* W0,
                         const float* W0_lo, const float* b0, int N, float* act0, float* stats_part,
                         float* zero_buf, int64_t zero_n, ctr_stream_t stream) {
   const char* fn = "ctr_embed_tower_fwd";
   CTR_ARCH_OR_RETURN();
-  CTR_REQUIRE(table && fields_dev && rows_out && E && W0 && W0_lo && b0 && act0, fn, "null pointer");
+  CTR_REQUIRE(table && (rows_in || (fields_dev && rows_out)) && E && W0 && W0_lo && b0 && act0, fn,
+              "null pointer");
   CTR_REQUIRE(D == kEtD, fn, "D must be 16");
   CTR_REQUIRE(B >= 0 && F > 0 && F <= kEtKS * kEtMaxFPC, fn, "need 0 < F <= 40");
   CTR_REQUIRE(N >= 16 && N <= 128 && (N & 3) == 0, fn, "need 16 <= N <= 128, N % 4 == 0");
-  CTR_REQUIRE(n_cont == 0 || (xcont && boundaries_dev), fn, "null xcont/boundaries");
-  CTR_REQUIRE(n_cat == 0 || xcat, fn, "null xcat");
+  CTR_REQUIRE(rows_in || n_cont == 0 || (xcont && boundaries_dev), fn, "null xcont/boundaries");
+  CTR_REQUIRE(rows_in || n_cat == 0 || xcat, fn, "null xcat");
   CTR_REQUIRE(n_boundaries >= 0 && n_boundaries <= 512, fn, "at most 512 bucket boundaries in total");
   CTR_REQUIRE(y1 == nullptr || w1 != nullptr, fn, "y1 requested without w1");
   CTR_REQUIRE(aligned16(table) && aligned16(E) && aligned16(E_lo) && aligned16(S) && aligned16(W0) &&
@@ -495,7 +790,7 @@ int ctr_embed_tower_fwd(const float* table, const float* w1, const float* xcont,
   EtParams p{};
   p.table = table; p.w1 = w1; p.ld = row_stride; p.ld1 = w1_stride; p.w1_fields = w1_fields;
   p.xcont = xcont; p.xcat = reinterpret_cast<const long long*>(xcat); p.fields = fields_dev;
-  p.bnd = boundaries_dev; p.n_cont = n_cont; p.n_cat = n_cat; p.n_bnd = n_boundaries; p.rows_out = rows_out; p.status = status;
+  p.bnd = boundaries_dev; p.n_cont = n_cont; p.n_cat = n_cat; p.n_bnd = n_boundaries; p.rows_in = rows_in; p.rows_out = rows_out; p.status = status;
   p.E = E; p.E_lo = E_lo; p.S = S; p.y1 = y1; p.y2 = y2; p.bias = b0; p.act0 = act0;
   p.stats_part = stats_part; p.zero_buf = zero_n > 0 ? zero_buf : nullptr; p.zero_n4 = zero_n >> 2;
   p.B = B; p.F = F; p.N = N; p.NT = (N + 15) / 16 * 16;
@@ -539,6 +834,57 @@ int ctr_embed_tower_fwd(const float* table, const float* w1, const float* xcont,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return check_cuda(cudaLaunchKernelEx(&cfg, embed_tower_fwd_kernel, tW, tWlo, p), fn);
+}
+
+int ctr_tower_embed_bwd(const float* dpre0, const float* dpre0_lo, const float* W0, const float* W0_lo,
+                        int N, const int32_t* rows, const float* E, const float* S, const float* dy2,
+                        const float* dy1, uint64_t w1_fields, const int64_t* row_offsets_host, int B,
+                        int F, int D, float* dtable, float* dw1, int64_t row_stride, int64_t w1_stride,
+                        ctr_stream_t stream) {
+  const char* fn = "ctr_tower_embed_bwd";
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(dpre0 && dpre0_lo && W0 && W0_lo && rows && dtable && row_offsets_host, fn, "null pointer");
+  CTR_REQUIRE(D == kEtD, fn, "D must be 16");
+  CTR_REQUIRE(B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, fn, "need 0 < F <= 64");
+  CTR_REQUIRE(N >= 16 && N <= 32 * kEbMaxKB && (N & 3) == 0, fn, "need 16 <= N <= 128, N % 4 == 0");
+  CTR_REQUIRE(!dy2 || (S && E), fn, "dy2 needs S and E");
+  CTR_REQUIRE(aligned16(dpre0) && aligned16(dpre0_lo) && aligned16(W0) && aligned16(W0_lo) &&
+                  aligned16(E) && aligned16(S) && aligned16(dtable),
+              fn, "pointers must be 16-byte aligned");
+  CTR_REQUIRE(row_offsets_host[F] < (1LL << 31), fn, "table too large for int32 rows");
+  if (row_stride <= 0) row_stride = D;
+  if (w1_stride <= 0) w1_stride = 1;
+  CTR_REQUIRE(row_stride >= D && (row_stride & 3) == 0, fn,
+              "row_stride must be >= D and a multiple of 4 floats");
+  if (B == 0) return CTR_OK;
+  EbParams p{};
+  p.rows = rows; p.E = E; p.S = S; p.dy2 = dy2; p.dy1 = dy1; p.dtable = dtable; p.dw1 = dw1;
+  p.ld_g = row_stride; p.ld_w = w1_stride; p.w1_fields = w1_fields; p.B = B; p.F = F; p.H = N;
+  for (int f = 0; f <= F; ++f) p.off[f] = static_cast<int>(row_offsets_host[f]);
+  for (int f = 0; f < F; ++f)
+    if (p.off[f + 1] - p.off[f] <= 32) p.tiny_fields |= 1ull << f;
+  p.nkb = (N + kTcKB - 1) / kTcKB;
+  p.last_ksteps = (N - (p.nkb - 1) * kTcKB + 7) / 8;
+  p.idesc = cin_idesc(kEbNT);
+  p.desc_k = cin_desc_hi();
+  p.timing = g_et_timing;
+  CUtensorMap tA, tAlo, tW, tWlo;
+  int r = make_map(&tA, dpre0, B, N, N, kTcBM);
+  if (r == CTR_OK) r = make_map(&tAlo, dpre0_lo, B, N, N, kTcBM);
+  if (r == CTR_OK) r = make_map(&tW, W0, static_cast<long long>(F) * D, N, N, kEbNT);
+  if (r == CTR_OK) r = make_map(&tWlo, W0_lo, static_cast<long long>(F) * D, N, N, kEbNT);
+  if (r != CTR_OK) return r;
+  const size_t smem = static_cast<size_t>(kEbMaxKB) * 2 * kTcABytes + 2 * kEbBStage + 256 + 1024;
+  static bool optin = false;
+  if (!optin) {
+    cudaFuncSetAttribute(tower_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         227 * 1024);
+    optin = true;
+  }
+  dim3 grid((B + kTcBM - 1) / kTcBM, (F + kEbFPC - 1) / kEbFPC);
+  tower_embed_bwd_kernel<<<grid, kEbThreads, smem, static_cast<cudaStream_t>(stream)>>>(tA, tAlo, tW, tWlo,
+                                                                                         p);
+  return check_cuda(cudaGetLastError(), fn);
 }
 
 }  // extern "C"

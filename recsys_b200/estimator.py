@@ -233,14 +233,17 @@ class GraphedTrainStep:
         self._loss_read.record(self.stream)
         self._slot = 0          # the buffer the next batch goes to
         self._last = 0          # the buffer of the latest batch
+        self._prefetch = None   # the model's id pipeline, run on the copy stream (_find_prefetcher)
         for k in range(self.nbuf):
             self._slot = k
             self._load(example_features, example_labels)
         self._slot = 0
         self.stream.wait_stream(self.copy_stream)
         with torch.cuda.stream(self.stream):
-            for _ in range(warmup):                 # allocator + lazy-init warm-up, eager
+            for w in range(max(warmup, 1)):         # allocator + lazy-init warm-up, eager
                 self._eager(0)
+                if w == 0:
+                    self._find_prefetcher()         # the model object exists after its first call
         self.stream.synchronize()
         import gc
         gc.collect()
@@ -253,6 +256,25 @@ class GraphedTrainStep:
             self.graphs.append(g)
             self.stream.synchronize()
         self.graph = self.graphs[0]
+
+    def _find_prefetcher(self):
+        """A model with a ``prefetch_ids(features)`` method gets the id pipeline of batch s+1 run on
+        the copy stream, right behind the batch's copy and beside the compute of step s: the step's
+        lookup kernel then starts from ready [B, F] ids (``PackedFeatures.rows``)."""
+        if not self._packed or os.environ.get("CTR_PREFETCH_IDS", "1") == "0":
+            return
+        cands = [m for m in store_of(self.params)._objs.values() if hasattr(m, "prefetch_ids")]
+        if len(cands) != 1 or not hasattr(cands[0], "F"):
+            return
+        m = cands[0]
+        for f in self._features:
+            B = (f.cat if f.cat is not None else f.cont).shape[0]
+            f.rows = torch.empty((B, m.F), dtype=torch.int32, device=self._blobs[0].device)
+        if all(m.prefetch_ids(f) for f in self._features):
+            self._prefetch = m.prefetch_ids
+        else:
+            for f in self._features:
+                f.rows = None
 
     # buffer 0's views under the old names (tests, callers that fill the static inputs themselves)
     @property
@@ -309,6 +331,8 @@ class GraphedTrainStep:
         with torch.cuda.stream(cs):
             for key, t in src.items():
                 dst[key].copy_(t, non_blocking=True)
+            if self._prefetch is not None:
+                self._prefetch(self._features[k])
             self._ready[k].record(cs)
         return k
 
@@ -345,6 +369,8 @@ class GraphedTrainStep:
         cs.wait_event(self._free[k])
         with torch.cuda.stream(cs):
             self._blobs[k].copy_(blob, non_blocking=True)
+            if self._prefetch is not None:
+                self._prefetch(self._features[k])
             self._ready[k].record(cs)
         return self._replay(k)
 

@@ -49,6 +49,9 @@ class PackedFeatures(dict):
         super().__init__()
         self.cont, self.cat = cont, cat
         self.cont_keys, self.cat_keys = list(cont_keys), list(cat_keys)
+        # optional: the [B, F] row ids of this batch, computed ahead of the step
+        # (estimator.GraphedTrainStep runs the model's ``prefetch_ids`` on its copy stream)
+        self.rows = None
         for j, k in enumerate(self.cont_keys):
             self[k] = cont[:, j:j + 1]
         for j, k in enumerate(self.cat_keys):
@@ -160,10 +163,11 @@ class IdPipeline:
         flat = [bytes(v) for v in _flatten(values)]
         return hash_strings(flat, self.lay.rows[f], self.device)
 
-    def __call__(self, features, want_logx: bool = False):
+    def __call__(self, features, want_logx: bool = False, out: Optional[torch.Tensor] = None):
         cont, cat = self.pack(features)
         B = (cont if cont is not None else cat).shape[0]
-        rows = torch.empty((B, self.lay.F), dtype=torch.int32, device=self.device)
+        rows = out if out is not None else \
+            torch.empty((B, self.lay.F), dtype=torch.int32, device=self.device)
         logx = torch.empty((B, len(self.cont_keys)), dtype=torch.float32, device=self.device) \
             if want_logx else None
         _call("ctr_criteo_rows", _p(cont), len(self.cont_keys), _p(cat), len(self.cat_keys),
@@ -223,7 +227,7 @@ class TFAdamState:
         self.t = 0
         self.state = None
         if device is not None:
-            self.state = torch.zeros(4, dtype=torch.float32, device=device)
+            self.state = torch.zeros(8, dtype=torch.float32, device=device)
             self.reset()
 
     def reset(self):
@@ -270,6 +274,10 @@ class DenseParams:
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.frozen = set(frozen)
+        # parameters whose 3xTF32 lo half was written by the latest optimiser launch (adam_step(lo=))
+        # and is still valid; ``load`` - the other way parameters change - clears it
+        self.lo_fresh = set()
+        self.lo_targets: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, torch.Tensor] = {}
         for n in self.names:
             o, sz = self.slots[n]
@@ -286,11 +294,18 @@ class DenseParams:
         return n in self.views
 
     def load(self, state: Dict[str, torch.Tensor]):
+        self.lo_fresh.clear()
         with torch.no_grad():
             for n in self.names:
                 if n in state:
                     self.views[n].copy_(state[n].to(self.flat.device, torch.float32)
                                         .reshape(self.shapes[n]))
+        # registered lo halves are rebuilt right away: a step graph captured earlier contains no
+        # split launch of its own
+        for n, dst in self.lo_targets.items():
+            if self.flat.is_cuda:
+                _call("ctr_split_lo", _p(self.views[n]), _p(dst), dst.numel(), _stream())
+                self.lo_fresh.add(n)
 
     def grads(self) -> Dict[str, torch.Tensor]:
         return {n: self.views[n].grad for n in self.names if n not in self.frozen}
@@ -298,11 +313,20 @@ class DenseParams:
     def zero_grad(self):
         self.grad.zero_()
 
-    def adam_step(self, lr_t, st: TFAdamState):
+    def adam_step(self, lr_t, st: TFAdamState, parties: int = 1, lo=None):
         """One launch over the flat buffer; frozen slots have zero gradient and
-        zero moments, so the rule leaves them untouched."""
-        _call("ctr_adam_dense", _p(self.flat), _p(self.m), _p(self.v), _p(self.grad), self.numel,
-              lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, 1, _stream())   # ends the step
+        zero moments, so the rule leaves them untouched.  ``parties``: optimiser kernels that end
+        the step together (the last one to finish advances the device schedule).  ``lo`` =
+        (name, dst): also write the 3xTF32 lo half of the updated parameter ``name`` to ``dst``."""
+        lo_dst, lo_beg, lo_n = None, 0, 0
+        self.lo_fresh.clear()
+        if lo is not None:
+            name, lo_dst = lo
+            lo_beg, lo_n = self.slots[name]
+            self.lo_fresh.add(name)
+        _call("ctr_adam_dense_ex", _p(self.flat), _p(self.m), _p(self.v), _p(self.grad), self.numel,
+              lr_t, st.beta1, st.beta2, st.eps, 1, st.state_ptr, parties, _p(lo_dst), lo_beg, lo_n,
+              _stream())   # ends the step
 
 
 # ------------------------------------------------------- fused multi-field lookup
@@ -420,10 +444,22 @@ class FieldEmbedding:
             return (rows, logx) + tuple(self.lookup(rows, **kw))
         cont, cat = idp.pack(features)
         B = (cont if cont is not None else cat).shape[0]
-        rows = torch.empty((B, self.F), dtype=torch.int32, device=self.device)
+        pre = getattr(features, "rows", None)
+        if pre is not None and not want_logx:
+            # ids computed ahead of the step: the lookup takes them as they are (the plain kernel
+            # stages them by TMA; the fused lookup + first layer kernel reads them directly)
+            if tower0 is None:
+                if zero_buf is not None:
+                    zero_buf.zero_()
+                return (pre, None) + tuple(self.lookup(pre, **kw))
+            rows = pre
+        else:
+            pre = None
+            rows = torch.empty((B, self.F), dtype=torch.int32, device=self.device)
         logx = torch.empty((B, len(idp.cont_keys)), dtype=torch.float32, device=self.device) \
             if want_logx else None
         self._raw = (idp, cont, cat, logx, zero_buf)
+        self._rows_in = pre
         # tower0 = FusedTower: its first layer is computed by the lookup kernel itself
         # (ctr_embed_tower_fwd); the result is left in ``tower0.l0`` for ``tower_head``
         self._tower0 = tower0 if (tower0 is not None and not want_logx) else None
@@ -461,9 +497,10 @@ class FieldEmbedding:
         self._fused = (lr_t, st, done)
         return True
 
-    def adam_step(self, rows: torch.Tensor, lr_t: float, st: TFAdamState):
+    def adam_step(self, rows: torch.Tensor, lr_t: float, st: TFAdamState, parties: int = 0):
         """Consume (and re-zero) the accumulated gradients.  ``lazy``: one update per
-        touched row (LazyAdam); ``exact_tf``: every row, as TF's sparse apply does."""
+        touched row (LazyAdam); ``exact_tf``: every row, as TF's sparse apply does.  ``parties`` > 0:
+        this launch is one of that many optimiser kernels ending the step together (lazy only)."""
         if self._fused_done:          # the backward already applied the update (ctr_embed_bwd_adam)
             self._fused_done = False
             return
@@ -489,12 +526,13 @@ class FieldEmbedding:
                   _p(self._m), _p(self._v), _p(self.dtable), _p(self.w1) if w else None,
                   _p(self._m1) if w else None, _p(self._v1) if w else None,
                   _p(self.dw1) if w else None, _p(self._claim), self._tag, lr_t, st.beta1, st.beta2,
-                  st.eps, st.state_ptr, self.ld, self.ld1, self.ldc, _stream())
+                  st.eps, st.state_ptr, self.ld, self.ld1, self.ldc, parties, _stream())
             return
-        _call("ctr_adam_rows", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
+        _call("ctr_adam_rows_ex", _p(rows), n, self.D, _p(self.table), _p(self._m), _p(self._v),
               _p(self.dtable), _p(self.w1) if w else None, _p(self._m1) if w else None,
               _p(self._v1) if w else None, _p(self.dw1) if w else None, _p(self._claim), self._tag,
-              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, self.ld, self.ld1, self.ldc, _stream())
+              lr_t, st.beta1, st.beta2, st.eps, st.state_ptr, self.ld, self.ld1, self.ldc, parties,
+              _stream())
 
 
 class _EmbedFn(torch.autograd.Function):
@@ -506,6 +544,7 @@ class _EmbedFn(torch.autograd.Function):
         B, F, D = rows.shape[0], emb.F, emb.D
         dev = rows.device
         rows = rows.contiguous()
+        ctx.tw0 = None
         E = torch.empty((B, F * D), dtype=torch.float32, device=dev)
         S = torch.empty((B, D), dtype=torch.float32, device=dev) if want_fm else None
         y2 = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
@@ -526,11 +565,13 @@ class _EmbedFn(torch.autograd.Function):
             parts = torch.empty((nparts, 2, N), dtype=torch.float32, device=dev)
             tw0.wait_w0_lo()
             _call("ctr_embed_tower_fwd", _p(emb.table), _p(emb.w1), _p(cont), len(idp.cont_keys),
-                  _p(cat), len(idp.cat_keys), _p(idp.fields_dev), _p(idp.bnd_dev), idp.n_bnd, _p(rows),
+                  _p(cat), len(idp.cat_keys), _p(idp.fields_dev), _p(idp.bnd_dev), idp.n_bnd,
+                  _p(getattr(emb, "_rows_in", None)), _p(rows),
                   _p(idp.status), B, F, D, emb.w1_fields, _p(E), _p(E_lo), _p(S), _p(y1), _p(y2),
                   emb.ld, emb.ld1, _p(tw0.P("0.w")), _p(tw0.w0_lo), _p(tw0.P("0.b")), N, _p(act0),
                   _p(parts), _p(zbuf), zbuf.numel() if zbuf is not None else 0, _stream())
             tw0.l0 = (act0, parts)
+            ctx.tw0 = tw0
         elif raw is not None:       # id pipeline fused in front: fills ``rows`` (and logx) as well
             idp, cont, cat, logx, zbuf = raw
             _call("ctr_embed_fwd_raw", _p(emb.table), _p(emb.w1), _p(cont), len(idp.cont_keys),
@@ -568,9 +609,28 @@ class _EmbedFn(torch.autograd.Function):
             _call("ctr_dcn_cross_bwd", _p(E), _p(ctx.cross_w), _p(ctx.cross_b), L, B, W,
                   _p(dxl.contiguous()), _p(dx0), _p(dcw), _p(dcb), _stream())
             dE = dx0 if dE is None else dE + dx0
-        dE = None if dE is None else dE.contiguous()
         dy2 = dy2.contiguous() if (want_fm and dy2 is not None) else None
         dy1 = dy1.contiguous() if (want_y1 and dy1 is not None) else None
+        tw0 = ctx.tw0
+        bwd0 = getattr(tw0, "bwd0", None) if tw0 is not None else None
+        if bwd0 is not None:
+            # the tower left dpre0 instead of dE: first-layer data gradient + scatter-add in one
+            # launch (ctr_tower_embed_bwd); ``dE`` is a placeholder
+            tw0.bwd0 = None
+            dpre0, dpre0_lo, after_scatter = bwd0
+            if emb._fused is not None:      # one-pass scatter + optimiser armed: it wants dE itself
+                dE = torch.empty((B, F * D), dtype=torch.float32, device=rows.device)
+                _call("ctr_tower_gemm_presplit", 1, _p(dpre0), _p(dpre0_lo), _p(tw0.P("0.w")),
+                      _p(tw0.w0_lo), B, F * D, tw0.sizes[1], _p(dE), None, None, 0, _stream())
+                after_scatter()
+                bwd0 = None
+        if bwd0 is not None:
+            _call("ctr_tower_embed_bwd", _p(dpre0), _p(dpre0_lo), _p(tw0.P("0.w")), _p(tw0.w0_lo),
+                  tw0.sizes[1], _p(rows), _p(E), _p(S), _p(dy2), _p(dy1), emb.w1_fields,
+                  emb._offsets_host, B, F, D, _p(emb.dtable), _p(emb.dw1), emb.ld, emb.ld1, _stream())
+            after_scatter()
+            return None, None, None, None, None, dcw, dcb
+        dE = None if dE is None else dE.contiguous()
         fused, emb._fused = emb._fused, None
         if fused is not None and (dE is not None or dy2 is not None):
             lr_t, st, counted = fused
@@ -833,8 +893,13 @@ class FusedTower:
         self.w0_lo = torch.zeros(self.sizes[0] * self.sizes[1], dtype=torch.float32,
                                  device=dense.flat.device)
         self._w0_ready = None
+        self._w0_fresh = False
+        dense.lo_targets[prefix + ".0.w"] = self.w0_lo
         self._ws = None
         self.l0 = None          # (act0, stats_part) left by the fused lookup + first layer kernel
+        self.bwd0 = None        # (dpre0, dpre0_lo) left for the fused data-gradient + scatter kernel
+        self._zero = torch.zeros((), dtype=torch.float32, device=dense.flat.device)
+        self.fuse_bwd0 = os.environ.get("CTR_FUSED_BWD0", "1") != "0" and self.sizes[1] <= 128
 
     def can_fuse_l0(self, F: int, D: int) -> bool:
         """The first layer can be computed inside the lookup kernel (ctr_embed_tower_fwd)."""
@@ -845,8 +910,9 @@ class FusedTower:
         """The current stream waits for the hi/lo split of the first layer's weights."""
         if self._w0_ready is None:
             self._begin_split()
-        torch.cuda.current_stream().wait_event(self._w0_ready)
-        self._w0_ready = None
+        if self._w0_ready is not None:
+            torch.cuda.current_stream().wait_event(self._w0_ready)
+            self._w0_ready = None
 
     @property
     def use_mid(self):
@@ -886,6 +952,13 @@ class FusedTower:
     def _begin_split(self):
         if not self.use_presplit:
             return
+        if (self.prefix + ".0.w") in self.dense.lo_fresh:
+            # the optimiser launch that updated W0 wrote its lo half as well (ordered before
+            # everything of this step by the end-of-step join): nothing to launch, nothing to wait for
+            self._w0_ready = None
+            self._w0_fresh = True
+            return
+        self._w0_fresh = False
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
@@ -1101,10 +1174,7 @@ class _TowerHeadFn(torch.autograd.Function):
         if l0 is not None:          # the lookup kernel has already produced act0 and its column sums
             acts[0] = l0[0]
         elif presplit:
-            if tw._w0_ready is None:
-                tw.begin_step()
-            torch.cuda.current_stream().wait_event(tw._w0_ready)
-            tw._w0_ready = None
+            tw.wait_w0_lo()
             if splitk:      # partial sums only; bias / ReLU / column sums happen in ctr_tower_mid
                 _call("ctr_tower_gemm_presplit", 3, _p(X), _p(X_lo), _p(tw.P("0.w")), _p(tw.w0_lo),
                       B, tw.sizes[0], Hs[0], _p(pre0), None, None, 0, _stream())
@@ -1188,20 +1258,57 @@ class _TowerHeadFn(torch.autograd.Function):
             g.G, g.ldg, g.a, g.lda, g.kind, g.train, g.eps = _p(G), H, None, 0, 2, 1, BN_EPS
             return g
 
-        with torch.cuda.stream(side):       # dW_l = P(a_{l-1})^T . dpre_l, off the critical path
+        fuse_bwd0 = presplit and ctx.l0 is not None and tw.fuse_bwd0
+
+        def dw0_presplit():
+            _call("ctr_tower_gemm_presplit", 2, _p(X), _p(X_lo), _p(dpre[0]), _p(dpre0_lo),
+                  B, tw.sizes[0], tw.sizes[1], _p(tw.G("0.w")), None, None, 0, side.cuda_stream)
+
+        defer_all = fuse_bwd0 and os.environ.get("CTR_DW_DEFER", "all") == "all"
+
+        def dw_hidden():
             for l in range(L):
                 H, K = tw.sizes[l + 1], tw.sizes[l]
                 if l == 0 and presplit:
-                    _call("ctr_tower_gemm_presplit", 2, _p(X), _p(X_lo), _p(dpre[0]), _p(dpre0_lo),
-                          B, K, H, _p(tw.G("0.w")), None, None, 0, side.cuda_stream)
+                    if not fuse_bwd0:
+                        dw0_presplit()
                     continue
                 gs = grad_src(dpre[l], H)
                 xin = acts[l - 1] if l > 0 else X
                 pro = C.byref(tw.bn_drop(l - 1, stats[l - 1], True)) if l > 0 else None
                 _call("ctr_tower_layer_bwd_weights", _p(xin), K, K, pro, C.byref(gs), H,
                       _p(tw.G("%d.w" % l)), None, B, side.cuda_stream)
+
+        if not defer_all:
+            with torch.cuda.stream(side):   # dW_l = P(a_{l-1})^T . dpre_l, off the critical path
+                dw_hidden()
         H0, K0 = tw.sizes[1], tw.sizes[0]
         gs0 = grad_src(dpre[0], H0)
+        if fuse_bwd0:
+            # dX = dpre0 . W0^T is formed inside the embedding's scatter kernel (ctr_tower_embed_bwd).
+            # Both that kernel and the first layer's weight-gradient GEMM want (nearly) a whole SM's
+            # shared memory: the GEMM is queued behind the scatter kernel (``after_scatter``), beside
+            # the row optimiser, and only the small hidden-layer kernels run next to the scatter.
+            for t_ in dpre + acts + [X, ws, X_lo, dpre0_lo]:
+                t_.record_stream(side)
+
+            def after_scatter():
+                ev2 = torch.cuda.Event()
+                ev2.record(torch.cuda.current_stream())
+                side.wait_event(ev2)
+                with torch.cuda.stream(side):
+                    dw0_presplit()
+                    if defer_all:
+                        dw_hidden()
+                    done = torch.cuda.Event()
+                    done.record(side)
+                tw._pending = done
+
+            tw.bwd0 = (dpre[0], dpre0_lo, after_scatter)
+            done = torch.cuda.Event()
+            done.record(side)
+            tw._pending = done
+            return (tw._zero.expand(B, K0), None, None, None, None, None, None) + tuple(dzs)
         dX = torch.empty((B, K0), dtype=torch.float32, device=dev)
         if presplit:
             _call("ctr_tower_gemm_presplit", 1, _p(dpre[0]), _p(dpre0_lo), _p(tw.P("0.w")),

@@ -40,7 +40,7 @@ def main():
     def bf(r):
         lib.ctr_adam_rows_bf(p(r), B, F, D, p(emb.table), p(emb._m), p(emb._v), p(emb.dtable),
                              p(emb.w1), p(emb._m1), p(emb._v1), p(emb.dw1), p(emb._claim), 0, 1e-3,
-                             0.9, 0.999, 1e-8, st.state_ptr, emb.ld, emb.ld1, emb.ldc, s.cuda_stream)
+                             0.9, 0.999, 1e-8, st.state_ptr, emb.ld, emb.ld1, emb.ldc, 0, s.cuda_stream)
 
     def timeit(fn):
         with torch.cuda.stream(s):

@@ -44,7 +44,7 @@ def main():
     def fused(i):
         cont, cat = packs[i % 8]
         rc = lib.ctr_embed_tower_fwd(p(emb.table), p(emb.w1), p(cont), len(pipe.cont_keys), p(cat),
-                                     len(pipe.cat_keys), p(pipe.fields_dev), p(pipe.bnd_dev), pipe.n_bnd, p(rows),
+                                     len(pipe.cat_keys), p(pipe.fields_dev), p(pipe.bnd_dev), pipe.n_bnd, None, p(rows),
                                      p(pipe.status), B, F, D, emb.w1_fields, p(E), p(E_lo), p(S), p(y1),
                                      p(y2), emb.ld, emb.ld1, p(W0), p(W0_lo), p(b0), N, p(act0), p(parts),
                                      p(zbuf), zbuf.numel(), s.cuda_stream)
@@ -78,8 +78,43 @@ def main():
 
     print("embed_fwd_raw (ids + lookup + E_lo) alone: %.2f us" % timeit(unfused))
     print("embed_tower_fwd alone: %.2f us" % timeit(fused))
+    # ---- the fused backward (dE GEMM + scatter) alone
+    dpre0 = torch.randn(B, N, device=dev) * 1e-3
+    dpre0_lo = ops.split_lo(dpre0)
+    dy = torch.randn(B, device=dev) * 1e-3
+    rows_b = []
+    for i in range(8):
+        fused(i)
+        rows_b.append(rows.clone())
+    s.synchronize()
+
+    def fbwd(i):
+        rc = lib.ctr_tower_embed_bwd(p(dpre0), p(dpre0_lo), p(W0), p(W0_lo), N, p(rows_b[i % 8]), p(E),
+                                     p(S), p(dy), p(dy), emb.w1_fields, emb._offsets_host, B, F, D,
+                                     p(emb.dtable), p(emb.dw1), emb.ld, emb.ld1, s.cuda_stream)
+        assert rc == 0, _lib.last_error()
+
+    dE = torch.randn(B, F * D, device=dev) * 1e-3
+
+    def ubwd(i):
+        lib.ctr_embed_bwd(p(rows_b[i % 8]), p(dE), p(E), p(emb.table), p(S), p(dy), p(dy), emb.w1_fields,
+                          emb._offsets_host, B, F, D, p(emb.dtable), p(emb.dw1), emb.ld, emb.ld1,
+                          s.cuda_stream)
+
+    print("embed_bwd (scatter only) alone: %.2f us" % timeit(ubwd))
+    print("tower_embed_bwd alone: %.2f us" % timeit(fbwd))
     tim = torch.zeros(10, dtype=torch.int64, device=dev)
     lib.ctr_embed_tower_timing(p(tim))
+    accb = []
+    with torch.cuda.stream(s):
+        for i in range(10):
+            fbwd(i)
+            s.synchronize()
+            t = tim.cpu().tolist()
+            accb.append([(t[k + 1] - t[k]) / 1e3 for k in range(4)])
+    medb = [sorted(a[k] for a in accb)[5] for k in range(4)]
+    print("bwd phases of CTA (0,0), warp 2, us: setup+preloads %.2f | wait for MMAs %.2f | epilogue %.2f | "
+          "CTA join %.2f" % tuple(medb))
     names = ["setup", "ids", "rid+loads issued", "A tiles written", "MMAs retired", "dump+cluster sync",
              "reduce", "stats+exit"]
     acc = []

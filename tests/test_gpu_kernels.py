@@ -209,7 +209,7 @@ def test_embed_tower_fwd_matches_unfused(cuda, B, N, fields):
     zbuf = torch.ones(64, device=cuda)
     st = torch.cuda.current_stream().cuda_stream
     rc = lib.ctr_embed_tower_fwd(p(emb.table), p(emb.w1), p(cont), len(pipe.cont_keys), p(cat),
-                                 len(pipe.cat_keys), p(pipe.fields_dev), p(pipe.bnd_dev), pipe.n_bnd, p(rows),
+                                 len(pipe.cat_keys), p(pipe.fields_dev), p(pipe.bnd_dev), pipe.n_bnd, None, p(rows),
                                  p(pipe.status), B, F, D, emb.w1_fields, p(E), p(E_lo), p(S), p(y1), p(y2),
                                  emb.ld, emb.ld1, p(W0), p(W0_lo), p(b0), N, p(act0), p(parts), p(zbuf),
                                  zbuf.numel(), st)
@@ -228,6 +228,59 @@ def test_embed_tower_fwd_matches_unfused(cuda, B, N, fields):
     cs = torch.stack([act0.double().sum(0), (act0.double() ** 2).sum(0)])
     got = parts.double().sum(0)
     assert torch.allclose(got, cs, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,N,F,use_fm", [(4096, 100, 39, True), (300, 100, 39, True), (256, 128, 39, False),
+                                          (515, 64, 12, True), (1000, 16, 40, True)])
+def test_tower_embed_bwd_matches_unfused(cuda, B, N, F, use_fm):
+    """ctr_tower_embed_bwd (dE = dpre0 . W0^T in TMEM, scattered from there) against ctr_embed_bwd fed
+    with the float64 product: table / first-order gradient accumulators to 3xTF32 tolerance.
+    Layouts with one-row, <= 32-row and large fields; ragged B."""
+    ops = _ops()
+    from recsys_b200 import _lib
+    from recsys_b200 import feature_column as fc
+    lib = _lib.load()
+    D = 16
+    rng = np.random.default_rng(B + N + F)
+    nrows = [int(n) for n in rng.integers(2, 4000, size=F)]
+    nrows[0], nrows[1], nrows[F // 2] = 1, 7, 32
+    cols = [fc.embedding_column(fc.categorical_column_with_hash_bucket("k%02d" % i, n), D)
+            for i, n in enumerate(nrows)]
+    lay = fc.layout(cols)
+    mask = (1 << F) - 1 - 2
+    rows_np = _rand_rows(B, lay.offsets, seed=B)
+    rows = torch.from_numpy(rows_np).to(cuda, torch.int32)
+    g = torch.Generator(device="cpu").manual_seed(N)
+    W0 = (torch.randn(F * D, N, generator=g) * (2.0 / (F * D)) ** 0.5).to(cuda)
+    dpre0 = (torch.randn(B, N, generator=g) * 1e-3).to(cuda)
+    dy1 = torch.randn(B, generator=g).to(cuda) * 1e-3
+    dy2 = torch.randn(B, generator=g).to(cuda) * 1e-3 if use_fm else None
+    res = []
+    for fused in (False, True):
+        emb = ops.FieldEmbedding(lay, cuda, with_w1=True, w1_fields=mask, seed=2)
+        with torch.no_grad():
+            E, _, _, _ = emb.lookup(rows)
+        S = E.view(B, F, D).sum(1).contiguous()
+        p = ops._p
+        st = torch.cuda.current_stream().cuda_stream
+        if fused:
+            dpre0_lo, W0_lo = ops.split_lo(dpre0), ops.split_lo(W0)
+            rc = lib.ctr_tower_embed_bwd(p(dpre0), p(dpre0_lo), p(W0), p(W0_lo), N,
+                                         p(rows), p(E), p(S), p(dy2), p(dy1), mask, emb._offsets_host, B, F,
+                                         D, p(emb.dtable), p(emb.dw1), emb.ld, emb.ld1, st)
+        else:
+            dE = (dpre0.double() @ W0.double().t()).float().contiguous()
+            rc = lib.ctr_embed_bwd(p(rows), p(dE), p(E), p(emb.table), p(S), p(dy2), p(dy1), mask,
+                                   emb._offsets_host, B, F, D, p(emb.dtable), p(emb.dw1), emb.ld, emb.ld1,
+                                   st)
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        res.append((emb.dtable.clone(), emb.dw1.clone()))
+    (gt, gw), (ft, fw) = res
+    scale = float(gt.abs().max())
+    assert scale > 0
+    assert float((ft - gt).abs().max()) <= 2e-5 * scale + 1e-9
+    assert float((fw - gw).abs().max()) <= 1e-5 * float(gw.abs().max()) + 1e-9
 
 
 @pytest.mark.parametrize("B,D,use_dE,use_fm,regather", [
