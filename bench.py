@@ -237,6 +237,9 @@ def workload_config(args):
             "l2": "table %.2f GB > 126 MB L2; a distinct id batch every step (no flush needed)"
                   % (rows * 64 / 1e9) if args.table == "full" else
                   "reference-capped table 53.8 MB is L2-resident; distinct id batch every step",
+            "pipeline": "two step graphs over two input buffers; the next batch's copy and its id "
+                        "pipeline (log/bucketize/offset -> [B,39] row ids) run on a copy stream beside "
+                        "the current step" if args.gpus == 1 else "one step graph per rank",
             "parallelism": "1 GPU" if args.gpus == 1 else "row-sharded table, %d GPUs" % args.gpus}
 
 
@@ -415,14 +418,19 @@ def run_ours(args):
         # one device->device copy of the resident batch into the static buffers + replay
         return step.run_device_batch(dev_blobs[i % len(dev_blobs)])
 
+    # e2e: every host batch as one pinned blob in the step's input layout (what the TFRecord decoder
+    # produces: it parses straight into pinned batch buffers), one H2D per step
+    host_blobs = [step.pin_batch(f, l) for f, l in host_batches] if step is not None else None
+
     def e2e_step(i, slot):
-        f, l = host_batches[i % len(host_batches)]
         if step is None:
+            f, l = host_batches[i % len(host_batches)]
             sp = mod.model_fn(f, l, "train", params)
             sp.train_op()
             slot.copy_(sp.loss, non_blocking=True)
         else:
-            step(f, l)
+            step.wait_loss_slot()
+            step.run_device_batch(host_blobs[i % len(host_blobs)])
             step.loss_to_host(slot)
 
     stream = step.stream if step is not None else torch.cuda.current_stream()
@@ -469,6 +477,8 @@ def run_ours(args):
     f, l = host_batches[0]
     tens = [f.cont, f.cat] if hasattr(f, "cont") else list(f.values())
     h2d = sum(t.numel() * t.element_size() for t in tens) + l.numel() * l.element_size()
+    if host_blobs is not None:
+        h2d = host_blobs[0].numel()        # the bytes actually copied per step (256-byte padded sections)
     peak, peak_src = measured_peak()
     line = {
         "metric": metric_name(args), "value": value, "unit": "samples/s",
@@ -477,7 +487,8 @@ def run_ours(args):
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
-                "api": "estimator.GraphedTrainStep(model_fn, params)(pinned PackedFeatures, labels)"
+                "api": "estimator.GraphedTrainStep(model_fn, params): run_device_batch(pinned host blob "
+                       "from pin_batch(features, labels)) + loss_to_host(pinned slot)"
                        if step is not None else "model_fn(features, labels, 'train', params).train_op()"},
         "gpu_launches": per_step_launches * K,
         "gpu_launches_per_step": per_step_launches,
@@ -491,14 +502,19 @@ def run_ours(args):
             "traffic": ncu_traffic(B), "peak_source": peak_src,
             "traffic_note": "ncu --set full, caches flushed before each kernel (dE / E / S of the "
                             "backward are L2 hits inside a real step); per launch pair, bytes",
-            "kernel": "embed_fwd_kernel<16,5,false> + embed_bwd_kernel<16,AGG> (one pair per step), "
-                      "each timed alone as 32 launches on distinct id batches inside a CUDA graph",
+            "kernel": "embed_fwd_kernel<16,5,false> (lookup + FM terms, TMA-staged ids) + "
+                      "embed_bwd_kernel<16,AGG> (scatter-add), each timed alone as 32 launches on "
+                      "distinct id batches inside a CUDA graph; the DeepFM step runs the lookup fused "
+                      "with the first tower layer (step_fused_lookup_layer0_us)",
             "algorithmic_bytes_per_launch_pair": ALG_BYTES * B,
             "fwd": {"us": kern["fwd_us"], "GBps": ALG_BYTES_FWD * B / kern["fwd_us"] / 1e3,
                     "moved_GBps": kern["fwd_moved"] * B / kern["fwd_us"] / 1e3},
             "bwd": {"us": kern["bwd_us"], "GBps": ALG_BYTES_BWD * B / kern["bwd_us"] / 1e3,
                     "moved_GBps": kern["bwd_moved"] * B / kern["bwd_us"] / 1e3},
             "adam_rows_us": kern["adam_us"],
+            # what the DeepFM step runs instead of lookup + first-layer GEMM: ids (precomputed on the
+            # copy stream) -> gather -> FM terms -> act0 = relu(E . W0 + b0) on tcgen05, one launch
+            "step_fused_lookup_layer0_us": kern.get("fused_fwd_us"),
             "scatter_plus_adam_us": kern.get("scatter_plus_adam_us"),
             "large_batch": kern.get("large"),
             # the same algorithmic bytes over the WHOLE step (tower, optimiser and launch gaps
@@ -592,6 +608,25 @@ def time_hot_kernels(model, devb, K, W, stream):
             return e0.elapsed_time(e1) * 1e3 / (reps * nb)
 
         res = {"fwd_us": timeit(fwd), "bwd_us": timeit(bwd), "adam_us": timeit(adam, once=True)}
+        # the kernel the DeepFM step itself runs in place of lookup + first-layer GEMM
+        tw = getattr(model, "tower", None)
+        if tw is not None and getattr(model, "name", "") == "deepfm" and tw.can_fuse_l0(F, D) and B >= 256:
+            N0 = tw.sizes[1]
+            act0 = torch.empty(B, N0, device=emb.device)
+            parts = torch.empty((B + 127) // 128, 2, N0, device=emb.device)
+            E_lo = torch.empty_like(Eb)
+            w0_lo = ops.split_lo(tw.P("0.w").detach())
+            idp = model.ids
+
+            def fused_fwd(i):
+                lib.ctr_embed_tower_fwd(p(emb.table), p(emb.w1), None, len(idp.cont_keys), None,
+                                        len(idp.cat_keys), p(idp.fields_dev), p(idp.bnd_dev), idp.n_bnd,
+                                        p(rows[i % len(rows)]), None, p(idp.status), B, F, D,
+                                        emb.w1_fields, p(Eb), p(E_lo), p(Sb), p(y1), p(y2), emb.ld,
+                                        emb.ld1, p(tw.P("0.w")), p(w0_lo), p(tw.P("0.b")), N0, p(act0),
+                                        p(parts), None, 0, st)
+            res["fused_fwd_us"] = timeit(fused_fwd)
+            ops.LAUNCHES["n"] += K + W
         ops.LAUNCHES["n"] += 3 * (K + W)
         # bytes the implementation actually moves per sample (DESIGN.md "data layout")
         res["fwd_moved"] = 156 + 2496 + 156 + 2496 + 64 + 8          # ids, rows, w1, E, S, y1/y2

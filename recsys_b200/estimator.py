@@ -223,14 +223,15 @@ class GraphedTrainStep:
                                                      f.cat_keys))
             else:       # plain dict of tensors (e.g. the DIN features)
                 self._features.append(dict(static))
-        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        # one loss slot per graph: the read-back of step s (third stream) then only has to finish
+        # before step s+2 rewrites its slot, and never holds up step s+1
+        self._loss = [torch.zeros((), dtype=torch.float32, device=dev) for _ in range(self.nbuf)]
         self._ready = [torch.cuda.Event() for _ in range(self.nbuf)]     # batch landed in blob k
         self._free = [torch.cuda.Event() for _ in range(self.nbuf)]      # graph k done with blob k
         self._loss_ready = torch.cuda.Event()
-        self._loss_read = torch.cuda.Event()
-        for e in self._free:
+        self._loss_read = [torch.cuda.Event() for _ in range(self.nbuf)]
+        for e in self._free + self._loss_read:
             e.record(self.stream)
-        self._loss_read.record(self.stream)
         self._slot = 0          # the buffer the next batch goes to
         self._last = 0          # the buffer of the latest batch
         self._prefetch = None   # the model's id pipeline, run on the copy stream (_find_prefetcher)
@@ -310,7 +311,7 @@ class GraphedTrainStep:
         main, aux = torch.cuda.current_stream(), self.aux_stream
         aux.wait_stream(main)
         with torch.cuda.stream(aux):
-            self.loss.copy_(spec.loss)
+            self._loss[k].copy_(spec.loss)
         spec.train_op()
         main.wait_stream(aux)
 
@@ -345,9 +346,18 @@ class GraphedTrainStep:
         self._slot = (k + 1) % self.nbuf
         return self.loss
 
+    @property
+    def loss(self):
+        """Device loss of the latest step."""
+        return self._loss[self._last]
+
+    def wait_loss_slot(self):
+        """Order the next replay behind the read-back of the loss slot it is going to rewrite."""
+        self.stream.wait_event(self._loss_read[self._slot])
+
     def __call__(self, features, labels):
         k = self._load(features, labels)
-        self.stream.wait_event(self._loss_read)      # the previous loss has been read back
+        self.stream.wait_event(self._loss_read[k])   # slot k's previous loss has been read back
         return self._replay(k)
 
     def to_device_batch(self, features, labels) -> torch.Tensor:
@@ -363,7 +373,28 @@ class GraphedTrainStep:
         self.stream.synchronize()
         return blob
 
+    def pin_batch(self, features, labels) -> torch.Tensor:
+        """The batch as ONE pinned host blob in the static buffers' layout (what an input pipeline
+        that decodes straight into pinned batch buffers hands over): ``run_device_batch`` then
+        moves it with a single host-to-device copy."""
+        src = self._sources(features, labels)
+        ex = dict(self._statics[0])
+        ex["__labels__"] = self._labels[0]
+        blob, views = self._make_blob(ex, torch.device("cpu"))
+        blob = blob.pin_memory()
+        offs, n = {}, 0
+        for k, t in ex.items():
+            offs[k] = n
+            n += (t.numel() * t.element_size() + 255) // 256 * 256
+        for k, t in src.items():
+            e = ex[k]
+            blob[offs[k]:offs[k] + e.numel() * e.element_size()].view(e.dtype).view(e.shape).copy_(
+                torch.as_tensor(t).to(e.dtype).reshape(e.shape))
+        return blob
+
     def run_device_batch(self, blob: torch.Tensor):
+        """One copy of a blob laid out like the static buffers (device resident: D2D; pinned host:
+        H2D) into the next buffer on the copy stream, then the replay."""
         k = self._slot
         cs = self.copy_stream
         cs.wait_event(self._free[k])
@@ -384,5 +415,5 @@ class GraphedTrainStep:
         self._loss_ready.record(self.stream)
         self.d2h_stream.wait_event(self._loss_ready)
         with torch.cuda.stream(self.d2h_stream):
-            pinned_slot.copy_(self.loss, non_blocking=True)
-            self._loss_read.record(self.d2h_stream)
+            pinned_slot.copy_(self._loss[self._last], non_blocking=True)
+            self._loss_read[self._last].record(self.d2h_stream)

@@ -899,7 +899,8 @@ class FusedTower:
         self.l0 = None          # (act0, stats_part) left by the fused lookup + first layer kernel
         self.bwd0 = None        # (dpre0, dpre0_lo) left for the fused data-gradient + scatter kernel
         self._zero = torch.zeros((), dtype=torch.float32, device=dense.flat.device)
-        self.fuse_bwd0 = os.environ.get("CTR_FUSED_BWD0", "1") != "0" and self.sizes[1] <= 128
+        # default off: measured slower than GEMM + scatter at batch 4096 (profiles/r02)
+        self.fuse_bwd0 = os.environ.get("CTR_FUSED_BWD0", "0") != "0" and self.sizes[1] <= 128
 
     def can_fuse_l0(self, F: int, D: int) -> bool:
         """The first layer can be computed inside the lookup kernel (ctr_embed_tower_fwd)."""
