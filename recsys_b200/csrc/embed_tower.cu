@@ -477,10 +477,26 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 //               summed into one lane (__match_any_sync), 4 vector REDs per distinct row; fields with
 //               <= 32 rows (every sample of the warp hits a handful of rows): the 32 slots are summed
 //               per row in a warp-private shared-memory tile first, one RED group per row that was hit
+// Lanes that hold the same key, from `nbits` ballots (one per key bit) instead of match.any: the
+// match instruction walks the warp's DISTINCT values one by one (~2000 cycles when all 32 differ,
+// the common case for a large field), and an epilogue warp would pay that once per field.
+// Lanes with valid == false match nobody.
+__device__ __forceinline__ unsigned warp_peers(int key, bool valid, int nbits, int lane) {
+  unsigned peers = __ballot_sync(0xffffffffu, valid);
+  for (int bit = 0; bit < nbits; ++bit) {
+    const bool one = (key >> bit) & 1;
+    const unsigned bal = __ballot_sync(0xffffffffu, one);
+    peers &= one ? bal : ~bal;
+  }
+  return valid ? peers : (1u << lane);
+}
+
 constexpr int kEbThreads = 256;
 constexpr int kEbFPC = 10;                       // fields per CTA
 constexpr int kEbNT = kEbFPC * kEtD;             // 160 accumulator columns
 constexpr int kEbBStage = 2 * kEbNT * kTcKB * 4; // W0 hi | lo k-block: 2 x 20 KB
+constexpr int kEbStage = 2 * kTcABytes + kEbBStage;   // one k-block of both operands: 72 KB
+constexpr int kEbStages = 2;                     // 144 KB: leaves room for a second resident kernel
 constexpr int kEbMaxKB = 4;                      // H0 <= 128
 constexpr int kEbFPW = kEbFPC / 2;               // fields per epilogue warp
 
@@ -500,26 +516,26 @@ struct EbParams {
   uint32_t idesc;
   uint64_t desc_k;
   unsigned long long* timing;
+  int debug;          // profiling aid ("eb_debug"): 1 = no epilogue at all, 2 = epilogue without REDs,
+                      // 4 = every field through the large-field path
 };
 
 // All 8 warps are epilogue warps (two per TMEM lane quarter, lane = sample); lane 0 of warp 0
 // first issues every TMA load, lane 0 of warp 1 issues the MMAs.  Everything the epilogue needs
 // that does not depend on the GEMM - row ids, S, dy, the E rows of the FM term - is requested
 // before the roles split, so it is in registers when the accumulator is ready.
-__global__ void __launch_bounds__(kEbThreads, 1)
+__global__ void __launch_bounds__(kEbThreads, 2)     // <= 128 registers: a second kernel fits beside it
 tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                        const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                        const EbParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  // [A: nkb x (hi | lo)] [B ring: 2 x (hi | lo)] [barriers]; the epilogue's tiles reuse A
-  uint8_t* a_all = smem;
-  uint8_t* b_ring = smem + static_cast<size_t>(kEbMaxKB) * 2 * kTcABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + 2 * kEbBStage);
-  uint64_t* a_full = bars;            // [kEbMaxKB]
-  uint64_t* b_full = bars + 4;        // [2]
-  uint64_t* b_empty = bars + 6;       // [2]
+  // [ring: 2 x (A hi | A lo | B hi | B lo)] [barriers]; the epilogue's tiles reuse the ring
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kEbStages * kEbStage);
+  uint64_t* full = bars;              // [2]
+  uint64_t* empty = bars + 2;         // [2]
   uint64_t* t_full = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -530,10 +546,9 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (stamp) p.timing[0] = gtime_ns();
 
   if (tid == 0) {
-    for (int s = 0; s < kEbMaxKB; ++s) mbar_init(&a_full[s], 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < kEbStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
     }
     mbar_init(t_full, 1);
     mbar_fence_init();
@@ -550,20 +565,18 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  auto load_stage = [&](int kb) {
+    const uint32_t st = kb % kEbStages;
+    uint8_t* sa = ring + static_cast<size_t>(st) * kEbStage;
+    mbar_expect_tx(&full[st], kEbStage);
+    tma_load_2d(sa, &tmA, kb * kTcKB, m0, &full[st]);
+    tma_load_2d(sa + kTcABytes, &tmAlo, kb * kTcKB, m0, &full[st]);
+    tma_load_2d(sa + 2 * kTcABytes, &tmW, kb * kTcKB, f0 * kEtD, &full[st]);
+    tma_load_2d(sa + 2 * kTcABytes + kEbBStage / 2, &tmWlo, kb * kTcKB, f0 * kEtD, &full[st]);
+  };
   if (tid == 0) {
-    // every A k-block and the first two B stages: in flight before anything else
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      mbar_expect_tx(&a_full[kb], 2 * kTcABytes);
-      uint8_t* sa = a_all + static_cast<size_t>(kb) * 2 * kTcABytes;
-      tma_load_2d(sa, &tmA, kb * kTcKB, m0, &a_full[kb]);
-      tma_load_2d(sa + kTcABytes, &tmAlo, kb * kTcKB, m0, &a_full[kb]);
-    }
-    for (int kb = 0; kb < min(2, p.nkb); ++kb) {
-      mbar_expect_tx(&b_full[kb], kEbBStage);
-      uint8_t* sb = b_ring + static_cast<size_t>(kb) * kEbBStage;
-      tma_load_2d(sb, &tmW, kb * kTcKB, f0 * kEtD, &b_full[kb]);
-      tma_load_2d(sb + kEbBStage / 2, &tmWlo, kb * kTcKB, f0 * kEtD, &b_full[kb]);
-    }
+    // the first two k-blocks of both operands: in flight before anything else
+    for (int kb = 0; kb < min(kEbStages, p.nkb); ++kb) load_stage(kb);
   }
   __syncwarp();
 
@@ -571,18 +584,23 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int quarter = warp & 3, sub = warp >> 2;             // two warps per lane quarter
   const int b = m0 + quarter * 32 + lane;
   const bool live = b < p.B;
-  const bool fm = p.dy2 != nullptr;
+  const bool fm = p.dy2 != nullptr && !(p.debug & 8);
   int rid[kEbFPW];
-  float4 Ev[kEbFPW][4];
 #pragma unroll
   for (int t = 0; t < kEbFPW; ++t) {
     const int f = f0 + sub + 2 * t;
     rid[t] = (live && f < p.F) ? __ldg(p.rows + static_cast<size_t>(b) * p.F + f) : -1;
+  }
+  // the E row of the FM term: one field ahead of the one being scattered
+  float4 En[4];
+  auto load_e = [&](int t) {
+    const int f = f0 + sub + 2 * t;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      Ev[t][c] = (fm && live && f < p.F)
-                     ? ldg4(p.E + (static_cast<size_t>(b) * p.F + f) * kEtD + 4 * c) : f4_zero();
-  }
+      En[c] = (fm && live && f < p.F)
+                  ? ldg4(p.E + (static_cast<size_t>(b) * p.F + f) * kEtD + 4 * c) : f4_zero();
+  };
+  load_e(0);
   float4 Sv[4];
   float d2 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -593,26 +611,22 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 
   if (tid == 0) {
-    // ------------------------------------------------ TMA producer: the remaining B stages
-    for (int kb = 2; kb < p.nkb; ++kb) {
-      const uint32_t st = kb & 1, ph = (kb >> 1) & 1;
-      mbar_wait(&b_empty[st], ph ^ 1);
-      mbar_expect_tx(&b_full[st], kEbBStage);
-      uint8_t* sb = b_ring + static_cast<size_t>(st) * kEbBStage;
-      tma_load_2d(sb, &tmW, kb * kTcKB, f0 * kEtD, &b_full[st]);
-      tma_load_2d(sb + kEbBStage / 2, &tmWlo, kb * kTcKB, f0 * kEtD, &b_full[st]);
+    // ------------------------------------------------ TMA producer: the remaining k-blocks
+    for (int kb = kEbStages; kb < p.nkb; ++kb) {
+      const uint32_t st = kb % kEbStages, ph = (kb / kEbStages) & 1;
+      mbar_wait(&empty[st], ph ^ 1);
+      load_stage(kb);
     }
   } else if (tid == 32) {
     // -------------------------------------------------------------------- MMA issuer
     uint32_t accum = 0;
     for (int kb = 0; kb < p.nkb; ++kb) {
-      const uint32_t st = kb & 1, ph = (kb >> 1) & 1;
-      mbar_wait(&a_full[kb], 0);
-      mbar_wait(&b_full[st], ph);
+      const uint32_t st = kb % kEbStages, ph = (kb / kEbStages) & 1;
+      mbar_wait(&full[st], ph);
       tc_fence_after();
-      const uint32_t ah = smem_u32(a_all + static_cast<size_t>(kb) * 2 * kTcABytes);
+      const uint32_t ah = smem_u32(ring + static_cast<size_t>(st) * kEbStage);
       const uint32_t al = ah + kTcABytes;
-      const uint32_t bh = smem_u32(b_ring + static_cast<size_t>(st) * kEbBStage);
+      const uint32_t bh = ah + 2 * kTcABytes;
       const uint32_t bl = bh + kEbBStage / 2;
       const int ks = kb == p.nkb - 1 ? p.last_ksteps : 4;
       for (int k = 0; k < ks; ++k) {
@@ -626,7 +640,7 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int k = 0; k < ks; ++k)   // (hi, lo)
         tc_mma_tf32(tmem_base, p.desc_k | (((ah + k * 32) >> 4) & 0x3FFF),
                     p.desc_k | (((bl + k * 32) >> 4) & 0x3FFF), p.idesc, 1);
-      tc_commit(&b_empty[st]);
+      tc_commit(&empty[st]);
     }
     tc_commit(t_full);
   }
@@ -637,22 +651,26 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   mbar_wait(t_full, 0);
   tc_fence_after();
   if (stamp) p.timing[2] = gtime_ns();
-  // warp-private tile for the <= 32-row fields: [32 rows][16 + 4] floats, in the retired A region
-  float* tileb = reinterpret_cast<float*>(a_all) + warp * (32 * 20 + 64);
+  // warp-private tile: [32 rows][16 + 4] floats, in the retired ring
+  float* tileb = reinterpret_cast<float*>(ring) + warp * (32 * 20 + 64);
   float* tw1 = tileb + 32 * 20;
   int* tcnt = reinterpret_cast<int*>(tw1 + 32);
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll
   for (int t = 0; t < kEbFPW; ++t) {
     const int j = sub + 2 * t, f = f0 + j;
-    if (f < p.F) {                                             // warp-uniform
+    if (f < p.F && !(p.debug & 1)) {                           // warp-uniform
+      float4 Ec[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Ec[c] = En[c];
+      if (t + 1 < kEbFPW) load_e(t + 1);
       float x[16];
       tc_ld<16>(taddr + j * kEtD, x);
       float4 g[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         g[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-        const float4 ev = Ev[t][c];
+        const float4 ev = Ec[c];
         g[c].x = fmaf(d2, Sv[c].x - ev.x, g[c].x);
         g[c].y = fmaf(d2, Sv[c].y - ev.y, g[c].y);
         g[c].z = fmaf(d2, Sv[c].z - ev.z, g[c].z);
@@ -661,44 +679,46 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool has_w1 = p.dw1 != nullptr && p.dy1 != nullptr && ((p.w1_fields >> f) & 1ull);
       const int r = rid[t];
       float gw = has_w1 ? d1 : 0.f;
-      if ((p.tiny_fields >> f) & 1ull) {
-        // every row of the field fits the tile: sum the warp's 32 slots per row, lanes that hit the
-        // same row take turns (rank inside their __match_any_sync group)
+      if (((p.tiny_fields >> f) & 1ull) && !(p.debug & 4)) {
+        // every row of the field fits 32 tile rows.  The warp's 32 slots go to shared memory once;
+        // then 4 lanes per row (8 rows per pass) add up the slots of that row - found through the
+        // row's peer mask - and RED the row's 64 bytes straight from registers.  No read-modify-write
+        // chain on shared memory: a row that all 32 samples hit costs 32 independent loads, not 32
+        // dependent turns.
         const int lid = r >= 0 ? r - p.off[f] : -1;
-        for (int i = lane; i < 32 * 20 / 4; i += 32) reinterpret_cast<float4*>(tileb)[i] = f4_zero();
-        tw1[lane] = 0.f;
-        tcnt[lane] = 0;
+        const unsigned peers = warp_peers(lid, lid >= 0, 5, lane);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(tileb + lane * 20 + 4 * c) = g[c];
+        tileb[lane * 20 + 16] = gw;
+        unsigned* pm = reinterpret_cast<unsigned*>(tcnt);
+        pm[lane] = 0u;
         __syncwarp();
-        const unsigned peers = __match_any_sync(0xffffffffu, lid >= 0 ? lid : -1 - lane);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int rounds = __reduce_max_sync(0xffffffffu, lid >= 0 ? rank : 0) + 1;
-        for (int k = 0; k < rounds; ++k) {
-          if (lid >= 0 && rank == k) {
-            float4* dst = reinterpret_cast<float4*>(tileb + lid * 20);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = f4_add(dst[c], g[c]);
-            tw1[lid] += gw;
-            tcnt[lid] += 1;
-          }
-          __syncwarp();
-        }
-        // flush: 4 lanes per row (one 64-byte RED group per row and instruction)
-        const int nrow = p.off[f + 1] - p.off[f];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        if (lid >= 0) pm[lid] = peers;            // every peer writes the same mask
+        __syncwarp();
+        const int nrow = (p.debug & 2) ? 0 : p.off[f + 1] - p.off[f];
+        for (int k = 0; 8 * k < nrow; ++k) {
           const int lr = 8 * k + (lane >> 2), cc = lane & 3;
-          if (lr < nrow && tcnt[lr] > 0) {
-            red_add_v4(p.dtable + static_cast<size_t>(p.off[f] + lr) * p.ld_g + 4 * cc,
-                       *reinterpret_cast<const float4*>(tileb + lr * 20 + 4 * cc));
-            if (has_w1 && cc == 0) red_add_f32(p.dw1 + static_cast<size_t>(p.off[f] + lr) * p.ld_w, tw1[lr]);
+          unsigned m = lr < nrow ? pm[lr] : 0u;
+          if (m != 0u) {
+            float4 acc = f4_zero();
+            float aw = 0.f;
+            while (m != 0u) {
+              const int i = __ffs(m) - 1;
+              m &= m - 1u;
+              acc = f4_add(acc, *reinterpret_cast<const float4*>(tileb + i * 20 + 4 * cc));
+              if (cc == 0) aw += tileb[i * 20 + 16];
+            }
+            red_add_v4(p.dtable + static_cast<size_t>(p.off[f] + lr) * p.ld_g + 4 * cc, acc);
+            if (has_w1 && cc == 0) red_add_f32(p.dw1 + static_cast<size_t>(p.off[f] + lr) * p.ld_w, aw);
           }
         }
         __syncwarp();
       } else {
         // large field: duplicates inside the warp are rare - sum them into the first lane of the group
-        const unsigned peers = __match_any_sync(0xffffffffu, r >= 0 ? r : -1 - lane);
+        const int nbits = 32 - __clz(max(1, p.off[f + 1] - p.off[f] - 1));
+        const unsigned peers = (p.debug & 16) ? (1u << lane) : warp_peers(r - p.off[f], r >= 0, nbits, lane);
         const bool leader = (peers & ((1u << lane) - 1u)) == 0u;
-        if (__reduce_max_sync(0xffffffffu, __popc(peers)) > 1) {
+        if (!(p.debug & 16) && __any_sync(0xffffffffu, __popc(peers) > 1)) {
           unsigned rest = peers & ~(1u << lane);
           while (__ballot_sync(0xffffffffu, rest != 0u) != 0u) {
             const int src = rest != 0u ? __ffs(rest) - 1 : lane;
@@ -718,7 +738,7 @@ tower_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(tileb + lane * 20 + 4 * c) = g[c];
         __syncwarp();
-        const int r_eff = (r >= 0 && leader) ? r : -1;
+        const int r_eff = (r >= 0 && leader && !(p.debug & 2)) ? r : -1;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int src = 8 * k + (lane >> 2), cc = lane & 3;
@@ -868,13 +888,14 @@ int ctr_tower_embed_bwd(const float* dpre0, const float* dpre0_lo, const float* 
   p.idesc = cin_idesc(kEbNT);
   p.desc_k = cin_desc_hi();
   p.timing = g_et_timing;
+  p.debug = option_get("eb_debug", 0);
   CUtensorMap tA, tAlo, tW, tWlo;
   int r = make_map(&tA, dpre0, B, N, N, kTcBM);
   if (r == CTR_OK) r = make_map(&tAlo, dpre0_lo, B, N, N, kTcBM);
   if (r == CTR_OK) r = make_map(&tW, W0, static_cast<long long>(F) * D, N, N, kEbNT);
   if (r == CTR_OK) r = make_map(&tWlo, W0_lo, static_cast<long long>(F) * D, N, N, kEbNT);
   if (r != CTR_OK) return r;
-  const size_t smem = static_cast<size_t>(kEbMaxKB) * 2 * kTcABytes + 2 * kEbBStage + 256 + 1024;
+  const size_t smem = static_cast<size_t>(kEbStages) * kEbStage + 256 + 1024;
   static bool optin = false;
   if (!optin) {
     cudaFuncSetAttribute(tower_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

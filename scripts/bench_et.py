@@ -103,6 +103,13 @@ def main():
 
     print("embed_bwd (scatter only) alone: %.2f us" % timeit(ubwd))
     print("tower_embed_bwd alone: %.2f us" % timeit(fbwd))
+    for dbg, what in ((1, "no epilogue (TMA + MMA only)"), (2, "epilogue without REDs"),
+                      (4, "all fields through the large-field path"), (6, "large-field path, no REDs"),
+                      (14, "large-field path, no REDs, no FM term (no E / S loads)"),
+                      (30, "large-field path, no REDs, no FM term, no match_any")):
+        lib.ctr_set_option(b"eb_debug", dbg)
+        print("  eb_debug=%d %s: %.2f us" % (dbg, what, timeit(fbwd)))
+    lib.ctr_set_option(b"eb_debug", 0)
     tim = torch.zeros(10, dtype=torch.int64, device=dev)
     lib.ctr_embed_tower_timing(p(tim))
     accb = []
