@@ -447,7 +447,12 @@ xtx_kernel(const float* __restrict__ A, int lda, int Ka, const float* __restrict
   extern __shared__ __align__(16) uint8_t xtx_smem[];
   MmaSmem& sm = *reinterpret_cast<MmaSmem*>(xtx_smem);
   __shared__ float s_red[2][kTwBN];
-  if (n_dev != nullptr) N = min(N, static_cast<long long>(*n_dev));
+  if (n_dev != nullptr) {
+    // the host sized the grid for the upper bound B * P; share out the rows that exist (about
+    // half of them at the benchmark's history lengths), so that no split is left idle
+    N = min(N, static_cast<long long>(*n_dev));
+    rows_per_split = ((N + gridDim.z - 1) / gridDim.z + kTwKC - 1) / kTwKC * kTwKC;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int a0 = blockIdx.x * (MT * 16), c0 = blockIdx.y * kTwBN;
   const long long rbeg = blockIdx.z * rows_per_split;
