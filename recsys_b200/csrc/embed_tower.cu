@@ -235,12 +235,13 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 #pragma unroll
     for (int i = 0; i < 2 * kEtMaxFPC; ++i)
       v[i] = rid[i] >= 0 ? ldg4(p.table + static_cast<size_t>(rid[i]) * p.ld + c * 4) : f4_zero();
-    if (p.y1 != nullptr && c == 1) {
+    // first-order weights: requested now, summed after the A tiles are out (a sum here would wait
+    // for the LAST load of the CTA before the first k-block could be handed to the tensor core)
+    float w1v[2 * kEtMaxFPC];
 #pragma unroll
-      for (int i = 0; i < 2 * kEtMaxFPC; ++i)
-        if (rid[i] >= 0 && ((p.w1_fields >> (f0 + (i >> 1))) & 1ull))
-          y1p[i & 1] += __ldg(p.w1 + static_cast<size_t>(rid[i]) * p.ld1);
-    }
+    for (int i = 0; i < 2 * kEtMaxFPC; ++i)
+      w1v[i] = (p.y1 != nullptr && c == 1 && rid[i] >= 0 && ((p.w1_fields >> (f0 + (i >> 1))) & 1ull))
+                   ? __ldg(p.w1 + static_cast<size_t>(rid[i]) * p.ld1) : 0.f;
     et_stamp(p, 2);
 #pragma unroll
     for (int kb = 0; kb < kEtMaxKB; ++kb) {
@@ -264,6 +265,8 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
       }
     }
     et_stamp(p, 3);
+#pragma unroll
+    for (int i = 0; i < 2 * kEtMaxFPC; ++i) y1p[i & 1] += w1v[i];
     // E / E_lo for the backward's weight-gradient GEMM: written behind the A tiles, so that the
     // 20 MB of stores overlap the MMAs instead of delaying them
 #pragma unroll
