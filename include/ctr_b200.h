@@ -82,6 +82,14 @@ int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_c
                     const ctr_field_desc* fields_dev, const float* boundaries_dev, int B, int F,
                     int32_t* rows, float* logx, int32_t* status, ctr_stream_t stream);
 
+/* The same ids from at most max_ctas CTAs (0 = 16): the variant for a copy stream beside a running
+ * training step, whose kernels want whole SMs - a full-width id kernel that reaches an SM first
+ * keeps them waiting (estimator.GraphedTrainStep runs the ids of batch s+1 beside step s). */
+int ctr_criteo_rows_bg(const float* xcont, int n_cont, const int64_t* xcat, int n_cat,
+                       const ctr_field_desc* fields_dev, const float* boundaries_dev, int n_boundaries,
+                       int B, int F, int32_t* rows, int32_t* status, int max_ctas,
+                       ctr_stream_t stream);
+
 /* FarmHash Fingerprint64(bytes) mod n_buckets for N strings (TF StringToHashBucketFast,
  * fm/fm.py:89).  bytes: concatenated strings; offsets[N+1]; field_of[N] (nullable) selects
  * n_buckets[field] and row_offset[field]; out[i] = row_offset + hash % n_buckets. */

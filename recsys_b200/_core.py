@@ -284,7 +284,7 @@ class _CriteoBase(_ModelBase):
         if getattr(self, "needs_logx", False) or self.world != 1 or \
                 getattr(features, "rows", None) is None or not hasattr(self.emb, "lookup_features"):
             return False
-        self.ids(features, out=features.rows)
+        self.ids(features, out=features.rows, background=int(os.environ.get("CTR_IDS_BG_CTAS", "16")))
         return True
 
     @staticmethod

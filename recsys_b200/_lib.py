@@ -92,6 +92,7 @@ SIGNATURES = {
     "ctr_device_check": (c_i, []),
     "ctr_set_option": (c_i, [C.c_char_p, c_i]),
     "ctr_criteo_rows": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f]),
+    "ctr_criteo_rows_bg": (c_i, [c_f, c_i, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_f]),
     "ctr_hash_strings": (c_i, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
     "ctr_hash_int64": (c_i, [c_f, c_i64, C.c_int32, c_f, c_f]),
     "ctr_hash_slots": (c_i, [c_f, c_i, c_f, c_i64, c_i, c_f, c_f, c_f]),

@@ -489,6 +489,43 @@ __global__ void criteo_rows_kernel(const float* __restrict__ xcont, int n_cont,
   }
 }
 
+// The same ids from a FEW CTAs (ctr_criteo_rows_bg): the variant that runs on a copy stream beside a
+// training step.  The step's kernels want whole SMs (one CTA per SM, all of its registers); a
+// full-width id kernel that reaches an SM first keeps such a CTA waiting, so this one stays on
+// `max_ctas` SMs and makes up for it with memory-level parallelism: tables in shared memory, four
+// feature loads in flight per thread.
+__global__ void __launch_bounds__(256)
+criteo_rows_bg_kernel(const float* __restrict__ xcont, int n_cont, const long long* __restrict__ xcat,
+                      int n_cat, const ctr_field_desc* __restrict__ fields,
+                      const float* __restrict__ bnd, int n_bnd, int B, int F, int* __restrict__ rows,
+                      int* __restrict__ status) {
+  __shared__ ctr_field_desc s_fields[CTR_MAX_FIELDS];
+  __shared__ float s_bnd[kFwdMaxBnd];
+  for (int i = threadIdx.x; i < F * 8; i += blockDim.x)
+    reinterpret_cast<int*>(s_fields)[i] = reinterpret_cast<const int*>(fields)[i];
+  for (int i = threadIdx.x; i < n_bnd; i += blockDim.x) s_bnd[i] = bnd[i];
+  __syncthreads();
+  const long long n = static_cast<long long>(B) * F;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < n;
+       i0 += 4 * stride) {
+    CriteoRaw raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      raw[u].xc = 0.f;
+      raw[u].xk = 0;
+      if (i < n)
+        raw[u] = criteo_load_raw(s_fields[i % F], xcont, n_cont, xcat, n_cat, static_cast<int>(i / F));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n) rows[i] = criteo_id_of(s_fields[i % F], s_bnd, raw[u], nullptr, status);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- Adam
 // Device-side Adam schedule (nullable `state`, 4 floats) so that a captured CUDA graph advances it
 // on replay:  [0] = t, optimiser steps completed so far;  [1] = lr_t of the step in progress
@@ -839,6 +876,27 @@ int ctr_criteo_rows(const float* xcont, int n_cont, const int64_t* xcat, int n_c
       xcont, n_cont, reinterpret_cast<const long long*>(xcat), n_cat, fields_dev, boundaries_dev, B,
       F, rows, logx, status);
   CTR_LAUNCH_CHECK("ctr_criteo_rows");
+}
+
+int ctr_criteo_rows_bg(const float* xcont, int n_cont, const int64_t* xcat, int n_cat,
+                       const ctr_field_desc* fields_dev, const float* boundaries_dev, int n_boundaries,
+                       int B, int F, int32_t* rows, int32_t* status, int max_ctas,
+                       ctr_stream_t stream) {
+  CTR_ARCH_OR_RETURN();
+  CTR_REQUIRE(fields_dev && rows && B >= 0 && F > 0 && F <= CTR_MAX_FIELDS, "ctr_criteo_rows_bg",
+              "null fields/rows or bad B/F");
+  CTR_REQUIRE(n_cont == 0 || (xcont && boundaries_dev), "ctr_criteo_rows_bg", "null xcont/boundaries");
+  CTR_REQUIRE(n_cat == 0 || xcat, "ctr_criteo_rows_bg", "null xcat");
+  CTR_REQUIRE(n_boundaries >= 0 && n_boundaries <= kFwdMaxBnd, "ctr_criteo_rows_bg",
+              "at most 512 bucket boundaries in total");
+  if (B == 0) return CTR_OK;
+  const long long n = static_cast<long long>(B) * F;
+  if (max_ctas <= 0) max_ctas = 16;
+  const int grid = static_cast<int>(std::min<long long>((n + 1023) / 1024, max_ctas));
+  criteo_rows_bg_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      xcont, n_cont, reinterpret_cast<const long long*>(xcat), n_cat, fields_dev, boundaries_dev,
+      n_boundaries, B, F, rows, status);
+  CTR_LAUNCH_CHECK("ctr_criteo_rows_bg");
 }
 
 static int embed_fwd_impl(const char* fn, const float* table, const float* w1, const int32_t* rows,

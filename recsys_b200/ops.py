@@ -163,11 +163,19 @@ class IdPipeline:
         flat = [bytes(v) for v in _flatten(values)]
         return hash_strings(flat, self.lay.rows[f], self.device)
 
-    def __call__(self, features, want_logx: bool = False, out: Optional[torch.Tensor] = None):
+    def __call__(self, features, want_logx: bool = False, out: Optional[torch.Tensor] = None,
+                 background: int = 0):
+        """``background`` > 0: at most that many CTAs (ctr_criteo_rows_bg), for a copy stream beside a
+        running step."""
         cont, cat = self.pack(features)
         B = (cont if cont is not None else cat).shape[0]
         rows = out if out is not None else \
             torch.empty((B, self.lay.F), dtype=torch.int32, device=self.device)
+        if background > 0 and not want_logx and self.n_bnd <= 512:
+            _call("ctr_criteo_rows_bg", _p(cont), len(self.cont_keys), _p(cat), len(self.cat_keys),
+                  _p(self.fields_dev), _p(self.bnd_dev), self.n_bnd, B, self.lay.F, _p(rows),
+                  _p(self.status), background, _stream())
+            return rows
         logx = torch.empty((B, len(self.cont_keys)), dtype=torch.float32, device=self.device) \
             if want_logx else None
         _call("ctr_criteo_rows", _p(cont), len(self.cont_keys), _p(cat), len(self.cat_keys),

@@ -11,7 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "recsys_b200", "libctr_b200.so")
 PAT = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS",
-       "REDG", "RED.", "ATOMG", "ATOMS", "MATCH", "HMMA", "MEMBAR", "ERRBAR", "CCTL", "ACQBULK"]
+       "REDG", "RED.", "ATOMG", "ATOMS", "MATCH", "HMMA", "MEMBAR", "ERRBAR", "CCTL", "ACQBULK",
+       "UCGABAR", "VOTE"]
 
 
 def main():
@@ -38,7 +39,8 @@ def main():
     print("SASS summary of recsys_b200/libctr_b200.so (cuobjdump -sass, sm_100a); per kernel: "
           "instruction count and the counts of the mnemonics that matter")
     print("UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld (TMEM), UTMALDG = TMA tensor load, UBLKCP = "
-          "cp.async.bulk (1-D TMA), REDG = red.global, MATCH = match.any, HMMA = mma.sync\n")
+          "cp.async.bulk (1-D TMA), REDG = red.global, MATCH = match.any, HMMA = mma.sync, "
+          "UCGABAR = barrier.cluster, VOTE = ballot\n")
     for (k, c), name in zip(counts.items(), demangle):
         name = re.sub(r"\(.*", "", name)[:90]
         tags = "  ".join("%s=%d" % (p, c[p]) for p in PAT if c[p])

@@ -57,6 +57,9 @@ def test_criteo_rows_bit_exact(cuda, B):
     assert len(bad) <= max(1, B // 1000)
     assert np.allclose(logx.cpu().numpy(), lx, rtol=3e-7, atol=1e-7, equal_nan=True)
     assert int(pipe.status.item()) == 0
+    # the few-CTA variant for a copy stream (ctr_criteo_rows_bg): the same ids, bit for bit
+    rows_bg = pipe(_to_torch_features(feats), background=4)
+    assert torch.equal(rows_bg, rows)
 
 
 @pytest.mark.parametrize("B", [1, 7, 256, 4099])
