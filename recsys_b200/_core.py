@@ -284,7 +284,12 @@ class _CriteoBase(_ModelBase):
         if getattr(self, "needs_logx", False) or self.world != 1 or \
                 getattr(features, "rows", None) is None or not hasattr(self.emb, "lookup_features"):
             return False
-        self.ids(features, out=features.rows, background=int(os.environ.get("CTR_IDS_BG_CTAS", "16")))
+        # a step whose kernels take whole SMs (the fused lookup + first layer kernel, ctr_tower_mid:
+        # one CTA per SM on 128 of the 148 SMs) gets the few-CTA id kernel, so that it can never keep
+        # one of those CTAs waiting; short steps (FM) get the full-width one, which is done sooner
+        tw = getattr(self, "tower", None)
+        bg = int(os.environ.get("CTR_IDS_BG_CTAS", "20")) if (tw is not None and tw.use_mid) else 0
+        self.ids(features, out=features.rows, background=bg)
         return True
 
     @staticmethod
@@ -354,6 +359,7 @@ class _CriteoBase(_ModelBase):
     def _dense_step(self, lr_t):
         if getattr(self.emb, "p2p", False):       # all-reduce + Adam over peer memory, no NCCL
             self.emb.dense_step(self.dense, lr_t, self.adam, getattr(self, "tower", None))
+            self.dense.lo_fresh.clear()            # the weights moved without their lo halves
         else:
             self._sync_dense_grads()
             self.dense.adam_step(lr_t, self.adam)
