@@ -493,8 +493,10 @@ def run_ours(args):
                 "api": "estimator.GraphedTrainStep(model_fn, params): run_device_batch(pinned host blob "
                        "from pin_batch(features, labels)) + loss_to_host(pinned slot)"
                        if step is not None else "model_fn(features, labels, 'train', params).train_op()"},
-        "gpu_launches": per_step_launches * K,
-        "gpu_launches_per_step": per_step_launches,
+        # kernels of ours per step: the C-ABI calls of one eager step, plus the id kernel that the
+        # graphed step runs on the copy stream instead of inside the lookup kernel
+        "gpu_launches": (per_step_launches + (1 if step is not None and step._prefetch is not None else 0)) * K,
+        "gpu_launches_per_step": per_step_launches + (1 if step is not None and step._prefetch is not None else 0),
         "final_loss": float(losses[K - 1]), "launch_mode": graph_note,
     }
     if kern is not None:

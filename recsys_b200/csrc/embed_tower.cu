@@ -177,59 +177,59 @@ embed_tower_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
         rid[i] = (j < p.fpc && bb < B && f < F) ? __ldg(p.rows_in + static_cast<size_t>(bb) * F + f) : -1;
       }
     } else {
-    // ids of the CTA's 128 x fpc (sample, field) pairs: every thread computes its share with
-    // independent loads (no shuffle between them), staged in the not yet used tail of the A
-    // ring, then each lane picks up the ids of its rows
-    int* ids_s = reinterpret_cast<int*>(a_ring + 4 * kTcABytes) - 128 * kEtMaxFPC;
-    ctr_field_desc* s_fields = reinterpret_cast<ctr_field_desc*>(reinterpret_cast<uint8_t*>(ids_s) - 4096);
-    float* s_bnd = reinterpret_cast<float*>(s_fields + kEtMaxFPC + 2);       // <= 512 boundaries
-    {
-      // the CTA's field descriptors and the bucket boundaries first (one L2 round trip), so that
-      // the id arithmetic itself only waits for the feature values
-      const int nf = min(p.fpc, F - f0);
-      const int* src = reinterpret_cast<const int*>(p.fields + f0);
-      for (int i = tid; i < nf * 8; i += kEtGather) reinterpret_cast<int*>(s_fields)[i] = __ldg(src + i);
-      for (int i = tid; i < p.n_bnd; i += kEtGather) s_bnd[i] = __ldg(p.bnd + i);
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    et_stamp(p, 9);
-    {
-      // all feature loads of the thread's (sample, field) pairs first, then the id arithmetic
-      constexpr int NU = (128 * kEtMaxFPC + kEtGather - 1) / kEtGather;
-      const int npair = 128 * p.fpc;
-      CriteoRaw raw[NU];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int i = tid + u * kEtGather;
-        const int bl = i / p.fpc, j = i - bl * p.fpc;
-        raw[u].xc = 0.f;
-        raw[u].xk = 0;
-        if (i < npair && m0 + bl < B && f0 + j < F)
-          raw[u] = criteo_load_raw(s_fields[j], p.xcont, p.n_cont, p.xcat, p.n_cat, m0 + bl);
+      // ids of the CTA's 128 x fpc (sample, field) pairs: every thread computes its share with
+      // independent loads (no shuffle between them), staged in the not yet used tail of the A
+      // ring, then each lane picks up the ids of its rows
+      int* ids_s = reinterpret_cast<int*>(a_ring + 4 * kTcABytes) - 128 * kEtMaxFPC;
+      ctr_field_desc* s_fields = reinterpret_cast<ctr_field_desc*>(reinterpret_cast<uint8_t*>(ids_s) - 4096);
+      float* s_bnd = reinterpret_cast<float*>(s_fields + kEtMaxFPC + 2);       // <= 512 boundaries
+      {
+        // the CTA's field descriptors and the bucket boundaries first (one L2 round trip), so that
+        // the id arithmetic itself only waits for the feature values
+        const int nf = min(p.fpc, F - f0);
+        const int* src = reinterpret_cast<const int*>(p.fields + f0);
+        for (int i = tid; i < nf * 8; i += kEtGather) reinterpret_cast<int*>(s_fields)[i] = __ldg(src + i);
+        for (int i = tid; i < p.n_bnd; i += kEtGather) s_bnd[i] = __ldg(p.bnd + i);
       }
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int i = tid + u * kEtGather;
-        if (i < npair) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      et_stamp(p, 9);
+      {
+        // all feature loads of the thread's (sample, field) pairs first, then the id arithmetic
+        constexpr int NU = (128 * kEtMaxFPC + kEtGather - 1) / kEtGather;
+        const int npair = 128 * p.fpc;
+        CriteoRaw raw[NU];
+  #pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int i = tid + u * kEtGather;
           const int bl = i / p.fpc, j = i - bl * p.fpc;
-          const int b = m0 + bl, f = f0 + j;
-          int id = -1;
-          if (b < B && f < F) {
-            id = criteo_id_of(s_fields[j], s_bnd, raw[u], nullptr, p.status);
-            p.rows_out[static_cast<size_t>(b) * F + f] = id;
+          raw[u].xc = 0.f;
+          raw[u].xk = 0;
+          if (i < npair && m0 + bl < B && f0 + j < F)
+            raw[u] = criteo_load_raw(s_fields[j], p.xcont, p.n_cont, p.xcat, p.n_cat, m0 + bl);
+        }
+  #pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int i = tid + u * kEtGather;
+          if (i < npair) {
+            const int bl = i / p.fpc, j = i - bl * p.fpc;
+            const int b = m0 + bl, f = f0 + j;
+            int id = -1;
+            if (b < B && f < F) {
+              id = criteo_id_of(s_fields[j], s_bnd, raw[u], nullptr, p.status);
+              p.rows_out[static_cast<size_t>(b) * F + f] = id;
+            }
+            ids_s[i] = id;
           }
-          ids_s[i] = id;
         }
       }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    et_stamp(p, 1);
-#pragma unroll
-    for (int i = 0; i < 2 * kEtMaxFPC; ++i) {
-      const int j = i >> 1, row = 16 * warp + 8 * (i & 1) + r8;
-      rid[i] = j < p.fpc ? ids_s[row * p.fpc + j] : -1;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");     // the staging area becomes an A tile again
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      et_stamp(p, 1);
+  #pragma unroll
+      for (int i = 0; i < 2 * kEtMaxFPC; ++i) {
+        const int j = i >> 1, row = 16 * warp + 8 * (i & 1) + r8;
+        rid[i] = j < p.fpc ? ids_s[row * p.fpc + j] : -1;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the staging area becomes an A tile again
     }
     float4 v[2 * kEtMaxFPC];
 #pragma unroll
