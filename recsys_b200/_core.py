@@ -365,6 +365,38 @@ class _CriteoBase(_ModelBase):
             self.dense.adam_step(lr_t, self.adam)
 
     def _apply_gradients(self, lr_t):
+        """One GPU, lazy rows: the step's two closing optimiser kernels run side by side - the touched
+        rows on the main stream, the dense weights on an optimiser stream that waits for everything
+        the main stream has produced so far (every dense gradient) and for the tower's side-stream
+        weight-gradient kernels.  The last of the two kernels to finish advances the device schedule
+        (``advance_parties``); for a tower with pre-split first-layer operands the dense launch also
+        leaves the lo half of those weights for the next step's lookup kernel."""
+        emb = self.emb
+        if (self.world == 1 and isinstance(emb, ops.FieldEmbedding) and emb.adam_mode == "lazy"
+                and self.adam.state is not None and not getattr(emb, "_fused_done", False)
+                and getattr(emb, "_fused", None) is None
+                and getattr(self, "tower", None) is not None     # FM's 4 dense weights: a fork + join
+                                                                 # costs more than the 4 us it hides
+                and os.environ.get("CTR_DENSE_ON_SIDE", "1") != "0"):
+            main = torch.cuda.current_stream()
+            if getattr(self, "_opt_stream", None) is None:
+                self._opt_stream = torch.cuda.Stream(device=self.device)
+            side = self._opt_stream
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            tw = getattr(self, "tower", None)
+            if tw is not None and tw._pending is not None:
+                side.wait_event(tw._pending)
+                tw._pending = None
+            emb.adam_step(self.rows, lr_t, self.adam, parties=2)
+            with torch.cuda.stream(side):
+                lo = (tw.prefix + ".0.w", tw.w0_lo) if (tw is not None and tw.use_presplit) else None
+                self.dense.adam_step(lr_t, self.adam, parties=2, lo=lo)
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+            return
         self.emb.adam_step(self.rows, lr_t, self.adam)     # overlaps the side-stream dW kernels
         if not getattr(self.emb, "p2p", False):
             self._join_tower()                             # (the peer path joins on its side stream)
@@ -432,29 +464,6 @@ class DeepFMModel(_CriteoBase):
                                         **({"tower0": self.tower} if fuse else {}))
         return self._tower_head(self.tower, E, [y1s, y2], labels, training, (-1,),
                                 X_lo=self.emb.last_E_lo if lo else None)      # :91,100-129
-
-    def _apply_gradients(self, lr_t):
-        """The step's two closing optimiser kernels side by side: the touched rows on the main
-        stream, the dense weights on the tower's side stream right behind the weight-gradient
-        kernels that feed them (every other dense gradient of this model is written by
-        ctr_tower_mid, before the fork).  The last of the two to finish advances the device
-        schedule; the dense launch also leaves the lo half of the first layer's weights for the
-        next step's lookup kernel."""
-        tw, emb = self.tower, self.emb
-        if (self.world != 1 or not self.fused or not isinstance(emb, ops.FieldEmbedding)
-                or emb.adam_mode != "lazy" or tw._pending is None or self.adam.state is None
-                or getattr(emb, "_fused_done", False) or getattr(emb, "_fused", None) is not None
-                or os.environ.get("CTR_DENSE_ON_SIDE", "1") == "0"):
-            return super()._apply_gradients(lr_t)
-        main = torch.cuda.current_stream()
-        emb.adam_step(self.rows, lr_t, self.adam, parties=2)
-        with torch.cuda.stream(tw.side):
-            self.dense.adam_step(lr_t, self.adam, parties=2,
-                                 lo=("dnn.0.w", tw.w0_lo) if tw.use_presplit else None)
-            done = torch.cuda.Event()
-            done.record(tw.side)
-        tw._pending = None
-        main.wait_event(done)
 
     def logits(self, features, training):
         P = self.dense
