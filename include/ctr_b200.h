@@ -52,7 +52,8 @@ int ctr_device_check(void);
  *   "mid_coop" (default 1): ctr_tower_mid training launches are cooperative; 0 = plain launch
  *   (equally safe while nothing resident on the device waits on that kernel).
  *   "tcg_dw_stages" (default 2), "tcg_dw_splits" (default 0 = automatic): TMA ring depth and
- *   split-K factor of the first tower layer's weight-gradient GEMM (it runs beside the scatter).
+ *   split-K factor of the first tower layer's weight-gradient GEMM (it runs beside the scatter);
+ *   "tower_dw_splits" (default 0 = automatic): row splits of ctr_tower_layer_bwd_weights.
  *   "adam_rows_inflight" (default 1): records in flight per lane group in ctr_adam_rows_bf
  *   (1 or 2). */
 int ctr_set_option(const char* name, int value);

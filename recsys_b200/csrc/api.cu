@@ -109,7 +109,7 @@ int ctr_set_option(const char* name, int value) {
   const std::string n(name);
   static const char* const known[] = {"bwd_aggregate", "adam_rows_inflight", "adam_rows_bf",
                                       "tcg_dw_stages", "tcg_dw_splits", "fwd_prefetch_record",
-                                      "mid_coop", "eb_debug"};
+                                      "mid_coop", "eb_debug", "tower_dw_splits"};
   bool ok = false;
   for (const char* k : known) ok = ok || n == k;
   if (!ok) return ctr::fail_arg("ctr_set_option", "unknown option");

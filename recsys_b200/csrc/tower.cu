@@ -1117,6 +1117,9 @@ int ctr_tower_layer_bwd_weights(const float* X, int ldx, int K, const ctr_bn_dro
   tower_smem_optin();
   const int tiles = ((K + kTwBM - 1) / kTwBM) * ((N + kTwBN - 1) / kTwBN);
   int splits = std::max(1, std::min((sm_count() * 3) / tiles, (B + 63) / 64));
+  // off the critical path (side stream): fewer, longer CTAs leave the SMs to the scatter / row
+  // optimiser kernels it runs beside ("tower_dw_splits", 0 = automatic)
+  if (const int o = option_get("tower_dw_splits", 0)) splits = std::max(1, std::min(splits, o));
   int rps = (B + splits - 1) / splits;
   rps = (rps + kTwKC - 1) / kTwKC * kTwKC;
   splits = (B + rps - 1) / rps;
