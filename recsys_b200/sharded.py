@@ -501,8 +501,11 @@ def bench_main(args, rank, local, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "deepfm 39-field emb16, %d-row table row-sharded (row %% G) over %d "
-                                   "GPUs, NCCL all-to-all of ids/vectors/grads, local batch %d, "
-                                   "fwd+bwd+Adam(lazy rows)" % (total_rows, world, B),
+                                   "GPUs, %s of ids/vectors/grads, local batch %d, "
+                                   "fwd+bwd+Adam(lazy rows)" % (
+                                       total_rows, world,
+                                       "peer-memory exchange" if exchange == "p2p" else "NCCL all-to-all",
+                                       B),
                        "fields": 39, "embedding_size": 16, "batch_per_gpu": B, "global_batch": B * world,
                        "table_rows": total_rows, "id_dist": getattr(args, "dist", "uniform"),
                        "exchange": ("device-initiated over NVLink peer memory (cudaIpc arenas, flag "
