@@ -199,15 +199,24 @@ def run_reference(args):
         "unit": "samples/s", "n_gpus": args.gpus, "steps": n, "warmup": max(0, args.warmup),
         "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args),
-                       reference_arm="oracle torch-CPU fp32 restatement: fwd+bwd only, no optimiser "
-                                     "step (so the CPU side is flattered)"),
+        # the arm under test's own config (N > 1: the sharded line's), so that the two lines name
+        # the same workload; what the CPU arm actually times is said in cpu_baseline.sample
+        "config": _reference_config(args),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "%d fwd+bwd steps of batch %d, oracle torch-CPU fp32 restatement "
-                                   "of deepfm.model_fn (TF is not installable here)" % (n, args.batch)},
+                         "sample": "%d fwd+bwd steps of batch %d on rank 0's host cores: oracle torch-CPU "
+                                   "fp32 restatement of %s.model_fn on the R-%s table, fwd+bwd only, no "
+                                   "optimiser step (so the CPU side is flattered); TF is not "
+                                   "installable here" % (n, args.batch, model, args.table)},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def _reference_config(args):
+    if args.gpus > 1:
+        from recsys_b200 import sharded
+        return sharded.bench_config(args, args.gpus)
+    return dict(workload_config(args), settle_steps=SETTLE)
 
 
 def metric_name(args):

@@ -340,6 +340,32 @@ def sharded_columns(total_rows: int, embedding_size: int, n_fields: int = 39):
     return lin, emb
 
 
+def bench_config(args, world: int) -> dict:
+    """The ``config`` object of the ``bench.py --gpus N`` line (N > 1), derived from the arguments
+    and the environment only, so that the reference arm (``--impl reference``, rank 0 on the host
+    cores) reports the very same workload."""
+    B = args.batch
+    total_rows = int(os.environ.get("CTR_SHARDED_ROWS", str(125_000_000 * world)))
+    exchange = os.environ.get("CTR_SHARD_EXCHANGE", "p2p")
+    slack = float(os.environ.get(
+        "CTR_SHARD_SLACK", "1.1" if getattr(args, "dist", "uniform") == "uniform" else str(world)))
+    return {"workload": "deepfm 39-field emb16, %d-row table row-sharded (row %% G) over %d "
+                        "GPUs, %s of ids/vectors/grads, local batch %d, "
+                        "fwd+bwd+Adam(lazy rows)" % (
+                            total_rows, world,
+                            "peer-memory exchange" if exchange == "p2p" else "NCCL all-to-all", B),
+            "fields": 39, "embedding_size": 16, "batch_per_gpu": B, "global_batch": B * world,
+            "table_rows": total_rows, "id_dist": getattr(args, "dist", "uniform"),
+            "exchange": ("device-initiated over NVLink peer memory (cudaIpc arenas, flag "
+                         "words; no NCCL call in the step; worst-case slabs)"
+                         if exchange == "p2p" else
+                         "3 NCCL all-to-alls per step (ids; row|w1 slab; gradient slab), "
+                         "slab slack %.2f" % slack),
+            "l2": "%.1f GB table shard per GPU > L2; distinct id batch every step"
+                  % (total_rows / world * 64 / 1e9),
+            "parallelism": "row-sharded table x%d + replicated dense weights (all-reduce)" % world}
+
+
 def bench_main(args, rank, local, world):
     """DeepFM, 39 fields, emb 16, 1e9-row table row-sharded over ``world`` GPUs, local batch
     ``args.batch`` per GPU (weak scaling).  Rank 0 prints the JSON line."""
@@ -500,22 +526,7 @@ def bench_main(args, rank, local, world):
             "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "deepfm 39-field emb16, %d-row table row-sharded (row %% G) over %d "
-                                   "GPUs, %s of ids/vectors/grads, local batch %d, "
-                                   "fwd+bwd+Adam(lazy rows)" % (
-                                       total_rows, world,
-                                       "peer-memory exchange" if exchange == "p2p" else "NCCL all-to-all",
-                                       B),
-                       "fields": 39, "embedding_size": 16, "batch_per_gpu": B, "global_batch": B * world,
-                       "table_rows": total_rows, "id_dist": getattr(args, "dist", "uniform"),
-                       "exchange": ("device-initiated over NVLink peer memory (cudaIpc arenas, flag "
-                                    "words; no NCCL call in the step; worst-case slabs)"
-                                    if exchange == "p2p" else
-                                    "3 NCCL all-to-alls per step (ids; row|w1 slab; gradient slab), "
-                                    "slab slack %.2f" % params["shard_slack"]),
-                       "l2": "%.1f GB table shard per GPU > L2; distinct id batch every step"
-                             % (total_rows / world * 64 / 1e9),
-                       "parallelism": "row-sharded table x%d + replicated dense weights (all-reduce)" % world},
+            "config": bench_config(args, world),
             "e2e": {"value": K * B * world / (max(ms_e2e, wall_e2e) / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": (f.cat.numel() * 8 + l.numel() * 4) * world,
                     "d2h_bytes_per_step": 4 * world,
