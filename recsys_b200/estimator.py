@@ -145,14 +145,21 @@ class Estimator:
         self.config = config
 
     def train(self, input_fn, steps=None, max_steps=None):
+        """``steps``: train that many more steps; ``max_steps``: stop once the global step has
+        reached it (a call at or past it trains nothing) - tf.estimator.Estimator.train."""
+        store = store_of(self.params)
         n = 0
         last = None
+        if max_steps is not None and store.global_step >= max_steps:
+            return None
         for features, labels in input_fn():
             spec = self.model_fn(features, labels, ModeKeys.TRAIN, self.params)
             spec.train_op()
             last = spec.loss
             n += 1
             if steps is not None and n >= steps:
+                break
+            if max_steps is not None and store.global_step >= max_steps:
                 break
         return None if last is None else float(last)
 
@@ -256,6 +263,8 @@ class GraphedTrainStep:
                 self._eager(k)
             self.graphs.append(g)
             self.stream.synchronize()
+        # capturing ran train_op's host-side bookkeeping without running a step
+        store_of(self.params).global_step -= len(self.graphs)
         self.graph = self.graphs[0]
 
     def _find_prefetcher(self):
@@ -344,6 +353,7 @@ class GraphedTrainStep:
             self._free[k].record(self.stream)
         self._last = k
         self._slot = (k + 1) % self.nbuf
+        store_of(self.params).global_step += 1       # the captured train_op's host-side bookkeeping
         return self.loss
 
     @property

@@ -66,3 +66,28 @@ def test_graphed_step_blob_layout():
     views["cat"].fill_(7)
     views["cont"].fill_(1.5)                          # neighbours do not overlap
     assert int(views["cat"].min()) == 7 and float(views["__labels__"].abs().sum()) == 0.0
+
+
+def test_estimator_train_honours_steps_and_max_steps():
+    """tf.estimator.Estimator.train(steps=, max_steps=): `steps` more steps, or up to the global step
+    `max_steps` (a call at or past it trains nothing).  Host logic only: a stand-in model_fn."""
+    from recsys_b200.estimator import Estimator, EstimatorSpec, ModeKeys, VariableStore
+
+    store = VariableStore()
+
+    def model_fn(features, labels, mode, params):
+        def train_op():
+            params["variable_store"].global_step += 1
+        return EstimatorSpec(mode=mode, predictions={}, loss=torch.tensor(0.5), train_op=train_op)
+
+    def input_fn():
+        while True:
+            yield {}, None
+
+    est = Estimator(model_fn, params={"variable_store": store})
+    assert est.train(input_fn, steps=3) == 0.5 and store.global_step == 3
+    est.train(input_fn, max_steps=10)
+    assert store.global_step == 10
+    assert est.train(input_fn, max_steps=10) is None and store.global_step == 10
+    est.train(input_fn, steps=2, max_steps=100)
+    assert store.global_step == 12
